@@ -1,0 +1,106 @@
+"""ctypes binding of ``libmemb.so`` (the C ABI declared in ``include/memb.h``).
+
+PyTorch is plumbing here: it owns device memory and streams, and this module
+hands raw pointers to the library.  There is no CPU or PyTorch fallback: if the
+shared library is missing or CUDA is unavailable, calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmemb.so")
+
+MEMB_OK, MEMB_EINVAL, MEMB_EOOB, MEMB_ECUDA, MEMB_EWORKSPACE = 0, -1, -2, -3, -4
+
+HIST_AUTO, HIST_GLOBAL, HIST_GLOBAL_AGG, HIST_TILE = 0, 1, 2, 3
+
+_c = ctypes
+_vp, _i32, _i64, _sz, _f32 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_size_t, _c.c_float
+
+# name -> (restype, argtypes).  Kept in step with include/memb.h; tests/test_abi.py
+# checks that every symbol the header declares is exported and listed here.
+SIGNATURES = {
+    "memb_last_error": (_c.c_char_p, []),
+    "memb_version": (_i32, []),
+    "memb_launch_count": (_i64, []),
+    "memb_hist_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32]),
+    "memb_hist_u8": (_i32, [_vp, _i64, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "memb_hist_status": (_i32, [_vp, _vp]),
+    "memb_hist_extent": (_i32, [_vp, _i64, _vp, _vp, _sz, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class MembError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libmemb error {code}: {msg}")
+        self.code = code
+
+
+def load() -> ctypes.CDLL:
+    """Load the library (once).  Raises if it has not been built -- run
+    ``python -c 'import __graft_entry__ as g; g.build()'`` at the repo root."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: the CUDA library has not been built and mem_b200 has "
+                    "no CPU fallback (build it with __graft_entry__.build()).")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def check(code: int) -> None:
+    if code == MEMB_OK:
+        return
+    msg = load().memb_last_error().decode("utf-8", "replace")
+    if code == MEMB_EOOB:
+        raise IndexError(msg)
+    if code == MEMB_EINVAL:
+        raise ValueError(msg)
+    raise MembError(code, msg)
+
+
+def launch_count() -> int:
+    return int(load().memb_launch_count())
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("mem_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch
+
+
+def stream_ptr(torch, device=None) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Workspace:
+    """Grow-only device scratch buffer owned by the caller side (PyTorch caching allocator)."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, torch, nbytes: int, device, tag: str = "default"):
+        key = (tag, str(device))
+        buf = self._buf.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._buf[key] = buf
+        return buf
+
+
+workspace = Workspace()

@@ -1,0 +1,474 @@
+// Event stream -> polarity-count image on sm_100a.
+//
+// Replaces EventArrToImg.__call__ (reference mem/datasets.py:566-595).  HBM-bound
+// integer work: one 32-byte float64[4] row per event is read exactly once with a
+// single 256-bit load (LDG.E.256), the scatter goes either to L2-resident u32
+// accumulators with fire-and-forget RED (one long stream) or to a shared-memory
+// privatised sensor tile (ragged training batches), and the uint8 image is
+// written once, coalesced.  Counters are wider than a byte and reduced modulo 256
+// at the end, which is exactly numpy's uint8 wrap.
+#include <algorithm>
+#include <climits>
+
+#include "common.cuh"
+
+namespace memb {
+namespace hist {
+
+constexpr int kHeaderBytes = 256;
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+constexpr int kTileThreads = 1024;
+constexpr int kTileMaxWords = 50 * 1024;        // 200 KB of packed u16x2 counters per CTA
+constexpr int kTileChunk = kTileThreads * 60;   // 61440 rows between folds (< 65535 - 255)
+
+struct Header {
+  int oob;            // set when an event fell outside [-H*W, H*W)
+  int pad;
+  long long max_x;    // memb_hist_extent
+  long long max_y;
+};
+
+struct Event { double x, y, t, p; };
+
+template <bool kAligned>
+__device__ __forceinline__ Event load_event(const double* __restrict__ ev, long long row) {
+  Event e;
+  const double* p = ev + 4 * row;
+  if constexpr (kAligned) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(e.x), "=d"(e.y), "=d"(e.t), "=d"(e.p) : "l"(p));
+  } else {
+    e.x = __ldg(p); e.y = __ldg(p + 1); e.t = __ldg(p + 2); e.p = __ldg(p + 3);
+  }
+  return e;
+}
+
+// Flat pixel index following numpy: trunc toward zero, x + W*y, one negative wrap.
+// Returns false (and leaves idx untouched) when the reference would raise IndexError.
+__device__ __forceinline__ bool pixel_index(double x, double y, int W, long long npix, long long& idx) {
+  // |coord| >= 2^40 (or NaN) can never index a sensor; numpy's cast gives INT64_MIN there.
+  if (!(fabs(x) < 1.0995116e12) || !(fabs(y) < 1.0995116e12)) return false;
+  long long i = __double2ll_rz(x) + (long long)W * __double2ll_rz(y);
+  if (i < -npix || i >= npix) return false;
+  idx = i < 0 ? i + npix : i;
+  return true;
+}
+
+__device__ __forceinline__ unsigned long long order_key(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_value(unsigned long long k) {
+  unsigned long long b = (k >> 63) ? (k ^ 0x8000000000000000ull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// ---------------------------------------------------------------- init
+__global__ void __launch_bounds__(256) hist_init(uint4* __restrict__ ws, long long n_vec,
+                                                 long long tkeys_vec, int B) {
+  // One 16-byte vector per stream holds {min key, max key}; everything else starts at zero.
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n_vec; i += stride) {
+    const bool key = tkeys_vec >= 0 && i >= tkeys_vec && i < tkeys_vec + B;
+    ws[i] = key ? make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// ---------------------------------------------------------------- per-stream min/max of t
+template <bool kAligned>
+__global__ void __launch_bounds__(kThreads) hist_time_range(const double* __restrict__ ev,
+                                                            const long long* __restrict__ offsets,
+                                                            long long n_total,
+                                                            unsigned long long* __restrict__ tkeys) {
+  const int b = blockIdx.y;
+  const long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
+  unsigned long long lo = ~0ull, hi = 0ull;
+  for (long long r = begin + blockIdx.x * (long long)kThreads + threadIdx.x; r < end;
+       r += (long long)gridDim.x * kThreads) {
+    unsigned long long k = order_key(load_event<kAligned>(ev, r).t);
+    lo = k < lo ? k : lo;
+    hi = k > hi ? k : hi;
+  }
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
+    atomicMin(&tkeys[2 * b], lo);
+    atomicMax(&tkeys[2 * b + 1], hi);
+  }
+}
+
+// ---------------------------------------------------------------- strategy GLOBAL
+// acc: u32 [B][2][npix] (pos plane, neg plane); last: u64 [B][npix] (row index + 1 of the last
+// writer, time surface only).
+template <bool kAligned, bool kAggregate, bool kTss>
+__global__ void __launch_bounds__(kThreads) hist_scatter_global(
+    const double* __restrict__ ev, const long long* __restrict__ offsets, long long n_total, int W,
+    long long npix, unsigned int* __restrict__ acc, unsigned long long* __restrict__ last,
+    Header* __restrict__ hdr) {
+  const int b = blockIdx.y;
+  const long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
+  unsigned int* acc_b = acc + (long long)b * 2 * npix;
+  unsigned long long* last_b = kTss ? last + (long long)b * npix : nullptr;
+  bool bad = false;
+
+  const long long step = (long long)gridDim.x * kThreads * kUnroll;
+  // Whole-warp iterations so that match.any sees a converged warp.
+  for (long long base = begin + blockIdx.x * (long long)(kThreads * kUnroll); base < end; base += step) {
+    Event e[kUnroll];
+    bool live[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      long long r = base + u * kThreads + threadIdx.x;
+      live[u] = r < end;
+      if (live[u]) e[u] = load_event<kAligned>(ev, r);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      long long idx = 0;
+      const bool pos = live[u] && e[u].p == 1.0, neg = live[u] && e[u].p == -1.0;
+      const bool need = kTss ? live[u] : (pos || neg);
+      const bool ok = need && pixel_index(e[u].x, e[u].y, W, npix, idx);
+      bad |= need && !ok;
+      const bool count = ok && (pos || neg);
+      const long long slot = (neg ? npix : 0) + idx;
+      if constexpr (kAggregate) {
+        const unsigned int active = __ballot_sync(0xffffffffu, count);
+        if (count) {
+          const unsigned int peers = __match_any_sync(active, slot);
+          if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(acc_b + slot, (unsigned int)__popc(peers));
+        }
+      } else {
+        if (count) atomicAdd(acc_b + slot, 1u);
+      }
+      if constexpr (kTss) {
+        if (ok) atomicMax(last_b + idx, (unsigned long long)(base + u * kThreads + threadIdx.x - begin + 1));
+      }
+    }
+  }
+  if (bad) hdr->oob = 1;
+}
+
+// 4 pixels per thread; out is uint8 [B][npix][C].
+template <bool kTss>
+__global__ void __launch_bounds__(256) hist_finalize(const unsigned int* __restrict__ acc,
+                                                     const unsigned long long* __restrict__ last,
+                                                     const unsigned long long* __restrict__ tkeys,
+                                                     const double* __restrict__ ev,
+                                                     const long long* __restrict__ offsets,
+                                                     long long npix, int C, uint8_t* __restrict__ out) {
+  const int b = blockIdx.y;
+  const unsigned int* pos = acc + (long long)b * 2 * npix;
+  const unsigned int* neg = pos + npix;
+  uint8_t* o = out + (long long)b * npix * C;
+  double tmin = 0.0, span = 0.0;
+  const double* ev_b = nullptr;
+  if constexpr (kTss) {
+    tmin = key_value(tkeys[2 * b]);
+    span = key_value(tkeys[2 * b + 1]) - tmin;
+    ev_b = ev + 4 * (offsets ? offsets[b] : 0);
+  }
+  for (long long px = blockIdx.x * (long long)blockDim.x + threadIdx.x; px < npix;
+       px += (long long)gridDim.x * blockDim.x) {
+    const uint8_t cp = (uint8_t)(pos[px] & 0xffu), cn = (uint8_t)(neg[px] & 0xffu);
+    if (C == 2) {
+      o[2 * px] = cp;
+      o[2 * px + 1] = cn;
+    } else {
+      uint8_t ts = 0;
+      if constexpr (kTss) {
+        const unsigned long long w = last[(long long)b * npix + px];
+        if (w) {
+          // (t - tmin) / (tmax - tmin) * 255, float64, same operation order as datasets.py:588-589.
+          const double v = (ev_b[4 * (w - 1) + 2] - tmin) / span * 255.0;
+          ts = (v == v) ? (uint8_t)(long long)v : (uint8_t)0;
+        }
+      }
+      o[3 * px] = cp;
+      o[3 * px + 1] = ts;
+      o[3 * px + 2] = cn;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- strategy TILE
+// CTA (tile, b) owns pixels [tile*tile_pix, ...) of stream b, keeps one packed word per pixel in
+// shared memory (low half: +1 events, high half: -1 events), reads the whole stream (L2 hits after
+// the first tile) and writes its part of the uint8 image directly: no global atomics, no zero-fill,
+// no finalize pass.  Halves are folded mod 256 between chunks so they can never carry.
+template <bool kAligned>
+__global__ void __launch_bounds__(kTileThreads, 1) hist_tile_smem(
+    const double* __restrict__ ev, const long long* __restrict__ offsets, long long n_total, int W,
+    long long npix, int tile_pix, int C, uint8_t* __restrict__ out, Header* __restrict__ hdr) {
+  extern __shared__ unsigned int tile[];
+  const int b = blockIdx.y;
+  const long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
+  const long long lo = (long long)blockIdx.x * tile_pix;
+  const int mine = (int)min((long long)tile_pix, npix - lo);
+  for (int i = threadIdx.x; i < tile_pix; i += kTileThreads) tile[i] = 0u;
+  __syncthreads();
+
+  bool bad = false;
+  for (long long chunk = begin; chunk < end; chunk += kTileChunk) {
+    const long long stop = min(end, chunk + (long long)kTileChunk);
+    for (long long base = chunk; base < stop; base += kTileThreads * kUnroll) {
+      Event e[kUnroll];
+      bool live[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        long long r = base + u * kTileThreads + threadIdx.x;
+        live[u] = r < stop;
+        if (live[u]) e[u] = load_event<kAligned>(ev, r);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const bool pos = live[u] && e[u].p == 1.0, neg = live[u] && e[u].p == -1.0;
+        if (pos || neg) {
+          long long idx;
+          if (!pixel_index(e[u].x, e[u].y, W, npix, idx)) {
+            bad = true;
+          } else {
+            idx -= lo;
+            if (idx >= 0 && idx < mine) atomicAdd(&tile[idx], pos ? 1u : 0x10000u);
+          }
+        }
+      }
+    }
+    if (stop < end) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < tile_pix; i += kTileThreads) tile[i] &= 0x00ff00ffu;
+      __syncthreads();
+    }
+  }
+  if (bad) hdr->oob = 1;
+  __syncthreads();
+
+  uint8_t* o = out + ((long long)b * npix + lo) * C;
+  if (C == 2 && (((uintptr_t)o) & 7u) == 0) {
+    // 4 pixels -> 8 bytes per thread per step
+    for (int i = threadIdx.x * 4; i < mine; i += kTileThreads * 4) {
+      if (i + 3 < mine) {
+        unsigned int w0 = tile[i], w1 = tile[i + 1], w2 = tile[i + 2], w3 = tile[i + 3];
+        uint2 v;
+        v.x = (w0 & 0xffu) | ((w0 >> 16 & 0xffu) << 8) | ((w1 & 0xffu) << 16) | ((w1 >> 16 & 0xffu) << 24);
+        v.y = (w2 & 0xffu) | ((w2 >> 16 & 0xffu) << 8) | ((w3 & 0xffu) << 16) | ((w3 >> 16 & 0xffu) << 24);
+        *reinterpret_cast<uint2*>(o + 2 * i) = v;
+      } else {
+        for (int j = i; j < mine; ++j) {
+          o[2 * j] = (uint8_t)(tile[j] & 0xffu);
+          o[2 * j + 1] = (uint8_t)(tile[j] >> 16 & 0xffu);
+        }
+      }
+    }
+  } else if (C == 3 && (((uintptr_t)o) & 3u) == 0) {
+    // 4 pixels -> 12 bytes per thread per step
+    for (int i = threadIdx.x * 4; i < mine; i += kTileThreads * 4) {
+      if (i + 3 < mine) {
+        unsigned int w0 = tile[i], w1 = tile[i + 1], w2 = tile[i + 2], w3 = tile[i + 3];
+        unsigned int* o32 = reinterpret_cast<unsigned int*>(o + 3 * i);
+        o32[0] = (w0 & 0xffu) | ((w0 >> 16 & 0xffu) << 16) | ((w1 & 0xffu) << 24);
+        o32[1] = (w1 >> 16 & 0xffu) << 8 | ((w2 & 0xffu) << 16);
+        o32[2] = (w2 >> 16 & 0xffu) | ((w3 & 0xffu) << 8) | ((w3 >> 16 & 0xffu) << 24);
+      } else {
+        for (int j = i; j < mine; ++j) {
+          o[3 * j] = (uint8_t)(tile[j] & 0xffu);
+          o[3 * j + 1] = 0;
+          o[3 * j + 2] = (uint8_t)(tile[j] >> 16 & 0xffu);
+        }
+      }
+    }
+  } else {
+    for (int j = threadIdx.x; j < mine; j += kTileThreads) {
+      if (C == 2) {
+        o[2 * j] = (uint8_t)(tile[j] & 0xffu);
+        o[2 * j + 1] = (uint8_t)(tile[j] >> 16 & 0xffu);
+      } else {
+        o[3 * j] = (uint8_t)(tile[j] & 0xffu);
+        o[3 * j + 1] = 0;
+        o[3 * j + 2] = (uint8_t)(tile[j] >> 16 & 0xffu);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- extent (H/W = None)
+template <bool kAligned>
+__global__ void __launch_bounds__(kThreads) hist_extent(const double* __restrict__ ev, long long n,
+                                                        Header* __restrict__ hdr) {
+  long long mx = LLONG_MIN, my = LLONG_MIN;
+  for (long long r = blockIdx.x * (long long)kThreads + threadIdx.x; r < n; r += (long long)gridDim.x * kThreads) {
+    Event e = load_event<kAligned>(ev, r);
+    // numpy: astype(int) of NaN / huge is INT64_MIN; keep that ordering.
+    long long xi = (fabs(e.x) < 9.2e18) ? __double2ll_rz(e.x) : LLONG_MIN;
+    long long yi = (fabs(e.y) < 9.2e18) ? __double2ll_rz(e.y) : LLONG_MIN;
+    mx = max(mx, xi);
+    my = max(my, yi);
+  }
+  for (int o = 16; o; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    my = max(my, __shfl_xor_sync(0xffffffffu, my, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&hdr->max_x, mx);
+    atomicMax(&hdr->max_y, my);
+  }
+}
+__global__ void hist_extent_init(Header* hdr) {
+  hdr->max_x = LLONG_MIN;
+  hdr->max_y = LLONG_MIN;
+}
+
+// ---------------------------------------------------------------- host side
+struct Plan {
+  int strategy;
+  int tiles, tile_pix;
+  size_t ws_bytes;
+  size_t off_tkeys, off_acc, off_last;
+};
+
+static Plan make_plan(int B, int64_t n, int H, int W, int timesurface, int strategy) {
+  Plan p{};
+  const long long npix = (long long)H * W;
+  if (timesurface) strategy = (strategy == MEMB_HIST_GLOBAL_AGG) ? MEMB_HIST_GLOBAL_AGG : MEMB_HIST_GLOBAL;
+  if (strategy == MEMB_HIST_AUTO) {
+    // Ragged training batches (many short streams): one privatised tile set per stream.
+    // One long stream: every SM streams its share and REDs into L2.
+    const long long per_stream = B > 0 ? n / B : n;
+    strategy = (B >= 16 && per_stream <= (1 << 20)) ? MEMB_HIST_TILE : MEMB_HIST_GLOBAL;
+  }
+  p.strategy = strategy;
+  p.tiles = (int)ceil_div<long long>(npix, kTileMaxWords);
+  p.tile_pix = (int)round_up<long long>(ceil_div<long long>(npix, p.tiles), 4);
+  p.off_tkeys = kHeaderBytes;
+  p.off_acc = p.off_tkeys + (timesurface ? round_up<size_t>((size_t)B * 16, 256) : 0);
+  p.off_last = p.off_acc + (strategy == MEMB_HIST_TILE ? 0 : (size_t)B * 2 * npix * 4);
+  p.off_last = round_up<size_t>(p.off_last, 16);
+  p.ws_bytes = round_up<size_t>(p.off_last + (timesurface ? (size_t)B * npix * 8 : 0), 16);
+  return p;
+}
+
+}  // namespace hist
+}  // namespace memb
+
+using namespace memb;
+using namespace memb::hist;
+
+extern "C" size_t memb_hist_workspace_bytes(int B, int64_t n, int H, int W, int timesurface, int strategy) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return make_plan(B, n, H, W, timesurface, strategy).ws_bytes;
+}
+
+extern "C" int memb_hist_u8(const double* ev, int64_t n, const int64_t* offsets, int B,
+                            int64_t max_stream_len, int H, int W, int C, int timesurface, int strategy,
+                            uint8_t* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
+  MEMB_REQUIRE(B >= 1 && H >= 1 && W >= 1, "hist: B, H, W must be positive (B=%d H=%d W=%d)", B, H, W);
+  MEMB_REQUIRE(C == 2 || C == 3, "hist: C must be 2 or 3, got %d", C);
+  MEMB_REQUIRE(!(timesurface && C != 3), "hist: the time surface needs C == 3");
+  MEMB_REQUIRE(n >= 0 && (n == 0 || ev != nullptr), "hist: null event pointer");
+  MEMB_REQUIRE(offsets != nullptr || B == 1, "hist: a batch needs row offsets");
+  MEMB_REQUIRE(out != nullptr && ws != nullptr, "hist: null output / workspace");
+  MEMB_REQUIRE((((uintptr_t)ev) & 7u) == 0 && (((uintptr_t)ws) & 15u) == 0, "hist: misaligned pointer");
+  MEMB_REQUIRE(strategy >= MEMB_HIST_AUTO && strategy <= MEMB_HIST_TILE, "hist: unknown strategy %d", strategy);
+  const long long npix = (long long)H * W;
+  const Plan p = make_plan(B, n, H, W, timesurface, strategy);
+  if (ws_bytes < p.ws_bytes)
+    return fail(MEMB_EWORKSPACE, "hist: workspace %zu B < required %zu B", ws_bytes, p.ws_bytes);
+  if (max_stream_len <= 0 || max_stream_len > n) max_stream_len = n;
+
+  char* wsb = static_cast<char*>(ws);
+  Header* hdr = reinterpret_cast<Header*>(wsb);
+  unsigned long long* tkeys = timesurface ? reinterpret_cast<unsigned long long*>(wsb + p.off_tkeys) : nullptr;
+  unsigned int* acc = reinterpret_cast<unsigned int*>(wsb + p.off_acc);
+  unsigned long long* last = reinterpret_cast<unsigned long long*>(wsb + p.off_last);
+  const bool aligned = (((uintptr_t)ev) & 31u) == 0;
+  const long long* offs = reinterpret_cast<const long long*>(offsets);
+  const int sms = num_sms();
+
+  {  // zero the header (+ accumulators) and seed the min/max keys
+    const long long n_vec = (long long)((p.strategy == MEMB_HIST_TILE ? (size_t)kHeaderBytes : p.ws_bytes) / 16);
+    const int blocks = (int)std::min<long long>(ceil_div<long long>(n_vec, 256), (long long)sms * 8);
+    hist_init<<<blocks, 256, 0, stream>>>(reinterpret_cast<uint4*>(wsb), n_vec,
+                                          timesurface ? (long long)(p.off_tkeys / 16) : -1LL, B);
+    MEMB_LAUNCH_OK("hist_init");
+  }
+
+  if (p.strategy == MEMB_HIST_TILE) {
+    const size_t smem = (size_t)p.tile_pix * 4;
+    auto kern = aligned ? hist_tile_smem<true> : hist_tile_smem<false>;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[aligned]) {
+      MEMB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxWords * 4));
+      attr_set[aligned] = true;
+    }
+    kern<<<dim3(p.tiles, B), kTileThreads, smem, stream>>>(ev, offs, n, W, npix, p.tile_pix, C, out, hdr);
+    MEMB_LAUNCH_OK("hist_tile_smem");
+    return MEMB_OK;
+  }
+
+  // grid.x: enough CTAs to cover the longest stream once, capped at ~8 resident CTAs per SM overall
+  const long long per_cta = (long long)kThreads * kUnroll;
+  long long gx = std::max<long long>(1, ceil_div<long long>(max_stream_len, per_cta));
+  const long long cap = std::max<long long>(1, ((long long)sms * 8 + B - 1) / B);
+  gx = std::min(gx, cap);
+  const dim3 grid((unsigned)gx, (unsigned)B);
+
+  if (timesurface && n > 0) {
+    if (aligned) hist_time_range<true><<<grid, kThreads, 0, stream>>>(ev, offs, n, tkeys);
+    else hist_time_range<false><<<grid, kThreads, 0, stream>>>(ev, offs, n, tkeys);
+    MEMB_LAUNCH_OK("hist_time_range");
+  }
+  if (n > 0) {
+    const bool agg = p.strategy == MEMB_HIST_GLOBAL_AGG;
+#define MEMB_SCATTER(A, G, T)                                                                        \
+  hist_scatter_global<A, G, T><<<grid, kThreads, 0, stream>>>(ev, offs, n, W, npix, acc, last, hdr)
+    if (timesurface) {
+      if (aligned) { if (agg) MEMB_SCATTER(true, true, true); else MEMB_SCATTER(true, false, true); }
+      else { if (agg) MEMB_SCATTER(false, true, true); else MEMB_SCATTER(false, false, true); }
+    } else {
+      if (aligned) { if (agg) MEMB_SCATTER(true, true, false); else MEMB_SCATTER(true, false, false); }
+      else { if (agg) MEMB_SCATTER(false, true, false); else MEMB_SCATTER(false, false, false); }
+    }
+#undef MEMB_SCATTER
+    MEMB_LAUNCH_OK("hist_scatter_global");
+  }
+  {
+    long long fx = std::min<long long>(ceil_div<long long>(npix, 256), std::max<long long>(1, (long long)sms * 8 / B));
+    const dim3 fgrid((unsigned)std::max<long long>(1, fx), (unsigned)B);
+    if (timesurface) hist_finalize<true><<<fgrid, 256, 0, stream>>>(acc, last, tkeys, ev, offs, npix, C, out);
+    else hist_finalize<false><<<fgrid, 256, 0, stream>>>(acc, nullptr, nullptr, ev, offs, npix, C, out);
+    MEMB_LAUNCH_OK("hist_finalize");
+  }
+  return MEMB_OK;
+}
+
+extern "C" int memb_hist_status(const void* ws, memb_stream_t stream) {
+  MEMB_REQUIRE(ws != nullptr, "hist_status: null workspace");
+  int flag = 0;
+  MEMB_CUDA_OK(cudaMemcpyAsync(&flag, ws, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  MEMB_CUDA_OK(cudaStreamSynchronize(stream));
+  if (flag) return fail(MEMB_EOOB, "hist: event index out of bounds for the sensor (reference: IndexError)");
+  return MEMB_OK;
+}
+
+extern "C" int memb_hist_extent(const double* ev, int64_t n, int64_t* max_xy_host, void* ws, size_t ws_bytes,
+                                memb_stream_t stream) {
+  MEMB_REQUIRE(ev != nullptr && n > 0, "hist_extent: empty stream (reference: ValueError on max of empty)");
+  MEMB_REQUIRE(ws != nullptr && ws_bytes >= (size_t)kHeaderBytes && max_xy_host != nullptr, "hist_extent: bad workspace");
+  Header* hdr = reinterpret_cast<Header*>(ws);
+  hist_extent_init<<<1, 1, 0, stream>>>(hdr);
+  MEMB_LAUNCH_OK("hist_extent_init");
+  const int blocks = (int)std::min<long long>(ceil_div<long long>(n, kThreads), (long long)num_sms() * 8);
+  if ((((uintptr_t)ev) & 31u) == 0) hist_extent<true><<<blocks, kThreads, 0, stream>>>(ev, n, hdr);
+  else hist_extent<false><<<blocks, kThreads, 0, stream>>>(ev, n, hdr);
+  MEMB_LAUNCH_OK("hist_extent");
+  long long host[3];
+  MEMB_CUDA_OK(cudaMemcpyAsync(host, reinterpret_cast<char*>(ws) + 8, 16, cudaMemcpyDeviceToHost, stream));
+  MEMB_CUDA_OK(cudaStreamSynchronize(stream));
+  max_xy_host[0] = host[0];
+  max_xy_host[1] = host[1];
+  return MEMB_OK;
+}

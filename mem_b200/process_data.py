@@ -1,0 +1,120 @@
+"""Event stream -> polarity-count histogram on the GPU.
+
+``histogram`` is the name ``BASELINE.json``'s north star uses; the reference
+keeps the rasteriser in ``EventArrToImg.__call__`` (``mem/datasets.py:566-595``,
+see SURVEY.md D1) and ``mem_b200.datasets.EventArrToImg`` wraps this function
+with that class's constructor and call signature.
+
+Results are bit-identical to the reference: truncation of x / y toward zero,
+``x + W*y`` flat index with numpy's single negative wrap, ``IndexError`` outside
+``[-H*W, H*W)``, exact ``p == +1`` / ``p == -1`` selection, uint8 wrap modulo
+256, and the optional last-writer time surface.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["histogram", "histogram_batch"]
+
+
+def _as_device_events(torch, events, device):
+    """(N,4) float64 rows on the device; returns (tensor, came_from_host)."""
+    if isinstance(events, torch.Tensor):
+        ev = events
+        host = not ev.is_cuda
+    else:
+        ev = torch.from_numpy(np.ascontiguousarray(np.asarray(events), dtype=np.float64))
+        host = True
+    if ev.ndim != 2 or ev.shape[1] != 4:
+        raise ValueError(f"events must be (N, 4) rows [x, y, t, p], got {tuple(ev.shape)}")
+    if ev.dtype != torch.float64:
+        ev = ev.to(torch.float64)
+    ev = ev.contiguous()
+    if host:
+        ev = ev.to(device, non_blocking=False)
+    return ev, host
+
+
+def _launch(torch, ev, offsets, B, max_len, H, W, channels, timesurface, strategy, out, check):
+    lib = _lib.load()
+    n = int(ev.shape[0])
+    need = lib.memb_hist_workspace_bytes(B, n, H, W, int(timesurface), strategy)
+    ws = _lib.workspace.get(torch, need, ev.device, "hist")
+    stream = _lib.stream_ptr(torch, ev.device)
+    _lib.check(lib.memb_hist_u8(
+        ev.data_ptr() if n else None, n, offsets.data_ptr() if offsets is not None else None, B, max_len,
+        H, W, channels, int(timesurface), strategy, out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    if check:
+        _lib.check(lib.memb_hist_status(ws.data_ptr(), stream))
+
+
+def histogram(events, H=None, W=None, timesurface=False, channels=3, *, device=None,
+              strategy=_lib.HIST_AUTO, check=True):
+    """Rasterise one event stream.
+
+    events: ``(N, 4)`` rows ``[x, y, t, p]`` (numpy array, CPU tensor or CUDA tensor).
+    Returns ``uint8 (H, W, channels)``: ``[pos, time-surface|0, neg]`` for 3 channels,
+    ``[pos, neg]`` for 2 (the ``[..., 0::2]`` map).  A numpy array in gives a numpy
+    array out; a tensor in gives a CUDA tensor out.  ``check=False`` skips the
+    (synchronising) out-of-bounds test.
+    """
+    torch = _lib.require_cuda()
+    if channels not in (2, 3):
+        raise ValueError("channels must be 2 or 3")
+    if timesurface and channels != 3:
+        raise ValueError("the time surface lives in channel 1 of a 3-channel image")
+    device = torch.device(device if device is not None else
+                          (events.device if isinstance(events, torch.Tensor) and events.is_cuda else "cuda"))
+    numpy_in = not isinstance(events, torch.Tensor)
+    with torch.cuda.device(device):
+        ev, _ = _as_device_events(torch, events, device)
+        n = int(ev.shape[0])
+        if H is None or W is None:
+            if n == 0:
+                raise ValueError("zero-size array to reduction operation maximum which has no identity")
+            lib = _lib.load()
+            ws = _lib.workspace.get(torch, 256, device, "hist")
+            ext = (_lib._i64 * 2)()
+            _lib.check(lib.memb_hist_extent(ev.data_ptr(), n, ext, ws.data_ptr(), ws.numel(),
+                                            _lib.stream_ptr(torch, device)))
+            W = int(ext[0]) + 1 if W is None else W
+            H = int(ext[1]) + 1 if H is None else H
+            if H <= 0 or W <= 0:
+                raise ValueError("negative dimensions are not allowed")
+        if timesurface and n == 0:
+            raise ValueError("zero-size array to reduction operation minimum which has no identity")
+        out = torch.empty((H, W, channels), dtype=torch.uint8, device=device)
+        _launch(torch, ev, None, 1, n, H, W, channels, timesurface, strategy, out, check)
+    return out.cpu().numpy() if numpy_in else out
+
+
+def histogram_batch(events, offsets, H, W, channels=3, timesurface=False, *, max_stream_len=None,
+                    strategy=_lib.HIST_AUTO, check=True, out=None):
+    """Rasterise a ragged batch: stream ``b`` is ``events[offsets[b]:offsets[b+1]]``.
+
+    events ``(sum N_b, 4)`` float64 and offsets ``int64 (B+1,)`` may be numpy or tensors;
+    returns ``uint8 (B, H, W, channels)`` (numpy if events was numpy, else CUDA tensor).
+    """
+    torch = _lib.require_cuda()
+    numpy_in = not isinstance(events, torch.Tensor)
+    device = torch.device(events.device if (not numpy_in and events.is_cuda) else "cuda")
+    with torch.cuda.device(device):
+        ev, _ = _as_device_events(torch, events, device)
+        if isinstance(offsets, torch.Tensor):
+            off = offsets.to(device=device, dtype=torch.int64).contiguous()
+            if max_stream_len is None:
+                max_stream_len = int(ev.shape[0])
+        else:
+            off_np = np.ascontiguousarray(np.asarray(offsets), dtype=np.int64)
+            if max_stream_len is None and len(off_np) > 1:
+                max_stream_len = int(np.diff(off_np).max())
+            off = torch.from_numpy(off_np).to(device)
+        B = int(off.numel()) - 1
+        if B < 1:
+            raise ValueError("offsets must have B+1 >= 2 entries")
+        if out is None:
+            out = torch.empty((B, H, W, channels), dtype=torch.uint8, device=device)
+        _launch(torch, ev, off, B, int(max_stream_len or 0), H, W, channels, timesurface, strategy, out, check)
+    return out.cpu().numpy() if numpy_in else out

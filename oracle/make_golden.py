@@ -1,0 +1,120 @@
+"""Oracle tooling (test infrastructure, not product): freeze golden vectors.
+
+Runs the UNMODIFIED reference (``/root/reference`` through ``oracle/ref_shims``)
+on small seeded inputs and stores inputs + outputs under ``tests/golden/``.
+The reference has no tests or fixtures of its own, so these vectors are what
+pins ``oracle/*_ref.py`` (and through it the CUDA path) to the reference.
+
+    python -m oracle.make_golden            # in the build container only
+
+The fixtures are committed; the GPU box never runs this script.
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shims  # noqa: E402
+
+
+def synth_events(rng, n, H, W, kind="uniform", polarity=(-1.0, 1.0), frac=False):
+    """Synthetic (n,4) float64 stream of SURVEY.md section 8(d) shapes."""
+    if kind == "uniform":
+        x = rng.integers(0, W, n).astype(np.float64)
+        y = rng.integers(0, H, n).astype(np.float64)
+    elif kind == "hot":
+        x = rng.integers(0, W, n).astype(np.float64)
+        y = rng.integers(0, H, n).astype(np.float64)
+        hot = rng.random(n) < 0.5
+        hx, hy = rng.integers(0, W, 4), rng.integers(0, H, 4)
+        pick = rng.integers(0, 4, n)
+        x[hot], y[hot] = hx[pick[hot]], hy[pick[hot]]
+    elif kind == "edge":
+        seg = rng.integers(0, 8, n)
+        x0, y0 = rng.uniform(0, W, 8), rng.uniform(0, H, 8)
+        dx, dy = rng.uniform(-1, 1, 8), rng.uniform(-1, 1, 8)
+        s = rng.uniform(0, min(H, W) / 2, n)
+        x = np.clip(x0[seg] + dx[seg] * s + rng.normal(0, 1, n), 0, W - 1e-3)
+        y = np.clip(y0[seg] + dy[seg] * s + rng.normal(0, 1, n), 0, H - 1e-3)
+    else:
+        raise ValueError(kind)
+    if frac:
+        x = np.clip(x + rng.uniform(-0.9, 0.9, n), -0.99, W - 1e-3)
+        y = np.clip(y + rng.uniform(0.0, 0.9, n), 0, H - 1e-3)
+    t = np.sort(rng.uniform(0, 3e5, n))
+    p = rng.choice(np.asarray(polarity, dtype=np.float64), n)
+    return np.stack([x, y, t, p], axis=1)
+
+
+def golden_histogram():
+    ds = ref_shims.ref_module("datasets")
+    rng = np.random.default_rng(20240117)
+    cases = {}
+
+    def add(name, ev, H, W, tss):
+        img = ds.EventArrToImg(H, W, tss)(ev.copy())
+        cases[name + "_ev"] = ev
+        cases[name + "_img"] = np.ascontiguousarray(img)
+        cases[name + "_cfg"] = np.array([-1 if H is None else H, -1 if W is None else W, int(tss)])
+
+    add("uniform_180x240", synth_events(rng, 6000, 180, 240), 180, 240, False)
+    add("wrap_100x100", synth_events(rng, 40000, 100, 100, "hot"), 100, 100, False)       # >255 per pixel
+    add("edge_frac_120x160", synth_events(rng, 5000, 120, 160, "edge", frac=True), 120, 160, False)
+    add("ncars_polarity01", synth_events(rng, 3000, 100, 120, polarity=(0.0, 1.0)), 100, 120, False)
+    add("infer_hw", synth_events(rng, 2000, 130, 170), None, None, False)
+    add("tss_180x240", synth_events(rng, 4000, 180, 240), 180, 240, True)
+    add("tss_infer_hot", synth_events(rng, 3000, 100, 110, "hot"), None, None, True)
+    neg = synth_events(rng, 500, 100, 100)
+    neg[::7, 1] = 0.0
+    neg[::7, 0] = -neg[::7, 0] - 1.0           # negative flat index -> numpy wraps once
+    add("negative_wrap", neg, 100, 100, False)
+    single = np.array([[5.0, 7.0, 10.0, 1.0]])
+    add("single_event", single, 100, 100, False)
+    add("empty_fixed", np.zeros((0, 4)), 100, 100, False)
+    np.savez_compressed(os.path.join(GOLD, "histogram.npz"), **cases)
+    print("histogram.npz:", len(cases) // 3, "cases")
+
+
+def golden_masks():
+    mg = ref_shims.ref_module("masking_generator")
+    out = {}
+    cfgs = [((14, 14), 75, 16), ((14, 14), 98, 16), ((14, 14), 75, 4), ((16, 16), 120, 8), ((7, 9), 20, 2)]
+    for ci, (hw, nmask, mn) in enumerate(cfgs):
+        masks = []
+        for seed in range(32):
+            random.seed(seed)
+            masks.append(mg.MaskingGenerator(hw, nmask, min_num_patches=mn)())
+        out[f"block_{ci}_cfg"] = np.array([hw[0], hw[1], nmask, mn])
+        out[f"block_{ci}_masks"] = np.stack(masks).astype(np.uint8)
+    # a stream of consecutive draws from one seed (what a DataLoader worker does)
+    random.seed(1234)
+    gen = mg.MaskingGenerator((14, 14), 75, min_num_patches=16)
+    out["stream_masks"] = np.stack([gen() for _ in range(64)]).astype(np.uint8)
+    masks = []
+    for seed in range(16):
+        random.seed(seed)
+        masks.append(mg.MaskingGeneratorRandomLocation((14, 14), 75)())
+    out["randloc_masks"] = np.stack(masks).astype(np.uint8)
+    np.savez_compressed(os.path.join(GOLD, "masks.npz"), **out)
+    print("masks.npz written")
+
+
+SECTIONS = {"histogram": golden_histogram, "masks": golden_masks}
+
+
+def main(argv):
+    os.makedirs(GOLD, exist_ok=True)
+    names = argv or list(SECTIONS)
+    for n in names:
+        SECTIONS[n]()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
