@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the MEM pretraining hot path on B200 (contract in the task prompt).
+
+    python bench.py --gpus 1 --steps K --warmup W             # our arm (CUDA, libmemb)
+    python bench.py --impl reference --gpus 1 --steps K ...   # reference's CPU path (oracle port)
+    torchrun ... bench.py --gpus N ...                        # one rank per GPU
+
+Prints ONE JSON line on rank 0.  Workloads:
+
+  histogram  event -> polarity histogram rasterisation, 10M uniform events at the
+             N-ImageNet 640x480 sensor (largest single-GPU case of BASELINE config 2)
+  pretrain   ViT-B/16 MEM pretraining step, batch 128/GPU (BASELINE config 3)
+
+`--workload auto` picks `pretrain` when the training-step kernels are built in,
+else `histogram`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "histogram", "pretrain"])
+    ap.add_argument("--events", type=int, default=10_000_000)
+    ap.add_argument("--sensor", default="640x480")
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index, self.rows, self.proc, self.thread = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=lambda: [self.rows.append(l) for l in self.proc.stdout], daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ----------------------------------------------------------------------------- histogram workload
+class HistogramWorkload:
+    metric = "Gevents/s histogram rasterise"
+    unit = "Gevents/s"
+    dtype = "u8"
+
+    def __init__(self, args):
+        w, h = (int(v) for v in args.sensor.split("x"))
+        self.H, self.W, self.n, self.C = h, w, args.events, 3
+        self.config = {"workload": f"event->histogram rasterise, uniform synthetic stream, {self.n} events, "
+                                   f"{w}x{h} sensor (N-ImageNet), float64[N,4] rows -> uint8[H,W,3]",
+                       "events": self.n, "sensor_wxh": [w, h], "channels": self.C,
+                       "l2_policy": "input (32 B/event, %.0f MB) larger than the 126 MB L2" % (self.n * 32 / 1e6),
+                       "parallelism": "independent streams per GPU (no collective)"}
+
+    def make_events(self, seed, n=None):
+        import numpy as np
+        n = n or self.n
+        rng = np.random.default_rng(seed)
+        ev = np.empty((n, 4), dtype=np.float64)
+        ev[:, 0] = rng.integers(0, self.W, n)
+        ev[:, 1] = rng.integers(0, self.H, n)
+        ev[:, 2] = np.sort(rng.uniform(0, 3e5, n))
+        ev[:, 3] = rng.integers(0, 2, n) * 2.0 - 1.0
+        return ev
+
+    # --- ours
+    def setup(self, torch, rank):
+        from mem_b200 import _lib
+        from mem_b200.process_data import histogram
+        self.torch, self._lib, self.histogram = torch, _lib, histogram
+        ev = self.make_events(rank)
+        self.ev_host = torch.from_numpy(ev).pin_memory()
+        self.ev_dev = self.ev_host.cuda(non_blocking=True)
+        self.out = None
+        self.units_per_step = self.n
+        self.h2d, self.d2h = self.n * 32, self.H * self.W * self.C
+
+    def step_device(self):
+        self.out = self.histogram(self.ev_dev, self.H, self.W, channels=self.C, check=False)
+
+    def step_e2e(self):
+        # public API with HOST input (pinned) and the result read back to the host
+        dev = self.ev_host.to("cuda", non_blocking=True)
+        out = self.histogram(dev, self.H, self.W, channels=self.C, check=True)
+        return out.cpu()
+
+    def verify(self):
+        import numpy as np
+        from oracle.histogram_ref import event_hist_ref
+        n = min(self.n, 2_000_000)
+        got = self.histogram(self.ev_dev[:n], self.H, self.W, channels=self.C).cpu().numpy()
+        return bool(np.array_equal(got, event_hist_ref(self.ev_host[:n].numpy(), self.H, self.W)))
+
+    def roofline(self, ms_per_step):
+        hbm, _, _, how = measured_peaks()
+        alg_bytes = 32.0 * self.n + self.C * self.H * self.W
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "hist_scatter_global (+init, finalize: whole step timed)",
+                "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
+                "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                "algorithmic_bytes_per_launch": alg_bytes, "traffic": None}
+
+    # --- reference's CPU path (numpy np.add.at restatement, oracle/histogram_ref.py)
+    def cpu_once(self, ev):
+        from oracle.histogram_ref import event_hist_ref
+        return event_hist_ref(ev, self.H, self.W)
+
+    def cpu_baseline(self):
+        n = min(self.n, 4_000_000)
+        ev = self.make_events(0, n)
+        self.cpu_once(ev[:100_000])
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or time.perf_counter() - t0 < 4.0:
+            self.cpu_once(ev)
+            reps += 1
+            if time.perf_counter() - t0 > 25:
+                break
+        dt = (time.perf_counter() - t0) / reps
+        return {"value": round(n / dt / 1e9, 6), "unit": self.unit, "cores": 1, "kind": "port",
+                "sample": f"{reps} passes of {n} events ({self.W}x{self.H}) through oracle/histogram_ref.py "
+                          f"(np.add.at is serial: 1 thread)"}
+
+
+_REF_EV = None
+
+
+def _ref_hist_init(n, H, W):
+    global _REF_EV
+    import numpy as np
+    rng = np.random.default_rng(os.getpid())
+    ev = np.empty((n, 4), dtype=np.float64)
+    ev[:, 0] = rng.integers(0, W, n); ev[:, 1] = rng.integers(0, H, n)
+    ev[:, 2] = np.sort(rng.uniform(0, 3e5, n)); ev[:, 3] = rng.integers(0, 2, n) * 2.0 - 1.0
+    _REF_EV = ev
+
+
+def _ref_hist_worker(a):
+    H, W = a
+    from oracle.histogram_ref import event_hist_ref
+    return int(event_hist_ref(_REF_EV, H, W)[0, 0, 0])
+
+
+def run_reference_histogram(args, wl):
+    """Reference CPU arm: every host core rasterises its own resident stream (how the reference's
+    DataLoader workers parallelise EventArrToImg, run_mem_pretraining.py:333-339)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    n_each = 1_000_000
+    steps, warm = args.steps or 10, args.warmup if args.warmup is not None else 3
+    with mp.get_context("fork").Pool(workers, initializer=_ref_hist_init, initargs=(n_each, wl.H, wl.W)) as pool:
+        for _ in range(max(1, warm)):
+            pool.map(_ref_hist_worker, [(wl.H, wl.W)] * workers, chunksize=1)
+        t0 = time.perf_counter()
+        for s in range(steps):
+            pool.map(_ref_hist_worker, [(wl.H, wl.W)] * workers, chunksize=1)
+        dt = time.perf_counter() - t0
+    value = workers * n_each * steps / dt / 1e9
+    return value, dt / steps * 1e3, workers, (f"{workers} worker processes (all host cores, capped at 64), each "
+                                              f"rasterising a resident {n_each}-event stream per step")
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    workload = args.workload
+    if workload == "auto":
+        try:
+            from mem_b200 import bench_pretrain  # noqa: F401
+            workload = "pretrain"
+        except Exception:
+            workload = "histogram"
+    if workload == "pretrain":
+        from mem_b200 import bench_pretrain
+        return bench_pretrain.main(args, rank, local_rank, world, ClockSampler, measured_peaks)
+
+    wl = HistogramWorkload(args)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        value, ms, workers, sample = run_reference_histogram(args, wl)
+        line = {"impl": "reference", "metric": wl.metric, "value": round(value, 6), "unit": wl.unit,
+                "n_gpus": args.gpus, "steps": args.steps or 10, "warmup": args.warmup if args.warmup is not None else 3,
+                "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": wl.dtype, "data": "synthetic", "config": wl.config,
+                "cpu_baseline": {"value": round(value, 6), "unit": wl.unit, "cores": workers, "kind": "port", "sample": sample},
+                "e2e": {"value": round(value, 6), "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    steps = args.steps or 50
+    warm = args.warmup if args.warmup is not None else 10
+    warm = max(warm, 3)
+
+    wl.setup(torch, rank)
+    ok = wl.verify()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(warm):
+        wl.step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = wl._lib.launch_count()
+    ms_total = timed(wl.step_device, steps)
+    launches = wl._lib.launch_count() - l0
+    # end-to-end through the public API with host buffers
+    for _ in range(3):
+        wl.step_e2e()
+    e2e_steps = max(3, min(steps, 10))
+    ms_e2e = timed(wl.step_e2e, e2e_steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_step = ms_total / steps
+    value = wl.units_per_step * world / (ms_step * 1e-3) / 1e9
+    e2e_val = wl.units_per_step * world / (ms_e2e / e2e_steps * 1e-3) / 1e9
+    line = {"metric": wl.metric, "value": round(value, 3), "unit": wl.unit, "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config,
+            "e2e": {"value": round(e2e_val, 4), "unit": wl.unit, "h2d_bytes_per_step": wl.h2d,
+                    "d2h_bytes_per_step": wl.d2h, "ms_per_step": round(ms_e2e / e2e_steps, 3)},
+            "gpu_launches": int(launches), "parity_vs_oracle": ok, "clocks": clocks,
+            "roofline": wl.roofline(ms_step)}
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = wl.cpu_baseline()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -17,9 +17,10 @@ namespace hist {
 
 constexpr int kHeaderBytes = 256;
 constexpr int kThreads = 256;
-constexpr int kUnroll = 4;
+constexpr int kUnroll = 2;   // measured on B200: short bursts + a large grid beat deep unrolling (tools/hist_tune.cu)
 constexpr int kTileThreads = 1024;
 constexpr int kTileMaxWords = 50 * 1024;        // 200 KB of packed u16x2 counters per CTA
+constexpr int kTileUnroll = 4;
 constexpr int kTileChunk = kTileThreads * 60;   // 61440 rows between folds (< 65535 - 255)
 
 struct Header {
@@ -215,17 +216,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) hist_tile_smem(
   bool bad = false;
   for (long long chunk = begin; chunk < end; chunk += kTileChunk) {
     const long long stop = min(end, chunk + (long long)kTileChunk);
-    for (long long base = chunk; base < stop; base += kTileThreads * kUnroll) {
-      Event e[kUnroll];
-      bool live[kUnroll];
+    for (long long base = chunk; base < stop; base += kTileThreads * kTileUnroll) {
+      Event e[kTileUnroll];
+      bool live[kTileUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+      for (int u = 0; u < kTileUnroll; ++u) {
         long long r = base + u * kTileThreads + threadIdx.x;
         live[u] = r < stop;
         if (live[u]) e[u] = load_event<kAligned>(ev, r);
       }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+      for (int u = 0; u < kTileUnroll; ++u) {
         const bool pos = live[u] && e[u].p == 1.0, neg = live[u] && e[u].p == -1.0;
         if (pos || neg) {
           long long idx;
@@ -409,10 +410,10 @@ extern "C" int memb_hist_u8(const double* ev, int64_t n, const int64_t* offsets,
     return MEMB_OK;
   }
 
-  // grid.x: enough CTAs to cover the longest stream once, capped at ~8 resident CTAs per SM overall
+  // grid.x: enough CTAs to cover the longest stream once, capped at 64 CTAs per SM overall
   const long long per_cta = (long long)kThreads * kUnroll;
   long long gx = std::max<long long>(1, ceil_div<long long>(max_stream_len, per_cta));
-  const long long cap = std::max<long long>(1, ((long long)sms * 8 + B - 1) / B);
+  const long long cap = std::max<long long>(1, ((long long)sms * 64 + B - 1) / B);
   gx = std::min(gx, cap);
   const dim3 grid((unsigned)gx, (unsigned)B);
 
