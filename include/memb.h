@@ -78,6 +78,57 @@ int memb_hist_status(const void* ws, memb_stream_t stream);
 int memb_hist_extent(const double* ev, int64_t n, int64_t* max_xy_host, void* ws, size_t ws_bytes,
                      memb_stream_t stream);
 
+
+/* ------------------------------------------------------------------------
+ * tcgen05 GEMM with fused epilogues:  D[M,N] = epi( A[M,K] * B[N,K]^T ).
+ * Replaces the cuBLASLt / cuDNN calls behind nn.Linear / nn.Conv2d on the hot
+ * path: mem/modeling_finetune.py:61-71 (Mlp), :130-155 (qkv, proj), :203-209
+ * (patch embedding), mem/modeling_pretrain.py:126 (lm_head) and the dVAE
+ * encoder convolutions eventvae/vae/vae_model.py:29-41,91-101.
+ * ---------------------------------------------------------------------- */
+#define MEMB_DT_BF16 0
+#define MEMB_DT_F32 1 /* as an input type: consumed by the tensor cores as TF32 */
+
+#define MEMB_EPI_STORE 0      /* d = act(alpha*(acc + bias) [+ aux fp32]); optional row remap / mask rows */
+#define MEMB_EPI_BIAS_GELU 1  /* d = gelu(acc + bias) (bf16); d2 = acc + bias (bf16, optional)            */
+#define MEMB_EPI_RESIDUAL 2   /* d = aux + rowscale[row/g]*colscale[n]*(acc + bias) (fp32); d2 = acc+bias  */
+#define MEMB_EPI_ATOMIC_ADD 3 /* d += alpha*acc (fp32, split-K, red.global.add)                           */
+#define MEMB_EPI_DGELU 4      /* d = acc * gelu'(aux) (aux = bf16 pre-activation)                          */
+#define MEMB_EPI_ARGMAX 5     /* d[row] = max over n of key(acc + bias, n) (uint64, atomicMax)             */
+
+typedef struct memb_gemm_desc {
+  const void* a;  /* a_layout 0: [M,K] row-major (K-major); 1: [K,M] row-major (MN-major, bf16 only) */
+  const void* b;  /* b_layout 0: [N,K] row-major (K-major); 1: [K,N] row-major (MN-major, bf16 only) */
+  int64_t lda, ldb; /* leading dimensions in elements */
+  int32_t m, n, k;
+  int32_t a_layout, b_layout;
+  int32_t in_dtype;        /* MEMB_DT_BF16 | MEMB_DT_F32 (tf32) */
+  int32_t out_dtype;       /* MEMB_DT_BF16 | MEMB_DT_F32 */
+  int32_t epilogue;        /* MEMB_EPI_* */
+  int32_t splits;          /* split-K factor for MEMB_EPI_ATOMIC_ADD (0 = auto) */
+  int32_t block_n;         /* 0 = auto, 128 or 256 */
+  int32_t split_precision; /* 1: 3xTF32 -- a = [hi|lo] (M x 2K), b = [hi|lo] (N x 2K), k = logical K */
+  int32_t act;             /* MEMB_EPI_STORE: 0 none, 1 relu */
+  int32_t out_split;       /* MEMB_EPI_STORE fp32: write tf32 hi at d[row, n] and lo at d[row, N + n]; d2 = full */
+  void* d;
+  int64_t ldd;
+  void* d2;
+  int64_t ldd2;
+  const float* bias;       /* [N] or NULL */
+  const void* aux;
+  int64_t ldaux;
+  const float* colscale;   /* [N] or NULL */
+  const float* rowscale;   /* [ceil(M / rows_per_group)] or NULL */
+  int32_t rows_per_group;
+  int32_t out_group_rows, out_group_stride, out_row_offset; /* STORE: out row = (r/g)*stride + off + r%g when g > 0 */
+  const uint8_t* rowmask;  /* STORE: rows with mask != 0 are replaced by maskvec */
+  const float* maskvec;    /* [N] */
+  float alpha;             /* 0 is read as 1 */
+  int32_t* err_flag;       /* device int, set before a trap if an internal wait times out (may be NULL) */
+} memb_gemm_desc;
+
+int memb_gemm(const memb_gemm_desc* desc, memb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,27 @@ SIGNATURES = {
     "memb_hist_extent": (_i32, [_vp, _i64, _vp, _vp, _sz, _vp]),
 }
 
+DT_BF16, DT_F32 = 0, 1
+EPI_STORE, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_ATOMIC_ADD, EPI_DGELU, EPI_ARGMAX = 0, 1, 2, 3, 4, 5
+
+
+class GemmDesc(_c.Structure):
+    """Mirror of ``memb_gemm_desc`` (include/memb.h)."""
+    _fields_ = [
+        ("a", _vp), ("b", _vp), ("lda", _i64), ("ldb", _i64),
+        ("m", _i32), ("n", _i32), ("k", _i32),
+        ("a_layout", _i32), ("b_layout", _i32), ("in_dtype", _i32), ("out_dtype", _i32),
+        ("epilogue", _i32), ("splits", _i32), ("block_n", _i32), ("split_precision", _i32),
+        ("act", _i32), ("out_split", _i32),
+        ("d", _vp), ("ldd", _i64), ("d2", _vp), ("ldd2", _i64),
+        ("bias", _vp), ("aux", _vp), ("ldaux", _i64), ("colscale", _vp), ("rowscale", _vp),
+        ("rows_per_group", _i32), ("out_group_rows", _i32), ("out_group_stride", _i32), ("out_row_offset", _i32),
+        ("rowmask", _vp), ("maskvec", _vp), ("alpha", _f32), ("err_flag", _vp),
+    ]
+
+
+SIGNATURES["memb_gemm"] = (_i32, [_c.POINTER(GemmDesc), _vp])
+
 _lib = None
 _lock = threading.Lock()
 
