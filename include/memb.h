@@ -124,10 +124,73 @@ typedef struct memb_gemm_desc {
   const uint8_t* rowmask;  /* STORE: rows with mask != 0 are replaced by maskvec */
   const float* maskvec;    /* [N] */
   float alpha;             /* 0 is read as 1 */
+  const float* alpha_dev;  /* optional device scalar multiplied into alpha (STORE / ATOMIC_ADD) */
   int32_t* err_flag;       /* device int, set before a trap if an internal wait times out (may be NULL) */
 } memb_gemm_desc;
 
 int memb_gemm(const memb_gemm_desc* desc, memb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Masked-ViT step kernels (HBM-bound pieces).  bf16 pointers are `void*`.
+ * Reference: mem/modeling_finetune.py:166-189 (Block: pre-LN, LayerScale, DropPath),
+ * :203-247 (PatchEmbed, RelativePositionBias); mem/modeling_pretrain.py:97-126.
+ * ---------------------------------------------------------------------- */
+
+/* y(bf16)[r] = LN(x[row_index ? row_index[r] : r]) * gamma + beta; saves mean / rstd.  With `count`
+ * (device int) rows >= *count are written as zeros.  D % 128 == 0.  nn.LayerNorm, modeling_finetune.py:166,172. */
+int memb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int rows, int D,
+                       void* y, int64_t ldy, float* mean, float* rstd, const int32_t* row_index, const int32_t* count,
+                       memb_stream_t stream);
+/* dx[target row] += LN backward of dy (bf16 or fp32); dgamma += ..., dbeta += ... (may be NULL). */
+int memb_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
+                       const float* mean, const float* rstd, int rows, int D, float* dx, int64_t lddx, float* dgamma,
+                       float* dbeta, const int32_t* row_index, const int32_t* count, memb_stream_t stream);
+/* Backward of x_out = x_in + rowscale[row/g]*colscale[n]*branch (modeling_finetune.py:187-188):
+ * dz(bf16) = rowscale*colscale*gout; dcolscale += sum rowscale*gout*branch; dbias += sum dz. */
+int memb_branch_bwd(const float* gout, int64_t ldg, const void* branch, int64_t ldb, const float* colscale,
+                    const float* rowscale, int rows_per_group, int rows, int D, void* dz, int64_t lddz, float* dcolscale,
+                    float* dbias, memb_stream_t stream);
+/* out[n] += sum over rows of x(bf16)[row, n]  (bias gradients). */
+int memb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float* out, memb_stream_t stream);
+/* img fp32 [B,C,H,W] -> bf16 [B*(H/P)*(W/P), C*P*P] in Conv2d weight order (PatchEmbed.proj, modeling_finetune.py:203,209). */
+int memb_patchify(const float* img, int B, int C, int H, int W, int P, void* out, memb_stream_t stream);
+/* x[b,0,:] = cls (+pos[0]); x[b,n,:] += pos[n] if pos (modeling_pretrain.py:101-112). */
+int memb_cls_pos(float* x, const float* cls, const float* pos, int B, int N, int D, memb_stream_t stream);
+/* Backward of the embedding assembly (mask-token blend, cls concat, pos add). */
+int memb_embed_bwd(const float* g0, const uint8_t* mask, int B, int P, int D, void* dpatch, float* dmask_token, float* dcls,
+                   float* dbias, float* dpos, memb_stream_t stream);
+/* Boolean-mask compaction in row-major (b,p) order (x[:,1:][bool_masked_pos], modeling_pretrain.py:126). */
+int memb_mask_compact(const uint8_t* mask, int B, int P, int32_t* row_index, int32_t* patch_index, int32_t* count, int cap,
+                      memb_stream_t stream);
+/* Mean cross entropy over the *count live rows + top-1 hits + dlogits (engine_for_pretraining.py:152,233).
+ * stats[0] += sum loss_i, stats[1] += hits, stats[2] = count. */
+int memb_cross_entropy(const float* logits, int64_t ld, const int64_t* tokens, const int32_t* patch_index,
+                       const int32_t* count, int cap, int V, void* dlogits, int64_t ldd, float* stats, float grad_scale,
+                       memb_stream_t stream);
+/* RelativePositionBias.forward (modeling_finetune.py:242-247): bias[h][q][k] (row stride ldk, padded) and its transpose. */
+int memb_relpos_gather(const float* table, const int64_t* index, int N, int heads, int ldk, float* bias, float* biasT,
+                       memb_stream_t stream);
+int memb_relpos_scatter(const float* dbias, int ldk, const int64_t* index, int N, int heads, float* dtable,
+                        memb_stream_t stream);
+/* acc[i] += sum_b x(bf16)[b*inner + i]. */
+int memb_batch_reduce_bf16(const void* x, int B, int64_t inner, float* acc, memb_stream_t stream);
+
+/* Fused attention with additive bias, N <= 208, head_dim == 64 (Attention.forward, modeling_finetune.py:128-157). */
+int memb_attention_fwd(const void* qkv, const float* bias, int ldb, int B, int N, int H, int head_dim, float scale,
+                       void* out, float* lse, memb_stream_t stream);
+int memb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias,
+                       const float* biasT, int ldb, int B, int N, int H, int head_dim, float scale, void* dqkv, void* ds,
+                       memb_stream_t stream);
+
+/* Flat-buffer optimizer pass (mem/utils.py:357-371 + torch.optim.AdamW with optim_factory.py:121 betas). */
+int memb_fill_f32(float* p, int64_t n, float v, memb_stream_t stream);
+int memb_cast_bf16(const float* src, void* dst, int64_t n, memb_stream_t stream);
+int memb_sqnorm(const float* g, int64_t n, float scale, float* out, memb_stream_t stream);
+/* One pass over the flat parameter buffer; tensors start on 1024-element boundaries and
+ * chunk_group[i/1024] (device uint8, 255 = skip) selects (group_lr_host[g], group_wd_host[g]). */
+int memb_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, const uint8_t* chunk_group,
+               const float* group_lr_host, const float* group_wd_host, int ngroups, float beta1, float beta2, float eps,
+               int step, float grad_scale, float max_norm, const float* sqnorm_dev, memb_stream_t stream);
 
 #ifdef __cplusplus
 }

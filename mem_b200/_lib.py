@@ -47,11 +47,31 @@ class GemmDesc(_c.Structure):
         ("d", _vp), ("ldd", _i64), ("d2", _vp), ("ldd2", _i64),
         ("bias", _vp), ("aux", _vp), ("ldaux", _i64), ("colscale", _vp), ("rowscale", _vp),
         ("rows_per_group", _i32), ("out_group_rows", _i32), ("out_group_stride", _i32), ("out_row_offset", _i32),
-        ("rowmask", _vp), ("maskvec", _vp), ("alpha", _f32), ("err_flag", _vp),
+        ("rowmask", _vp), ("maskvec", _vp), ("alpha", _f32), ("alpha_dev", _vp), ("err_flag", _vp),
     ]
 
 
 SIGNATURES["memb_gemm"] = (_i32, [_c.POINTER(GemmDesc), _vp])
+SIGNATURES.update({
+    "memb_layernorm_fwd": (_i32, [_vp, _i64, _vp, _vp, _f32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "memb_layernorm_bwd": (_i32, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "memb_branch_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "memb_colsum_bf16": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "memb_patchify": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "memb_cls_pos": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "memb_embed_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "memb_mask_compact": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "memb_cross_entropy": (_i32, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _f32, _vp]),
+    "memb_relpos_gather": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "memb_relpos_scatter": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "memb_batch_reduce_bf16": (_i32, [_vp, _i32, _i64, _vp, _vp]),
+    "memb_attention_fwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
+    "memb_attention_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
+    "memb_fill_f32": (_i32, [_vp, _i64, _f32, _vp]),
+    "memb_cast_bf16": (_i32, [_vp, _vp, _i64, _vp]),
+    "memb_sqnorm": (_i32, [_vp, _i64, _f32, _vp, _vp]),
+    "memb_adamw": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _i32, _f32, _f32, _vp, _vp]),
+})
 
 _lib = None
 _lock = threading.Lock()

@@ -54,6 +54,7 @@ struct Params {
   const unsigned char* rowmask;
   const float* maskvec;
   float alpha;
+  const float* alpha_dev;
   int act;        // STORE: 0 none, 1 relu
   int out_split;  // STORE fp32: also write tf32 hi at [n] and lo at [N + n]
   int* err_flag;
@@ -151,9 +152,10 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, int row, int col
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] += (i < valid) ? __ldg(p.bias + col0 + i) : 0.f;
     }
-    if (p.alpha != 1.0f) {
+    const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
+    if (alpha != 1.0f) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+      for (int i = 0; i < 32; ++i) v[i] *= alpha;
     }
     if (p.aux) {  // residual add (fp32), e.g. dVAE ResBlock skip connection
       float r[32];
@@ -209,16 +211,17 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, int row, int col
     if (p.d2) store_row32(reinterpret_cast<__nv_bfloat16*>(p.d2) + (long long)row * p.ldd2 + col0, v, valid);
   } else if constexpr (EPI == MEMB_EPI_ATOMIC_ADD) {
     float* dst = reinterpret_cast<float*>(p.d) + (long long)row * p.ldd + col0;
+    const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
     if (valid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "f"(v[4 * i] * p.alpha),
-                     "f"(v[4 * i + 1] * p.alpha), "f"(v[4 * i + 2] * p.alpha), "f"(v[4 * i + 3] * p.alpha)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "f"(v[4 * i] * alpha),
+                     "f"(v[4 * i + 1] * alpha), "f"(v[4 * i + 2] * alpha), "f"(v[4 * i + 3] * alpha)
                      : "memory");
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (i < valid) atomicAdd(dst + i, v[i] * p.alpha);
+        if (i < valid) atomicAdd(dst + i, v[i] * alpha);
     }
   } else if constexpr (EPI == MEMB_EPI_DGELU) {
     float pre[32];
@@ -564,6 +567,7 @@ extern "C" int memb_gemm(const memb_gemm_desc* gp, memb_stream_t stream) {
   p.out_group_rows = g.out_group_rows; p.out_group_stride = g.out_group_stride; p.out_row_offset = g.out_row_offset;
   p.rowmask = g.rowmask; p.maskvec = g.maskvec;
   p.alpha = g.alpha == 0.0f ? 1.0f : g.alpha;
+  p.alpha_dev = g.alpha_dev;
   p.act = g.act; p.out_split = g.out_split;
   p.err_flag = g.err_flag;
 

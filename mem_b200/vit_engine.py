@@ -1,0 +1,422 @@
+"""Execution engine of the masked ViT: flat parameter storage + forward / backward over libmemb.
+
+The ``nn.Module`` classes in ``modeling_finetune`` / ``modeling_pretrain`` are parameter containers
+with the reference's names (so ``state_dict`` keys match ``mem/modeling_pretrain.py`` /
+``mem/modeling_finetune.py``); this module is what runs them:
+
+* parameters live in ONE flat fp32 buffer (every tensor on a 1024-element boundary, ordered by when
+  backward finishes with them), gradients in a parallel flat buffer, weights have a bf16 shadow --
+  one fused AdamW pass, one (bucketed) all-reduce stream, no per-tensor loops;
+* forward / backward are explicit kernel sequences (tcgen05 GEMMs with fused epilogues, fused
+  attention, LayerNorm, cross entropy ...); the residual stream stays fp32 like the reference under
+  autocast, GEMM operands are bf16, LayerNorm / softmax / CE math is fp32.
+
+Reference call stack restated here: ``forward_features`` (modeling_pretrain.py:97-117), ``Block.forward``
+(modeling_finetune.py:182-189), ``Attention.forward`` (:128-157), ``Mlp.forward`` (:66-71),
+``forward`` + ``CrossEntropyLoss`` (modeling_pretrain.py:119-126, engine_for_pretraining.py:152).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib, ops
+from ._lib import (DT_BF16, DT_F32, EPI_ATOMIC_ADD, EPI_BIAS_GELU, EPI_DGELU, EPI_RESIDUAL, EPI_STORE)
+
+CHUNK = 1024  # flat-buffer alignment (elements) == AdamW chunk size
+
+
+def _sp(torch_mod=torch, device=None):
+    return _lib.stream_ptr(torch_mod, device)
+
+
+class FlatParams:
+    """One fp32 buffer for all parameters of a model (+ grads + bf16 shadow)."""
+
+    def __init__(self, model, order):
+        params = dict(model.named_parameters())
+        names = [n for n in order if n in params] + [n for n in params if n not in set(order)]
+        dev = next(iter(params.values())).device
+        self.names, self.offsets, self.sizes = names, {}, {}
+        off = 0
+        for n in names:
+            self.offsets[n] = off
+            self.sizes[n] = params[n].numel()
+            off += (params[n].numel() + CHUNK - 1) // CHUNK * CHUNK
+        self.numel = off
+        self.device = dev
+        self.data = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        self.params = params
+        with torch.no_grad():
+            for n in names:
+                p = params[n]
+                view = self.data[self.offsets[n]: self.offsets[n] + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+        self.shadow_version = -1
+        self.grad_views = {n: self.grad[self.offsets[n]: self.offsets[n] + self.sizes[n]].view_as(params[n])
+                           for n in names}
+
+    def valid(self):
+        p0 = self.params[self.names[0]]
+        return p0.data_ptr() == self.data.data_ptr() + 4 * self.offsets[self.names[0]] and \
+            self.params[self.names[-1]].data_ptr() == self.data.data_ptr() + 4 * self.offsets[self.names[-1]]
+
+    def refresh_shadow(self, force=False):
+        v = self.data._version
+        if force or v != self.shadow_version:
+            lib = _lib.load()
+            _lib.check(lib.memb_cast_bf16(self.data.data_ptr(), self.shadow.data_ptr(), self.numel, _sp(device=self.device)))
+            self.shadow_version = v
+
+    def w16(self, name):
+        p = self.params[name]
+        return self.shadow[self.offsets[name]: self.offsets[name] + p.numel()].view_as(p)
+
+    def g(self, name):
+        return self.grad_views[name]
+
+    def zero_grad(self):
+        lib = _lib.load()
+        _lib.check(lib.memb_fill_f32(self.grad.data_ptr(), self.numel, 0.0, _sp(device=self.device)))
+
+
+def get_flat(model, order_fn):
+    flat = getattr(model, "_memb_flat", None)
+    if flat is None or not flat.valid() or flat.device != next(model.parameters()).device:
+        flat = FlatParams(model, order_fn())
+        model._memb_flat = flat
+    return flat
+
+
+class _Bufs:
+    """Named scratch / activation tensors, allocated once per shape."""
+
+    def __init__(self):
+        self.t = {}
+
+    def get(self, name, shape, dtype, device, zero=False):
+        key = name
+        cur = self.t.get(key)
+        shape = tuple(int(s) for s in shape)
+        if cur is None or tuple(cur.shape) != shape or cur.dtype != dtype or cur.device != device:
+            cur = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+            self.t[key] = cur
+        return cur
+
+
+def _ln_fwd(lib, x, w, b, eps, y, mean, rstd, rows, D, row_index=None, count=None):
+    _lib.check(lib.memb_layernorm_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), b.data_ptr(), eps, rows, D,
+                                      y.data_ptr(), y.stride(0), mean.data_ptr(), rstd.data_ptr(),
+                                      ops._ptr(row_index), ops._ptr(count), _sp(device=x.device)))
+
+
+def _ln_bwd(lib, dy, x, w, mean, rstd, rows, D, dx, dw, db, row_index=None, count=None):
+    _lib.check(lib.memb_layernorm_bwd(dy.data_ptr(), DT_BF16 if dy.dtype == torch.bfloat16 else DT_F32, dy.stride(0),
+                                      x.data_ptr(), x.stride(0), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, D,
+                                      dx.data_ptr(), dx.stride(0), ops._ptr(dw), ops._ptr(db), ops._ptr(row_index),
+                                      ops._ptr(count), _sp(device=x.device)))
+
+
+class VitEngine:
+    """Runs forward/backward of a (masked) ViT whose parameters follow the reference naming."""
+
+    def __init__(self, model):
+        self.model = model
+        self.bufs = _Bufs()
+        self.saved = None
+
+    # ---- static description of the model ---------------------------------------------------
+    def cfg(self):
+        m = self.model
+        pe = m.patch_embed
+        D = m.embed_dim
+        depth = len(m.blocks)
+        H = m.blocks[0].attn.num_heads
+        hidden = m.blocks[0].mlp.fc1.out_features
+        gh, gw = pe.patch_shape
+        return dict(D=D, depth=depth, H=H, hidden=hidden, P=gh * gw, N=gh * gw + 1, patch=pe.patch_size[0],
+                    C=pe.proj.in_channels, img=pe.img_size, eps=m.blocks[0].norm1.eps)
+
+    def param_order(self):
+        """Backward-completion order: head first, then blocks last-to-first, then the embedding."""
+        m = self.model
+        order = []
+        for n in ("lm_head.weight", "lm_head.bias", "head.weight", "head.bias", "fc_norm.weight", "fc_norm.bias",
+                  "norm.weight", "norm.bias"):
+            order.append(n)
+        per_block = ["gamma_2", "mlp.fc2.weight", "mlp.fc2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "norm2.weight",
+                     "norm2.bias", "gamma_1", "attn.proj.weight", "attn.proj.bias", "attn.qkv.weight", "attn.q_bias",
+                     "attn.v_bias", "attn.relative_position_bias_table", "norm1.weight", "norm1.bias"]
+        for i in reversed(range(len(m.blocks))):
+            order += [f"blocks.{i}.{n}" for n in per_block]
+        order += ["patch_embed.proj.weight", "patch_embed.proj.bias", "cls_token", "mask_token", "pos_embed",
+                  "rel_pos_bias.relative_position_bias_table"]
+        return order
+
+    def flat(self):
+        return get_flat(self.model, self.param_order)
+
+    # ---- forward ----------------------------------------------------------------------------
+    def forward_features(self, x, mask_u8, need_grad, droppath_scales=None):
+        """x fp32 [B,C,H,W] -> residual stream fp32 [B*N, D] after the last block (pre final norm).
+
+        mask_u8: uint8 [B*P] or None.  droppath_scales: list over blocks of (s1, s2) fp32 [B] tensors or
+        None (per-sample DropPath keep/(1-p) factors, timm drop_path semantics)."""
+        lib = _lib.load()
+        c = self.cfg()
+        m, flat = self.model, self.flat()
+        flat.refresh_shadow()
+        dev = x.device
+        B = x.shape[0]
+        D, N, P, H, depth, hidden = c["D"], c["N"], c["P"], c["H"], c["depth"], c["hidden"]
+        M = B * N
+        assert x.shape[1] == c["C"] and tuple(x.shape[2:]) == tuple(c["img"]), \
+            f"Input image size ({x.shape[2]}*{x.shape[3]}) doesn't match model ({c['img'][0]}*{c['img'][1]})."
+        x = x.contiguous().float()
+        bf, f32 = torch.bfloat16, torch.float32
+        g = self.bufs.get
+        sp = _sp(device=dev)
+
+        # patch embedding: patchify -> GEMM (+bias, mask-token rows, write at row offset 1) -> cls / pos
+        kdim = c["C"] * c["patch"] ** 2
+        a0 = g("a0", (B * P, kdim), bf, dev)
+        _lib.check(lib.memb_patchify(x.data_ptr(), B, c["C"], c["img"][0], c["img"][1], c["patch"], a0.data_ptr(), sp))
+        xs = [g(f"x{i}", (M, D), f32, dev) for i in range(depth + 1)] if need_grad else \
+            [g("x_a", (M, D), f32, dev), g("x_b", (M, D), f32, dev)]
+        x0 = xs[0]
+        w_pe = flat.w16("patch_embed.proj.weight").view(D, kdim)
+        mask_tok = m.mask_token.view(-1) if (mask_u8 is not None and getattr(m, "mask_token", None) is not None) else None
+        ops.gemm(a0, w_pe, out=x0, bias=m.patch_embed.proj.bias, row_remap=(P, N, 1, M),
+                 rowmask=mask_u8 if mask_tok is not None else None, maskvec=mask_tok)
+        pos = m.pos_embed.view(N, D) if getattr(m, "pos_embed", None) is not None else None
+        _lib.check(lib.memb_cls_pos(x0.data_ptr(), m.cls_token.data_ptr(), ops._ptr(pos), B, N, D, sp))
+
+        # relative position bias (shared table: once per step; per-block tables: once per block)
+        ldk = (N + 7) // 8 * 8
+        shared_bias = None
+        if getattr(m, "rel_pos_bias", None) is not None:
+            shared_bias = (g("relb", (H, N, ldk), f32, dev), g("relbT", (H, N, ldk), f32, dev))
+            rp = m.rel_pos_bias
+            _lib.check(lib.memb_relpos_gather(rp.relative_position_bias_table.data_ptr(), rp.relative_position_index.data_ptr(),
+                                              N, H, ldk, shared_bias[0].data_ptr(), shared_bias[1].data_ptr(), sp))
+
+        # q/v biases -> one [depth, 3D] vector table (k part stays zero), modeling_finetune.py:131-133
+        qkvb = g("qkvb", (depth, 3 * D), f32, dev, zero=True)
+        has_qkv_bias = m.blocks[0].attn.q_bias is not None
+        if has_qkv_bias:
+            for i, blk in enumerate(m.blocks):
+                qkvb[i, :D].copy_(blk.attn.q_bias.detach())
+                qkvb[i, 2 * D:].copy_(blk.attn.v_bias.detach())
+
+        saved = []
+        scale = m.blocks[0].attn.scale
+        for i, blk in enumerate(m.blocks):
+            tag = f"L{i}_" if need_grad else "L_"
+            xin = xs[i] if need_grad else xs[i % 2]
+            xout = xs[i + 1] if need_grad else xs[(i + 1) % 2]
+            pre = f"blocks.{i}."
+            s1, s2 = droppath_scales[i] if droppath_scales is not None else (None, None)
+            ln1 = g(tag + "ln1", (M, D), bf, dev); mu1 = g(tag + "mu1", (M,), f32, dev); rs1 = g(tag + "rs1", (M,), f32, dev)
+            _ln_fwd(lib, xin, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, ln1, mu1, rs1, M, D)
+            qkv = g(tag + "qkv", (M, 3 * D), bf, dev)
+            ops.gemm(ln1, flat.w16(pre + "attn.qkv.weight"), out=qkv, bias=qkvb[i] if has_qkv_bias else None)
+            bias_pair = shared_bias
+            if blk.attn.relative_position_bias_table is not None:
+                own = (g(tag + "relb", (H, N, ldk), f32, dev), g(tag + "relbT", (H, N, ldk), f32, dev))
+                _lib.check(lib.memb_relpos_gather(blk.attn.relative_position_bias_table.data_ptr(),
+                                                  blk.attn.relative_position_index.data_ptr(), N, H, ldk,
+                                                  own[0].data_ptr(), own[1].data_ptr(), sp))
+                assert shared_bias is None, "shared and per-block relative position bias together are not supported"
+                bias_pair = own
+            ao = g(tag + "ao", (M, D), bf, dev); lse = g(tag + "lse", (B, H, N), f32, dev)
+            _lib.check(lib.memb_attention_fwd(qkv.data_ptr(), ops._ptr(bias_pair[0]) if bias_pair else None, ldk, B, N, H,
+                                              D // H, scale, ao.data_ptr(), lse.data_ptr(), sp))
+            xmid = g(tag + "xmid", (M, D), f32, dev)
+            br1 = g(tag + "br1", (M, D), bf, dev) if need_grad else None
+            ops.gemm(ao, flat.w16(pre + "attn.proj.weight"), out=xmid, epilogue=EPI_RESIDUAL, bias=blk.attn.proj.bias,
+                     aux=xin, d2=br1, colscale=blk.gamma_1, rowscale=s1, rows_per_group=N)
+            ln2 = g(tag + "ln2", (M, D), bf, dev); mu2 = g(tag + "mu2", (M,), f32, dev); rs2 = g(tag + "rs2", (M,), f32, dev)
+            _ln_fwd(lib, xmid, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, ln2, mu2, rs2, M, D)
+            act = g(tag + "act", (M, hidden), bf, dev)
+            fpre = g(tag + "fpre", (M, hidden), bf, dev) if need_grad else None
+            ops.gemm(ln2, flat.w16(pre + "mlp.fc1.weight"), out=act, epilogue=EPI_BIAS_GELU, bias=blk.mlp.fc1.bias, d2=fpre)
+            br2 = g(tag + "br2", (M, D), bf, dev) if need_grad else None
+            ops.gemm(act, flat.w16(pre + "mlp.fc2.weight"), out=xout, epilogue=EPI_RESIDUAL, bias=blk.mlp.fc2.bias,
+                     aux=xmid, d2=br2, colscale=blk.gamma_2, rowscale=s2, rows_per_group=N)
+            if need_grad:
+                saved.append(dict(xin=xin, ln1=ln1, mu1=mu1, rs1=rs1, qkv=qkv, ao=ao, lse=lse, xmid=xmid, br1=br1,
+                                  ln2=ln2, mu2=mu2, rs2=rs2, act=act, fpre=fpre, br2=br2, s1=s1, s2=s2, bias=bias_pair))
+        xlast = xs[depth] if need_grad else xs[depth % 2]
+        ctx = dict(B=B, M=M, a0=a0, mask=mask_u8, blocks=saved, ldk=ldk, shared_bias=shared_bias, cfg=c)
+        return xlast, ctx
+
+    # ---- masked-token head + cross entropy (pretraining) ----------------------------------------
+    def pretrain_head(self, xlast, ctx, mask_u8, tokens, need_grad, cap=None, want_logits=False):
+        """final LN on the masked rows -> lm_head -> (optional) CE.  Returns dict with logits [cap,V],
+        count (device int32), stats (device fp32 [4]: loss_sum, hits, count, -)."""
+        lib = _lib.load()
+        m, flat, c = self.model, self.flat(), ctx["cfg"]
+        dev = xlast.device
+        B, D, N, P = ctx["B"], c["D"], c["N"], c["P"]
+        V = m.lm_head.out_features
+        cap = cap or B * P
+        g = self.bufs.get
+        sp = _sp(device=dev)
+        row_index = g("row_index", (cap,), torch.int32, dev); patch_index = g("patch_index", (cap,), torch.int32, dev)
+        count = g("count", (1,), torch.int32, dev)
+        _lib.check(lib.memb_mask_compact(mask_u8.data_ptr(), B, P, row_index.data_ptr(), patch_index.data_ptr(),
+                                         count.data_ptr(), cap, sp))
+        xm = g("xm", (cap, D), torch.bfloat16, dev); mu = g("mu_f", (cap,), torch.float32, dev); rs = g("rs_f", (cap,), torch.float32, dev)
+        _ln_fwd(lib, xlast, m.norm.weight, m.norm.bias, m.norm.eps, xm, mu, rs, cap, D, row_index, count)
+        logits = g("logits", (cap, V), torch.float32, dev)
+        ops.gemm(xm, flat.w16("lm_head.weight"), out=logits, bias=m.lm_head.bias)
+        out = dict(logits=logits, count=count, row_index=row_index, patch_index=patch_index, xm=xm, mu=mu, rs=rs, cap=cap)
+        if tokens is not None:
+            stats = g("stats", (4,), torch.float32, dev)
+            stats.zero_()
+            dlogits = g("dlogits", (cap, V), torch.bfloat16, dev) if need_grad else None
+            _lib.check(lib.memb_cross_entropy(logits.data_ptr(), logits.stride(0), tokens.data_ptr(), patch_index.data_ptr(),
+                                              count.data_ptr(), cap, V, ops._ptr(dlogits), V, stats.data_ptr(), 1.0, sp))
+            out.update(stats=stats, dlogits=dlogits)
+        return out
+
+    # ---- backward -----------------------------------------------------------------------------
+    def backward_pretrain(self, ctx, head, grad_scale_dev, dlogits=None, bucket_hook=None):
+        """Accumulates all parameter gradients into flat.grad.  dlogits (bf16 [cap,V]) defaults to the one
+        the fused CE produced; grad_scale_dev is an optional device scalar multiplied into it."""
+        lib = _lib.load()
+        m, flat, c = self.model, self.flat(), ctx["cfg"]
+        B, M, D, N, P, H, hidden = ctx["B"], ctx["M"], c["D"], c["N"], c["P"], c["H"], c["hidden"]
+        dev = flat.device
+        g = self.bufs.get
+        sp = _sp(device=dev)
+        V = m.lm_head.out_features
+        cap = head["cap"]
+        dl = dlogits if dlogits is not None else head["dlogits"]
+        # lm_head: wgrad (both operands MN-major), bias grad, dgrad (B = W as stored)
+        ops.gemm(dl, head["xm"], out=flat.g("lm_head.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD,
+                 alpha_dev=grad_scale_dev)
+        dxm = g("dxm", (cap, D), torch.bfloat16, dev)
+        ops.gemm(dl, flat.w16("lm_head.weight"), out=dxm, b_layout=1, alpha_dev=grad_scale_dev)
+        if grad_scale_dev is None:
+            _lib.check(lib.memb_colsum_bf16(dl.data_ptr(), V, cap, V, flat.g("lm_head.bias").data_ptr(), sp))
+        else:  # rare path (scaled loss): bias grad through a scaled temporary
+            tmp = torch.zeros(V, dtype=torch.float32, device=dev)
+            _lib.check(lib.memb_colsum_bf16(dl.data_ptr(), V, cap, V, tmp.data_ptr(), sp))
+            flat.g("lm_head.bias").add_(tmp * grad_scale_dev)
+        gres = g("gres", (M, D), torch.float32, dev)
+        _lib.check(lib.memb_fill_f32(gres.data_ptr(), gres.numel(), 0.0, sp))
+        xlast = ctx["xlast"]
+        _ln_bwd(lib, dxm, xlast, m.norm.weight, head["mu"], head["rs"], cap, D, gres, flat.g("norm.weight"),
+                flat.g("norm.bias"), head["row_index"], head["count"])
+        if bucket_hook:
+            bucket_hook("head")
+        self._backward_blocks(ctx, gres, bucket_hook)
+        self._backward_embed(ctx, gres)
+        if bucket_hook:
+            bucket_hook("embed")
+
+    def _backward_blocks(self, ctx, gres, bucket_hook=None):
+        lib = _lib.load()
+        m, flat, c = self.model, self.flat(), ctx["cfg"]
+        B, M, D, N, H, hidden, ldk = ctx["B"], ctx["M"], c["D"], c["N"], c["H"], c["hidden"], ctx["ldk"]
+        dev = flat.device
+        g = self.bufs.get
+        sp = _sp(device=dev)
+        bf = torch.bfloat16
+        dz = g("dz", (M, D), bf, dev); dh = g("dh", (M, hidden), bf, dev); dln = g("dln", (M, D), bf, dev)
+        dao = g("dao", (M, D), bf, dev); dqkv = g("dqkv", (M, 3 * D), bf, dev)
+        ds = g("ds", (B, H, N, ldk), bf, dev)
+        shared = ctx["shared_bias"] is not None
+        dbias_acc = g("dbias_acc", (H, N, ldk), torch.float32, dev)
+        if shared:
+            _lib.check(lib.memb_fill_f32(dbias_acc.data_ptr(), dbias_acc.numel(), 0.0, sp))
+        scale = m.blocks[0].attn.scale
+        for i in reversed(range(len(m.blocks))):
+            blk, s, pre = m.blocks[i], ctx["blocks"][i], f"blocks.{i}."
+            G = lambda n: flat.g(pre + n)  # noqa: E731
+            has_ls = blk.gamma_1 is not None
+            # ---- MLP branch
+            _lib.check(lib.memb_branch_bwd(gres.data_ptr(), D, ops._ptr(s["br2"]), D, ops._ptr(blk.gamma_2), ops._ptr(s["s2"]), N,
+                                           M, D, dz.data_ptr(), D, G("gamma_2").data_ptr() if has_ls else None,
+                                           G("mlp.fc2.bias").data_ptr(), sp))
+            ops.gemm(dz, s["act"], out=G("mlp.fc2.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD)
+            ops.gemm(dz, flat.w16(pre + "mlp.fc2.weight"), out=dh, b_layout=1, epilogue=EPI_DGELU, aux=s["fpre"])
+            _lib.check(lib.memb_colsum_bf16(dh.data_ptr(), hidden, M, hidden, G("mlp.fc1.bias").data_ptr(), sp))
+            ops.gemm(dh, s["ln2"], out=G("mlp.fc1.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD)
+            ops.gemm(dh, flat.w16(pre + "mlp.fc1.weight"), out=dln, b_layout=1)
+            _ln_bwd(lib, dln, s["xmid"], blk.norm2.weight, s["mu2"], s["rs2"], M, D, gres, G("norm2.weight"), G("norm2.bias"))
+            # ---- attention branch
+            _lib.check(lib.memb_branch_bwd(gres.data_ptr(), D, ops._ptr(s["br1"]), D, ops._ptr(blk.gamma_1), ops._ptr(s["s1"]), N,
+                                           M, D, dz.data_ptr(), D, G("gamma_1").data_ptr() if has_ls else None,
+                                           G("attn.proj.bias").data_ptr(), sp))
+            ops.gemm(dz, s["ao"], out=G("attn.proj.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD)
+            ops.gemm(dz, flat.w16(pre + "attn.proj.weight"), out=dao, b_layout=1)
+            bias_pair = s["bias"]
+            _lib.check(lib.memb_attention_bwd(s["qkv"].data_ptr(), s["ao"].data_ptr(), dao.data_ptr(), s["lse"].data_ptr(),
+                                              ops._ptr(bias_pair[0]) if bias_pair else None,
+                                              ops._ptr(bias_pair[1]) if bias_pair else None, ldk, B, N, H, D // H, scale,
+                                              dqkv.data_ptr(), ds.data_ptr() if bias_pair else None, sp))
+            if bias_pair is not None:
+                if not shared:
+                    _lib.check(lib.memb_fill_f32(dbias_acc.data_ptr(), dbias_acc.numel(), 0.0, sp))
+                _lib.check(lib.memb_batch_reduce_bf16(ds.data_ptr(), B, H * N * ldk, dbias_acc.data_ptr(), sp))
+                if not shared:
+                    _lib.check(lib.memb_relpos_scatter(dbias_acc.data_ptr(), ldk, blk.attn.relative_position_index.data_ptr(),
+                                                       N, H, G("attn.relative_position_bias_table").data_ptr(), sp))
+            if blk.attn.q_bias is not None:
+                _lib.check(lib.memb_colsum_bf16(dqkv.data_ptr(), 3 * D, M, D, G("attn.q_bias").data_ptr(), sp))
+                _lib.check(lib.memb_colsum_bf16(dqkv.data_ptr() + 2 * D * 2, 3 * D, M, D, G("attn.v_bias").data_ptr(), sp))
+            ops.gemm(dqkv, s["ln1"], out=G("attn.qkv.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD)
+            ops.gemm(dqkv, flat.w16(pre + "attn.qkv.weight"), out=dln, b_layout=1)
+            _ln_bwd(lib, dln, s["xin"], blk.norm1.weight, s["mu1"], s["rs1"], M, D, gres, G("norm1.weight"), G("norm1.bias"))
+            if bucket_hook:
+                bucket_hook(i)
+        if shared:
+            rp = m.rel_pos_bias
+            _lib.check(lib.memb_relpos_scatter(dbias_acc.data_ptr(), ldk, rp.relative_position_index.data_ptr(), N, H,
+                                               flat.g("rel_pos_bias.relative_position_bias_table").data_ptr(), sp))
+
+    def _backward_embed(self, ctx, gres):
+        lib = _lib.load()
+        m, flat, c = self.model, self.flat(), ctx["cfg"]
+        B, D, N, P = ctx["B"], c["D"], c["N"], c["P"]
+        dev = flat.device
+        sp = _sp(device=dev)
+        dpatch = self.bufs.get("dpatch", (B * P, D), torch.bfloat16, dev)
+        mask = ctx["mask"]
+        if mask is None:
+            mask = self.bufs.get("zero_mask", (B * P,), torch.uint8, dev, zero=True)
+        has_mt = getattr(m, "mask_token", None) is not None
+        has_pos = getattr(m, "pos_embed", None) is not None
+        _lib.check(lib.memb_embed_bwd(gres.data_ptr(), mask.data_ptr(), B, P, D, dpatch.data_ptr(),
+                                      flat.g("mask_token").data_ptr() if has_mt else None, flat.g("cls_token").data_ptr(),
+                                      flat.g("patch_embed.proj.bias").data_ptr(),
+                                      flat.g("pos_embed").data_ptr() if has_pos else None, sp))
+        kdim = ctx["a0"].shape[1]
+        ops.gemm(dpatch, ctx["a0"], out=flat.g("patch_embed.proj.weight").view(D, kdim), a_layout=1, b_layout=1,
+                 epilogue=EPI_ATOMIC_ADD)
+
+
+def droppath_scales(model, B, device, training):
+    """Per-block, per-sample keep/(1-p) factors with timm 0.4.12 ``drop_path`` semantics
+    (``floor(keep + U[0,1)) / keep``, call site mem/modeling_finetune.py:49-50), drawn from torch's
+    generator in the order the reference would draw them (attention branch, then MLP branch)."""
+    if not training:
+        return None
+    out, any_dp = [], False
+    for blk in model.blocks:
+        p = float(getattr(blk.drop_path, "drop_prob", 0.0) or 0.0)
+        if p > 0.0:
+            keep = 1.0 - p
+            s1 = (torch.rand(B, device=device) + keep).floor_().div_(keep)
+            s2 = (torch.rand(B, device=device) + keep).floor_().div_(keep)
+            out.append((s1, s2))
+            any_dp = True
+        else:
+            out.append((None, None))
+    return out if any_dp else None
