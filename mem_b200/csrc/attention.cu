@@ -23,7 +23,8 @@ constexpr int kMaxTiles = 13;               // 13 x 16 = 208 >= 197 tokens
 constexpr int kMaxRows = kMaxTiles * 16;
 constexpr int kThreads = kMaxTiles * 32;    // one warp per 16-row tile
 constexpr int kTileBytes = kMaxRows * 128;  // [208][64] bf16, 128 B per row, 16B chunks XOR-swizzled by row&7
-constexpr int kHalfChunks = 7;              // forward keeps <= 7 key chunks (112 keys) of S in registers
+constexpr int kHalfChunks = 4;              // forward keeps 4 key chunks (64 keys) of S in registers per pass
+// Register budget: 13 warps are allocated as 16 (granularity 4), so 16 * 32 * regs <= 65536 -> 128 per thread.
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
@@ -65,6 +66,10 @@ __device__ __forceinline__ void load_a_frags(uint32_t tile, int row0, uint32_t (
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) ldsm_x4(tile_addr(tile, row0 + (mat & 1) * 8 + r, 2 * ks + (mat >> 1)), f[ks]);
 }
+__device__ __forceinline__ void load_a_frag(uint32_t tile, int row0, int ks, uint32_t (&f)[4]) {
+  const int lane = threadIdx.x & 31, mat = lane >> 3, r = lane & 7;
+  ldsm_x4(tile_addr(tile, row0 + (mat & 1) * 8 + r, 2 * ks + (mat >> 1)), f);
+}
 // B fragments "rows are n, columns are k" (K/Q/V/dO used as the [n][k] operand): rows [n0, n0+16), k-step ks.
 // r[0],r[1] -> n8 tile n0..n0+7; r[2],r[3] -> n8 tile n0+8..n0+15.
 __device__ __forceinline__ void load_b_nk(uint32_t tile, int n0, int ks, uint32_t (&r)[4]) {
@@ -78,7 +83,7 @@ __device__ __forceinline__ void load_b_kn(uint32_t tile, int k0, int np, uint32_
 }
 
 // ------------------------------------------------------------------------------------------ forward
-__global__ void __maxnreg__(152)
+__global__ void __maxnreg__(128)
 attention_fwd(const bf16* __restrict__ qkv, const float* __restrict__ bias, int ldb, int B, int N, int H, float scale,
               bf16* __restrict__ out, float* __restrict__ lse) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -108,9 +113,7 @@ attention_fwd(const bf16* __restrict__ qkv, const float* __restrict__ bias, int 
   const float* bias_b = bias ? bias + ((long long)h * N + min(qb, N - 1)) * ldb : nullptr;
 
 #pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    const int c0 = half * kHalfChunks;
-    if (c0 >= ntiles) break;
+  for (int c0 = 0; c0 < ntiles; c0 += kHalfChunks) {
     float s[2 * kHalfChunks][4];
 #pragma unroll
     for (int kc = 0; kc < kHalfChunks; ++kc) {
@@ -195,7 +198,7 @@ attention_fwd(const bf16* __restrict__ qkv, const float* __restrict__ bias, int 
 }
 
 // ------------------------------------------------------------------------------------------ backward
-__global__ void __maxnreg__(152)
+__global__ void __maxnreg__(128)
 attention_bwd(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
               const float* __restrict__ lse, const float* __restrict__ bias, const float* __restrict__ biasT, int ldb,
               int B, int N, int H, float scale, bf16* __restrict__ dqkv, bf16* __restrict__ ds) {
@@ -246,9 +249,6 @@ attention_bwd(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const 
 
   // ---- phase A: this warp owns keys [row0, row0+16): dK, dV
   {
-    uint32_t kf[4][4], vf[4][4];
-    load_a_frags(sk, row0, kf);
-    load_a_frags(sv, row0, vf);
     float dk[8][4], dv[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
@@ -261,13 +261,15 @@ attention_bwd(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const 
       for (int t = 0; t < 2; ++t) { st[t][0] = st[t][1] = st[t][2] = st[t][3] = 0.f; dpt[t][0] = dpt[t][1] = dpt[t][2] = dpt[t][3] = 0.f; }
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        uint32_t bb[4];
+        uint32_t bb[4], af[4];
+        load_a_frag(sk, row0, ks, af);   // K/V fragments are re-read from smem (register budget)
         load_b_nk(sq, qc * 16, ks, bb);  // S^T = K_j Q^T
-        mma16816(st[0], kf[ks], bb[0], bb[1]);
-        mma16816(st[1], kf[ks], bb[2], bb[3]);
+        mma16816(st[0], af, bb[0], bb[1]);
+        mma16816(st[1], af, bb[2], bb[3]);
+        load_a_frag(sv, row0, ks, af);
         load_b_nk(sdo, qc * 16, ks, bb);  // dP^T = V_j dO^T
-        mma16816(dpt[0], vf[ks], bb[0], bb[1]);
-        mma16816(dpt[1], vf[ks], bb[2], bb[3]);
+        mma16816(dpt[0], af, bb[0], bb[1]);
+        mma16816(dpt[1], af, bb[2], bb[3]);
       }
       uint32_t pa[4], dsa[4];
 #pragma unroll

@@ -207,10 +207,10 @@ class VitEngine:
         # q/v biases -> one [depth, 3D] vector table (k part stays zero), modeling_finetune.py:131-133
         qkvb = g("qkvb", (depth, 3 * D), f32, dev, zero=True)
         has_qkv_bias = m.blocks[0].attn.q_bias is not None
-        if has_qkv_bias:
-            for i, blk in enumerate(m.blocks):
-                qkvb[i, :D].copy_(blk.attn.q_bias.detach())
-                qkvb[i, 2 * D:].copy_(blk.attn.v_bias.detach())
+        if has_qkv_bias:  # plumbing only: two strided copies per step
+            with torch.no_grad():
+                torch.stack([blk.attn.q_bias for blk in m.blocks], out=qkvb[:, :D])
+                torch.stack([blk.attn.v_bias for blk in m.blocks], out=qkvb[:, 2 * D:])
 
         saved = []
         scale = m.blocks[0].attn.scale
@@ -251,7 +251,7 @@ class VitEngine:
                 saved.append(dict(xin=xin, ln1=ln1, mu1=mu1, rs1=rs1, qkv=qkv, ao=ao, lse=lse, xmid=xmid, br1=br1,
                                   ln2=ln2, mu2=mu2, rs2=rs2, act=act, fpre=fpre, br2=br2, s1=s1, s2=s2, bias=bias_pair))
         xlast = xs[depth] if need_grad else xs[depth % 2]
-        ctx = dict(B=B, M=M, a0=a0, mask=mask_u8, blocks=saved, ldk=ldk, shared_bias=shared_bias, cfg=c)
+        ctx = dict(B=B, M=M, a0=a0, mask=mask_u8, blocks=saved, ldk=ldk, shared_bias=shared_bias, cfg=c, xlast=xlast)
         return xlast, ctx
 
     # ---- masked-token head + cross entropy (pretraining) ----------------------------------------
@@ -420,3 +420,108 @@ def droppath_scales(model, B, device, training):
         else:
             out.append((None, None))
     return out if any_dp else None
+
+
+# ------------------------------------------------------------------------------------------------
+# Model-level entry points (what modeling_pretrain / engine_for_pretraining call)
+# ------------------------------------------------------------------------------------------------
+def engine_of(model) -> VitEngine:
+    eng = getattr(model, "_memb_engine", None)
+    if eng is None or eng.model is not model:
+        eng = VitEngine(model)
+        object.__setattr__(model, "_memb_engine", eng)  # not a sub-module / not in the state_dict
+    return eng
+
+
+def _mask_u8(bool_masked_pos, B, P):
+    m = bool_masked_pos.reshape(B, -1)
+    assert m.shape[1] == P, f"bool_masked_pos has {m.shape[1]} entries per sample, the model has {P} patches"
+    return m.to(torch.uint8).contiguous().view(-1)
+
+
+def bind_param_grads(flat: FlatParams, params):
+    """Make every ``p.grad`` a view into the flat gradient buffer (zeroing segments whose grad was None),
+    so torch optimizers / clip_grad_norm_ see the gradients the kernels accumulate."""
+    todo = [n for n in flat.names if params[n].requires_grad and params[n].grad is not flat.grad_views[n]]
+    if len(todo) == len(flat.names):
+        flat.zero_grad()
+    for n in todo:
+        p = params[n]
+        if len(todo) != len(flat.names):
+            if p.grad is not None:
+                flat.grad_views[n].copy_(p.grad)
+            else:
+                flat.grad_views[n].zero_()
+        p.grad = flat.grad_views[n]
+
+
+class _MaskedVitFn(torch.autograd.Function):
+    """logits[sum(mask), V] = lm_head(norm(blocks(embed(x, mask)))[:, 1:][mask]) with a kernel backward
+    that accumulates straight into the flat gradient buffer (``p.grad`` are views of it)."""
+
+    @staticmethod
+    def forward(ctx, model, x, mask_u8, head_mask_u8, droppath, *params):
+        eng = engine_of(model)
+        need_grad = bool(ctx.needs_input_grad and any(ctx.needs_input_grad[5:]))
+        xlast, fctx = eng.forward_features(x, mask_u8, need_grad, droppath)
+        head = eng.pretrain_head(xlast, fctx, head_mask_u8, None, need_grad)
+        n = int(head["count"].item())  # the output shape is data dependent: one host sync on this path
+        ctx.eng, ctx.fctx, ctx.head, ctx.n = eng, fctx, head, n
+        return head["logits"][:n].clone()
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        eng, head = ctx.eng, ctx.head
+        flat = eng.flat()
+        bind_param_grads(flat, flat.params)
+        V = grad_logits.shape[1]
+        dl = eng.bufs.get("dlogits", (head["cap"], V), torch.bfloat16, grad_logits.device)
+        dl.zero_()
+        dl[:ctx.n].copy_(grad_logits)
+        eng.backward_pretrain(ctx.fctx, head, None, dlogits=dl)
+        return (None,) * (5 + len(flat.params))
+
+
+def masked_forward(model, x, bool_masked_pos, return_all_tokens=False):
+    """``VisionTransformerForMaskedImageModeling.forward`` (mem/modeling_pretrain.py:119-126)."""
+    _lib.require_cuda()
+    if not x.is_cuda:
+        raise RuntimeError("mem_b200 models run on CUDA tensors only (no CPU path)")
+    eng = engine_of(model)
+    c = eng.cfg()
+    B, P = x.shape[0], c["P"]
+    mask = _mask_u8(bool_masked_pos, B, P)
+    head_mask = torch.ones_like(mask) if return_all_tokens else mask
+    dp = droppath_scales(model, B, x.device, model.training)
+    flat = eng.flat()
+    params = [flat.params[n] for n in flat.names]
+    out = _MaskedVitFn.apply(model, x, mask, head_mask, dp, *params)
+    if return_all_tokens:
+        out = out.view(B, P, -1)
+    return out
+
+
+def pretrain_step(model, samples, bool_masked_pos, tokens, grad_scale_dev=None, bucket_hook=None, backward=True):
+    """Fused MEM step body: forward + masked cross entropy (+ accuracy) + backward into the flat gradient
+    buffer.  Replaces engine_for_pretraining.py:147-161 (autocast forward, CrossEntropyLoss, scaled backward)
+    and :233 (mlm_acc).  ``tokens``: int64 [B, P] codebook indices (get_codebook_indices output); labels are
+    tokens[mask].  Returns the device stats tensor [sum of per-token losses, top-1 hits, masked count, 0]."""
+    eng = engine_of(model)
+    c = eng.cfg()
+    B = samples.shape[0]
+    mask = _mask_u8(bool_masked_pos, B, c["P"])
+    tokens = tokens.reshape(-1).contiguous()
+    assert tokens.dtype == torch.int64 and tokens.numel() == B * c["P"]
+    flat = eng.flat()
+    if backward:
+        bind_param_grads(flat, flat.params)
+    dp = droppath_scales(model, B, samples.device, model.training)
+    xlast, fctx = eng.forward_features(samples, mask, backward, dp)
+    head = eng.pretrain_head(xlast, fctx, mask, tokens, backward)
+    if backward:
+        eng.backward_pretrain(fctx, head, grad_scale_dev, bucket_hook=bucket_hook)
+    return head["stats"]
+
+
+def classify_forward(model, x):
+    raise NotImplementedError("ft_vit forward: see vit_engine.classify_* (config 5)")

@@ -106,7 +106,61 @@ def golden_masks():
     print("masks.npz written")
 
 
-SECTIONS = {"histogram": golden_histogram, "masks": golden_masks}
+def _grad_digest(named_grads):
+    """Full gradient for small tensors, (norm, sum, first 256 values) for large ones."""
+    out = {}
+    for k, g in named_grads.items():
+        g = g.detach().float().reshape(-1).numpy()
+        if g.size <= 4096:
+            out["grad_full/" + k] = g
+        else:
+            out["grad_head/" + k] = g[:256].copy()
+        out["grad_norm/" + k] = np.array([np.sqrt((g.astype(np.float64) ** 2).sum()), g.astype(np.float64).sum()])
+    return out
+
+
+def golden_vit():
+    """Loss / logits / gradients of the UNMODIFIED reference pt_vit and ft_vit on the seeded tiny cases."""
+    import torch
+    from oracle import vit_ref
+    torch.manual_seed(0)
+    out = {}
+    # ---- pretraining model (mem/modeling_pretrain.py) through the reference's own CrossEntropyLoss step
+    model = ref_shims.ref_create_model("pt_vit", **vit_ref.TINY)
+    sd = vit_ref.synth_state_dict(model.state_dict(), seed=11)
+    model.load_state_dict(sd)
+    model.train()
+    P = 49
+    img, mask, tokens = vit_ref.synth_inputs(3, 2, 112, 112, P, vit_ref.TINY["vocab_size"], seed=5, n_mask=20)
+    logits = model(img, bool_masked_pos=mask, return_all_tokens=False)
+    labels = tokens[mask]
+    loss = torch.nn.CrossEntropyLoss()(input=logits, target=labels)
+    loss.backward()
+    out["pt/loss"] = np.array(loss.item())
+    out["pt/logits"] = logits.detach().numpy()
+    out["pt/acc"] = np.array((logits.max(-1)[1] == labels).float().mean().item())
+    out.update({"pt/" + k: v for k, v in _grad_digest({n: p.grad for n, p in model.named_parameters()}).items()})
+    with torch.no_grad():
+        model.eval()
+        out["pt/all_tokens_logits_b0"] = model(img, bool_masked_pos=mask, return_all_tokens=True)[0].numpy()
+    # ---- finetune model (mem/modeling_finetune.py ft_vit), plain CE on 2 classes
+    ft = ref_shims.ref_create_model("ft_vit", **vit_ref.TINY_FT)
+    sdf = vit_ref.synth_state_dict(ft.state_dict(), seed=12)
+    ft.load_state_dict(sdf)
+    ft.train()
+    img3, _, _ = vit_ref.synth_inputs(4, 3, 112, 112, P, 2, seed=6, n_mask=1)
+    target = torch.tensor([0, 1, 1, 0])
+    lg = ft(img3)
+    lossf = torch.nn.CrossEntropyLoss()(lg, target)
+    lossf.backward()
+    out["ft/loss"] = np.array(lossf.item())
+    out["ft/logits"] = lg.detach().numpy()
+    out.update({"ft/" + k: v for k, v in _grad_digest({n: p.grad for n, p in ft.named_parameters()}).items()})
+    np.savez_compressed(os.path.join(GOLD, "vit_tiny.npz"), **out)
+    print("vit_tiny.npz:", len(out), "arrays, pt loss", loss.item(), "ft loss", lossf.item())
+
+
+SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit}
 
 
 def main(argv):

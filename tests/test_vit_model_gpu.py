@@ -1,0 +1,122 @@
+"""GPU: the masked ViT (pt_vit / beit_base_patch16_224_8k_vocab) forward, loss and every parameter
+gradient through libmemb against the fp32 oracle (oracle/vit_ref.py, pinned to the reference by
+tests/golden/vit_tiny.npz) on the same weights and inputs.
+
+Tolerance: the build computes GEMMs / attention with bf16 operands and fp32 accumulation (north_star:
+"within bf16-vs-fp32 tolerance of the reference loss and gradients"): loss within 2e-2 relative,
+logits within 3e-2 of their RMS, each gradient tensor within 6e-2 relative L2 (tiny tensors whose
+gradient is dominated by bf16 noise are compared against the global gradient scale)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mem_b200 import registry, vit_engine
+from mem_b200 import modeling_pretrain  # noqa: F401  (registers the models)
+from oracle import vit_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _oracle(sd_cpu, img, mask, tokens, heads, patch, device, droppath=None):
+    sd = {k: (v.to(device).requires_grad_(True) if v.is_floating_point() else v.to(device)) for k, v in sd_cpu.items()}
+    loss, acc, logits = vit_ref.mem_loss(img.to(device), mask.to(device), tokens.to(device), sd, heads, patch, droppath)
+    loss.backward()
+    return loss.item(), acc.item(), logits.detach(), {k: v.grad for k, v in sd.items() if v.is_floating_point() and v.grad is not None}
+
+
+def _compare_grads(model, ref_grads, tol=6e-2):
+    gnorm = torch.sqrt(sum((g.double() ** 2).sum() for g in ref_grads.values())).item()
+    bad = []
+    for n, p in model.named_parameters():
+        assert p.grad is not None, n
+        r = ref_grads[n]
+        err = (p.grad.double().flatten() - r.double().flatten()).norm().item()
+        if err > tol * r.double().norm().item() and err > 2e-3 * gnorm:
+            bad.append((n, err / max(r.norm().item(), 1e-30), r.norm().item()))
+    assert not bad, f"gradient mismatch (name, rel err, ref norm): {bad[:8]} (global grad norm {gnorm:.4g})"
+
+
+def test_tiny_pt_vit_matches_golden_and_oracle(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "vit_tiny.npz"))
+    model = registry.create_model("pt_vit", **vit_ref.TINY)
+    sd = vit_ref.synth_state_dict(model.state_dict(), seed=11)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    img, mask, tokens = vit_ref.synth_inputs(3, 2, 112, 112, 49, 512, seed=5, n_mask=20)
+    logits = model(img.cuda(), mask.cuda())
+    g_logits = torch.from_numpy(gold["pt/logits"]).cuda()
+    assert logits.shape == g_logits.shape
+    assert rel(logits, g_logits) < 3e-2
+    labels = tokens.cuda()[mask.cuda()]
+    loss = torch.nn.functional.cross_entropy(logits, labels)
+    assert abs(loss.item() - float(gold["pt/loss"])) < 2e-2 * float(gold["pt/loss"])
+    loss.backward()
+    _, _, _, ref_grads = _oracle(sd, img, mask, tokens, 2, 16, "cpu")
+    _compare_grads(model, {k: v.cuda() for k, v in ref_grads.items()})
+    # fused step entry: same loss / accuracy / gradients without the logits round trip
+    for p in model.parameters():
+        p.grad = None
+    stats = vit_engine.pretrain_step(model, img.cuda(), mask.cuda(), tokens.cuda())
+    n = int(mask.sum())
+    assert stats[2].item() == n
+    assert abs(stats[0].item() / n - float(gold["pt/loss"])) < 2e-2 * float(gold["pt/loss"])
+    _compare_grads(model, {k: v.cuda() for k, v in ref_grads.items()})
+    # eval / return_all_tokens
+    model.eval()
+    with torch.no_grad():
+        allt = model(img.cuda(), mask.cuda(), return_all_tokens=True)
+    assert allt.shape == (3, 49, 512)
+    assert rel(allt[0], torch.from_numpy(gold["pt/all_tokens_logits_b0"]).cuda()) < 3e-2
+
+
+def test_vit_base_step_vs_oracle_with_droppath():
+    """ViT-B/16 at batch 4 (BASELINE config 3 architecture), shared DropPath keep factors."""
+    torch.manual_seed(0)
+    kw = dict(drop_path_rate=0.1, use_shared_rel_pos_bias=True, use_abs_pos_emb=False, init_values=0.1, in_chans=2)
+    model = registry.create_model("beit_base_patch16_224_8k_vocab", **kw)
+    sd = vit_ref.synth_state_dict(model.state_dict(), seed=3)
+    # keep activations in a realistic range for a 12-block stack
+    for k in sd:
+        if sd[k].is_floating_point() and sd[k].dim() >= 2 and "relative_position" not in k:
+            sd[k] = sd[k] * 0.4
+    model.load_state_dict(sd)
+    model.cuda().train()
+    B = 4
+    img, mask, tokens = vit_ref.synth_inputs(B, 2, 224, 224, 196, 8192, seed=7, n_mask=75)
+    dp = vit_engine.droppath_scales(model, B, torch.device("cuda"), True)
+    assert dp is not None and dp[0] == (None, None) and dp[11][0].shape == (B,)
+    eng = vit_engine.engine_of(model)
+    flat = eng.flat()
+    vit_engine.bind_param_grads(flat, flat.params)
+    m8 = mask.cuda().to(torch.uint8).view(-1)
+    xlast, fctx = eng.forward_features(img.cuda(), m8, True, dp)
+    head = eng.pretrain_head(xlast, fctx, m8, tokens.cuda().view(-1), True)
+    eng.backward_pretrain(fctx, head, None)
+    n = int(mask.sum())
+    loss = head["stats"][0].item() / n
+    ref_loss, ref_acc, ref_logits, ref_grads = _oracle(sd, img, mask, tokens, 12, 16, "cuda", droppath=dp)
+    assert abs(loss - ref_loss) < 2e-2 * ref_loss, (loss, ref_loss)
+    assert rel(head["logits"][:n], ref_logits) < 3e-2
+    assert abs(head["stats"][1].item() / n - ref_acc) <= 2.0 / n
+    _compare_grads(model, ref_grads)
+
+
+def test_gradient_accumulates_and_zero_grad():
+    model = registry.create_model("pt_vit", **vit_ref.TINY).cuda().train()
+    img, mask, tokens = vit_ref.synth_inputs(2, 2, 112, 112, 49, 512, seed=9, n_mask=10)
+    img, mask, tokens = img.cuda(), mask.cuda(), tokens.cuda()
+    vit_engine.pretrain_step(model, img, mask, tokens)
+    g1 = model.lm_head.weight.grad.clone()
+    vit_engine.pretrain_step(model, img, mask, tokens)
+    assert rel(model.lm_head.weight.grad, 2 * g1) < 1e-2       # accumulation (atomic order differs)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    opt.zero_grad()                                            # set_to_none
+    vit_engine.pretrain_step(model, img, mask, tokens)
+    assert rel(model.lm_head.weight.grad, g1) < 1e-2
