@@ -131,6 +131,42 @@ typedef struct memb_gemm_desc {
 int memb_gemm(const memb_gemm_desc* desc, memb_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * dVAE tokenizer (fp32-faithful: every operand is a TF32 hi/lo pair, 3 MMAs per K block).
+ * Replaces DiscreteVAE.get_codebook_indices / forward(return_logits) / ResBlock,
+ * eventvae/vae/vae_model.py:29-41, 91-101, 153-158, 182-189.
+ * ---------------------------------------------------------------------- */
+typedef struct memb_conv_desc {
+  const float* a_hi;  /* input activations, "pixel-slot" layout [r_slots][x_slots][inner], TF32 hi parts */
+  const float* a_lo;  /* same layout, lo parts */
+  int32_t inner, x_slots, r_slots;
+  int32_t rows_per_img;            /* virtual output rows per image (>= OH); rows >= OH are dropped */
+  int32_t taps_y, taps_x;          /* tap grid: K = taps_y*taps_x*inner, tap-major */
+  int32_t tap_y0, tap_x0;          /* slot offset of tap (0,0) relative to the output pixel */
+  const float* w;                  /* weights [Cout][2K]: hi parts then lo parts, K ordered (tap, inner) */
+  const float* bias;               /* [Cout] */
+  int32_t B, OH, OW, Cout;
+  int32_t relu;
+  const float* aux;                /* optional fp32 residual, plain [B*OH*OW][Cout] */
+  float* d_full;                   /* optional fp32 result, plain [B*OH*OW][Cout] (may alias aux) */
+  uint64_t* keys;                  /* optional: per-pixel argmax keys over Cout (atomicMax; zero before the call) */
+  int32_t seg_kblocks;             /* K blocks (32 floats) accumulated in the tensor core before an fp32 RN add; 0 = 4 */
+  float* d_hi;                     /* optional result hi / lo parts at  b*sB + f(oy) + f(ox) + n  with         */
+  float* d_lo;                     /* f(o) = ((o+pad)>>shift)*s_major + ((o+pad)&(2^shift-1))*s_minor          */
+  int64_t sB, sy_major, sy_minor, sx_major, sx_minor;
+  int32_t pad, shift;
+  int32_t* err_flag;
+} memb_conv_desc;
+int memb_conv_tf32x3(const memb_conv_desc* desc, memb_stream_t stream);
+/* First encoder layer: im2col of the 4x4/s2/p1 window of img fp32 [B,C,H,W] -> hi/lo [B*(H/2)*(W/2)][Kpad],
+ * k = c*16+ky*4+kx; optional per-channel (x-mean)/std (DiscreteVAE.norm, vae_model.py:133-141). */
+int memb_dvae_im2col_l1(const float* img, int B, int C, int H, int W, int Kpad, const float* mean, const float* stdv,
+                        float* a_hi, float* a_lo, memb_stream_t stream);
+/* hi = tf32(v), lo = tf32(v - hi)  (weight preparation). */
+int memb_split_tf32(const float* src, float* hi, float* lo, int64_t n, memb_stream_t stream);
+/* MEMB_EPI_ARGMAX keys -> int64 indices (logits.argmax(dim=1), first maximum wins). */
+int memb_argmax_decode(const uint64_t* keys, int64_t* idx, int64_t n, memb_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Masked-ViT step kernels (HBM-bound pieces).  bf16 pointers are `void*`.
  * Reference: mem/modeling_finetune.py:166-189 (Block: pre-LN, LayerScale, DropPath),
  * :203-247 (PatchEmbed, RelativePositionBias); mem/modeling_pretrain.py:97-126.

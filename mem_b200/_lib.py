@@ -73,6 +73,27 @@ SIGNATURES.update({
     "memb_adamw": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _i32, _f32, _f32, _vp, _vp]),
 })
 
+
+
+class ConvDesc(_c.Structure):
+    """Mirror of ``memb_conv_desc`` (include/memb.h)."""
+    _fields_ = [
+        ("a_hi", _vp), ("a_lo", _vp), ("inner", _i32), ("x_slots", _i32), ("r_slots", _i32), ("rows_per_img", _i32),
+        ("taps_y", _i32), ("taps_x", _i32), ("tap_y0", _i32), ("tap_x0", _i32),
+        ("w", _vp), ("bias", _vp), ("B", _i32), ("OH", _i32), ("OW", _i32), ("Cout", _i32), ("relu", _i32),
+        ("aux", _vp), ("d_full", _vp), ("keys", _vp), ("seg_kblocks", _i32), ("d_hi", _vp), ("d_lo", _vp),
+        ("sB", _i64), ("sy_major", _i64), ("sy_minor", _i64), ("sx_major", _i64), ("sx_minor", _i64),
+        ("pad", _i32), ("shift", _i32), ("err_flag", _vp),
+    ]
+
+
+SIGNATURES.update({
+    "memb_conv_tf32x3": (_i32, [_c.POINTER(ConvDesc), _vp]),
+    "memb_dvae_im2col_l1": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "memb_split_tf32": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "memb_argmax_decode": (_i32, [_vp, _vp, _i64, _vp]),
+})
+
 _lib = None
 _lock = threading.Lock()
 

@@ -21,8 +21,14 @@
 // The epilogue adds bias (+ fp32 residual), applies ReLU, splits the result into TF32 hi / lo and
 // writes it directly in the slot layout the NEXT layer reads (space-to-depth, padded or plain).
 //
+// Accumulation is two-level.  Tensor-core accumulators round toward zero at every MMA, so a long K loop
+// (K = 6144 -> 2304 dependent accumulations) drifts by ~1e-4 relative -- far above the ~1e-6 argmax
+// margins.  The K loop is therefore cut into segments of `seg_kblocks` K blocks; each segment accumulates
+// into a fresh TMEM buffer and the epilogue warps add the segments in registers with round-to-nearest
+// FADDs while the tensor core works on the next segment (the two TMEM buffers alternate).
+//
 // Pipeline: warp 0 TMA producer (A_hi, A_lo, W_hi, W_lo per stage), warp 1 MMA issuer, warp 2 TMEM
-// allocator, warps 4-7 epilogue; persistent over tiles, two TMEM accumulator stages.
+// allocator, warps 4-11 epilogue (two warps per TMEM lane quarter, 96 columns each); persistent over tiles.
 #include <algorithm>
 
 #include "common.cuh"
@@ -37,7 +43,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 192;  // 384 output channels = 2 tiles
 constexpr int BLOCK_K = 32;   // floats: one 128-byte swizzle row
 constexpr int UMMA_K = 8;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
+constexpr int kEpiCols = BLOCK_N / 2;  // columns per epilogue warp
 constexpr int A_BYTES = BLOCK_M * 128;
 constexpr int B_BYTES = BLOCK_N * 128;
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 80 KB
@@ -48,12 +55,13 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 struct Params {
   int B, OH, OW, Cout;
   int rows_per_img, BW, BR, x_tiles, m_tiles, n_tiles, num_tiles;
-  int taps_x, ntaps, tap_y0, tap_x0, kc_per_tap, K;
+  int taps_x, ntaps, tap_y0, tap_x0, kc_per_tap, K, seg;
   const float* bias;
   const float* aux;
   float* d_full;
   float* d_hi;
   float* d_lo;
+  unsigned long long* keys;
   long long sB, sy_major, sy_minor, sx_major, sx_minor;
   int pad, shift, relu;
   int* err_flag;
@@ -63,6 +71,12 @@ __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+__device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {
+  // larger value wins; on equal values the smaller index wins (torch.argmax: first maximum)
+  uint32_t b = __float_as_uint(v);
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)b << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
 }
 __device__ __forceinline__ void st_row32(float* dst, const float (&v)[32]) {
 #pragma unroll
@@ -89,7 +103,7 @@ conv_tf32x3(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -126,33 +140,36 @@ conv_tf32x3(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, p.err_flag, 12);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int it = 0; it < iters; ++it) {
-          mbar_wait(&full_bar[stage], phase, p.err_flag, 13);
+        for (int it0 = 0; it0 < iters; it0 += p.seg) {
+          const int it1 = min(iters, it0 + p.seg);
+          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, p.err_flag, 12);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES), a_lo = a_hi + A_BYTES;
-          const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
-          // small terms first: lo*hi, hi*lo, then hi*hi
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          for (int it = it0; it < it1; ++it) {
+            mbar_wait(&full_bar[stage], phase, p.err_flag, 13);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+            const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+            // small terms first: lo*hi, hi*lo, then hi*hi
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_tf32(d_tmem, make_smem_desc_sw128(a_lo + k * 32, 0, 1024), make_smem_desc_sw128(b_hi + k * 32, 0, 1024), idesc, (it | k) != 0);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_tf32(d_tmem, make_smem_desc_sw128(a_lo + k * 32, 0, 1024), make_smem_desc_sw128(b_hi + k * 32, 0, 1024), idesc, (it != it0) || k != 0);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_tf32(d_tmem, make_smem_desc_sw128(a_hi + k * 32, 0, 1024), make_smem_desc_sw128(b_lo + k * 32, 0, 1024), idesc, 1);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_tf32(d_tmem, make_smem_desc_sw128(a_hi + k * 32, 0, 1024), make_smem_desc_sw128(b_lo + k * 32, 0, 1024), idesc, 1);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_tf32(d_tmem, make_smem_desc_sw128(a_hi + k * 32, 0, 1024), make_smem_desc_sw128(b_hi + k * 32, 0, 1024), idesc, 1);
-          umma_commit(&empty_bar[stage]);
-          if (it == iters - 1) umma_commit(&tmem_full_bar[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_tf32(d_tmem, make_smem_desc_sw128(a_hi + k * 32, 0, 1024), make_smem_desc_sw128(b_hi + k * 32, 0, 1024), idesc, 1);
+            umma_commit(&empty_bar[stage]);
+            if (it == it1 - 1) umma_commit(&tmem_full_bar[acc]);  // this segment's partial sum is complete
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    const int quad = warp & 3;
+    const int quad = warp & 3, half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -166,19 +183,36 @@ conv_tf32x3(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant
       const int py = oy + p.pad, px = ox + p.pad, msk = (1 << p.shift) - 1;
       const long long off = (long long)b * p.sB + (long long)(py >> p.shift) * p.sy_major + (long long)(py & msk) * p.sy_minor +
                             (long long)(px >> p.shift) * p.sx_major + (long long)(px & msk) * p.sx_minor;
-      mbar_wait(&tmem_full_bar[acc], acc_phase, p.err_flag, 14);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(taddr + c * 32, raw);
-        tmem_ld_wait();
-        const int col0 = n_tile * BLOCK_N + c * 32;
+      float sum[kEpiCols];
+#pragma unroll
+      for (int j = 0; j < kEpiCols; ++j) sum[j] = 0.f;
+      // ---- add the K segments with round-to-nearest fp32 adds
+      for (int it0 = 0; it0 < iters; it0 += p.seg) {
+        mbar_wait(&tmem_full_bar[acc], acc_phase, p.err_flag, 14);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N + half * kEpiCols;
+#pragma unroll
+        for (int c = 0; c < kEpiCols / 32; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(taddr + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(raw[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      // ---- fused epilogue from registers
+      unsigned long long best = 0ull;
+#pragma unroll
+      for (int c = 0; c < kEpiCols / 32; ++c) {
+        const int col0 = n_tile * BLOCK_N + half * kEpiCols + c * 32;
         if (live && col0 < p.Cout) {  // Cout % 32 == 0
           float v[32], lo[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + __ldg(p.bias + col0 + j);
+          for (int j = 0; j < 32; ++j) v[j] = sum[c * 32 + j] + __ldg(p.bias + col0 + j);
           if (p.aux) {
             const float4* a4 = reinterpret_cast<const float4*>(p.aux + plain * p.Cout + col0);
 #pragma unroll
@@ -192,20 +226,26 @@ conv_tf32x3(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (p.d_full) st_row32(p.d_full + plain * p.Cout + col0, v);
+          if (p.keys) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float h = tf32_rna(v[j]);
-            lo[j] = tf32_rna(v[j] - h);
-            v[j] = h;
+            for (int j = 0; j < 32; ++j) {
+              const unsigned long long key = argmax_key(v[j], col0 + j);
+              best = key > best ? key : best;
+            }
           }
-          st_row32(p.d_hi + off + col0, v);
-          st_row32(p.d_lo + off + col0, lo);
+          if (p.d_hi) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float h = tf32_rna(v[j]);
+              lo[j] = tf32_rna(v[j] - h);
+              v[j] = h;
+            }
+            st_row32(p.d_hi + off + col0, v);
+            st_row32(p.d_lo + off + col0, lo);
+          }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (p.keys && live) atomicMax(p.keys + plain, best);
     }
   }
   tc_fence_before();
@@ -311,7 +351,9 @@ using namespace memb::conv;
 extern "C" int memb_conv_tf32x3(const memb_conv_desc* dp, memb_stream_t stream) {
   MEMB_REQUIRE(dp != nullptr, "conv: null descriptor");
   const memb_conv_desc& d = *dp;
-  MEMB_REQUIRE(d.a_hi && d.a_lo && d.w && d.bias && d.d_hi && d.d_lo, "conv: null operand");
+  MEMB_REQUIRE(d.a_hi && d.a_lo && d.w && d.bias, "conv: null operand");
+  MEMB_REQUIRE((d.d_hi != nullptr) == (d.d_lo != nullptr), "conv: d_hi and d_lo go together");
+  MEMB_REQUIRE(d.d_hi || d.d_full || d.keys, "conv: no output requested");
   MEMB_REQUIRE(d.inner > 0 && d.inner % BLOCK_K == 0, "conv: inner slot length must be a multiple of 32 floats, got %d", d.inner);
   MEMB_REQUIRE(d.Cout > 0 && d.Cout % 32 == 0, "conv: Cout must be a multiple of 32, got %d", d.Cout);
   MEMB_REQUIRE(d.B > 0 && d.OH > 0 && d.OW > 0 && d.taps_x > 0 && d.taps_y > 0 && d.rows_per_img >= d.OH, "conv: bad geometry");
@@ -330,6 +372,8 @@ extern "C" int memb_conv_tf32x3(const memb_conv_desc* dp, memb_stream_t stream) 
   p.taps_x = d.taps_x; p.ntaps = d.taps_x * d.taps_y; p.tap_y0 = d.tap_y0; p.tap_x0 = d.tap_x0;
   p.kc_per_tap = d.inner / BLOCK_K;
   p.K = p.ntaps * d.inner;
+  p.seg = d.seg_kblocks > 0 ? d.seg_kblocks : 4;
+  p.keys = reinterpret_cast<unsigned long long*>(d.keys);
   p.bias = d.bias; p.aux = d.aux; p.d_full = d.d_full; p.d_hi = d.d_hi; p.d_lo = d.d_lo;
   p.sB = d.sB; p.sy_major = d.sy_major; p.sy_minor = d.sy_minor; p.sx_major = d.sx_major; p.sx_minor = d.sx_minor;
   p.pad = d.pad; p.shift = d.shift; p.relu = d.relu; p.err_flag = d.err_flag;

@@ -57,6 +57,7 @@ class FlatParams:
                 view.copy_(p.data)
                 p.data = view
         self.shadow_version = -1
+        self._plist = [params[n] for n in names]
         self.grad_views = {n: self.grad[self.offsets[n]: self.offsets[n] + self.sizes[n]].view_as(params[n])
                            for n in names}
 
@@ -66,7 +67,9 @@ class FlatParams:
             self.params[self.names[-1]].data_ptr() == self.data.data_ptr() + 4 * self.offsets[self.names[-1]]
 
     def refresh_shadow(self, force=False):
-        v = self.data._version
+        # p.data are views of the flat buffer but carry their own version counters (load_state_dict, manual
+        # in-place edits); libmemb's AdamW writes through raw pointers and refreshes the shadow itself.
+        v = sum(p._version for p in self._plist)
         if force or v != self.shadow_version:
             lib = _lib.load()
             _lib.check(lib.memb_cast_bf16(self.data.data_ptr(), self.shadow.data_ptr(), self.numel, _sp(device=self.device)))

@@ -160,7 +160,69 @@ def golden_vit():
     print("vit_tiny.npz:", len(out), "arrays, pt loss", loss.item(), "ft loss", lossf.item())
 
 
-SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit}
+def golden_dvae():
+    """Logits / indices of the UNMODIFIED reference DiscreteVAE (eventvae/vae/vae_model.py) on seeded tiny cases."""
+    import torch
+    from oracle import dvae_ref
+    vm = ref_shims.ref_module("vae.vae_model")
+    out = {}
+    for name, cfg, B, seed, gain in (("a", dvae_ref.TINY_A, 3, 21, 1.0), ("b", dvae_ref.TINY_B, 2, 22, 4.0),
+                                     ("c", dvae_ref.TINY_C, 5, 23, 1.0)):
+        torch.manual_seed(0)
+        vae = vm.DiscreteVAE(**cfg)
+        vae.load_state_dict(dvae_ref.synth_state_dict(vae.state_dict(), seed, gain))
+        vae.train()   # get_codebook_indices must switch to eval and back (eval_decorator)
+        img = dvae_ref.synth_images(B, cfg["channels"], cfg["input_H"], cfg["input_W"], seed + 100)
+        idx = vae.get_codebook_indices(img)
+        assert vae.training
+        with torch.no_grad():
+            logits = vae(img, return_logits=True)
+        out[f"{name}/indices"] = idx.numpy()
+        out[f"{name}/logits"] = logits.numpy()
+        print(name, "indices", tuple(idx.shape), "distinct tokens", idx.unique().numel())
+    np.savez_compressed(os.path.join(GOLD, "dvae_tiny.npz"), **out)
+
+
+def golden_engine():
+    """Three steps of the UNMODIFIED reference train_one_epoch (mem/engine_for_pretraining.py:108-287) on CPU fp32:
+    tiny pt_vit + tiny dVAE, AdamW with the reference's parameter groups, per-step lr / wd schedule, clip 1.0."""
+    import torch
+    from oracle import dvae_ref, engine_ref, vit_ref
+    eng = ref_shims.ref_module("engine_for_pretraining")
+    rutils = ref_shims.ref_module("utils")
+    optf = ref_shims.ref_module("optim_factory")
+    vm = ref_shims.ref_module("vae.vae_model")
+    torch.cuda.synchronize = lambda *a, **k: None       # SURVEY.md D7: CPU run of a CUDA-only loop
+    rutils.is_main_process = lambda: False               # skips the wandb / make_grid branch
+
+    class Scaler(rutils.NativeScalerWithGradNormCount):  # GradScaler disables itself on CPU -> state_dict() == {}
+        def state_dict(self):
+            return {"scale": 1.0}
+
+    torch.manual_seed(0)
+    model = ref_shims.ref_create_model("pt_vit", **vit_ref.TINY)
+    model.load_state_dict(vit_ref.synth_state_dict(model.state_dict(), seed=31))
+    vae = vm.DiscreteVAE(**engine_ref.TINY_VAE)
+    vae.load_state_dict(dvae_ref.synth_state_dict(vae.state_dict(), seed=32, head_gain=4.0))
+    groups = optf.get_parameter_groups(model, engine_ref.WD[0], model.no_weight_decay())
+    opt = torch.optim.AdamW(groups, lr=engine_ref.LR[0], betas=(0.9, 0.95), eps=1e-8)
+    scaler = Scaler()
+    out = {}
+    for it, batch in enumerate(engine_ref.synth_batches()):
+        stats = eng.train_one_epoch(model, vae, [(batch, None)], opt, torch.device("cpu"), 0, scaler, engine_ref.MAX_NORM,
+                                    start_steps=it, lr_schedule_values=engine_ref.LR, wd_schedule_values=engine_ref.WD)
+        for k, v in stats.items():
+            out[f"step{it}/{k}"] = np.array(v)
+        print(it, {k: round(float(v), 6) for k, v in stats.items()})
+    out["keys"] = np.array(sorted(stats.keys()))
+    sd = model.state_dict()
+    for k in ("lm_head.weight", "blocks.0.attn.qkv.weight", "cls_token", "rel_pos_bias.relative_position_bias_table", "blocks.1.gamma_2"):
+        out["final/" + k] = sd[k].detach().numpy().reshape(-1)[:512]
+    np.savez_compressed(os.path.join(GOLD, "engine_tiny.npz"), **out)
+
+
+SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit, "dvae": golden_dvae,
+            "engine": golden_engine}
 
 
 def main(argv):
