@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--events", type=int, default=10_000_000)
     ap.add_argument("--sensor", default="640x480")
     ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--model", default="base", choices=["base", "large"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

@@ -92,6 +92,8 @@ def train_one_epoch(model: torch.nn.Module, d_vae: torch.nn.Module, data_loader:
                     group["weight_decay"] = wd_schedule_values[it]
 
         samples, images, bool_masked_pos = batch
+        # masked-patch count from the host copy of the mask: sizes the lm_head / CE kernels without a device sync
+        n_masked = int(bool_masked_pos.ne(0).sum()) if not bool_masked_pos.is_cuda else None
         images = images.to(device, non_blocking=True)
         samples = samples.to(device, non_blocking=True)
         bool_masked_pos = bool_masked_pos.to(device, non_blocking=True)
@@ -100,7 +102,7 @@ def train_one_epoch(model: torch.nn.Module, d_vae: torch.nn.Module, data_loader:
             input_ids = d_vae.get_codebook_indices(images).flatten(1)      # [B, P] int64
 
         optimizer.zero_grad()
-        stats = pretrain_step(core, samples, bool_masked_pos.flatten(1), input_ids,
+        stats = pretrain_step(core, samples, bool_masked_pos.flatten(1), input_ids, cap=n_masked,
                               bucket_hook=reducer.hook if reducer is not None else None)
         if reducer is not None:
             reducer.finish()
@@ -159,11 +161,12 @@ def evaluate(data_loader, model, d_vae, device, args, plotting=False, MAE=False)
     hand_off = _StepStats(device)
     for batch in metric_logger.log_every(data_loader, 10, "Test:"):
         samples, images, bool_masked_pos = batch[0]
+        n_masked = int(bool_masked_pos.ne(0).sum()) if not bool_masked_pos.is_cuda else None
         images = images.to(device, non_blocking=True)
         samples = samples.to(device, non_blocking=True)
         bool_masked_pos = bool_masked_pos.to(device, non_blocking=True)
         input_ids = d_vae.get_codebook_indices(images).flatten(1)
-        stats = pretrain_step(core, samples, bool_masked_pos.flatten(1), input_ids, backward=False)
+        stats = pretrain_step(core, samples, bool_masked_pos.flatten(1), input_ids, backward=False, cap=n_masked)
         loss_value, mlm_acc, _, _ = hand_off.read(stats, None)
         metric_logger.update(loss=loss_value)
         metric_logger.meters["mlm_acc"].update(mlm_acc)

@@ -266,22 +266,27 @@ class VitEngine:
         dev = xlast.device
         B, D, N, P = ctx["B"], c["D"], c["N"], c["P"]
         V = m.lm_head.out_features
-        cap = cap or B * P
+        cap = min(int(cap), B * P) if cap else B * P
+        cap = max(cap, 1)
+        # buffers are sized for the largest cap seen (rounded to 1024 rows) and sliced, so a varying masked
+        # count does not reallocate the big logits / dlogits tensors every step
+        self._cap_alloc = max(getattr(self, "_cap_alloc", 0), (cap + 1023) // 1024 * 1024)
+        ca = self._cap_alloc
         g = self.bufs.get
         sp = _sp(device=dev)
-        row_index = g("row_index", (cap,), torch.int32, dev); patch_index = g("patch_index", (cap,), torch.int32, dev)
+        row_index = g("row_index", (ca,), torch.int32, dev)[:cap]; patch_index = g("patch_index", (ca,), torch.int32, dev)[:cap]
         count = g("count", (1,), torch.int32, dev)
         _lib.check(lib.memb_mask_compact(mask_u8.data_ptr(), B, P, row_index.data_ptr(), patch_index.data_ptr(),
                                          count.data_ptr(), cap, sp))
-        xm = g("xm", (cap, D), torch.bfloat16, dev); mu = g("mu_f", (cap,), torch.float32, dev); rs = g("rs_f", (cap,), torch.float32, dev)
+        xm = g("xm", (ca, D), torch.bfloat16, dev)[:cap]; mu = g("mu_f", (ca,), torch.float32, dev)[:cap]; rs = g("rs_f", (ca,), torch.float32, dev)[:cap]
         _ln_fwd(lib, xlast, m.norm.weight, m.norm.bias, m.norm.eps, xm, mu, rs, cap, D, row_index, count)
-        logits = g("logits", (cap, V), torch.float32, dev)
+        logits = g("logits", (ca, V), torch.float32, dev)[:cap]
         ops.gemm(xm, flat.w16("lm_head.weight"), out=logits, bias=m.lm_head.bias)
         out = dict(logits=logits, count=count, row_index=row_index, patch_index=patch_index, xm=xm, mu=mu, rs=rs, cap=cap)
         if tokens is not None:
             stats = g("stats", (4,), torch.float32, dev)
             stats.zero_()
-            dlogits = g("dlogits", (cap, V), torch.bfloat16, dev) if need_grad else None
+            dlogits = g("dlogits", (ca, V), torch.bfloat16, dev)[:cap] if need_grad else None
             _lib.check(lib.memb_cross_entropy(logits.data_ptr(), logits.stride(0), tokens.data_ptr(), patch_index.data_ptr(),
                                               count.data_ptr(), cap, V, ops._ptr(dlogits), V, stats.data_ptr(), 1.0, sp))
             out.update(stats=stats, dlogits=dlogits)
@@ -303,7 +308,7 @@ class VitEngine:
         # lm_head: wgrad (both operands MN-major), bias grad, dgrad (B = W as stored)
         ops.gemm(dl, head["xm"], out=flat.g("lm_head.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD,
                  alpha_dev=grad_scale_dev)
-        dxm = g("dxm", (cap, D), torch.bfloat16, dev)
+        dxm = g("dxm", (self._cap_alloc, D), torch.bfloat16, dev)[:cap]
         ops.gemm(dl, flat.w16("lm_head.weight"), out=dxm, b_layout=1, alpha_dev=grad_scale_dev)
         if grad_scale_dev is None:
             _lib.check(lib.memb_colsum_bf16(dl.data_ptr(), V, cap, V, flat.g("lm_head.bias").data_ptr(), sp))
@@ -478,7 +483,7 @@ class _MaskedVitFn(torch.autograd.Function):
         flat = eng.flat()
         bind_param_grads(flat, flat.params)
         V = grad_logits.shape[1]
-        dl = eng.bufs.get("dlogits", (head["cap"], V), torch.bfloat16, grad_logits.device)
+        dl = eng.bufs.get("dlogits", (eng._cap_alloc, V), torch.bfloat16, grad_logits.device)[:head["cap"]]
         dl.zero_()
         dl[:ctx.n].copy_(grad_logits)
         eng.backward_pretrain(ctx.fctx, head, None, dlogits=dl)
@@ -504,11 +509,13 @@ def masked_forward(model, x, bool_masked_pos, return_all_tokens=False):
     return out
 
 
-def pretrain_step(model, samples, bool_masked_pos, tokens, grad_scale_dev=None, bucket_hook=None, backward=True):
+def pretrain_step(model, samples, bool_masked_pos, tokens, grad_scale_dev=None, bucket_hook=None, backward=True, cap=None):
     """Fused MEM step body: forward + masked cross entropy (+ accuracy) + backward into the flat gradient
     buffer.  Replaces engine_for_pretraining.py:147-161 (autocast forward, CrossEntropyLoss, scaled backward)
     and :233 (mlm_acc).  ``tokens``: int64 [B, P] codebook indices (get_codebook_indices output); labels are
-    tokens[mask].  Returns the device stats tensor [sum of per-token losses, top-1 hits, masked count, 0]."""
+    tokens[mask].  ``cap``: upper bound of the number of masked patches in the batch (sizes the lm_head GEMM; masked
+    patches beyond it would be dropped) -- default B*P; train_one_epoch passes the exact count taken from the host
+    copy of the mask.  Returns the device stats tensor [sum of per-token losses, top-1 hits, masked count, 0]."""
     eng = engine_of(model)
     c = eng.cfg()
     B = samples.shape[0]
@@ -520,7 +527,7 @@ def pretrain_step(model, samples, bool_masked_pos, tokens, grad_scale_dev=None, 
         bind_param_grads(flat, flat.params)
     dp = droppath_scales(model, B, samples.device, model.training)
     xlast, fctx = eng.forward_features(samples, mask, backward, dp)
-    head = eng.pretrain_head(xlast, fctx, mask, tokens, backward)
+    head = eng.pretrain_head(xlast, fctx, mask, tokens, backward, cap=cap)
     if backward:
         eng.backward_pretrain(fctx, head, grad_scale_dev, bucket_hook=bucket_hook)
     return head["stats"]
