@@ -9,7 +9,9 @@
 //                             instruction), accumulators live in TMEM, tcgen05.commit frees smem slots
 //   warp 2   TMEM allocator : 2 x BLOCK_N columns = two accumulator stages (epilogue of tile i
 //                             overlaps the main loop of tile i+1)
-//   warps 4-7 epilogue      : tcgen05.ld (32 lanes x 32 columns per warp) -> fused epilogue -> global
+//   warps 4-11 epilogue     : two warps per TMEM lane quarter (each takes half of the tile's columns);
+//                             tcgen05.ld of 32-column chunks is software-pipelined one chunk ahead of the
+//                             fused epilogue math -> global stores
 //
 // Operands may be K-major (row-major [rows,K]) or MN-major (row-major [K,rows]); the latter is what
 // dgrad (B = W as stored) and wgrad (A = dY, B = X as stored) need, so backward needs no transposes.
@@ -32,7 +34,7 @@ namespace gemm {
 using namespace memb::ptx;
 
 constexpr int BLOCK_M = 128;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;  // warps 0-2 producer / MMA / TMEM alloc, warp 3 idle, warps 4-11 epilogue
 constexpr int kSwizzleBytes = 128;  // one swizzle atom row = BLOCK_K elements
 
 struct Params {
@@ -60,11 +62,29 @@ struct Params {
   int* err_flag;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU (nn.GELU(), modeling_finetune.py:62) evaluated with the Abramowitz-Stegun 7.1.26 erfc form
+// (|erf error| <= 1.5e-7, two MUFU ops) -- libdevice erff costs ~3x the instructions and made the fc1 epilogue
+// the bottleneck.  Phi(x) = 0.5*erfc(-x/sqrt2) is formed without cancellation on the negative side.
+__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  e = __expf(-z * z);
+  const float h = 0.5f * poly * t * e;  // 0.5 * erfc(z)
+  cdf = x < 0.f ? h : 1.0f - h;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, e;
+  gelu_terms(x, cdf, e);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, e;
+  gelu_terms(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);  // cdf + x * pdf,  pdf = exp(-x^2/2)/sqrt(2 pi)
 }
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
@@ -144,13 +164,30 @@ __device__ __forceinline__ void load_row32(const __nv_bfloat16* src, float (&v)[
   }
 }
 
+// 32 consecutive floats of a per-column vector (bias, LayerScale, mask token): the address is warp-uniform, so
+// the eight 16-byte loads are broadcasts served by L1.
+__device__ __forceinline__ void load_vec32(const float* src, float (&v)[32], int valid) {
+  if (valid == 32 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(src) + i);
+      v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = i < valid ? __ldg(src + i) : 0.f;
+  }
+}
+
 // Fused epilogue for one (row, 32-column chunk).  `v` holds the fp32 accumulators.
 template <int EPI, typename OutT>
 __device__ __forceinline__ void epilogue_chunk(const Params& p, int row, int col0, float (&v)[32], int valid) {
   if constexpr (EPI == MEMB_EPI_STORE) {
     if (p.bias) {
+      float b[32];
+      load_vec32(p.bias + col0, b, valid);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += (i < valid) ? __ldg(p.bias + col0 + i) : 0.f;
+      for (int i = 0; i < 32; ++i) v[i] += b[i];
     }
     const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
     if (alpha != 1.0f) {
@@ -170,10 +207,7 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, int row, int col
     long long orow = row;
     if (p.out_group_rows > 0)
       orow = (long long)(row / p.out_group_rows) * p.out_group_stride + p.out_row_offset + row % p.out_group_rows;
-    if (p.rowmask && p.rowmask[row]) {  // masked patch: the row becomes the mask token
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = (i < valid) ? __ldg(p.maskvec + col0 + i) : 0.f;
-    }
+    if (p.rowmask && p.rowmask[row]) load_vec32(p.maskvec + col0, v, valid);  // masked patch: the row becomes the mask token
     if constexpr (sizeof(OutT) == 4) {
       if (p.out_split) {
         float hi[32], lo[32];
@@ -188,9 +222,14 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, int row, int col
     store_row32(reinterpret_cast<OutT*>(p.d) + orow * p.ldd + col0, v, valid);
   } else if constexpr (EPI == MEMB_EPI_BIAS_GELU) {
     float pre[32];
+    if (p.bias) load_vec32(p.bias + col0, pre, valid);
+    else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) pre[i] = 0.f;
+    }
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      pre[i] = v[i] + ((p.bias && i < valid) ? __ldg(p.bias + col0 + i) : 0.f);
+      pre[i] += v[i];
       v[i] = gelu_erf(pre[i]);
     }
     store_row32(reinterpret_cast<OutT*>(p.d) + (long long)row * p.ldd + col0, v, valid);
@@ -200,12 +239,20 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, int row, int col
     float r[32];
     load_row32(reinterpret_cast<const float*>(p.aux) + (long long)row * p.ldaux + col0, r, valid);
     const float rs = p.rowscale ? __ldg(p.rowscale + row / p.rows_per_group) : 1.0f;
+    if (p.bias) {
+      float b[32];
+      load_vec32(p.bias + col0, b, valid);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float b = (p.bias && i < valid) ? __ldg(p.bias + col0 + i) : 0.f;
-      const float g = (p.colscale && i < valid) ? __ldg(p.colscale + col0 + i) : 1.f;
-      v[i] += b;
-      r[i] += rs * g * v[i];
+      for (int i = 0; i < 32; ++i) v[i] += b[i];
+    }
+    if (p.colscale) {
+      float g[32];
+      load_vec32(p.colscale + col0, g, valid);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = fmaf(rs * g[i], v[i], r[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = fmaf(rs, v[i], r[i]);
     }
     store_row32(reinterpret_cast<float*>(p.d) + (long long)row * p.ldd + col0, r, valid);
     if (p.d2) store_row32(reinterpret_cast<__nv_bfloat16*>(p.d2) + (long long)row * p.ldd2 + col0, v, valid);
@@ -273,7 +320,7 @@ gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[s], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -369,8 +416,9 @@ gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    // -------------------------------------------------------------- epilogue (4 warps = 128 TMEM lanes)
-    const int quad = warp & 3;
+    // -------------------------------------------------------------- epilogue (8 warps: lane quarter x column half)
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    constexpr int kCols = BLOCK_N / 2, kChunks = kCols / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -379,40 +427,37 @@ gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       mbar_wait(&tmem_full_bar[acc], acc_phase, p.err_flag, 4);
       tc_fence_after();
       const int row = m_tile * BLOCK_M + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
-      if constexpr (EPI == MEMB_EPI_ARGMAX) {
-        unsigned long long best = 0ull;
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
-          tmem_ld_wait();
-          const int col0 = n_tile * BLOCK_N + c * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N + half * kCols;
+      const int colbase = n_tile * BLOCK_N + half * kCols;
+      uint32_t r[2][32];
+      tmem_ld32(taddr, r[0]);  // warp-collective: every lane takes part even for rows >= M
+      unsigned long long best = 0ull;
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < kChunks) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);  // next chunk in flight during the math
+        const int col0 = colbase + c * 32;
+        const int valid = min(32, p.N - col0);
+        if constexpr (EPI == MEMB_EPI_ARGMAX) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (col0 + i < p.N) {
-              const float val = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + col0 + i) : 0.f);
+              const float val = __uint_as_float(r[c & 1][i]) + (p.bias ? __ldg(p.bias + col0 + i) : 0.f);
               const unsigned long long key = argmax_key(val, col0 + i);
               best = key > best ? key : best;
             }
           }
-        }
-        if (row < p.M) atomicMax(reinterpret_cast<unsigned long long*>(p.d) + row, best);
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);  // warp-collective: every lane takes part even for rows >= M
-          tmem_ld_wait();
-          const int col0 = n_tile * BLOCK_N + c * 32;
-          const int valid = min(32, p.N - col0);
+        } else {
           if (row < p.M && valid > 0) {
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[c & 1][i]);
             epilogue_chunk<EPI, OutT>(p, row, col0, v, valid);
           }
         }
+      }
+      if constexpr (EPI == MEMB_EPI_ARGMAX) {
+        if (row < p.M) atomicMax(reinterpret_cast<unsigned long long*>(p.d) + row, best);
       }
       tc_fence_before();
       __syncwarp();
