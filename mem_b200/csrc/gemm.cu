@@ -26,9 +26,13 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "epilogue_math.cuh"
 #include "sm100.cuh"
 
 namespace memb {
+namespace gemm_pair {
+int try_launch(const memb_gemm_desc& g, cudaStream_t stream, bool* handled);  // gemm_pair.cu
+}
 namespace gemm {
 
 using namespace memb::ptx;
@@ -62,30 +66,6 @@ struct Params {
   int* err_flag;
 };
 
-// Exact-erf GELU (nn.GELU(), modeling_finetune.py:62) evaluated with the Abramowitz-Stegun 7.1.26 erfc form
-// (|erf error| <= 1.5e-7, two MUFU ops) -- libdevice erff costs ~3x the instructions and made the fc1 epilogue
-// the bottleneck.  Phi(x) = 0.5*erfc(-x/sqrt2) is formed without cancellation on the negative side.
-__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  e = __expf(-z * z);
-  const float h = 0.5f * poly * t * e;  // 0.5 * erfc(z)
-  cdf = x < 0.f ? h : 1.0f - h;
-}
-__device__ __forceinline__ float gelu_erf(float x) {
-  float cdf, e;
-  gelu_terms(x, cdf, e);
-  return x * cdf;
-}
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf, e;
-  gelu_terms(x, cdf, e);
-  return fmaf(x * 0.39894228040143267794f, e, cdf);  // cdf + x * pdf,  pdf = exp(-x^2/2)/sqrt(2 pi)
-}
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -230,7 +210,7 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, int row, int col
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       pre[i] += v[i];
-      v[i] = gelu_erf(pre[i]);
+      v[i] = epi::gelu_fwd(pre[i]);
     }
     store_row32(reinterpret_cast<OutT*>(p.d) + (long long)row * p.ldd + col0, v, valid);
     if (p.d2) store_row32(reinterpret_cast<__nv_bfloat16*>(p.d2) + (long long)row * p.ldd2 + col0, pre, valid);
@@ -274,7 +254,7 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, int row, int col
     float pre[32];
     load_row32(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col0, pre, valid);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad(pre[i]);
+    for (int i = 0; i < 32; ++i) v[i] *= epi::gelu_grad(pre[i]);
     store_row32(reinterpret_cast<OutT*>(p.d) + (long long)row * p.ldd + col0, v, valid);
   }
 }
@@ -583,6 +563,11 @@ extern "C" int memb_gemm(const memb_gemm_desc* gp, memb_stream_t stream) {
   MEMB_REQUIRE(g.a && g.b && g.d, "gemm: null operand");
   MEMB_REQUIRE(g.in_dtype == MEMB_DT_BF16 || g.in_dtype == MEMB_DT_F32, "gemm: in_dtype must be bf16 or fp32(tf32)");
   MEMB_REQUIRE(g.epilogue >= MEMB_EPI_STORE && g.epilogue <= MEMB_EPI_ARGMAX, "gemm: unknown epilogue %d", g.epilogue);
+  {  // large bf16 K-major-A problems with a fused epilogue run on the CTA-pair kernel
+    bool handled = false;
+    if (int rc = gemm_pair::try_launch(g, stream, &handled)) return rc;
+    if (handled) return MEMB_OK;
+  }
   const int eb = g.in_dtype == MEMB_DT_BF16 ? 2 : 4;
   const int block_k = kSwizzleBytes / eb;
   const int block_n = (g.block_n == 128 || g.block_n == 256) ? g.block_n : ((g.n % 256 == 0 || g.n > 1024) ? 256 : 128);

@@ -17,6 +17,7 @@ h = torch.randn(M, Hd, device=dev).bfloat16()
 wqkv = torch.randn(3 * D, D, device=dev).bfloat16()
 w1 = torch.randn(Hd, D, device=dev).bfloat16()
 w2 = torch.randn(D, Hd, device=dev).bfloat16()
+wp = torch.randn(D, D, device=dev).bfloat16()
 bias3 = torch.randn(3 * D, device=dev)
 bias1 = torch.randn(Hd, device=dev)
 biasD = torch.randn(D, device=dev)
@@ -34,6 +35,9 @@ cases = {
     "fc2_residual": (lambda: ops.gemm(h, w2, out=out_res, epilogue=EPI_RESIDUAL, bias=biasD, aux=res, d2=br, colscale=gamma), 2.0 * M * Hd * D),
     "fc2_dgrad_dgelu": (lambda: ops.gemm(x, w2, out=out_h, b_layout=1, epilogue=EPI_DGELU, aux=pre_h), 2.0 * M * Hd * D),
     "fc1_dgrad": (lambda: ops.gemm(h, w1, out=br, b_layout=1), 2.0 * M * Hd * D),
+    "proj_residual": (lambda: ops.gemm(x, wp, out=out_res, epilogue=EPI_RESIDUAL, bias=biasD, aux=res, d2=br, colscale=gamma), 2.0 * M * D * D),
+    "proj_dgrad": (lambda: ops.gemm(x, wp, out=br, b_layout=1), 2.0 * M * D * D),
+    "qkv_dgrad": (lambda: ops.gemm(out_qkv, wqkv, out=br, b_layout=1), 2.0 * M * 3 * D * D),
     "fc1_wgrad": (lambda: ops.gemm(h, x, out=gw, a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD), 2.0 * M * Hd * D),
 }
 only = sys.argv[1:] or list(cases)
