@@ -166,6 +166,42 @@ int memb_split_tf32(const float* src, float* hi, float* lo, int64_t n, memb_stre
 /* MEMB_EPI_ARGMAX keys -> int64 indices (logits.argmax(dim=1), first maximum wins). */
 int memb_argmax_decode(const uint64_t* keys, int64_t* idx, int64_t n, memb_stream_t stream);
 
+/* fp16-pair variant of the same convolution (csrc/conv_f16.cu): operands are fp16 hi / lo parts of value * 2^exp
+ * (11 + 11 significand bits like the TF32 pair, half the bytes, twice the MMA rate), CTA-pair tcgen05 MMAs.
+ * Exponents are the caller's: a_exp / w_exp scale the inputs, out_exp the hi / lo result; d_full, keys and the
+ * residual `aux` stay unscaled fp32.  `absmax` (optional) receives atomicMax(float bits of |result|) so the caller
+ * can calibrate / monitor the exponents (fp16 overflows at 65504). */
+typedef struct memb_conv16_desc {
+  const void* a_hi;   /* fp16 [r_slots][x_slots][inner] */
+  const void* a_lo;
+  int32_t inner, x_slots, r_slots;   /* inner % 64 == 0 */
+  int32_t rows_per_img;
+  int32_t taps_y, taps_x;
+  int32_t tap_y0, tap_x0;
+  const void* w;      /* fp16 [Cout][2K]: hi parts then lo parts of weight * 2^w_exp */
+  const float* bias;  /* [Cout], unscaled */
+  int32_t B, OH, OW, Cout;
+  int32_t relu;
+  int32_t a_exp, w_exp, out_exp;
+  const float* aux;
+  float* d_full;
+  uint64_t* keys;
+  int32_t seg_kblocks;   /* K blocks (64 halves) per tensor-core accumulation segment; 0 = 2 */
+  void* d_hi;            /* fp16 result parts, addressing as in memb_conv_desc (strides in elements) */
+  void* d_lo;
+  int64_t sB, sy_major, sy_minor, sx_major, sx_minor;
+  int32_t pad, shift;
+  uint32_t* absmax;
+  int32_t* err_flag;
+} memb_conv16_desc;
+int memb_conv_f16x2(const memb_conv16_desc* desc, memb_stream_t stream);
+/* First encoder layer im2col with fp16 hi / lo of value * 2^exp2 (Kpad % 64 == 0); absmax as above (of the
+ * normalised pixels). */
+int memb_dvae_im2col_l1_f16(const float* img, int B, int C, int H, int W, int Kpad, const float* mean, const float* stdv,
+                            int exp2, void* a_hi, void* a_lo, uint32_t* absmax, memb_stream_t stream);
+/* hi = fp16(v * 2^exp2), lo = fp16(v * 2^exp2 - hi)  (weight preparation). */
+int memb_split_f16(const float* src, int exp2, void* hi, void* lo, int64_t n, memb_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Masked-ViT step kernels (HBM-bound pieces).  bf16 pointers are `void*`.
  * Reference: mem/modeling_finetune.py:166-189 (Block: pre-LN, LayerScale, DropPath),

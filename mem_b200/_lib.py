@@ -87,7 +87,23 @@ class ConvDesc(_c.Structure):
     ]
 
 
+class Conv16Desc(_c.Structure):
+    """Mirror of ``memb_conv16_desc`` (include/memb.h)."""
+    _fields_ = [
+        ("a_hi", _vp), ("a_lo", _vp), ("inner", _i32), ("x_slots", _i32), ("r_slots", _i32), ("rows_per_img", _i32),
+        ("taps_y", _i32), ("taps_x", _i32), ("tap_y0", _i32), ("tap_x0", _i32),
+        ("w", _vp), ("bias", _vp), ("B", _i32), ("OH", _i32), ("OW", _i32), ("Cout", _i32), ("relu", _i32),
+        ("a_exp", _i32), ("w_exp", _i32), ("out_exp", _i32),
+        ("aux", _vp), ("d_full", _vp), ("keys", _vp), ("seg_kblocks", _i32), ("d_hi", _vp), ("d_lo", _vp),
+        ("sB", _i64), ("sy_major", _i64), ("sy_minor", _i64), ("sx_major", _i64), ("sx_minor", _i64),
+        ("pad", _i32), ("shift", _i32), ("absmax", _vp), ("err_flag", _vp),
+    ]
+
+
 SIGNATURES.update({
+    "memb_conv_f16x2": (_i32, [_c.POINTER(Conv16Desc), _vp]),
+    "memb_dvae_im2col_l1_f16": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "memb_split_f16": (_i32, [_vp, _i32, _vp, _vp, _i64, _vp]),
     "memb_conv_tf32x3": (_i32, [_c.POINTER(ConvDesc), _vp]),
     "memb_dvae_im2col_l1": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "memb_split_tf32": (_i32, [_vp, _vp, _vp, _i64, _vp]),

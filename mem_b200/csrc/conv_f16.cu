@@ -1,0 +1,457 @@
+// fp32-faithful convolution for the dVAE tokenizer on the fp16 tensor path: 2 x fp16 split operands on
+// tcgen05 (kind::f16, fp32 accumulation), CTA pairs (cta_group::2).
+//
+// Same algorithm as conv.cu (implicit GEMM over "pixel-slot" activations, two-level accumulation, fused
+// bias / residual / ReLU / split / argmax epilogue -- see the header of that file for the layouts; reference:
+// eventvae/vae/vae_model.py:29-41 ResBlock, :91 Conv2d(4, s2, p1)+ReLU, :101 Conv2d 1x1), with a cheaper
+// operand representation.  conv.cu carries every operand as a TF32 pair (4 B + 4 B per element, TF32 MMAs run at
+// half the 16-bit rate) and is bound by L2 -> SMEM operand traffic (~5.2 KB/clk chip-wide, the LTS ceiling).
+// Here a value v is carried as
+//        v * 2^e  =  hi + lo,      hi = fp16(v * 2^e),  lo = fp16(v * 2^e - hi)
+// with a per-tensor power-of-two exponent e chosen by the host (activations: calibrated on the first batch with a
+// 16x overflow margin and monitored through `absmax`; weights: from their own maximum).  fp16 carries 11
+// significand bits like TF32, so hi + lo holds 22 bits exactly as the TF32 pair does -- when |v 2^e| >= 2^-3; below
+// that lo enters the fp16 subnormals and the ABSOLUTE error floors at 2^-25 (in scaled units), i.e. tiny operands
+// lose relative but not absolute accuracy, which is what a dot product needs.  fp16 x fp16 products are exact in
+// fp32 (22 bits), the three MMAs  lo*hi + hi*lo + hi*hi  accumulate in fp32 in TMEM exactly like the TF32 path.
+// Per K element this halves the operand bytes and doubles the MMA rate.
+//
+// CTA pair: UMMA M = 256 (two 128-pixel M tiles, one per CTA), N = 192; each CTA stages its own A tiles and half
+// (96 rows) of the weight tile.  Stage = A_hi + A_lo + W_hi/2 + W_lo/2 = 56 KB, 4 stages.
+#include <algorithm>
+
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace memb {
+namespace conv16 {
+
+using namespace memb::ptx;
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 192;  // 384 output channels = 2 tiles
+constexpr int BLOCK_K = 64;   // halves: one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 384;
+constexpr int kEpiCols = BLOCK_N / 2;  // columns per epilogue warp
+constexpr int A_BYTES = BLOCK_M * 128;
+constexpr int B_BYTES = (BLOCK_N / 2) * 128;  // this CTA's half of the weight tile
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 56 KB
+constexpr int STAGES = 4;
+constexpr int TMEM_COLS = 512;  // 2 x 192 accumulator columns, power-of-two allocation
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;
+
+struct Params {
+  int B, OH, OW, Cout;
+  int rows_per_img, BW, BR, x_tiles, m_tiles, n_tiles, num_tiles;
+  int taps_x, ntaps, tap_y0, tap_x0, kc_per_tap, K, seg;
+  const float* bias;
+  const float* aux;
+  float* d_full;
+  __half* d_hi;
+  __half* d_lo;
+  unsigned long long* keys;
+  unsigned int* absmax;
+  long long sB, sy_major, sy_minor, sx_major, sx_minor;
+  int pad, shift, relu;
+  float acc_scale, out_scale;
+  int* err_flag;
+};
+
+__device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {
+  // larger value wins; on equal values the smaller index wins (torch.argmax: first maximum)
+  uint32_t b = __float_as_uint(v);
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)b << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
+           const __grid_constant__ CUtensorMap tmap_w, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0 && p.err_flag) atomicExch(p.err_flag, 91);
+    return;
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a_hi);
+    prefetch_tmap(&tmap_a_lo);
+    prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 16); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int iters = p.ntaps * p.kc_per_tap;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+      const int n_tile = tile % p.n_tiles, m_tile = (tile / p.n_tiles) * 2 + (int)cta_rank;
+      const int x0 = (m_tile % p.x_tiles) * p.BW, r0 = (m_tile / p.x_tiles) * p.BR;
+      const int wrow = n_tile * BLOCK_N + (int)cta_rank * (BLOCK_N / 2);
+      for (int it = 0; it < iters; ++it) {
+        const int tap = it / p.kc_per_tap, kc = it - tap * p.kc_per_tap;
+        const int ty = tap / p.taps_x, tx = tap - ty * p.taps_x;
+        mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 11);
+        if (elect_one()) {
+          const uint32_t fb = mapa(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+          const uint32_t s0 = smem_u32(smem + stage * STAGE_BYTES);
+          tma_load_3d_pair(s0, &tmap_a_hi, fb, kc * BLOCK_K, x0 + tx + p.tap_x0, r0 + ty + p.tap_y0);
+          tma_load_3d_pair(s0 + A_BYTES, &tmap_a_lo, fb, kc * BLOCK_K, x0 + tx + p.tap_x0, r0 + ty + p.tap_y0);
+          tma_load_2d_pair(s0 + 2 * A_BYTES, &tmap_w, fb, it * BLOCK_K, wrow);
+          tma_load_2d_pair(s0 + 2 * A_BYTES + B_BYTES, &tmap_w, fb, p.K + it * BLOCK_K, wrow);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ---------------------------------------------------------------- MMA issuer (leader CTA)
+      constexpr uint32_t idesc = make_idesc(0, false, false, 2 * BLOCK_M, BLOCK_N);  // f16 x f16 -> f32
+      const uint64_t desc0 = make_smem_desc_sw128(smem_u32(smem), 0, 1024);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        for (int it0 = 0; it0 < iters; it0 += p.seg) {
+          const int it1 = min(iters, it0 + p.seg);
+          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, p.err_flag, 12);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          for (int it = it0; it < it1; ++it) {
+            mbar_wait(&full_bar[stage], phase, p.err_flag, 13);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t a_hi = desc0 + (uint64_t)((stage * STAGE_BYTES) >> 4), a_lo = a_hi + (A_BYTES >> 4);
+              const uint64_t b_hi = a_hi + (2 * A_BYTES >> 4), b_lo = b_hi + (B_BYTES >> 4);
+              // small terms first: lo*hi, hi*lo, then hi*hi
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_bf16_pair(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, (it != it0) || k != 0);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_bf16_pair(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_bf16_pair(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+              umma_commit_pair(&empty_bar[stage], 3);
+              if (it == it1 - 1) umma_commit_pair(&tmem_full_bar[acc], 3);  // this segment's partial sum is complete
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // -------------------------------------------------------------------- epilogue (lane quarter x column half)
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const uint32_t tmem_empty_leader0 = mapa(smem_u32(&tmem_empty_bar[0]), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float amax = 0.f;
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+      const int n_tile = tile % p.n_tiles, m_tile = (tile / p.n_tiles) * 2 + (int)cta_rank;
+      const int x0 = (m_tile % p.x_tiles) * p.BW, r0 = (m_tile / p.x_tiles) * p.BR;
+      const int i = quad * 32 + lane;
+      const int ox = x0 + i % p.BW, r = r0 + i / p.BW;
+      const int b = r / p.rows_per_img, oy = r - b * p.rows_per_img;
+      const bool live = ox < p.OW && oy < p.OH && b < p.B;
+      const long long plain = ((long long)b * p.OH + oy) * p.OW + ox;
+      const int py = oy + p.pad, px = ox + p.pad, msk = (1 << p.shift) - 1;
+      const long long off = (long long)b * p.sB + (long long)(py >> p.shift) * p.sy_major + (long long)(py & msk) * p.sy_minor +
+                            (long long)(px >> p.shift) * p.sx_major + (long long)(px & msk) * p.sx_minor;
+      float sum[kEpiCols];
+#pragma unroll
+      for (int j = 0; j < kEpiCols; ++j) sum[j] = 0.f;
+      // ---- add the K segments with round-to-nearest fp32 adds
+      for (int it0 = 0; it0 < iters; it0 += p.seg) {
+        mbar_wait(&tmem_full_bar[acc], acc_phase, p.err_flag, 14);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N + half * kEpiCols;
+#pragma unroll
+        for (int c = 0; c < kEpiCols / 32; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(taddr + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(raw[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader0 + acc * 8);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      // ---- fused epilogue from registers
+      unsigned long long best = 0ull;
+#pragma unroll
+      for (int c = 0; c < kEpiCols / 32; ++c) {
+        const int col0 = n_tile * BLOCK_N + half * kEpiCols + c * 32;
+        if (live && col0 < p.Cout) {  // Cout % 32 == 0
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+            v[4 * j] = fmaf(sum[c * 32 + 4 * j], p.acc_scale, bq.x);
+            v[4 * j + 1] = fmaf(sum[c * 32 + 4 * j + 1], p.acc_scale, bq.y);
+            v[4 * j + 2] = fmaf(sum[c * 32 + 4 * j + 2], p.acc_scale, bq.z);
+            v[4 * j + 3] = fmaf(sum[c * 32 + 4 * j + 3], p.acc_scale, bq.w);
+          }
+          if (p.aux) {
+            const float4* a4 = reinterpret_cast<const float4*>(p.aux + plain * p.Cout + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 q = a4[j];
+              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(v[j]));
+          if (p.d_full) {
+            float4* dst = reinterpret_cast<float4*>(p.d_full + plain * p.Cout + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.keys) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const unsigned long long key = argmax_key(v[j], col0 + j);
+              best = key > best ? key : best;
+            }
+          }
+          if (p.d_hi) {
+            uint32_t hh[16], ll[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float s0 = v[2 * j] * p.out_scale, s1 = v[2 * j + 1] * p.out_scale;
+              const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
+              hh[j] = pack_h2(h0, h1);
+              ll[j] = pack_h2(__float2half_rn(s0 - __half2float(h0)), __float2half_rn(s1 - __half2float(h1)));
+            }
+            uint4* dh = reinterpret_cast<uint4*>(p.d_hi + off + col0);
+            uint4* dl = reinterpret_cast<uint4*>(p.d_lo + off + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              dh[j] = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
+              dl[j] = make_uint4(ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
+            }
+          }
+        }
+      }
+      if (p.keys && live) atomicMax(p.keys + plain, best);
+    }
+    if (p.absmax) {  // |result| maximum seen by this warp -> one atomic (float bits order like unsigned for x >= 0)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      if (lane == 0) atomicMax(p.absmax, __float_as_uint(amax));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------- small helpers
+// First dVAE layer (C in {2,3}): explicit im2col of the 4x4 / stride 2 / pad 1 window, k = c*16 + ky*4 + kx
+// (Conv2d weight order), zero for padding and for k >= C*16; optional per-channel normalisation
+// (DiscreteVAE.norm, vae_model.py:133-141) applied to in-bounds pixels; fp16 hi / lo of value * scale.
+__global__ void __launch_bounds__(256) im2col_l1_f16(const float* __restrict__ img, int B, int C, int H, int W, int Kpad,
+                                                     const float* __restrict__ mean, const float* __restrict__ stdv, float scale,
+                                                     __half* __restrict__ a_hi, __half* __restrict__ a_lo,
+                                                     unsigned int* __restrict__ absmax) {
+  const int OH = H / 2, OW = W / 2, kq = Kpad / 4;
+  const long long total = (long long)B * OH * OW * kq;
+  float amax = 0.f;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(t % kq);
+    const long long pix = t / kq;
+    const int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH), b = (int)(pix / ((long long)OW * OH));
+    const int k0 = q * 4, c = k0 / 16, ky = (k0 % 16) / 4;  // the 4 k's share (c, ky); kx = 0..3
+    __half hi[4], lo[4];
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) hi[kx] = lo[kx] = __float2half_rn(0.f);
+    const int iy = 2 * oy + ky - 1;
+    if (c < C && iy >= 0 && iy < H) {
+      const float* row = img + (((long long)b * C + c) * H + iy) * W;
+      const float mu = mean ? mean[c] : 0.f, sd = stdv ? stdv[c] : 1.f;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int ix = 2 * ox + kx - 1;
+        if (ix >= 0 && ix < W) {
+          float v = row[ix];
+          if (mean) v = (v - mu) / sd;
+          amax = fmaxf(amax, fabsf(v));
+          const float s = v * scale;
+          hi[kx] = __float2half_rn(s);
+          lo[kx] = __float2half_rn(s - __half2float(hi[kx]));
+        }
+      }
+    }
+    *reinterpret_cast<uint2*>(a_hi + pix * Kpad + k0) = make_uint2(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]));
+    *reinterpret_cast<uint2*>(a_lo + pix * Kpad + k0) = make_uint2(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]));
+  }
+  if (absmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(absmax, __float_as_uint(amax));
+  }
+}
+
+__global__ void __launch_bounds__(256) split_f16(const float* __restrict__ src, float scale, __half* __restrict__ hi,
+                                                 __half* __restrict__ lo, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float s = src[i] * scale;
+    const __half h = __float2half_rn(s);
+    hi[i] = h;
+    lo[i] = __float2half_rn(s - __half2float(h));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<EncodeTiledFn>(sym);
+    return (EncodeTiledFn) nullptr;
+  }();
+  return fn;
+}
+
+// fp16 tensor [d2][d1][d0] (d0 innermost, dense), box [b2][b1][64 halves], 128B swizzle.
+static int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const long long* dims, const int* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(MEMB_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+  MEMB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0 && dims[0] % 8 == 0, "conv16: operand must be 16-byte aligned");
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bdim[3], estr[3] = {1, 1, 1};
+  unsigned long long stride = (unsigned long long)dims[0] * 2;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = (cuuint64_t)dims[i];
+    bdim[i] = (cuuint32_t)box[i];
+    if (i > 0) { gstr[i - 1] = stride; stride *= (unsigned long long)dims[i]; }
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MEMB_ECUDA, "cuTensorMapEncodeTiled (conv16) failed with CUresult %d", (int)r);
+  return MEMB_OK;
+}
+
+}  // namespace conv16
+}  // namespace memb
+
+using namespace memb;
+using namespace memb::conv16;
+
+extern "C" int memb_conv_f16x2(const memb_conv16_desc* dp, memb_stream_t stream) {
+  MEMB_REQUIRE(dp != nullptr, "conv16: null descriptor");
+  const memb_conv16_desc& d = *dp;
+  MEMB_REQUIRE(d.a_hi && d.a_lo && d.w && d.bias, "conv16: null operand");
+  MEMB_REQUIRE((d.d_hi != nullptr) == (d.d_lo != nullptr), "conv16: d_hi and d_lo go together");
+  MEMB_REQUIRE(d.d_hi || d.d_full || d.keys, "conv16: no output requested");
+  MEMB_REQUIRE(d.inner > 0 && d.inner % BLOCK_K == 0, "conv16: inner slot length must be a multiple of 64 halves, got %d", d.inner);
+  MEMB_REQUIRE(d.Cout > 0 && d.Cout % 32 == 0, "conv16: Cout must be a multiple of 32, got %d", d.Cout);
+  MEMB_REQUIRE(d.B > 0 && d.OH > 0 && d.OW > 0 && d.taps_x > 0 && d.taps_y > 0 && d.rows_per_img >= d.OH, "conv16: bad geometry");
+  MEMB_REQUIRE(d.shift == 0 || d.shift == 1, "conv16: output shift must be 0 or 1");
+  MEMB_REQUIRE(abs(d.a_exp + d.w_exp) < 120 && abs(d.out_exp) < 120, "conv16: exponents out of range");
+  Params p{};
+  p.B = d.B; p.OH = d.OH; p.OW = d.OW; p.Cout = d.Cout;
+  p.rows_per_img = d.rows_per_img;
+  int bw = 1;
+  while (bw < 128 && d.OW % (bw * 2) == 0) bw *= 2;
+  p.BW = bw; p.BR = BLOCK_M / bw;
+  p.x_tiles = ceil_div(d.OW, p.BW);
+  const long long vrows = (long long)d.B * d.rows_per_img;
+  p.m_tiles = p.x_tiles * (int)ceil_div<long long>(vrows, p.BR);
+  p.n_tiles = ceil_div(d.Cout, BLOCK_N);
+  p.num_tiles = ceil_div(p.m_tiles, 2) * p.n_tiles;
+  p.taps_x = d.taps_x; p.ntaps = d.taps_x * d.taps_y; p.tap_y0 = d.tap_y0; p.tap_x0 = d.tap_x0;
+  p.kc_per_tap = d.inner / BLOCK_K;
+  p.K = p.ntaps * d.inner;
+  p.seg = d.seg_kblocks > 0 ? d.seg_kblocks : 2;
+  p.keys = reinterpret_cast<unsigned long long*>(d.keys);
+  p.absmax = d.absmax;
+  p.bias = d.bias; p.aux = d.aux; p.d_full = d.d_full;
+  p.d_hi = reinterpret_cast<__half*>(d.d_hi); p.d_lo = reinterpret_cast<__half*>(d.d_lo);
+  p.sB = d.sB; p.sy_major = d.sy_major; p.sy_minor = d.sy_minor; p.sx_major = d.sx_major; p.sx_minor = d.sx_minor;
+  p.pad = d.pad; p.shift = d.shift; p.relu = d.relu; p.err_flag = d.err_flag;
+  p.acc_scale = ldexpf(1.0f, -(d.a_exp + d.w_exp));
+  p.out_scale = ldexpf(1.0f, d.out_exp);
+
+  CUtensorMap ta_hi, ta_lo, tw;
+  const long long adims[3] = {d.inner, d.x_slots, d.r_slots};
+  const int abox[3] = {BLOCK_K, p.BW, p.BR};
+  if (int rc = make_tmap_f16(&ta_hi, d.a_hi, 3, adims, abox)) return rc;
+  if (int rc = make_tmap_f16(&ta_lo, d.a_lo, 3, adims, abox)) return rc;
+  const long long wdims[2] = {2LL * p.K, d.Cout};
+  const int wbox[2] = {BLOCK_K, BLOCK_N / 2};
+  if (int rc = make_tmap_f16(&tw, d.w, 2, wdims, wbox)) return rc;
+
+  static bool configured = false;
+  if (!configured) {
+    MEMB_CUDA_OK(cudaFuncSetAttribute(conv_f16x2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  const int clusters = std::max(1, std::min(p.num_tiles, num_sms() / 2));
+  conv_f16x2<<<2 * clusters, kThreads, SMEM_BYTES, stream>>>(ta_hi, ta_lo, tw, p);
+  MEMB_LAUNCH_OK("conv_f16x2");
+  return MEMB_OK;
+}
+
+extern "C" int memb_dvae_im2col_l1_f16(const float* img, int B, int C, int H, int W, int Kpad, const float* mean,
+                                       const float* stdv, int exp2, void* a_hi, void* a_lo, uint32_t* absmax,
+                                       memb_stream_t s) {
+  MEMB_REQUIRE(img && a_hi && a_lo && B > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, "im2col_l1_f16: bad arguments");
+  MEMB_REQUIRE(Kpad % 64 == 0 && Kpad >= 16 * C, "im2col_l1_f16: Kpad must be a multiple of 64 and >= 16*C");
+  MEMB_REQUIRE((mean == nullptr) == (stdv == nullptr), "im2col_l1_f16: mean and std go together");
+  const long long total = (long long)B * (H / 2) * (W / 2) * (Kpad / 4);
+  const int grid = (int)std::min<long long>(ceil_div<long long>(total, 256), (long long)num_sms() * 32);
+  im2col_l1_f16<<<grid, 256, 0, s>>>(img, B, C, H, W, Kpad, mean, stdv, ldexpf(1.0f, exp2), reinterpret_cast<__half*>(a_hi),
+                                     reinterpret_cast<__half*>(a_lo), absmax);
+  MEMB_LAUNCH_OK("im2col_l1_f16");
+  return MEMB_OK;
+}
+
+extern "C" int memb_split_f16(const float* src, int exp2, void* hi, void* lo, int64_t n, memb_stream_t s) {
+  MEMB_REQUIRE(src && hi && lo && n > 0, "split_f16: bad arguments");
+  const int grid = (int)std::min<long long>(ceil_div<long long>(n, 256), (long long)num_sms() * 16);
+  split_f16<<<grid, 256, 0, s>>>(src, ldexpf(1.0f, exp2), reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), n);
+  MEMB_LAUNCH_OK("split_f16");
+  return MEMB_OK;
+}

@@ -113,6 +113,8 @@ def train_one_epoch(model: torch.nn.Module, d_vae: torch.nn.Module, data_loader:
         loss_scale_value = loss_scaler.state_dict()["scale"]
 
         loss_value, mlm_acc, grad_norm_value, _ = hand_off.read(stats, grad_norm)
+        if hasattr(d_vae, "verify_range"):
+            d_vae.verify_range()   # fp16-pair tokenizer: activation maxima of this step vs its calibrated exponents
         if not math.isfinite(loss_value):
             print("Loss is {}, stopping training".format(loss_value))
             print("INFO:", "samples", samples.shape, "bool_masked_pos", bool_masked_pos.shape, "images", images.shape)

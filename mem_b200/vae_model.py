@@ -14,6 +14,7 @@ reference pipeline) and ``decode`` are outside the pretraining hot path (SURVEY.
 from __future__ import annotations
 
 import ctypes
+import math
 
 import torch
 from torch import nn
@@ -95,8 +96,14 @@ class DiscreteVAE(nn.Module):
 
     def _tokenizer(self):
         if self._tok is None:
-            object.__setattr__(self, "_tok", _Tokenizer(self))
+            object.__setattr__(self, "_tok", _Tokenizer(self, precision=getattr(self, "tokenizer_precision", "auto")))
         return self._tok
+
+    def verify_range(self):
+        """fp16-pair tokenizer only: raise if an activation overflowed its calibrated range in the last call
+        (engine_for_pretraining calls this at its per-step sync)."""
+        if self._tok is not None and self._tok.f16:
+            self._tok.verify(block=True)
 
 
 def _out_layout(kind, C, OH, OW):
@@ -112,37 +119,73 @@ def _out_layout(kind, C, OH, OW):
 
 
 class _Tokenizer:
-    """Kernel schedule of the encoder: im2col(l1) -> L conv stages -> R residual blocks -> head GEMM + argmax."""
+    """Kernel schedule of the encoder: im2col(l1) -> L conv stages -> R residual blocks -> head conv + argmax.
 
-    def __init__(self, vae: DiscreteVAE, chunk: int = 64):
-        self.vae, self.chunk = vae, chunk
-        self.seg_kblocks = 2   # K blocks per tensor-core accumulation segment (csrc/conv.cu; profiles/r01_dvae_probe_seg_sweep.json)
+    ``precision``: ``"f16x2"`` (default; fp16 hi/lo operand pairs with calibrated power-of-two exponents,
+    csrc/conv_f16.cu) or ``"tf32x3"`` (TF32 hi/lo pairs, csrc/conv.cu; no range management needed).  Both carry
+    22 significand bits per operand and give fp32-faithful logits.
+
+    fp16 range management: every activation tensor t is stored as ``value * 2^exp[t]``.  The exponents are fixed by a
+    calibration pass over the first chunk seen (layer by layer: run, read the layer's |output| maximum, place it at
+    2^12 -- a 16x margin to the fp16 overflow at 65504 -- and re-run the layer if the exponent moved).  Afterwards
+    every call records the per-layer maxima on the device; ``verify()`` (called by the training engine at its
+    per-step sync, and lazily at the next call) raises if a tensor overflowed and re-calibrates when the margin
+    is half used.  Weights get their exponent from their own maximum when they are packed."""
+
+    TARGET_LOG2 = 12       # calibrated |activation| maximum -> 2^12 in scaled units
+    W_TARGET_LOG2 = 10
+
+    def __init__(self, vae: DiscreteVAE, chunk: int = 128, precision: str = "auto"):
+        assert precision in ("auto", "f16x2", "tf32x3")
+        if precision == "auto":   # the fp16 kernel consumes K in blocks of 64 channels
+            precision = "f16x2" if vae.hidden_dim % 64 == 0 else "tf32x3"
+        self.vae, self.chunk, self.precision = vae, chunk, precision
+        # K blocks per tensor-core accumulation segment: 128 K elements (f16x2: 2 x 64) / 64 (tf32x3: 2 x 32); max logit
+        # error vs fp64 9.0e-8 / 8.0e-8 of the logit scale, torch's own fp32 path: 1.5e-7 (profiles/r01_dvae_probe_v2.json)
+        self.seg_kblocks = 2
         self.packed_version = None
         self.bufs = {}
+        self.exps = None           # layer name -> exponent of its fp16 output (None: calibrate on the next run)
+        self._pending = None       # (event, host maxima, exponents used) of the last run
+
+    @property
+    def f16(self):
+        return self.precision == "f16x2"
 
     # ---- weights: [Cout][2K] hi | lo, K ordered to match the activation slot layouts
     def _pack(self, w2d, device):
         lib = _lib.load()
         w2d = w2d.detach().to(device=device, dtype=torch.float32).contiguous()
-        out = torch.empty(w2d.shape[0], 2 * w2d.shape[1], dtype=torch.float32, device=device)
-        hi, lo = torch.empty_like(w2d), torch.empty_like(w2d)
-        _lib.check(lib.memb_split_tf32(w2d.data_ptr(), hi.data_ptr(), lo.data_ptr(), w2d.numel(), _lib.stream_ptr(torch, device)))
+        sp = _lib.stream_ptr(torch, device)
+        if self.f16:
+            m = float(w2d.abs().max())
+            e = 0 if not (m > 0.0 and math.isfinite(m)) else self.W_TARGET_LOG2 - math.ceil(math.log2(m))
+            out = torch.empty(w2d.shape[0], 2 * w2d.shape[1], dtype=torch.float16, device=device)
+            hi, lo = (torch.empty(w2d.shape, dtype=torch.float16, device=device) for _ in range(2))
+            _lib.check(lib.memb_split_f16(w2d.data_ptr(), e, hi.data_ptr(), lo.data_ptr(), w2d.numel(), sp))
+        else:
+            e = 0
+            out = torch.empty(w2d.shape[0], 2 * w2d.shape[1], dtype=torch.float32, device=device)
+            hi, lo = torch.empty_like(w2d), torch.empty_like(w2d)
+            _lib.check(lib.memb_split_tf32(w2d.data_ptr(), hi.data_ptr(), lo.data_ptr(), w2d.numel(), sp))
         out[:, :w2d.shape[1]] = hi
         out[:, w2d.shape[1]:] = lo
-        return out
+        return out, e
 
     def _prepare(self, device):
         v = self.vae
-        version = tuple(p._version for p in v.encoder.parameters()) + (str(device),)
+        version = tuple(p._version for p in v.encoder.parameters()) + (str(device), self.precision)
         if version == self.packed_version:
             return
         L, R, Hd = v.num_layers, v.num_resnet_blocks, v.hidden_dim
-        assert Hd % 32 == 0 and v.num_tokens % 32 == 0, "hidden_dim / num_tokens must be multiples of 32 for the tcgen05 conv kernel"
+        kq = 64 if self.f16 else 32
+        assert Hd % kq == 0 and v.num_tokens % 32 == 0, \
+            f"hidden_dim must be a multiple of {kq} and num_tokens of 32 for the tcgen05 conv kernel"
         f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
         self.w, self.b = [], []
         conv = v.encoder[0][0]
         C = conv.in_channels
-        self.kpad = (16 * C + 31) // 32 * 32
+        self.kpad = (16 * C + kq - 1) // kq * kq
         w0 = torch.zeros(Hd, self.kpad, device=device)
         w0[:, :16 * C] = f32(conv.weight).reshape(Hd, 16 * C)
         self.w.append(self._pack(w0, device)); self.b.append(f32(conv.bias))
@@ -163,6 +206,12 @@ class _Tokenizer:
             self.mean, self.std = (torch.as_tensor(t, dtype=torch.float32, device=device).contiguous() for t in v.normalization)
         else:
             self.mean = self.std = None
+        # one |output| maximum per produced tensor: input (im2col), L stages, 3 per residual block, head
+        self.layer_names = ["in"] + [f"act{i}" for i in range(L)] + [f"res{j}_{k}" for j in range(R) for k in range(3)] + ["head"]
+        self.layer_index = {n: i for i, n in enumerate(self.layer_names)}
+        self.absmax = torch.zeros(len(self.layer_names), dtype=torch.float32, device=device)
+        self.absmax_host = torch.zeros(len(self.layer_names), dtype=torch.float32).pin_memory()
+        self.exps, self._pending = None, None
         self.packed_version = version
 
     def _buf(self, name, shape, device, dtype=torch.float32):
@@ -173,17 +222,70 @@ class _Tokenizer:
             self.bufs[key] = t
         return t
 
-    def _conv(self, lib, a, geom, w, bias, B, OH, OW, relu, out_kind, out_name, device, aux=None, full=None, keys=None):
-        """a = (hi, lo) tensors [B*rows_per_img, x_slots, inner]; geom = (taps_y, taps_x, tap_y0, tap_x0).
+    # ---- fp16 range management ------------------------------------------------------------------
+    def _absmax_ptr(self, name):
+        return self.absmax.data_ptr() + 4 * self.layer_index[name]
+
+    def _exp_for(self, m):
+        return 0 if not (m > 0.0 and math.isfinite(m)) else self.TARGET_LOG2 - math.ceil(math.log2(m))
+
+    def _layer(self, name, launch, calibrating):
+        """Run ``launch(out_exp)``; while calibrating, fix the exponent from the measured maximum (one host sync)."""
+        if not calibrating:
+            launch(self.exps[name])
+            return self.exps[name]
+        e = self.exps.get(name, 0)
+        for _ in range(3):
+            self.absmax[self.layer_index[name]] = 0.0
+            launch(e)
+            m = float(self.absmax[self.layer_index[name]])
+            if not math.isfinite(m):
+                if e <= -100:
+                    raise RuntimeError(f"dVAE tokenizer: layer {name} produces non-finite values")
+                e -= 8
+                continue
+            want = self._exp_for(m)
+            if want == e:
+                break
+            e = want
+        self.exps[name] = e
+        return e
+
+    def verify(self, block=True):
+        """Check the activation maxima recorded by the last run against the exponents it used."""
+        if self._pending is None:
+            return
+        ev, used = self._pending
+        if not block and not ev.query():
+            return
+        ev.synchronize()
+        self._pending = None
+        for name, e in used.items():
+            m = float(self.absmax_host[self.layer_index[name]])
+            if name == "head":
+                continue                                   # logits are never stored as fp16
+            if not math.isfinite(m) or m * 2.0 ** e >= 65504.0:
+                self.exps = None
+                raise RuntimeError(f"dVAE tokenizer: fp16 operand overflow in layer {name} (|x| max {m:g}, exponent {e}); the "
+                                   "tokens of the last batch are invalid -- re-run it (the tokenizer re-calibrates)")
+            if m * 2.0 ** e >= 32768.0:                    # half of the margin used: move the exponents
+                self.exps = None
+
+    # ---- one convolution ------------------------------------------------------------------------
+    def _conv(self, lib, a, geom, w, bias, B, OH, OW, relu, out_kind, out_name, device, aux=None, full=None, keys=None,
+              layer=None, calibrating=False):
+        """a = (hi, lo, exp) tensors [B*rows_per_img, x_slots, inner]; geom = (taps_y, taps_x, tap_y0, tap_x0).
         out_kind: slot layout of the hi/lo result for its consumer, or None (only ``full`` / ``keys`` outputs)."""
+        w, w_exp = w
         Cout = w.shape[0]
-        d = ConvDesc()
+        d = _lib.Conv16Desc() if self.f16 else ConvDesc()
         out = None
         if out_kind is not None:
             lay = _out_layout(out_kind, Cout, OH, OW)
             sh = lay["slots"]
-            hi = self._buf(out_name + "_hi", (B * sh[0], sh[1], sh[2]), device)
-            lo = self._buf(out_name + "_lo", (B * sh[0], sh[1], sh[2]), device)
+            dt = torch.float16 if self.f16 else torch.float32
+            hi = self._buf(out_name + "_hi", (B * sh[0], sh[1], sh[2]), device, dt)
+            lo = self._buf(out_name + "_lo", (B * sh[0], sh[1], sh[2]), device, dt)
             d.d_hi, d.d_lo, out = hi.data_ptr(), lo.data_ptr(), (hi, lo)
             d.sB, d.sy_major, d.sy_minor, d.sx_major, d.sx_minor = lay["sB"], lay["sy_major"], lay["sy_minor"], lay["sx_major"], lay["sx_minor"]
             d.pad, d.shift = lay["pad"], lay["shift"]
@@ -197,8 +299,27 @@ class _Tokenizer:
         d.aux, d.d_full, d.keys = ops._ptr(aux), ops._ptr(full), ops._ptr(keys)
         d.seg_kblocks = self.seg_kblocks
         d.err_flag = ops._err_flag(torch, device).data_ptr()
-        _lib.check(lib.memb_conv_tf32x3(ctypes.byref(d), _lib.stream_ptr(torch, device)))
-        return out
+        sp = _lib.stream_ptr(torch, device)
+        if not self.f16:
+            _lib.check(lib.memb_conv_tf32x3(ctypes.byref(d), sp))
+            return None if out is None else out + (0,)
+        d.a_exp, d.w_exp = a[2], w_exp
+        d.absmax = self._absmax_ptr(layer)
+
+        # an in-place residual update must not be applied twice when calibration re-runs the layer
+        snapshot = aux.clone() if (calibrating and aux is not None and full is aux) else None
+
+        def launch(out_exp):
+            if snapshot is not None:
+                aux.copy_(snapshot)
+            d.out_exp = out_exp
+            _lib.check(lib.memb_conv_f16x2(ctypes.byref(d), sp))
+
+        if out is None:
+            launch(0)
+            return None
+        e = self._layer(layer, launch, calibrating)
+        return out + (e,)
 
     def run(self, images, want_logits):
         _lib.require_cuda()
@@ -215,14 +336,26 @@ class _Tokenizer:
         h, w = v.input_H >> v.num_layers, v.input_W >> v.num_layers
         tokens = torch.empty(Btot, h * w, dtype=torch.int64, device=device)
         logits = torch.empty(Btot, h * w, v.num_tokens, dtype=torch.float32, device=device) if want_logits else None
+        if self.f16:
+            self.verify(block=False)
+            if self.exps is None:      # calibration pass over the first chunk (host syncs, once)
+                self.exps = {}
+                b1 = min(Btot, self.chunk)
+                self._run_chunk(images[:b1], tokens[:b1], None, calibrating=True)
+            self.absmax.zero_()
         for b0 in range(0, Btot, self.chunk):
             b1 = min(Btot, b0 + self.chunk)
             self._run_chunk(images[b0:b1], tokens[b0:b1], logits[b0:b1] if want_logits else None)
+        if self.f16:
+            self.absmax_host.copy_(self.absmax, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            self._pending = (ev, dict(self.exps))
         if want_logits:
             return logits.view(Btot, h, w, v.num_tokens).permute(0, 3, 1, 2)
         return tokens
 
-    def _run_chunk(self, img, tokens, logits):
+    def _run_chunk(self, img, tokens, logits, calibrating=False):
         lib = _lib.load()
         v = self.vae
         device = img.device
@@ -230,37 +363,48 @@ class _Tokenizer:
         B, C, H, W = img.shape
         L, R, Hd = v.num_layers, v.num_resnet_blocks, v.hidden_dim
         tag = f"B{B}_"
+        cal = dict(calibrating=calibrating)
         # ---- layer 1: explicit im2col (K = 16*C is tiny), then a one-tap "conv" over the plain matrix
         OH, OW = H // 2, W // 2
-        a_hi = self._buf(tag + "a1_hi", (B * OH, OW, self.kpad), device)
-        a_lo = self._buf(tag + "a1_lo", (B * OH, OW, self.kpad), device)
-        _lib.check(lib.memb_dvae_im2col_l1(img.data_ptr(), B, C, H, W, self.kpad, ops._ptr(self.mean), ops._ptr(self.std),
-                                           a_hi.data_ptr(), a_lo.data_ptr(), sp))
+        adt = torch.float16 if self.f16 else torch.float32
+        a_hi = self._buf(tag + "a1_hi", (B * OH, OW, self.kpad), device, adt)
+        a_lo = self._buf(tag + "a1_lo", (B * OH, OW, self.kpad), device, adt)
+        if self.f16:
+            def im2col(e):
+                _lib.check(lib.memb_dvae_im2col_l1_f16(img.data_ptr(), B, C, H, W, self.kpad, ops._ptr(self.mean), ops._ptr(self.std),
+                                                       e, a_hi.data_ptr(), a_lo.data_ptr(), self._absmax_ptr("in"), sp))
+            e_in = self._layer("in", im2col, calibrating)
+        else:
+            _lib.check(lib.memb_dvae_im2col_l1(img.data_ptr(), B, C, H, W, self.kpad, ops._ptr(self.mean), ops._ptr(self.std),
+                                               a_hi.data_ptr(), a_lo.data_ptr(), sp))
+            e_in = 0
 
         def consumer(stage):  # layout wanted by whatever reads the output of conv stage `stage` (0-based)
             return "s2d" if stage + 1 < L else "pad"
 
         x_full = self._buf(tag + "x_full", (B * (H >> L) * (W >> L), Hd), device) if R > 0 else None
-        cur = self._conv(lib, (a_hi, a_lo), (1, 1, 0, 0), self.w[0], self.b[0], B, OH, OW, True, consumer(0), tag + "act0", device,
-                         full=x_full if (L == 1 and R > 0) else None)
+        cur = self._conv(lib, (a_hi, a_lo, e_in), (1, 1, 0, 0), self.w[0], self.b[0], B, OH, OW, True, consumer(0), tag + "act0",
+                         device, full=x_full if (L == 1 and R > 0) else None, layer="act0", **cal)
         for i in range(1, L):
             OH, OW = OH // 2, OW // 2
             cur = self._conv(lib, cur, (2, 2, 0, 0), self.w[i], self.b[i], B, OH, OW, True, consumer(i), tag + f"act{i}", device,
-                             full=x_full if (i == L - 1 and R > 0) else None)
+                             full=x_full if (i == L - 1 and R > 0) else None, layer=f"act{i}", **cal)
         # ---- residual blocks: x + conv1x1(relu(conv3x3(relu(conv3x3(x)))))
         wi = L
         for j in range(R):
-            t1 = self._conv(lib, cur, (3, 3, 0, 0), self.w[wi], self.b[wi], B, OH, OW, True, "pad", tag + "res_t1", device)
-            t2 = self._conv(lib, t1, (3, 3, 0, 0), self.w[wi + 1], self.b[wi + 1], B, OH, OW, True, "pad", tag + "res_t2", device)
+            t1 = self._conv(lib, cur, (3, 3, 0, 0), self.w[wi], self.b[wi], B, OH, OW, True, "pad", tag + "res_t1", device,
+                            layer=f"res{j}_0", **cal)
+            t2 = self._conv(lib, t1, (3, 3, 0, 0), self.w[wi + 1], self.b[wi + 1], B, OH, OW, True, "pad", tag + "res_t2", device,
+                            layer=f"res{j}_1", **cal)
             cur = self._conv(lib, t2, (1, 1, 1, 1), self.w[wi + 2], self.b[wi + 2], B, OH, OW, False, "pad", tag + f"act{L - 1}",
-                             device, aux=x_full, full=x_full)
+                             device, aux=x_full, full=x_full, layer=f"res{j}_2", **cal)
             wi += 3
         # ---- head: 1x1 conv to num_tokens with the codebook argmax in the epilogue (logits only on request)
         rows = B * OH * OW
         if logits is not None:
             self._conv(lib, cur, (1, 1, 1, 1), self.w_head, self.b_head, B, OH, OW, False, None, None, device,
-                       full=logits.view(rows, v.num_tokens))
+                       full=logits.view(rows, v.num_tokens), layer="head")
         keys = self._buf(tag + "keys", (rows,), device, torch.int64)
         keys.zero_()
-        self._conv(lib, cur, (1, 1, 1, 1), self.w_head, self.b_head, B, OH, OW, False, None, None, device, keys=keys)
+        self._conv(lib, cur, (1, 1, 1, 1), self.w_head, self.b_head, B, OH, OW, False, None, None, device, keys=keys, layer="head")
         _lib.check(lib.memb_argmax_decode(keys.data_ptr(), tokens.data_ptr(), rows, sp))

@@ -1,4 +1,4 @@
-"""GPU: dVAE tokenizer (3xTF32 tcgen05 convolutions + fused argmax) against the fp32 oracle.
+"""GPU: dVAE tokenizer (fp16-pair / TF32-pair tcgen05 convolutions + fused argmax) against the fp32 oracle.
 
 north_star asks for bit-exact token indices on the same fp32 inputs.  Two fp32 evaluation orders of the
 same network already differ by ~3e-7 in the logits, so a token may legitimately differ
@@ -31,10 +31,12 @@ def _check_tokens(idx, ref_logits, noise):
     return int(diff.sum())
 
 
+@pytest.mark.parametrize("precision", ["auto", "tf32x3"])
 @pytest.mark.parametrize("name,cfg,B,seed,gain", CASES)
-def test_tiny_tokens_and_logits_vs_golden(golden_dir, name, cfg, B, seed, gain):
+def test_tiny_tokens_and_logits_vs_golden(golden_dir, name, cfg, B, seed, gain, precision):
     gold = np.load(os.path.join(golden_dir, "dvae_tiny.npz"))
     vae = DiscreteVAE(**cfg)
+    vae.tokenizer_precision = precision       # auto: fp16 pairs when hidden_dim % 64 == 0 (case b), else TF32 pairs
     vae.load_state_dict(dvae_ref.synth_state_dict(vae.state_dict(), seed, gain))
     vae.cuda()
     img = dvae_ref.synth_images(B, cfg["channels"], cfg["input_H"], cfg["input_W"], seed + 100).cuda()
@@ -51,12 +53,14 @@ def test_tiny_tokens_and_logits_vs_golden(golden_dir, name, cfg, B, seed, gain):
     assert n_diff <= 1
 
 
-def test_full_size_tokenizer_vs_oracle():
+@pytest.mark.parametrize("precision", ["f16x2", "tf32x3"])
+def test_full_size_tokenizer_vs_oracle(precision):
     """BASELINE config: 224x224, C=2, hidden 384, 3 res blocks, 8192 tokens; random init like the reference."""
     torch.manual_seed(0)
     cfg = dict(input_H=224, input_W=224, num_tokens=8192, codebook_dim=32, num_layers=4, num_resnet_blocks=3,
                hidden_dim=384, channels=2)
     vae = DiscreteVAE(**cfg).cuda()
+    vae.tokenizer_precision = precision
     B = 6
     img = dvae_ref.synth_images(B, 2, 224, 224, seed=5).cuda()
     idx = vae.get_codebook_indices(img)
@@ -70,3 +74,28 @@ def test_full_size_tokenizer_vs_oracle():
     tok = vae._tokenizer()
     tok.chunk = 4
     assert torch.equal(vae.get_codebook_indices(img), idx)
+    assert tok.precision == precision
+    vae.verify_range()
+
+
+def test_f16_range_monitor_detects_overflow_and_recalibrates():
+    """The fp16-pair path stores activations as value * 2^e with e calibrated on the first batch: a later batch whose
+    activations are 1000x larger must be reported (not silently tokenised wrongly), after which it re-calibrates."""
+    torch.manual_seed(1)
+    cfg = dvae_ref.TINY_B
+    vae = DiscreteVAE(**cfg).cuda()
+    img = dvae_ref.synth_images(4, cfg["channels"], cfg["input_H"], cfg["input_W"], 7).cuda()
+    ref = vae.get_codebook_indices(img)
+    vae.verify_range()
+    assert vae._tokenizer().precision == "f16x2"
+    vae.get_codebook_indices(img * 1000.0)
+    with pytest.raises(RuntimeError, match="overflow"):
+        vae.verify_range()
+    big = vae.get_codebook_indices(img * 1000.0)          # re-calibrated for the new range
+    vae.verify_range()
+    vae.tokenizer_precision = "tf32x3"
+    object.__setattr__(vae, "_tok", None)
+    assert torch.equal(vae.get_codebook_indices(img * 1000.0), big) or (vae.get_codebook_indices(img * 1000.0) != big).float().mean() < 0.02
+    vae.tokenizer_precision = "auto"
+    object.__setattr__(vae, "_tok", None)
+    assert torch.equal(vae.get_codebook_indices(img), ref)

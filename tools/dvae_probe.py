@@ -29,24 +29,29 @@ margin = (top2[..., 0] - top2[..., 1])
 out = {"scale": scale, "oracle_margin_min": margin.min().item(), "oracle_margin_median": margin.median().item(),
        "torch_fp32_cuda_max_err_vs_fp64": (ref32.double() - ref).abs().max().item(),
        "torch_fp32_cuda_token_diffs": int((ref32.flatten(2).argmax(1) != ref.flatten(2).argmax(1)).sum()), "runs": []}
-tok = vae._tokenizer()
-big = dvae_ref.synth_images(64, 2, 224, 224, seed=6).cuda()
-for seg in (1, 2, 4, 8, 16, 100000):
-    tok.seg_kblocks = seg
-    logits = vae(img, return_logits=True)
-    idx = vae.get_codebook_indices(img)
-    err = (logits.double() - ref).abs().max().item()
-    diffs = int((idx != ref.flatten(2).argmax(1)).sum())
-    vae.get_codebook_indices(big)
-    torch.cuda.synchronize()
-    t0 = time.time()
-    for _ in range(3):
+big = dvae_ref.synth_images(128, 2, 224, 224, seed=6).cuda()
+for precision, segs in (("f16x2", (1, 2, 4, 100000)), ("tf32x3", (2, 4))):
+    vae.tokenizer_precision = precision
+    object.__setattr__(vae, "_tok", None)
+    tok = vae._tokenizer()
+    for seg in segs:
+        tok.seg_kblocks = seg
+        logits = vae(img, return_logits=True)
+        idx = vae.get_codebook_indices(img)
+        err = (logits.double() - ref).abs().max().item()
+        diffs = int((idx != ref.flatten(2).argmax(1)).sum())
         vae.get_codebook_indices(big)
-    torch.cuda.synchronize()
-    ms = (time.time() - t0) / 3 * 1e3
-    out["runs"].append({"seg_kblocks": seg, "max_logit_err_vs_fp64": err, "token_diffs_of": [diffs, idx.numel()],
-                        "ms_per_64_images": ms, "tflops_algorithmic": 24.26e9 * 64 / (ms * 1e-3) / 1e12})
-    print(out["runs"][-1], flush=True)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(3):
+            vae.get_codebook_indices(big)
+        torch.cuda.synchronize()
+        ms = (time.time() - t0) / 3 * 1e3
+        vae.verify_range()
+        out["runs"].append({"precision": precision, "seg_kblocks": seg, "max_logit_err_vs_fp64": err, "token_diffs_of": [diffs, idx.numel()],
+                            "ms_per_128_images": ms, "tflops_algorithmic": 24.26e9 * 128 / (ms * 1e-3) / 1e12,
+                            "exps": dict(tok.exps) if tok.exps else None})
+        print(out["runs"][-1], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/dvae_probe.json", "w"), indent=1)
 print(json.dumps({k: v for k, v in out.items() if k != "runs"}))
