@@ -247,12 +247,20 @@ int memb_relpos_scatter(const float* dbias, int ldk, const int64_t* index, int N
 /* acc[i] += sum_b x(bf16)[b*inner + i]. */
 int memb_batch_reduce_bf16(const void* x, int B, int64_t inner, float* acc, memb_stream_t stream);
 
-/* Fused attention with additive bias, N <= 208, head_dim == 64 (Attention.forward, modeling_finetune.py:128-157). */
-int memb_attention_fwd(const void* qkv, const float* bias, int ldb, int B, int N, int H, int head_dim, float scale,
+/* Fused attention with additive bias on tcgen05, N <= 208, head_dim == 64 (Attention.forward,
+ * modeling_finetune.py:128-157).  `bias` / `biasT` (nullable, together) are the bias and its transpose in the packed
+ * layout of memb_attention_pack_bias: fp32 [H][MEMB_ATTN_BIAS_GROUPS][256][4] = (head, group of 4 columns, row, column
+ * in group), pre-multiplied by log2(e), -inf in columns >= N.  lse is the natural-log row logsumexp [B, H, N].
+ * The backward writes dsT = dS^T as bf16 [B, H, N (key), ld_ds (query)] (nullable) for the bias gradient. */
+#define MEMB_ATTN_BIAS_GROUPS 52
+#define MEMB_ATTN_BIAS_FLOATS_PER_HEAD (MEMB_ATTN_BIAS_GROUPS * 256 * 4)
+int memb_attention_pack_bias(const float* dense /* [H, N, ld] */, int ld, int N, int heads, float* packed,
+                             memb_stream_t stream);
+int memb_attention_fwd(const void* qkv, const float* bias, int ld_ds, int B, int N, int H, int head_dim, float scale,
                        void* out, float* lse, memb_stream_t stream);
 int memb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias,
-                       const float* biasT, int ldb, int B, int N, int H, int head_dim, float scale, void* dqkv, void* ds,
-                       memb_stream_t stream);
+                       const float* biasT, int ld_ds, int B, int N, int H, int head_dim, float scale, void* dqkv,
+                       void* dsT, memb_stream_t stream);
 
 /* Flat-buffer optimizer pass (mem/utils.py:357-371 + torch.optim.AdamW with optim_factory.py:121 betas). */
 int memb_fill_f32(float* p, int64_t n, float v, memb_stream_t stream);

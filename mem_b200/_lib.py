@@ -33,6 +33,7 @@ SIGNATURES = {
 }
 
 DT_BF16, DT_F32 = 0, 1
+ATTN_BIAS_FLOATS_PER_HEAD = 52 * 256 * 4  # MEMB_ATTN_BIAS_FLOATS_PER_HEAD
 EPI_STORE, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_ATOMIC_ADD, EPI_DGELU, EPI_ARGMAX = 0, 1, 2, 3, 4, 5
 
 
@@ -65,6 +66,7 @@ SIGNATURES.update({
     "memb_relpos_gather": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "memb_relpos_scatter": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     "memb_batch_reduce_bf16": (_i32, [_vp, _i32, _i64, _vp, _vp]),
+    "memb_attention_pack_bias": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "memb_attention_fwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
     "memb_attention_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
     "memb_fill_f32": (_i32, [_vp, _i64, _f32, _vp]),

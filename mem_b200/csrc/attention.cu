@@ -1,387 +1,604 @@
-// Fused multi-head self-attention with an additive (relative-position) bias, forward and backward,
-// for short sequences (N <= 208 tokens, head dim 64): one CTA per (batch, head), the whole K/V (and
-// Q/dO) of the head resident in swizzled shared memory, one warp per 16-row tile, bf16 tensor-core
-// MMAs (m16n8k16) with fp32 softmax.  Nothing of size N x N is written to HBM in the forward; the
-// backward writes dS once (bf16) so that the bias gradient can be reduced over the batch.
+// Fused multi-head self-attention with an additive (relative-position) bias on the 5th-gen tensor cores
+// (tcgen05.mma, accumulators in TMEM, operands staged by TMA), forward and backward, for the short
+// sequences of a ViT (N <= 208 tokens, head dim 64): a whole head -- Q, K, V (and dO) -- is resident in
+// 128B-swizzled shared memory, nothing of size N x N goes to HBM in the forward, and the backward writes
+// dS^T once (bf16, by TMA store) so that the bias gradient can be reduced over the batch.
 //
-// Reference: Attention.forward, mem/modeling_finetune.py:128-157  (q*scale, q@k^T, + rel_pos_bias,
+// Reference: Attention.forward, mem/modeling_finetune.py:128-157 (q*scale, q@k^T, + rel_pos_bias,
 // softmax, @v) and its autograd backward.
 //
 // Layouts: qkv / dqkv bf16 [B, N, 3, H, 64] (the QKV GEMM output viewed as in modeling_finetune.py:134);
-// out / dout bf16 [B, N, H*64]; bias fp32 [H, N, ldb] (+ transposed copy for the backward);
-// lse fp32 [B, H, N]; ds bf16 [B, H, N, ldb].
+// out / dout bf16 [B, N, H*64]; bias (forward) and its transpose (backward) in the packed layout written by
+// memb_attention_pack_bias: fp32 [H][52][256][4] = (head, column group, row, 4 columns), times log2(e), -inf past N;
+// lse fp32 [B, H, N] (natural log); dsT bf16 [B, H, N(key), ldb(query)].
+//
+// Forward (persistent, one CTA per SM, 288 threads):
+//   warp 8   control: TMA loads (Q, K, V of the NEXT head are fetched while the current one is in softmax / PV),
+//            tcgen05.mma issue: S_p = Q_p K^T (M=128 query tile p, N=208 keys, fp32 in TMEM), O_p = P_p V
+//   warps 0-7 softmax: two warps per TMEM lane quarter, each thread owns half a row (104 keys) in registers:
+//            x = s*scale*log2e + bias*log2e, row max exchanged through smem, p = 2^(x-m) -> bf16 P tile in
+//            swizzled smem (the A operand of the PV MMA), then the O epilogue (1/l, bf16, global) and lse.
+// Backward (one CTA per (b, h), 288 threads), keys on the M axis so that P^T / dS^T come out of TMEM in the
+// orientation dV = P^T dO, dK = dS^T Q and dQ = dS K need; query chunks of 128 (then 80) columns:
+//   S^T = K_t Q_c^T, dP^T = V_t dO_c^T  ->  p = 2^(s*c1 + b*log2e - lse2), ds = p (dp - delta)  ->  bf16 P^T, dS^T
+//   tiles in smem  ->  dV_t += P^T dO_c, dK_t += dS^T Q_c, dQ_c += dS K_t (MN-major A straight from the dS^T tile);
+//   TMEM: S^T 128 + dP^T 128 + dV 64 + dK 64 + dQ 2x64 = 512 columns.
+#include <algorithm>
+
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "sm100.cuh"
 
 namespace memb {
 namespace attn {
 
+using namespace memb::ptx;
 using bf16 = __nv_bfloat16;
-constexpr int kHeadDim = 64;
-constexpr int kMaxTiles = 13;               // 13 x 16 = 208 >= 197 tokens
-constexpr int kMaxRows = kMaxTiles * 16;
-constexpr int kThreads = kMaxTiles * 32;    // one warp per 16-row tile
-constexpr int kTileBytes = kMaxRows * 128;  // [208][64] bf16, 128 B per row, 16B chunks XOR-swizzled by row&7
-constexpr int kHalfChunks = 4;              // forward keeps 4 key chunks (64 keys) of S in registers per pass
-// Register budget: 13 warps are allocated as 16 (granularity 4), so 16 * 32 * regs <= 65536 -> 128 per thread.
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
-  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
-}
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
+constexpr int kHeadDim = 64;
+constexpr int kMaxN = 208;                    // 13 x 16
+constexpr int kLoadBytes = kMaxN * 128;       // one TMA box: [208 rows][64 bf16]
+constexpr int kThreads = 288;                 // 8 compute warps + 1 control warp
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kBiasGroups = MEMB_ATTN_BIAS_GROUPS;  // packed bias: [H][52 column groups][256 rows][4]
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// Copy rows [0,N) x 64 bf16 (row stride `stride` elements) into a swizzled tile; rows [N, 208) are zeroed.
-__device__ __forceinline__ void load_tile(uint32_t tile, const bf16* src, long long stride, int N) {
-  for (int t = threadIdx.x; t < kMaxRows * 8; t += kThreads) {
-    const int row = t >> 3, chunk = t & 7;
-    const uint32_t dst = tile_addr(tile, row, chunk);
-    if (row < N) cp_async16(dst, src + (long long)row * stride + chunk * 8);
-    else asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0u) : "memory");
-  }
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-
-// A fragments (16 rows x 64 d) of rows [row0, row0+16) from a tile: 4 k-steps x 4 regs.
-__device__ __forceinline__ void load_a_frags(uint32_t tile, int row0, uint32_t (&f)[4][4]) {
-  const int lane = threadIdx.x & 31, mat = lane >> 3, r = lane & 7;
+// [rows][128 B] tile, 16-byte chunks XOR-swizzled by (row & 7)  (== TMA SWIZZLE_128B, UMMA layout type 2)
+__device__ __forceinline__ uint32_t sw128(uint32_t base, int row, int chunk) {
+  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float* dst) {  // dst[0..31], constant-indexed by the caller
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) ldsm_x4(tile_addr(tile, row0 + (mat & 1) * 8 + r, 2 * ks + (mat >> 1)), f[ks]);
-}
-__device__ __forceinline__ void load_a_frag(uint32_t tile, int row0, int ks, uint32_t (&f)[4]) {
-  const int lane = threadIdx.x & 31, mat = lane >> 3, r = lane & 7;
-  ldsm_x4(tile_addr(tile, row0 + (mat & 1) * 8 + r, 2 * ks + (mat >> 1)), f);
-}
-// B fragments "rows are n, columns are k" (K/Q/V/dO used as the [n][k] operand): rows [n0, n0+16), k-step ks.
-// r[0],r[1] -> n8 tile n0..n0+7; r[2],r[3] -> n8 tile n0+8..n0+15.
-__device__ __forceinline__ void load_b_nk(uint32_t tile, int n0, int ks, uint32_t (&r)[4]) {
-  const int lane = threadIdx.x & 31, mat = lane >> 3, rr = lane & 7;
-  ldsm_x4(tile_addr(tile, n0 + (mat >> 1) * 8 + rr, 2 * ks + (mat & 1)), r);
-}
-// B fragments "rows are k, columns are n" (tile row = reduction index): k rows [k0, k0+16), n8 tiles 2*np, 2*np+1.
-__device__ __forceinline__ void load_b_kn(uint32_t tile, int k0, int np, uint32_t (&r)[4]) {
-  const int lane = threadIdx.x & 31, mat = lane >> 3, rr = lane & 7;
-  ldsm_x4_t(tile_addr(tile, k0 + (mat & 1) * 8 + rr, 2 * np + (mat >> 1)), r);
+  for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(r[i]);
 }
 
-// ------------------------------------------------------------------------------------------ forward
-__global__ void __maxnreg__(128)
-attention_fwd(const bf16* __restrict__ qkv, const float* __restrict__ bias, int ldb, int B, int N, int H, float scale,
-              bf16* __restrict__ out, float* __restrict__ lse) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sq = smem_u32(smem), sk = sq + kTileBytes, sv = sk + kTileBytes;
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
-  const long long rs = 3LL * H * kHeadDim;
-  const bf16* qp = qkv + (long long)b * N * rs + h * kHeadDim;
-  load_tile(sq, qp, rs, N);
-  load_tile(sk, qp + H * kHeadDim, rs, N);
-  load_tile(sv, qp + 2 * H * kHeadDim, rs, N);
-  cp_async_wait_all();
-  __syncthreads();
+// =========================================================================================== forward
+namespace fwd {
+constexpr int OFF_Q = 0;                       // [256][128 B]  (rows >= 208 stale: they only feed unused S rows)
+constexpr int OFF_K = 32768;                   // [208][128 B]
+constexpr int OFF_V = OFF_K + kLoadBytes;      // [208][128 B]
+constexpr int OFF_P = OFF_V + kLoadBytes;      // 2 query tiles x 4 key blocks x [128][128 B]
+constexpr int P_TILE = 4 * 16384;
+constexpr int OFF_MAX = OFF_P + 2 * P_TILE;    // float [2 tiles][2 halves][128]
+constexpr int OFF_SUM = OFF_MAX + 2048;        // float [2 tiles][2 halves][128]
+constexpr int OFF_BAR = OFF_SUM + 2048;
+constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;  // + alignment slack
+enum { B_QK = 0, B_V, B_S0, B_S1, B_P0, B_P1, B_O0, B_O1, B_OFREE, B_COUNT };
+__host__ __device__ constexpr int s_col(int t) { return t * 256; }  // TMEM columns of S_p; O_p reuses the first 64
+}  // namespace fwd
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
-  const int ntiles = (N + 15) / 16;
-  if (warp >= ntiles) return;
-  const int row0 = warp * 16;
-  uint32_t qf[4][4];
-  load_a_frags(sq, row0, qf);
+struct FwdParams {
+  const float* bias;
+  int ldb, B, N, H;
+  float c1;  // scale * log2(e)
+  bf16* out;
+  float* lse;
+};
 
-  float o[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // rows row0+g and row0+g+8
-  const int qa = row0 + g, qb = row0 + g + 8;
-  const float* bias_a = bias ? bias + ((long long)h * N + min(qa, N - 1)) * ldb : nullptr;
-  const float* bias_b = bias ? bias + ((long long)h * N + min(qb, N - 1)) * ldb : nullptr;
-
-#pragma unroll 1
-  for (int c0 = 0; c0 < ntiles; c0 += kHalfChunks) {
-    float s[2 * kHalfChunks][4];
-#pragma unroll
-    for (int kc = 0; kc < kHalfChunks; ++kc) {
-      s[2 * kc][0] = s[2 * kc][1] = s[2 * kc][2] = s[2 * kc][3] = 0.f;
-      s[2 * kc + 1][0] = s[2 * kc + 1][1] = s[2 * kc + 1][2] = s[2 * kc + 1][3] = 0.f;
-      if (c0 + kc < ntiles) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t bb[4];
-          load_b_nk(sk, (c0 + kc) * 16, ks, bb);
-          mma16816(s[2 * kc], qf[ks], bb[0], bb[1]);
-          mma16816(s[2 * kc + 1], qf[ks], bb[2], bb[3]);
-        }
-      }
-    }
-    // scale + bias + key mask, running max
-    float mx0 = m0, mx1 = m1;
-#pragma unroll
-    for (int t = 0; t < 2 * kHalfChunks; ++t) {
-      const int key = (c0 + t / 2) * 16 + (t & 1) * 8 + 2 * c;
-      float2 ba = make_float2(0.f, 0.f), bb2 = make_float2(0.f, 0.f);
-      if (bias && key < N) {  // ldb is even and >= N+1 rounded, so the float2 is in bounds and aligned
-        ba = *reinterpret_cast<const float2*>(bias_a + key);
-        bb2 = *reinterpret_cast<const float2*>(bias_b + key);
-      }
-      s[t][0] = key < N ? s[t][0] * scale + ba.x : -INFINITY;
-      s[t][1] = key + 1 < N ? s[t][1] * scale + ba.y : -INFINITY;
-      s[t][2] = key < N ? s[t][2] * scale + bb2.x : -INFINITY;
-      s[t][3] = key + 1 < N ? s[t][3] * scale + bb2.y : -INFINITY;
-      mx0 = fmaxf(mx0, fmaxf(s[t][0], s[t][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[t][2], s[t][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float r0 = __expf(m0 - mx0), r1 = __expf(m1 - mx1);  // first half: exp(-inf) = 0
-    m0 = mx0; m1 = mx1;
-    float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-    for (int t = 0; t < 2 * kHalfChunks; ++t) {
-      s[t][0] = __expf(s[t][0] - m0); s[t][1] = __expf(s[t][1] - m0);
-      s[t][2] = __expf(s[t][2] - m1); s[t][3] = __expf(s[t][3] - m1);
-      sum0 += s[t][0] + s[t][1];
-      sum1 += s[t][2] + s[t][3];
-    }
-    l0 = l0 * r0 + sum0;
-    l1 = l1 * r1 + sum1;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { o[i][0] *= r0; o[i][1] *= r0; o[i][2] *= r1; o[i][3] *= r1; }
-    // O += P V
-#pragma unroll
-    for (int kc = 0; kc < kHalfChunks; ++kc) {
-      if (c0 + kc < ntiles) {
-        uint32_t a[4];
-        a[0] = pack_bf16(s[2 * kc][0], s[2 * kc][1]);
-        a[1] = pack_bf16(s[2 * kc][2], s[2 * kc][3]);
-        a[2] = pack_bf16(s[2 * kc + 1][0], s[2 * kc + 1][1]);
-        a[3] = pack_bf16(s[2 * kc + 1][2], s[2 * kc + 1][3]);
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {
-          uint32_t bb[4];
-          load_b_kn(sv, (c0 + kc) * 16, np, bb);
-          mma16816(o[2 * np], a, bb[0], bb[1]);
-          mma16816(o[2 * np + 1], a, bb[2], bb[3]);
-        }
-      }
-    }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.f / l0, i1 = 1.f / l1;
-  bf16* oa = out + ((long long)b * N + qa) * H * kHeadDim + h * kHeadDim;
-  bf16* ob = out + ((long long)b * N + qb) * H * kHeadDim + h * kHeadDim;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (qa < N) *reinterpret_cast<uint32_t*>(oa + 8 * i + 2 * c) = pack_bf16(o[i][0] * i0, o[i][1] * i0);
-    if (qb < N) *reinterpret_cast<uint32_t*>(ob + 8 * i + 2 * c) = pack_bf16(o[i][2] * i1, o[i][3] * i1);
-  }
-  if (c == 0) {
-    if (qa < N) lse[((long long)b * H + h) * N + qa] = m0 + __logf(l0);
-    if (qb < N) lse[((long long)b * H + h) * N + qb] = m1 + __logf(l1);
-  }
-}
-
-// ------------------------------------------------------------------------------------------ backward
-__global__ void __maxnreg__(128)
-attention_bwd(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
-              const float* __restrict__ lse, const float* __restrict__ bias, const float* __restrict__ biasT, int ldb,
-              int B, int N, int H, float scale, bf16* __restrict__ dqkv, bf16* __restrict__ ds) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sq = smem_u32(smem), sk = sq + kTileBytes, sv = sk + kTileBytes, sdo = sv + kTileBytes;
-  float* s_lse = reinterpret_cast<float*>(smem + 4 * kTileBytes);
-  float* s_delta = s_lse + kMaxRows;
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
-  const long long rs = 3LL * H * kHeadDim, os = (long long)H * kHeadDim;
-  const bf16* qp = qkv + (long long)b * N * rs + h * kHeadDim;
-  const bf16* dop = dout + (long long)b * N * os + h * kHeadDim;
-  const bf16* op = out + (long long)b * N * os + h * kHeadDim;
-  load_tile(sq, qp, rs, N);
-  load_tile(sk, qp + H * kHeadDim, rs, N);
-  load_tile(sv, qp + 2 * H * kHeadDim, rs, N);
-  load_tile(sdo, dop, os, N);
-  // delta[q] = sum_d dO[q,d] * O[q,d]  (read straight from global), lse -> smem
-  for (int q = threadIdx.x; q < kMaxRows; q += kThreads) {
-    float d = 0.f, l = 0.f;
-    if (q < N) {
-      const uint4* o4 = reinterpret_cast<const uint4*>(op + (long long)q * os);
-      const uint4* g4 = reinterpret_cast<const uint4*>(dop + (long long)q * os);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 ov = o4[i], gv = g4[i];
-        const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov);
-        const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gv);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 a = __bfloat1622float2(oh[j]), bb = __bfloat1622float2(gh[j]);
-          d += a.x * bb.x + a.y * bb.y;
-        }
-      }
-      l = lse[((long long)b * H + h) * N + q];
-    }
-    s_delta[q] = d;
-    s_lse[q] = l;
-  }
-  cp_async_wait_all();
-  __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
-  const int ntiles = (N + 15) / 16;
-  if (warp >= ntiles) return;
-  const int row0 = warp * 16;
-  const int ra = row0 + g, rb = row0 + g + 8;
-  bf16* dq_base = dqkv + (long long)b * N * rs + h * kHeadDim;
-
-  // ---- phase A: this warp owns keys [row0, row0+16): dK, dV
+template <int TILE>
+__device__ __forceinline__ void fwd_softmax_tile(const FwdParams& p, uint8_t* smem, uint32_t tmem_base, int h, int quarter,
+                                                 int half, int lane, float& m_out) {
+  using namespace fwd;
+  const int rl = quarter * 32 + lane;          // row within the tile == TMEM lane
+  const int row = TILE * 128 + rl;             // query index
+  const bool rv = row < p.N;
+  float* smax = reinterpret_cast<float*>(smem + OFF_MAX) + TILE * 256;
+  float* ssum = reinterpret_cast<float*>(smem + OFF_SUM) + TILE * 256;
+  float x[104];
   {
-    float dk[8][4], dv[8][4];
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + s_col(TILE) + half * 104;
+    tmem_ld32f(taddr, x);
+    tmem_ld32f(taddr + 32, x + 32);
+    tmem_ld32f(taddr + 64, x + 64);
+    uint32_t r8[8];
+    tmem_ld8(taddr + 96, r8);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
-    const float* bt_a = biasT ? biasT + ((long long)h * N + min(ra, N - 1)) * ldb : nullptr;
-    const float* bt_b = biasT ? biasT + ((long long)h * N + min(rb, N - 1)) * ldb : nullptr;
-#pragma unroll 1
-    for (int qc = 0; qc < ntiles; ++qc) {
-      float st[2][4], dpt[2][4];
+    for (int i = 0; i < 8; ++i) x[96 + i] = __uint_as_float(r8[i]);
+    tmem_ld_wait();
+  }
+  float mx = -INFINITY;
+  if (rv) {
+    // packed bias: float4 (h, column group g, row) -> lanes of a warp read 512 contiguous bytes
+    const float4* bp = p.bias ? reinterpret_cast<const float4*>(p.bias) + ((long long)h * kBiasGroups + half * 26) * 256 + row
+                              : nullptr;
 #pragma unroll
-      for (int t = 0; t < 2; ++t) { st[t][0] = st[t][1] = st[t][2] = st[t][3] = 0.f; dpt[t][0] = dpt[t][1] = dpt[t][2] = dpt[t][3] = 0.f; }
+    for (int i = 0; i < 26; ++i) {
+      if (bp) {  // pre-multiplied by log2(e); columns >= N hold -inf
+        const float4 b = __ldg(bp + i * 256);
+        x[4 * i + 0] = fmaf(x[4 * i + 0], p.c1, b.x);
+        x[4 * i + 1] = fmaf(x[4 * i + 1], p.c1, b.y);
+        x[4 * i + 2] = fmaf(x[4 * i + 2], p.c1, b.z);
+        x[4 * i + 3] = fmaf(x[4 * i + 3], p.c1, b.w);
+      } else {
+        const int c = half * 104 + 4 * i;  // warp-uniform
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t bb[4], af[4];
-        load_a_frag(sk, row0, ks, af);   // K/V fragments are re-read from smem (register budget)
-        load_b_nk(sq, qc * 16, ks, bb);  // S^T = K_j Q^T
-        mma16816(st[0], af, bb[0], bb[1]);
-        mma16816(st[1], af, bb[2], bb[3]);
-        load_a_frag(sv, row0, ks, af);
-        load_b_nk(sdo, qc * 16, ks, bb);  // dP^T = V_j dO^T
-        mma16816(dpt[0], af, bb[0], bb[1]);
-        mma16816(dpt[1], af, bb[2], bb[3]);
+        for (int j = 0; j < 4; ++j) x[4 * i + j] = (c + j < p.N) ? x[4 * i + j] * p.c1 : -INFINITY;
       }
-      uint32_t pa[4], dsa[4];
+      mx = fmaxf(mx, fmaxf(fmaxf(x[4 * i], x[4 * i + 1]), fmaxf(x[4 * i + 2], x[4 * i + 3])));
+    }
+  }
+  smax[half * 128 + rl] = mx;
+  named_bar_sync(1, 256);
+  const float m = fmaxf(mx, smax[(half ^ 1) * 128 + rl]);
+  m_out = m;
+  if (rv) {
+    float sum = 0.f;
+    const uint32_t sp = smem_u32(smem + OFF_P) + TILE * P_TILE;
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int q = qc * 16 + t * 8 + 2 * c;  // columns q, q+1
-        float2 ba = make_float2(0.f, 0.f), bb2 = make_float2(0.f, 0.f);
-        if (biasT && q < N) {
-          ba = *reinterpret_cast<const float2*>(bt_a + q);
-          bb2 = *reinterpret_cast<const float2*>(bt_b + q);
+    for (int i = 0; i < 13; ++i) {
+      float e[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        e[j] = ex2(x[8 * i + j] - m);
+        sum += e[j];
+      }
+      const int c0 = half * 104 + 8 * i;
+      st_shared_v4(sw128(sp + (c0 >> 6) * 16384, rl, (c0 & 63) >> 3), pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]),
+                   pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+    }
+    ssum[half * 128 + rl] = sum;
+  }
+}
+
+template <int TILE>
+__device__ __forceinline__ void fwd_out_tile(const FwdParams& p, uint8_t* smem, uint32_t tmem_base, int b, int h, int quarter,
+                                             int half, int lane, float m) {
+  using namespace fwd;
+  const int rl = quarter * 32 + lane, row = TILE * 128 + rl;
+  float o[32];
+  tmem_ld32f(tmem_base + ((uint32_t)(quarter * 32) << 16) + s_col(TILE) + half * 32, o);
+  tmem_ld_wait();
+  if (row < p.N) {
+    const float* ssum = reinterpret_cast<const float*>(smem + OFF_SUM) + TILE * 256;
+    const float l = ssum[rl] + ssum[128 + rl];
+    const float inv = 1.f / l;
+    bf16* dst = p.out + ((long long)b * p.N + row) * p.H * kHeadDim + h * kHeadDim + half * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      reinterpret_cast<uint4*>(dst)[i] =
+          make_uint4(pack_bf16(o[8 * i] * inv, o[8 * i + 1] * inv), pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
+                     pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv), pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
+    if (half == 0) p.lse[((long long)b * p.H + h) * p.N + row] = (m + lg2(l)) * kLn2;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p) {
+  using namespace fwd;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nheads = p.B * p.H;
+  const bool two = p.N > 128;  // second query tile in use
+
+  if (warp == 8) {
+    if (lane == 0) {
+      prefetch_tmap(&tmap_qkv);
+      mbar_init(&bar[B_QK], 1); mbar_init(&bar[B_V], 1);
+      mbar_init(&bar[B_S0], 1); mbar_init(&bar[B_S1], 1);
+      mbar_init(&bar[B_P0], 256); mbar_init(&bar[B_P1], 256);
+      mbar_init(&bar[B_O0], 1); mbar_init(&bar[B_O1], 1);
+      mbar_init(&bar[B_OFREE], 256);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // -------------------------------------------------------------------------- control thread
+      const uint32_t sq = smem_u32(smem + OFF_Q), sk = smem_u32(smem + OFF_K), sv = smem_u32(smem + OFF_V);
+      const uint32_t spp = smem_u32(smem + OFF_P);
+      constexpr uint32_t idesc_s = make_idesc(1, false, false, 128, kMaxN);
+      constexpr uint32_t idesc_o = make_idesc(1, false, true, 128, kHeadDim);
+      const int nks = (p.N + 15) / 16;  // key steps of the PV product
+      auto load_qk = [&](int head) {
+        const int b = head / p.H, h = head % p.H;
+        mbar_arrive_expect_tx(&bar[B_QK], 2 * kLoadBytes);
+        tma_load_2d(smem + OFF_Q, &tmap_qkv, &bar[B_QK], h * kHeadDim, b * p.N);
+        tma_load_2d(smem + OFF_K, &tmap_qkv, &bar[B_QK], (p.H + h) * kHeadDim, b * p.N);
+      };
+      auto load_v = [&](int head) {
+        const int b = head / p.H, h = head % p.H;
+        mbar_arrive_expect_tx(&bar[B_V], kLoadBytes);
+        tma_load_2d(smem + OFF_V, &tmap_qkv, &bar[B_V], (2 * p.H + h) * kHeadDim, b * p.N);
+      };
+      if ((int)blockIdx.x < nheads) { load_qk(blockIdx.x); load_v(blockIdx.x); }
+      uint32_t ph = 0;
+      for (int head = blockIdx.x; head < nheads; head += gridDim.x, ph ^= 1) {
+        mbar_wait(&bar[B_QK], ph, nullptr, 1);
+        if (head != (int)blockIdx.x) mbar_wait(&bar[B_OFREE], ph ^ 1, nullptr, 2);
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t == 0 || two) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16(tmem_base + s_col(t), make_smem_desc_sw128(sq + t * 16384 + ks * 32, 0, 1024),
+                        make_smem_desc_sw128(sk + ks * 32, 0, 1024), idesc_s, ks != 0);
+          }
+          umma_commit(&bar[B_S0 + t]);
         }
-        const float l0 = s_lse[q], l1 = s_lse[q + 1], d0 = s_delta[q], d1 = s_delta[q + 1];
-        const bool q0 = q < N, q1 = q + 1 < N, ka = ra < N, kb = rb < N;
-        const float p00 = (q0 && ka) ? __expf(st[t][0] * scale + ba.x - l0) : 0.f;
-        const float p01 = (q1 && ka) ? __expf(st[t][1] * scale + ba.y - l1) : 0.f;
-        const float p10 = (q0 && kb) ? __expf(st[t][2] * scale + bb2.x - l0) : 0.f;
-        const float p11 = (q1 && kb) ? __expf(st[t][3] * scale + bb2.y - l1) : 0.f;
-        pa[2 * t] = pack_bf16(p00, p01);
-        pa[2 * t + 1] = pack_bf16(p10, p11);
-        dsa[2 * t] = pack_bf16(p00 * (dpt[t][0] - d0), p01 * (dpt[t][1] - d1));
-        dsa[2 * t + 1] = pack_bf16(p10 * (dpt[t][2] - d0), p11 * (dpt[t][3] - d1));
-      }
+        mbar_wait(&bar[B_S1], ph, nullptr, 3);  // both S tiles done: Q and K are free
+        const int next = head + gridDim.x;
+        if (next < nheads) load_qk(next);
+        mbar_wait(&bar[B_V], ph, nullptr, 4);
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t bb[4];
-        load_b_kn(sdo, qc * 16, np, bb);  // dV += P^T dO
-        mma16816(dv[2 * np], pa, bb[0], bb[1]);
-        mma16816(dv[2 * np + 1], pa, bb[2], bb[3]);
-        load_b_kn(sq, qc * 16, np, bb);   // dK += dS^T Q
-        mma16816(dk[2 * np], dsa, bb[0], bb[1]);
-        mma16816(dk[2 * np + 1], dsa, bb[2], bb[3]);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&bar[B_P0 + t], ph, nullptr, 5);
+          tc_fence_after();
+          if (t == 0 || two) {
+            for (int ks = 0; ks < nks; ++ks)
+              umma_bf16(tmem_base + s_col(t),
+                        make_smem_desc_sw128(spp + t * P_TILE + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
+                        make_smem_desc_sw128(sv + ks * 2048, 8192, 1024), idesc_o, ks != 0);
+          }
+          umma_commit(&bar[B_O0 + t]);
+        }
+        mbar_wait(&bar[B_O1], ph, nullptr, 6);  // V is free
+        if (next < nheads) load_v(next);
       }
     }
-    bf16* dk_a = dq_base + (long long)ra * rs + H * kHeadDim;
-    bf16* dk_b = dq_base + (long long)rb * rs + H * kHeadDim;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (ra < N) {
-        *reinterpret_cast<uint32_t*>(dk_a + 8 * i + 2 * c) = pack_bf16(dk[i][0] * scale, dk[i][1] * scale);
-        *reinterpret_cast<uint32_t*>(dk_a + H * kHeadDim + 8 * i + 2 * c) = pack_bf16(dv[i][0], dv[i][1]);
-      }
-      if (rb < N) {
-        *reinterpret_cast<uint32_t*>(dk_b + 8 * i + 2 * c) = pack_bf16(dk[i][2] * scale, dk[i][3] * scale);
-        *reinterpret_cast<uint32_t*>(dk_b + H * kHeadDim + 8 * i + 2 * c) = pack_bf16(dv[i][2], dv[i][3]);
-      }
+  } else {
+    // ------------------------------------------------------------------------------ softmax / epilogue warps
+    const int quarter = warp & 3, half = warp >> 2;
+    uint32_t ph = 0;
+    for (int head = blockIdx.x; head < nheads; head += gridDim.x, ph ^= 1) {
+      const int b = head / p.H, h = head % p.H;
+      float m0 = 0.f, m1 = 0.f;
+      mbar_wait(&bar[B_S0], ph, nullptr, 7);
+      tc_fence_after();
+      fwd_softmax_tile<0>(p, smem, tmem_base, h, quarter, half, lane, m0);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bar[B_P0]);
+      mbar_wait(&bar[B_S1], ph, nullptr, 8);
+      tc_fence_after();
+      if (two) fwd_softmax_tile<1>(p, smem, tmem_base, h, quarter, half, lane, m1);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bar[B_P1]);
+      mbar_wait(&bar[B_O0], ph, nullptr, 9);
+      tc_fence_after();
+      fwd_out_tile<0>(p, smem, tmem_base, b, h, quarter, half, lane, m0);
+      mbar_wait(&bar[B_O1], ph, nullptr, 10);
+      tc_fence_after();
+      if (two) fwd_out_tile<1>(p, smem, tmem_base, b, h, quarter, half, lane, m1);
+      tc_fence_before();
+      mbar_arrive(&bar[B_OFREE]);
     }
   }
 
-  // ---- phase B: this warp owns queries [row0, row0+16): dQ, dS
-  {
-    uint32_t qf[4][4], dof[4][4];
-    load_a_frags(sq, row0, qf);
-    load_a_frags(sdo, row0, dof);
-    float dq[8][4];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =========================================================================================== backward
+namespace bwd {
+constexpr int OFF_Q = 0;                        // [208][128 B]
+constexpr int OFF_DO = kLoadBytes;              // [208][128 B]
+constexpr int OFF_K = 2 * kLoadBytes;           // [256][128 B] (rows >= 208 stale: unused S^T rows only)
+constexpr int OFF_V = OFF_K + 32768;            // [256][128 B]
+constexpr int OFF_PT = OFF_V + 32768;           // 2 query blocks x [128 keys][64 queries]
+constexpr int OFF_DST = OFF_PT + 32768;         // same shape: dS^T
+constexpr int OFF_NL = OFF_DST + 32768;         // float[208]: -lse*log2e  (-inf for q >= N)
+constexpr int OFF_DELTA = OFF_NL + 1024;        // float[208]: rowsum(dO * O)
+constexpr int OFF_BAR = OFF_DELTA + 1024;
+constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+enum { B_LOAD = 0, B_S, B_PD, B_MMA2, B_ACCFREE, B_COUNT };
+constexpr int COL_ST = 0, COL_DPT = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
+}  // namespace bwd
+
+struct BwdParams {
+  const bf16* out;
+  const bf16* dout;
+  const float* lse;
+  const float* biasT;
+  int ldb, B, N, H;
+  float scale, c1;
+  bf16* dqkv;
+  int write_ds;
+};
+
+// One group of G (32 or 8) query columns of this thread's key row: S^T, dP^T -> P^T, dS^T (bf16, swizzled smem).
+template <int G>
+__device__ __forceinline__ void bwd_group(const BwdParams& p, uint8_t* smem, uint32_t taddr, const float4* btrow, bool kv,
+                                          int q0 /* global query index */, int cl0 /* column within the chunk */, int rl) {
+  using namespace bwd;
+  float s[G], dp[G];
+  if constexpr (G == 32) {
+    tmem_ld32f(taddr + COL_ST, s);
+    tmem_ld32f(taddr + COL_DPT, dp);
+  } else {
+    uint32_t a[8], c[8];
+    tmem_ld8(taddr + COL_ST, a);
+    tmem_ld8(taddr + COL_DPT, c);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-    const float* b_a = bias ? bias + ((long long)h * N + min(ra, N - 1)) * ldb : nullptr;
-    const float* b_b = bias ? bias + ((long long)h * N + min(rb, N - 1)) * ldb : nullptr;
-    const float la = s_lse[ra], lb = s_lse[rb], da = s_delta[ra], db = s_delta[rb];
-    bf16* ds_a = ds ? ds + (((long long)b * H + h) * N + min(ra, N - 1)) * ldb : nullptr;
-    bf16* ds_b = ds ? ds + (((long long)b * H + h) * N + min(rb, N - 1)) * ldb : nullptr;
-#pragma unroll 1
-    for (int kc = 0; kc < ntiles; ++kc) {
-      float s[2][4], dp[2][4];
+    for (int i = 0; i < 8; ++i) { s[i] = __uint_as_float(a[i]); dp[i] = __uint_as_float(c[i]); }
+  }
+  tmem_ld_wait();
+  const float* nl = reinterpret_cast<const float*>(smem + OFF_NL);
+  const float* dl = reinterpret_cast<const float*>(smem + OFF_DELTA);
+  const uint32_t spt = smem_u32(smem + OFF_PT), sdst = smem_u32(smem + OFF_DST);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) { s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0.f; dp[t][0] = dp[t][1] = dp[t][2] = dp[t][3] = 0.f; }
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t bb[4];
-        load_b_nk(sk, kc * 16, ks, bb);  // S = Q_i K^T
-        mma16816(s[0], qf[ks], bb[0], bb[1]);
-        mma16816(s[1], qf[ks], bb[2], bb[3]);
-        load_b_nk(sv, kc * 16, ks, bb);  // dP = dO_i V^T
-        mma16816(dp[0], dof[ks], bb[0], bb[1]);
-        mma16816(dp[1], dof[ks], bb[2], bb[3]);
+  for (int c = 0; c < G / 8; ++c) {
+    const int q = q0 + 8 * c, cl = cl0 + 8 * c;
+    uint32_t pw[4] = {0u, 0u, 0u, 0u}, dw[4] = {0u, 0u, 0u, 0u};
+    if (kv && q < p.N) {
+      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+      if (btrow) {  // packed: (column group, row = key) float4s, pre-multiplied by log2(e)
+        b0 = __ldg(btrow + (q >> 2) * 256);
+        b1 = __ldg(btrow + ((q >> 2) + 1) * 256);
       }
-      uint32_t dsa[4];
+      const float4 n0 = *reinterpret_cast<const float4*>(nl + q), n1 = *reinterpret_cast<const float4*>(nl + q + 4);
+      const float4 d0 = *reinterpret_cast<const float4*>(dl + q), d1 = *reinterpret_cast<const float4*>(dl + q + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float nn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+      const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      float pe[8], de[8];
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int k = kc * 16 + t * 8 + 2 * c;
-        float2 ba = make_float2(0.f, 0.f), bb2 = make_float2(0.f, 0.f);
-        if (bias && k < N) {
-          ba = *reinterpret_cast<const float2*>(b_a + k);
-          bb2 = *reinterpret_cast<const float2*>(b_b + k);
-        }
-        const bool k0 = k < N, k1 = k + 1 < N, qa = ra < N, qb = rb < N;
-        const float p00 = (k0 && qa) ? __expf(s[t][0] * scale + ba.x - la) : 0.f;
-        const float p01 = (k1 && qa) ? __expf(s[t][1] * scale + ba.y - la) : 0.f;
-        const float p10 = (k0 && qb) ? __expf(s[t][2] * scale + bb2.x - lb) : 0.f;
-        const float p11 = (k1 && qb) ? __expf(s[t][3] * scale + bb2.y - lb) : 0.f;
-        dsa[2 * t] = pack_bf16(p00 * (dp[t][0] - da), p01 * (dp[t][1] - da));
-        dsa[2 * t + 1] = pack_bf16(p10 * (dp[t][2] - db), p11 * (dp[t][3] - db));
-        if (ds && k < ldb) {  // padded columns [N, ldb) receive zeros
-          if (qa) *reinterpret_cast<uint32_t*>(ds_a + k) = dsa[2 * t];
-          if (qb) *reinterpret_cast<uint32_t*>(ds_b + k) = dsa[2 * t + 1];
-        }
+      for (int j = 0; j < 8; ++j) {
+        pe[j] = ex2(fmaf(s[8 * c + j], p.c1, bb[j] + nn[j]));  // nn = -inf for q >= N -> p = 0
+        de[j] = pe[j] * (dp[8 * c + j] - dd[j]);
       }
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t bb[4];
-        load_b_kn(sk, kc * 16, np, bb);  // dQ += dS K
-        mma16816(dq[2 * np], dsa, bb[0], bb[1]);
-        mma16816(dq[2 * np + 1], dsa, bb[2], bb[3]);
+      for (int j = 0; j < 4; ++j) {
+        pw[j] = pack_bf16(pe[2 * j], pe[2 * j + 1]);
+        dw[j] = pack_bf16(de[2 * j], de[2 * j + 1]);
       }
     }
-    bf16* dq_a = dq_base + (long long)ra * rs;
-    bf16* dq_b = dq_base + (long long)rb * rs;
+    const int blk = cl >> 6, chunk = (cl & 63) >> 3;
+    st_shared_v4(sw128(spt + blk * 16384, rl, chunk), pw[0], pw[1], pw[2], pw[3]);
+    st_shared_v4(sw128(sdst + blk * 16384, rl, chunk), dw[0], dw[1], dw[2], dw[3]);
+  }
+}
+
+// 64 fp32 accumulator columns of this thread's TMEM lane -> bf16 row (128 B) in global memory
+__device__ __forceinline__ void store_acc_row(uint32_t taddr, float mul, bf16* dst, bool valid) {
+  float v[64];
+  tmem_ld32f(taddr, v);
+  tmem_ld32f(taddr + 32, v + 32);
+  tmem_ld_wait();
+  if (valid) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (ra < N) *reinterpret_cast<uint32_t*>(dq_a + 8 * i + 2 * c) = pack_bf16(dq[i][0] * scale, dq[i][1] * scale);
-      if (rb < N) *reinterpret_cast<uint32_t*>(dq_b + 8 * i + 2 * c) = pack_bf16(dq[i][2] * scale, dq[i][3] * scale);
+    for (int i = 0; i < 8; ++i)
+      reinterpret_cast<uint4*>(dst)[i] =
+          make_uint4(pack_bf16(v[8 * i] * mul, v[8 * i + 1] * mul), pack_bf16(v[8 * i + 2] * mul, v[8 * i + 3] * mul),
+                     pack_bf16(v[8 * i + 4] * mul, v[8 * i + 5] * mul), pack_bf16(v[8 * i + 6] * mul, v[8 * i + 7] * mul));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_bwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                 const __grid_constant__ CUtensorMap tmap_ds, const BwdParams p) {
+  using namespace bwd;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int nt = p.N > 128 ? 2 : 1;  // key tiles == query chunks in use
+
+  if (warp == 8) {
+    if (lane == 0) {
+      prefetch_tmap(&tmap_qkv); prefetch_tmap(&tmap_do); prefetch_tmap(&tmap_ds);
+      mbar_init(&bar[B_LOAD], 1);
+      mbar_init(&bar[B_S], 1);
+      mbar_init(&bar[B_PD], 256);
+      mbar_init(&bar[B_MMA2], 1);
+      mbar_init(&bar[B_ACCFREE], 256);
+      fence_barrier_init();
+      mbar_arrive_expect_tx(&bar[B_LOAD], 4 * kLoadBytes);
+      tma_load_2d(smem + OFF_Q, &tmap_qkv, &bar[B_LOAD], h * kHeadDim, b * p.N);
+      tma_load_2d(smem + OFF_K, &tmap_qkv, &bar[B_LOAD], (p.H + h) * kHeadDim, b * p.N);
+      tma_load_2d(smem + OFF_V, &tmap_qkv, &bar[B_LOAD], (2 * p.H + h) * kHeadDim, b * p.N);
+      tma_load_2d(smem + OFF_DO, &tmap_do, &bar[B_LOAD], h * kHeadDim, b * p.N);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  } else {
+    // delta[q] = sum_d dO[q,d] * O[q,d] (straight from global), -lse*log2e -> smem
+    float* nl = reinterpret_cast<float*>(smem + OFF_NL);
+    float* dl = reinterpret_cast<float*>(smem + OFF_DELTA);
+    const long long os = (long long)p.H * kHeadDim;
+    for (int q = threadIdx.x; q < kMaxN; q += 256) {
+      float d = 0.f, l = -INFINITY;
+      if (q < p.N) {
+        const uint4* o4 = reinterpret_cast<const uint4*>(p.out + ((long long)b * p.N + q) * os + h * kHeadDim);
+        const uint4* g4 = reinterpret_cast<const uint4*>(p.dout + ((long long)b * p.N + q) * os + h * kHeadDim);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 ov = __ldg(o4 + i), gv = __ldg(g4 + i);
+          const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov);
+          const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 a = __bfloat1622float2(oh[j]), g = __bfloat1622float2(gh[j]);
+            d = fmaf(a.x, g.x, fmaf(a.y, g.y, d));
+          }
+        }
+        l = -p.lse[((long long)b * p.H + h) * p.N + q] * kLog2e;
+      }
+      dl[q] = d;
+      nl[q] = l;
     }
   }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // -------------------------------------------------------------------------- control thread
+      const uint32_t sq = smem_u32(smem + OFF_Q), sdo = smem_u32(smem + OFF_DO), sk = smem_u32(smem + OFF_K);
+      const uint32_t sv = smem_u32(smem + OFF_V), spt = smem_u32(smem + OFF_PT), sdst = smem_u32(smem + OFF_DST);
+      constexpr uint32_t idesc_s128 = make_idesc(1, false, false, 128, 128);
+      constexpr uint32_t idesc_s80 = make_idesc(1, false, false, 128, 80);
+      constexpr uint32_t idesc_kv = make_idesc(1, false, true, 128, kHeadDim);  // A K-major (P^T / dS^T), B MN-major
+      constexpr uint32_t idesc_dq = make_idesc(1, true, true, 128, kHeadDim);   // A MN-major (dS), B MN-major (K)
+      mbar_wait(&bar[B_LOAD], 0, nullptr, 1);
+      tc_fence_after();
+      uint32_t it = 0;
+      for (int t = 0; t < nt; ++t) {
+        for (int c = 0; c < nt; ++c, ++it) {
+          const uint32_t ph = it & 1;
+          // ---- S^T = K_t Q_c^T, dP^T = V_t dO_c^T
+          const uint32_t idesc_s = c ? idesc_s80 : idesc_s128;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem_base + COL_ST, make_smem_desc_sw128(sk + t * 16384 + ks * 32, 0, 1024),
+                      make_smem_desc_sw128(sq + c * 16384 + ks * 32, 0, 1024), idesc_s, ks != 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem_base + COL_DPT, make_smem_desc_sw128(sv + t * 16384 + ks * 32, 0, 1024),
+                      make_smem_desc_sw128(sdo + c * 16384 + ks * 32, 0, 1024), idesc_s, ks != 0);
+          umma_commit(&bar[B_S]);
+          mbar_wait(&bar[B_PD], ph, nullptr, 2);  // P^T, dS^T tiles written; S^T, dP^T consumed
+          tc_fence_after();
+          if (t == 1 && c == 0) mbar_wait(&bar[B_ACCFREE], 0, nullptr, 3);  // dV_0 / dK_0 read out
+          // ---- dV_t += P^T dO_c, dK_t += dS^T Q_c   (reduction over the chunk's queries)
+          const int nq = c ? 5 : 8;
+          for (int ks = 0; ks < nq; ++ks) {
+            const uint32_t aoff = (ks >> 2) * 16384 + (ks & 3) * 32, boff = (c * 128 + ks * 16) * 128;
+            umma_bf16(tmem_base + COL_DV, make_smem_desc_sw128(spt + aoff, 0, 1024),
+                      make_smem_desc_sw128(sdo + boff, 8192, 1024), idesc_kv, (c | ks) != 0);
+            umma_bf16(tmem_base + COL_DK, make_smem_desc_sw128(sdst + aoff, 0, 1024),
+                      make_smem_desc_sw128(sq + boff, 8192, 1024), idesc_kv, (c | ks) != 0);
+          }
+          // ---- dQ_c += dS K_t   (reduction over the tile's keys; A = dS read MN-major out of the dS^T tile)
+          const int nk = t ? 5 : 8;
+          for (int ks = 0; ks < nk; ++ks)
+            umma_bf16(tmem_base + COL_DQ + 64 * c, make_smem_desc_sw128(sdst + ks * 2048, 16384, 1024),
+                      make_smem_desc_sw128(sk + (t * 128 + ks * 16) * 128, 8192, 1024), idesc_dq, (t | ks) != 0);
+          umma_commit(&bar[B_MMA2]);
+          if (p.write_ds) {  // dS^T[b, h, keys of tile t, queries of chunk c]  (rows >= N, columns >= ldb clipped)
+            for (int j = 0; j < 2; ++j)
+              if (c * 128 + j * 64 < p.ldb) tma_store_3d(&tmap_ds, sdst + j * 16384, c * 128 + j * 64, t * 128, blockIdx.x);
+            bulk_commit();
+            bulk_wait_read<0>();  // the next S commit (below) then also covers "dS^T tile is reusable"
+          }
+        }
+      }
+      if (p.write_ds) bulk_wait<0>();
+    }
+  } else {
+    // ------------------------------------------------------------------------------ elementwise / epilogue warps
+    const int quarter = warp & 3, half = warp >> 2;
+    const int rl = quarter * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const long long rs = 3LL * p.H * kHeadDim;
+    bf16* dq_base = p.dqkv + (long long)b * p.N * rs + h * kHeadDim;
+    uint32_t it = 0;
+    for (int t = 0; t < nt; ++t) {
+      const int key = t * 128 + rl;
+      const bool kv = key < p.N;
+      const float4* btrow = (p.biasT && kv) ? reinterpret_cast<const float4*>(p.biasT) + (long long)h * kBiasGroups * 256 + key
+                                            : nullptr;
+      for (int c = 0; c < nt; ++c, ++it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(&bar[B_S], ph, nullptr, 4);
+        tc_fence_after();
+        if (c == 0) {  // 128 queries: 64 per thread
+          bwd_group<32>(p, smem, tlane + half * 64, btrow, kv, half * 64, half * 64, rl);
+          bwd_group<32>(p, smem, tlane + half * 64 + 32, btrow, kv, half * 64 + 32, half * 64 + 32, rl);
+        } else {       // 80 queries: 40 per thread
+          bwd_group<32>(p, smem, tlane + half * 40, btrow, kv, 128 + half * 40, half * 40, rl);
+          bwd_group<8>(p, smem, tlane + half * 40 + 32, btrow, kv, 128 + half * 40 + 32, half * 40 + 32, rl);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&bar[B_PD]);
+        mbar_wait(&bar[B_MMA2], ph, nullptr, 5);
+        tc_fence_after();
+        if (c == nt - 1) {  // dV_t (half 0) / dK_t (half 1) complete
+          bf16* dst = dq_base + (long long)key * rs + (half ? 1 : 2) * p.H * kHeadDim;
+          store_acc_row(tlane + (half ? COL_DK : COL_DV), half ? p.scale : 1.f, dst, kv);
+          tc_fence_before();
+          mbar_arrive(&bar[B_ACCFREE]);
+        }
+      }
+    }
+    // dQ: query tile `half`
+    if (half < nt) {
+      const int q = half * 128 + rl;
+      store_acc_row(tlane + COL_DQ + 64 * half, p.scale, dq_base + (long long)q * rs, q < p.N);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<EncodeTiledFn>(sym);
+    return (EncodeTiledFn) nullptr;
+  }();
+  return fn;
+}
+// bf16 tensor, dims[0] innermost (dense), 128B swizzle, box[0] = 64 elements
+static int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const long long* dims, const long long* strides_elems,
+                          const int* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(MEMB_ECUDA, "cuTensorMapEncodeTiled is unavailable");
+  MEMB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, "attention: tensors must be 16-byte aligned");
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bdim[3], estr[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = (cuuint64_t)dims[i];
+    bdim[i] = (cuuint32_t)box[i];
+    if (i > 0) {
+      MEMB_REQUIRE((strides_elems[i - 1] * 2) % 16 == 0, "attention: row strides must be multiples of 16 bytes");
+      gstr[i - 1] = (cuuint64_t)strides_elems[i - 1] * 2;
+    }
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MEMB_ECUDA, "cuTensorMapEncodeTiled (attention) failed with CUresult %d", (int)r);
+  return MEMB_OK;
 }
 
 }  // namespace attn
@@ -391,42 +608,66 @@ using namespace memb;
 using namespace memb::attn;
 
 static int check_shape(int B, int N, int H, int head_dim, int ldb, bool has_bias) {
-  MEMB_REQUIRE(B > 0 && H > 0 && N > 0 && N <= kMaxRows, "attention: N must be in [1, %d], got %d", kMaxRows, N);
+  MEMB_REQUIRE(B > 0 && H > 0 && N > 0 && N <= kMaxN, "attention: N must be in [1, %d], got %d", kMaxN, N);
   MEMB_REQUIRE(head_dim == kHeadDim, "attention: head dim must be %d, got %d", kHeadDim, head_dim);
-  MEMB_REQUIRE(!has_bias || (ldb % 2 == 0 && ldb >= N), "attention: bias row stride must be even and >= N");
+  MEMB_REQUIRE(!has_bias || (ldb % 8 == 0 && ldb >= N), "attention: dS^T row stride must be a multiple of 8 and >= N");
   return MEMB_OK;
 }
 
 extern "C" int memb_attention_fwd(const void* qkv, const float* bias, int ldb, int B, int N, int H, int head_dim,
                                   float scale, void* out, float* lse, memb_stream_t s) {
-  if (int rc = check_shape(B, N, H, head_dim, ldb, bias != nullptr)) return rc;
+  if (int rc = check_shape(B, N, H, head_dim, ldb, false)) return rc;
   MEMB_REQUIRE(qkv && out && lse, "attention_fwd: null pointer");
-  const int smem = 3 * kTileBytes;
+  MEMB_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0, "attention_fwd: bias must be 16-byte aligned");
+  CUtensorMap tq;
+  const long long dims[2] = {3LL * H * kHeadDim, (long long)B * N}, str[1] = {3LL * H * kHeadDim};
+  const int box[2] = {64, kMaxN};
+  if (int rc = make_tmap_bf16(&tq, qkv, 2, dims, str, box)) return rc;
   static bool configured = false;
   if (!configured) {
-    MEMB_CUDA_OK(cudaFuncSetAttribute(attention_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MEMB_CUDA_OK(cudaFuncSetAttribute(attention_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::SMEM_BYTES));
     configured = true;
   }
-  attention_fwd<<<B * H, kThreads, smem, s>>>((const bf16*)qkv, bias, ldb, B, N, H, scale, (bf16*)out, lse);
-  MEMB_LAUNCH_OK("attention_fwd");
+  FwdParams p{bias, ldb, B, N, H, scale * kLog2e, (bf16*)out, lse};
+  const int grid = std::min(B * H, num_sms());
+  attention_fwd_tc<<<grid, kThreads, fwd::SMEM_BYTES, s>>>(tq, p);
+  MEMB_LAUNCH_OK("attention_fwd_tc");
   return MEMB_OK;
 }
 
 extern "C" int memb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias,
                                   const float* biasT, int ldb, int B, int N, int H, int head_dim, float scale, void* dqkv,
-                                  void* ds, memb_stream_t s) {
-  if (int rc = check_shape(B, N, H, head_dim, ldb, bias != nullptr)) return rc;
+                                  void* dsT, memb_stream_t s) {
+  (void)bias;  // the backward reads the transposed copy only
+  if (int rc = check_shape(B, N, H, head_dim, ldb, dsT != nullptr)) return rc;
   MEMB_REQUIRE(qkv && out && dout && lse && dqkv, "attention_bwd: null pointer");
   MEMB_REQUIRE((bias == nullptr) == (biasT == nullptr), "attention_bwd: bias and its transpose go together");
-  MEMB_REQUIRE(!ds || (ldb % 2 == 0 && ldb >= N), "attention_bwd: dS row stride must be even and >= N");
-  const int smem = 4 * kTileBytes + 2 * kMaxRows * (int)sizeof(float);
+  MEMB_REQUIRE(!biasT || (reinterpret_cast<uintptr_t>(biasT) & 15u) == 0, "attention_bwd: biasT must be 16-byte aligned");
+  CUtensorMap tq, tdo, tds;
+  {
+    const long long dims[2] = {3LL * H * kHeadDim, (long long)B * N}, str[1] = {3LL * H * kHeadDim};
+    const int box[2] = {64, kMaxN};
+    if (int rc = make_tmap_bf16(&tq, qkv, 2, dims, str, box)) return rc;
+  }
+  {
+    const long long dims[2] = {(long long)H * kHeadDim, (long long)B * N}, str[1] = {(long long)H * kHeadDim};
+    const int box[2] = {64, kMaxN};
+    if (int rc = make_tmap_bf16(&tdo, dout, 2, dims, str, box)) return rc;
+  }
+  if (dsT) {
+    const long long dims[3] = {ldb, N, (long long)B * H}, str[2] = {ldb, (long long)N * ldb};
+    const int box[3] = {64, 128, 1};
+    if (int rc = make_tmap_bf16(&tds, dsT, 3, dims, str, box)) return rc;
+  } else {
+    tds = tdo;  // never dereferenced
+  }
   static bool configured = false;
   if (!configured) {
-    MEMB_CUDA_OK(cudaFuncSetAttribute(attention_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MEMB_CUDA_OK(cudaFuncSetAttribute(attention_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES));
     configured = true;
   }
-  attention_bwd<<<B * H, kThreads, smem, s>>>((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, bias, biasT, ldb, B,
-                                              N, H, scale, (bf16*)dqkv, (bf16*)ds);
-  MEMB_LAUNCH_OK("attention_bwd");
+  BwdParams p{(const bf16*)out, (const bf16*)dout, lse, biasT, ldb, B, N, H, scale, scale * kLog2e, (bf16*)dqkv, dsT ? 1 : 0};
+  attention_bwd_tc<<<B * H, kThreads, bwd::SMEM_BYTES, s>>>(tq, tdo, tds, p);
+  MEMB_LAUNCH_OK("attention_bwd_tc");
   return MEMB_OK;
 }

@@ -442,6 +442,22 @@ __global__ void __launch_bounds__(256) relpos_gather(const float* __restrict__ t
     if (biasT) biasT[t] = k < N ? table[index[k * N + q] * heads + h] : 0.f;  // biasT[h][q'][k'] = bias[h][k'][q']
   }
 }
+// Dense bias [H][N][ld] -> the attention kernels' packed layout [H][52][256][4] (head, column group, row, 4 columns),
+// multiplied by log2(e); columns >= N hold -inf (they mask the padded keys), rows >= N hold 0.
+__global__ void __launch_bounds__(256) attn_bias_pack(const float* __restrict__ dense, int ld, int N, int heads,
+                                                      float4* __restrict__ packed) {
+  const int total = heads * MEMB_ATTN_BIAS_GROUPS * 256;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int r = t & 255, g = (t >> 8) % MEMB_ATTN_BIAS_GROUPS, h = t / (256 * MEMB_ATTN_BIAS_GROUPS);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 4 * g + j;
+      v[j] = c >= N ? -INFINITY : (r < N ? dense[((long long)h * N + r) * ld + c] * 1.4426950408889634f : 0.f);
+    }
+    packed[t] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
 // dtable[index[q*N+k]][h] += dbias[h][q][k (row stride ldk)]
 __global__ void __launch_bounds__(256) relpos_scatter(const float* __restrict__ dbias, int ldk,
                                                       const long long* __restrict__ index, int N, int heads,
@@ -652,6 +668,13 @@ extern "C" int memb_relpos_gather(const float* table, const int64_t* index, int 
   MEMB_REQUIRE(table && index && bias && N > 0 && heads > 0 && ldk >= N, "relpos_gather: bad arguments");
   relpos_gather<<<flat_grid((long long)N * ldk * heads), 256, 0, s>>>(table, (const long long*)index, N, heads, ldk, bias, biasT);
   MEMB_LAUNCH_OK("relpos_gather");
+  return MEMB_OK;
+}
+extern "C" int memb_attention_pack_bias(const float* dense, int ld, int N, int heads, float* packed, memb_stream_t s) {
+  MEMB_REQUIRE(dense && packed && N > 0 && N <= 4 * MEMB_ATTN_BIAS_GROUPS && heads > 0 && ld >= N, "attention_pack_bias: bad arguments");
+  MEMB_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15u) == 0, "attention_pack_bias: packed must be 16-byte aligned");
+  attn_bias_pack<<<flat_grid((long long)heads * MEMB_ATTN_BIAS_GROUPS * 256), 256, 0, s>>>(dense, ld, N, heads, (float4*)packed);
+  MEMB_LAUNCH_OK("attn_bias_pack");
   return MEMB_OK;
 }
 extern "C" int memb_relpos_scatter(const float* dbias, int ldk, const int64_t* index, int N, int heads, float* dtable,

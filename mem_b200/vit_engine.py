@@ -124,6 +124,17 @@ def _ln_bwd(lib, dy, x, w, mean, rstd, rows, D, dx, dw, db, row_index=None, coun
                                       ops._ptr(count), _sp(device=x.device)))
 
 
+def _index_t(mod):
+    """Transposed relative_position_index (cached on the module): attention_bwd emits dS^T[b, h, key, query], so
+    the scatter into the table walks index[q, k] at position [k, q]."""
+    idx = mod.relative_position_index
+    cached = getattr(mod, "_index_t_cache", None)
+    if cached is None or cached.device != idx.device or cached.shape != idx.shape:
+        cached = idx.t().contiguous()
+        mod._index_t_cache = cached
+    return cached
+
+
 class VitEngine:
     """Runs forward/backward of a (masked) ViT whose parameters follow the reference naming."""
 
@@ -202,10 +213,8 @@ class VitEngine:
         ldk = (N + 7) // 8 * 8
         shared_bias = None
         if getattr(m, "rel_pos_bias", None) is not None:
-            shared_bias = (g("relb", (H, N, ldk), f32, dev), g("relbT", (H, N, ldk), f32, dev))
             rp = m.rel_pos_bias
-            _lib.check(lib.memb_relpos_gather(rp.relative_position_bias_table.data_ptr(), rp.relative_position_index.data_ptr(),
-                                              N, H, ldk, shared_bias[0].data_ptr(), shared_bias[1].data_ptr(), sp))
+            shared_bias = self._packed_bias(lib, rp.relative_position_bias_table, rp.relative_position_index, "", N, H, ldk, dev, sp)
 
         # q/v biases -> one [depth, 3D] vector table (k part stays zero), modeling_finetune.py:131-133
         qkvb = g("qkvb", (depth, 3 * D), f32, dev, zero=True)
@@ -229,10 +238,8 @@ class VitEngine:
             ops.gemm(ln1, flat.w16(pre + "attn.qkv.weight"), out=qkv, bias=qkvb[i] if has_qkv_bias else None)
             bias_pair = shared_bias
             if blk.attn.relative_position_bias_table is not None:
-                own = (g(tag + "relb", (H, N, ldk), f32, dev), g(tag + "relbT", (H, N, ldk), f32, dev))
-                _lib.check(lib.memb_relpos_gather(blk.attn.relative_position_bias_table.data_ptr(),
-                                                  blk.attn.relative_position_index.data_ptr(), N, H, ldk,
-                                                  own[0].data_ptr(), own[1].data_ptr(), sp))
+                own = self._packed_bias(lib, blk.attn.relative_position_bias_table, blk.attn.relative_position_index,
+                                        tag, N, H, ldk, dev, sp)
                 assert shared_bias is None, "shared and per-block relative position bias together are not supported"
                 bias_pair = own
             ao = g(tag + "ao", (M, D), bf, dev); lse = g(tag + "lse", (B, H, N), f32, dev)
@@ -256,6 +263,18 @@ class VitEngine:
         xlast = xs[depth] if need_grad else xs[depth % 2]
         ctx = dict(B=B, M=M, a0=a0, mask=mask_u8, blocks=saved, ldk=ldk, shared_bias=shared_bias, cfg=c, xlast=xlast)
         return xlast, ctx
+
+    def _packed_bias(self, lib, table, index, tag, N, H, ldk, dev, sp):
+        """RelativePositionBias.forward (modeling_finetune.py:242-247) -> (bias, bias^T) in the attention kernels'
+        packed layout (include/memb.h: memb_attention_pack_bias)."""
+        g, f32 = self.bufs.get, torch.float32
+        dense, denseT = g("relb_dense", (H, N, ldk), f32, dev), g("relbT_dense", (H, N, ldk), f32, dev)
+        _lib.check(lib.memb_relpos_gather(table.data_ptr(), index.data_ptr(), N, H, ldk, dense.data_ptr(), denseT.data_ptr(), sp))
+        packed = (g(tag + "relb", (H, _lib.ATTN_BIAS_FLOATS_PER_HEAD), f32, dev),
+                  g(tag + "relbT", (H, _lib.ATTN_BIAS_FLOATS_PER_HEAD), f32, dev))
+        _lib.check(lib.memb_attention_pack_bias(dense.data_ptr(), ldk, N, H, packed[0].data_ptr(), sp))
+        _lib.check(lib.memb_attention_pack_bias(denseT.data_ptr(), ldk, N, H, packed[1].data_ptr(), sp))
+        return packed
 
     # ---- masked-token head + cross entropy (pretraining) ----------------------------------------
     def pretrain_head(self, xlast, ctx, mask_u8, tokens, need_grad, cap=None, want_logits=False):
@@ -374,7 +393,7 @@ class VitEngine:
                     _lib.check(lib.memb_fill_f32(dbias_acc.data_ptr(), dbias_acc.numel(), 0.0, sp))
                 _lib.check(lib.memb_batch_reduce_bf16(ds.data_ptr(), B, H * N * ldk, dbias_acc.data_ptr(), sp))
                 if not shared:
-                    _lib.check(lib.memb_relpos_scatter(dbias_acc.data_ptr(), ldk, blk.attn.relative_position_index.data_ptr(),
+                    _lib.check(lib.memb_relpos_scatter(dbias_acc.data_ptr(), ldk, _index_t(blk.attn).data_ptr(),
                                                        N, H, G("attn.relative_position_bias_table").data_ptr(), sp))
             if blk.attn.q_bias is not None:
                 _lib.check(lib.memb_colsum_bf16(dqkv.data_ptr(), 3 * D, M, D, G("attn.q_bias").data_ptr(), sp))
@@ -386,7 +405,7 @@ class VitEngine:
                 bucket_hook(i)
         if shared:
             rp = m.rel_pos_bias
-            _lib.check(lib.memb_relpos_scatter(dbias_acc.data_ptr(), ldk, rp.relative_position_index.data_ptr(), N, H,
+            _lib.check(lib.memb_relpos_scatter(dbias_acc.data_ptr(), ldk, _index_t(rp).data_ptr(), N, H,
                                                flat.g("rel_pos_bias.relative_position_bias_table").data_ptr(), sp))
 
     def _backward_embed(self, ctx, gres):

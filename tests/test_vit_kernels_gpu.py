@@ -87,7 +87,7 @@ def _attn_ref(qkv, bias, B, N, H, scale):
     return (p @ v).transpose(1, 2).reshape(B, N, H * 64), p
 
 
-@pytest.mark.parametrize("B,N,H,with_bias", [(2, 197, 12, True), (3, 50, 2, True), (2, 17, 2, False), (1, 208, 4, True)])
+@pytest.mark.parametrize("B,N,H,with_bias", [(2, 197, 12, True), (3, 50, 2, True), (2, 17, 2, False), (1, 208, 4, True), (13, 197, 12, True), (5, 129, 3, True)])
 def test_attention_fwd_bwd(L, B, N, H, with_bias):
     torch.manual_seed(2)
     D = H * 64
@@ -99,10 +99,16 @@ def test_attention_fwd_bwd(L, B, N, H, with_bias):
     bias_r = bias.clone().requires_grad_(True)
     biasT = torch.zeros(H, N, ldk, device="cuda")
     biasT[:, :, :N] = bias[:, :, :N].transpose(1, 2)
+    from mem_b200._lib import ATTN_BIAS_FLOATS_PER_HEAD as PF
+    bias_p = torch.empty(H, PF, device="cuda"); biasT_p = torch.empty(H, PF, device="cuda")
+    ck(L.memb_attention_pack_bias(bias.data_ptr(), ldk, N, H, bias_p.data_ptr(), sp()))
+    ck(L.memb_attention_pack_bias(biasT.data_ptr(), ldk, N, H, biasT_p.data_ptr(), sp()))
+    v = bias_p.view(H, 52, 256, 4).permute(0, 2, 1, 3).reshape(H, 256, 208)   # [h, row, col]
+    assert torch.equal(v[:, :N, :N], bias[:, :, :N] * 1.4426950408889634) and (v[:, :, N:] == float("-inf")).all()
     scale = 64 ** -0.5
     out = torch.empty(B, N, D, device="cuda", dtype=torch.bfloat16)
     lse = torch.empty(B, H, N, device="cuda")
-    ck(L.memb_attention_fwd(qkv.data_ptr(), bias.data_ptr() if with_bias else None, ldk, B, N, H, 64, scale, out.data_ptr(),
+    ck(L.memb_attention_fwd(qkv.data_ptr(), bias_p.data_ptr() if with_bias else None, ldk, B, N, H, 64, scale, out.data_ptr(),
                             lse.data_ptr(), sp()))
     ref, _ = _attn_ref(qkv_r, bias_r if with_bias else None, B, N, H, scale)
     assert rel_err(out.float(), ref) < 1e-2       # bf16 P and bf16 output
@@ -111,17 +117,17 @@ def test_attention_fwd_bwd(L, B, N, H, with_bias):
     dqkv = torch.zeros(B, N, 3 * D, device="cuda", dtype=torch.bfloat16)
     ds = torch.zeros(B, H, N, ldk, device="cuda", dtype=torch.bfloat16) if with_bias else None
     ck(L.memb_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
-                            bias.data_ptr() if with_bias else None, biasT.data_ptr() if with_bias else None, ldk, B, N, H, 64,
+                            bias_p.data_ptr() if with_bias else None, biasT_p.data_ptr() if with_bias else None, ldk, B, N, H, 64,
                             scale, dqkv.data_ptr(), ds.data_ptr() if with_bias else None, sp()))
     g = qkv_r.grad.view(B, N, 3, D)
     got = dqkv.float().view(B, N, 3, D)
     for i, name in enumerate("qkv"):
         assert rel_err(got[:, :, i], g[:, :, i]) < 2e-2, name
     if with_bias:
-        dbias = torch.zeros(H, N, ldk, device="cuda")
-        ck(L.memb_batch_reduce_bf16(ds.data_ptr(), B, H * N * ldk, dbias.data_ptr(), sp()))
-        assert rel_err(dbias[:, :, :N], bias_r.grad[:, :, :N]) < 2e-2
-        assert (dbias[:, :, N:] == 0).all()
+        dbiasT = torch.zeros(H, N, ldk, device="cuda")   # the kernel emits dS^T[b, h, key, query]
+        ck(L.memb_batch_reduce_bf16(ds.data_ptr(), B, H * N * ldk, dbiasT.data_ptr(), sp()))
+        assert rel_err(dbiasT[:, :, :N].transpose(1, 2), bias_r.grad[:, :, :N]) < 2e-2
+        assert (dbiasT[:, :, N:] == 0).all()
 
 
 def test_mask_compact_and_cross_entropy(L):
