@@ -258,9 +258,10 @@ int memb_attention_pack_bias(const float* dense /* [H, N, ld] */, int ld, int N,
                              memb_stream_t stream);
 int memb_attention_fwd(const void* qkv, const float* bias, int ld_ds, int B, int N, int H, int head_dim, float scale,
                        void* out, float* lse, memb_stream_t stream);
+size_t memb_attention_bwd_workspace_bytes(int B, int N, int H);
 int memb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias,
                        const float* biasT, int ld_ds, int B, int N, int H, int head_dim, float scale, void* dqkv,
-                       void* dsT, memb_stream_t stream);
+                       void* dsT, void* workspace, size_t ws_bytes, memb_stream_t stream);
 
 /* Flat-buffer optimizer pass (mem/utils.py:357-371 + torch.optim.AdamW with optim_factory.py:121 betas). */
 int memb_fill_f32(float* p, int64_t n, float v, memb_stream_t stream);

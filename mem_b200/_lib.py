@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmemb.so")
+LIB_PATH = os.environ.get("MEMB_LIB_PATH") or os.path.join(_HERE, "libmemb.so")  # override: debugging builds only
 
 MEMB_OK, MEMB_EINVAL, MEMB_EOOB, MEMB_ECUDA, MEMB_EWORKSPACE = 0, -1, -2, -3, -4
 
@@ -68,7 +68,8 @@ SIGNATURES.update({
     "memb_batch_reduce_bf16": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "memb_attention_pack_bias": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "memb_attention_fwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
-    "memb_attention_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
+    "memb_attention_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "memb_attention_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "memb_fill_f32": (_i32, [_vp, _i64, _f32, _vp]),
     "memb_cast_bf16": (_i32, [_vp, _vp, _i64, _vp]),
     "memb_sqnorm": (_i32, [_vp, _i64, _f32, _vp, _vp]),

@@ -12,17 +12,21 @@
 // memb_attention_pack_bias: fp32 [H][52][256][4] = (head, column group, row, 4 columns), times log2(e), -inf past N;
 // lse fp32 [B, H, N] (natural log); dsT bf16 [B, H, N(key), ldb(query)].
 //
-// Forward (persistent, one CTA per SM, 288 threads):
-//   warp 8   control: TMA loads (Q, K, V of the NEXT head are fetched while the current one is in softmax / PV),
+// Forward (persistent, one CTA per SM, 416 threads):
+//   warp 12  control: TMA loads (Q, K, V of the NEXT head are fetched while the current one is in softmax / PV),
 //            tcgen05.mma issue: S_p = Q_p K^T (M=128 query tile p, N=208 keys, fp32 in TMEM), O_p = P_p V
-//   warps 0-7 softmax: two warps per TMEM lane quarter, each thread owns half a row (104 keys) in registers:
-//            x = s*scale*log2e + bias*log2e, row max exchanged through smem, p = 2^(x-m) -> bf16 P tile in
-//            swizzled smem (the A operand of the PV MMA), then the O epilogue (1/l, bf16, global) and lse.
-// Backward (one CTA per (b, h), 288 threads), keys on the M axis so that P^T / dS^T come out of TMEM in the
-// orientation dV = P^T dO, dK = dS^T Q and dQ = dS K need; query chunks of 128 (then 80) columns:
-//   S^T = K_t Q_c^T, dP^T = V_t dO_c^T  ->  p = 2^(s*c1 + b*log2e - lse2), ds = p (dp - delta)  ->  bf16 P^T, dS^T
-//   tiles in smem  ->  dV_t += P^T dO_c, dK_t += dS^T Q_c, dQ_c += dS K_t (MN-major A straight from the dS^T tile);
-//   TMEM: S^T 128 + dP^T 128 + dV 64 + dK 64 + dQ 2x64 = 512 columns.
+//   warps 0-11 softmax: three warps per TMEM lane quarter, each thread owns a third of a row (72/64 keys) in
+//            registers, preloaded with the bias: x = s*scale*log2e + bias*log2e, row max exchanged through smem,
+//            p = 2^(x-m) -> bf16 P tile in swizzled smem (the A operand of the PV MMA), then the O epilogue
+//            (1/l, bf16, global) and lse.
+// Backward (one CTA per (b, h), 320 threads: 8 elementwise warps, one warp issuing batch 1, one issuing batch 2), keys on the M axis so that P^T / dS^T come out of TMEM in the
+// orientation dV = P^T dO, dK = dS^T Q and dQ = dS K need; per key tile t the queries go by in chunks of 64:
+//   batch 1 (chunk g):  S^T = K_t Q_g^T, dP^T = V_t dO_g^T                    (TMEM buffer g & 1)
+//   elementwise:        p = 2^(s*c1 + b - lse2), ds = p (dp - delta) -> bf16 P^T (slot g & 1), dS^T (4 slots) in smem
+//   batch 2 (chunk g):  dV_t += P^T dO_g, dK_t += dS^T Q_g; after a pair of chunks dQ_pair += dS K_t with dS read
+//                       MN-major straight out of the two adjacent dS^T slots; dS^T also leaves by TMA store.
+//   Batch 1 of chunk g+2 is issued before batch 2 of chunk g, so the tensor pipe works in the shadow of the
+//   elementwise warps.  TMEM: 2 x (S^T 64 + dP^T 64) + dV 64 + dK 64 + dQ 2x64 = 512 columns.
 #include <algorithm>
 
 #include <cuda_bf16.h>
@@ -39,7 +43,8 @@ using bf16 = __nv_bfloat16;
 constexpr int kHeadDim = 64;
 constexpr int kMaxN = 208;                    // 13 x 16
 constexpr int kLoadBytes = kMaxN * 128;       // one TMA box: [208 rows][64 bf16]
-constexpr int kThreads = 288;                 // 8 compute warps + 1 control warp
+constexpr int kFwdThreads = 512;              // 12 softmax warps + a control warpgroup (1 working warp)
+constexpr int kBwdThreads = 320;              // 8 elementwise warps + 2 MMA-issuing warps
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kBiasGroups = MEMB_ATTN_BIAS_GROUPS;  // packed bias: [H][52 column groups][256 rows][4]
@@ -62,6 +67,11 @@ __device__ __forceinline__ float lg2(float x) {
 __device__ __forceinline__ uint32_t sw128(uint32_t base, int row, int chunk) {
   return base + row * 128 + ((chunk ^ (row & 7)) << 4);
 }
+__device__ __forceinline__ float4 ldg_f4(const float4* p) {  // volatile: stays where it is written (issued early)
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float* dst) {  // dst[0..31], constant-indexed by the caller
   uint32_t r[32];
   tmem_ld32(taddr, r);
@@ -76,11 +86,12 @@ constexpr int OFF_K = 32768;                   // [208][128 B]
 constexpr int OFF_V = OFF_K + kLoadBytes;      // [208][128 B]
 constexpr int OFF_P = OFF_V + kLoadBytes;      // 2 query tiles x 4 key blocks x [128][128 B]
 constexpr int P_TILE = 4 * 16384;
-constexpr int OFF_MAX = OFF_P + 2 * P_TILE;    // float [2 tiles][2 halves][128]
-constexpr int OFF_SUM = OFF_MAX + 2048;        // float [2 tiles][2 halves][128]
-constexpr int OFF_BAR = OFF_SUM + 2048;
+constexpr int OFF_MAX = OFF_P + 2 * P_TILE;    // float [2 tiles][<=4 column parts][128]
+constexpr int OFF_SUM = OFF_MAX + 4096;        // float [2 tiles][<=4 column parts][128]
+constexpr int OFF_BAR = OFF_SUM + 4096;
 constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;  // + alignment slack
-enum { B_QK = 0, B_V, B_S0, B_S1, B_P0, B_P1, B_O0, B_O1, B_OFREE, B_COUNT };
+constexpr int kSoftmaxThreads = 384;
+enum { B_QK = 0, B_V, B_S0, B_S1, B_P0, B_P1, B_O0, B_O1, B_OFREE0, B_OFREE1, B_COUNT };
 __host__ __device__ constexpr int s_col(int t) { return t * 256; }  // TMEM columns of S_p; O_p reuses the first 64
 }  // namespace fwd
 
@@ -92,94 +103,113 @@ struct FwdParams {
   float* lse;
 };
 
+// Column third ct of a 208-key row: [0,72) [72,136) [136,208)  -> 9 / 8 / 9 chunks of 8
+__device__ __forceinline__ int ct_start(int ct) { return ct == 0 ? 0 : (ct == 1 ? 72 : 136); }
+
+// x <- this thread's bias values (times log2 e; -inf past N).  Issued BEFORE the wait for S so that the L2
+// latency hides behind the MMA / the previous epilogue.
 template <int TILE>
-__device__ __forceinline__ void fwd_softmax_tile(const FwdParams& p, uint8_t* smem, uint32_t tmem_base, int h, int quarter,
-                                                 int half, int lane, float& m_out) {
+__device__ __forceinline__ void fwd_load_bias(const FwdParams& p, int h, int quarter, int ct, int lane, float (&x)[72]) {
+  const int row = TILE * 128 + quarter * 32 + lane;
+  const int c0 = ct_start(ct), ng = ct == 1 ? 16 : 18;
+  if (p.bias && row < p.N) {
+    // packed bias: float4 (h, column group g, row) -> the lanes of a warp read 512 contiguous bytes
+    const float4* bp = reinterpret_cast<const float4*>(p.bias) + ((long long)h * kBiasGroups + (c0 >> 2)) * 256 + row;
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      if (i < ng) {
+        const float4 b = ldg_f4(bp + i * 256);
+        x[4 * i] = b.x; x[4 * i + 1] = b.y; x[4 * i + 2] = b.z; x[4 * i + 3] = b.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 72; ++i) x[i] = (c0 + i < p.N) ? 0.f : -INFINITY;
+  }
+}
+
+template <int TILE>
+__device__ __forceinline__ void fwd_softmax_tile(const FwdParams& p, uint8_t* smem, uint32_t tmem_base, int quarter, int ct,
+                                                 int lane, float (&x)[72], float& m_out) {
   using namespace fwd;
   const int rl = quarter * 32 + lane;          // row within the tile == TMEM lane
   const int row = TILE * 128 + rl;             // query index
   const bool rv = row < p.N;
-  float* smax = reinterpret_cast<float*>(smem + OFF_MAX) + TILE * 256;
-  float* ssum = reinterpret_cast<float*>(smem + OFF_SUM) + TILE * 256;
-  float x[104];
-  {
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + s_col(TILE) + half * 104;
-    tmem_ld32f(taddr, x);
-    tmem_ld32f(taddr + 32, x + 32);
-    tmem_ld32f(taddr + 64, x + 64);
-    uint32_t r8[8];
-    tmem_ld8(taddr + 96, r8);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[96 + i] = __uint_as_float(r8[i]);
-    tmem_ld_wait();
-  }
+  const int c0 = ct_start(ct), nc8 = ct == 1 ? 8 : 9;
+  float* smax = reinterpret_cast<float*>(smem + OFF_MAX) + TILE * 512;
+  float* ssum = reinterpret_cast<float*>(smem + OFF_SUM) + TILE * 512;
+  const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + s_col(TILE) + c0;
   float mx = -INFINITY;
-  if (rv) {
-    // packed bias: float4 (h, column group g, row) -> lanes of a warp read 512 contiguous bytes
-    const float4* bp = p.bias ? reinterpret_cast<const float4*>(p.bias) + ((long long)h * kBiasGroups + half * 26) * 256 + row
-                              : nullptr;
 #pragma unroll
-    for (int i = 0; i < 26; ++i) {
-      if (bp) {  // pre-multiplied by log2(e); columns >= N hold -inf
-        const float4 b = __ldg(bp + i * 256);
-        x[4 * i + 0] = fmaf(x[4 * i + 0], p.c1, b.x);
-        x[4 * i + 1] = fmaf(x[4 * i + 1], p.c1, b.y);
-        x[4 * i + 2] = fmaf(x[4 * i + 2], p.c1, b.z);
-        x[4 * i + 3] = fmaf(x[4 * i + 3], p.c1, b.w);
-      } else {
-        const int c = half * 104 + 4 * i;  // warp-uniform
+  for (int k = 0; k < 9; ++k) {  // 8 columns at a time keeps the live set small
+    if (k < nc8) {
+      uint32_t r[8];
+      tmem_ld8(taddr + 8 * k, r);
+      tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) x[4 * i + j] = (c + j < p.N) ? x[4 * i + j] * p.c1 : -INFINITY;
+      for (int i = 0; i < 8; ++i) {
+        x[8 * k + i] = fmaf(__uint_as_float(r[i]), p.c1, x[8 * k + i]);
+        mx = fmaxf(mx, x[8 * k + i]);
       }
-      mx = fmaxf(mx, fmaxf(fmaxf(x[4 * i], x[4 * i + 1]), fmaxf(x[4 * i + 2], x[4 * i + 3])));
     }
   }
-  smax[half * 128 + rl] = mx;
-  named_bar_sync(1, 256);
-  const float m = fmaxf(mx, smax[(half ^ 1) * 128 + rl]);
+  if (!rv) mx = -INFINITY;  // stale rows may hold NaN
+  smax[ct * 128 + rl] = mx;
+  named_bar_sync(1, kSoftmaxThreads);
+  const float m = fmaxf(fmaxf(smax[rl], smax[128 + rl]), smax[256 + rl]);
   m_out = m;
   if (rv) {
     float sum = 0.f;
     const uint32_t sp = smem_u32(smem + OFF_P) + TILE * P_TILE;
 #pragma unroll
-    for (int i = 0; i < 13; ++i) {
-      float e[8];
+    for (int i = 0; i < 9; ++i) {
+      if (i < nc8) {
+        float e[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        e[j] = ex2(x[8 * i + j] - m);
-        sum += e[j];
+        for (int j = 0; j < 8; ++j) {
+          e[j] = ex2(x[8 * i + j] - m);
+          sum += e[j];
+        }
+        const int c = c0 + 8 * i;
+        st_shared_v4(sw128(sp + (c >> 6) * 16384, rl, (c & 63) >> 3), pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]),
+                     pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
       }
-      const int c0 = half * 104 + 8 * i;
-      st_shared_v4(sw128(sp + (c0 >> 6) * 16384, rl, (c0 & 63) >> 3), pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]),
-                   pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
     }
-    ssum[half * 128 + rl] = sum;
+    ssum[ct * 128 + rl] = sum;
   }
 }
 
+// O epilogue: column third ct takes head-dim columns [0,24) [24,48) [48,64)
 template <int TILE>
 __device__ __forceinline__ void fwd_out_tile(const FwdParams& p, uint8_t* smem, uint32_t tmem_base, int b, int h, int quarter,
-                                             int half, int lane, float m) {
+                                             int ct, int lane, float m) {
   using namespace fwd;
   const int rl = quarter * 32 + lane, row = TILE * 128 + rl;
-  float o[32];
-  tmem_ld32f(tmem_base + ((uint32_t)(quarter * 32) << 16) + s_col(TILE) + half * 32, o);
+  uint32_t o[24];
+  uint32_t (&o0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&o[0]);
+  uint32_t (&o1)[8] = *reinterpret_cast<uint32_t(*)[8]>(&o[16]);
+  const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + s_col(TILE) + ct * 24;
+  tmem_ld16(taddr, o0);
+  if (ct < 2) tmem_ld8(taddr + 16, o1);
   tmem_ld_wait();
   if (row < p.N) {
-    const float* ssum = reinterpret_cast<const float*>(smem + OFF_SUM) + TILE * 256;
-    const float l = ssum[rl] + ssum[128 + rl];
+    const float* ssum = reinterpret_cast<const float*>(smem + OFF_SUM) + TILE * 512;
+    const float l = ssum[rl] + ssum[128 + rl] + ssum[256 + rl];
     const float inv = 1.f / l;
-    bf16* dst = p.out + ((long long)b * p.N + row) * p.H * kHeadDim + h * kHeadDim + half * 32;
+    bf16* dst = p.out + ((long long)b * p.N + row) * p.H * kHeadDim + h * kHeadDim + ct * 24;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      reinterpret_cast<uint4*>(dst)[i] =
-          make_uint4(pack_bf16(o[8 * i] * inv, o[8 * i + 1] * inv), pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
-                     pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv), pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
-    if (half == 0) p.lse[((long long)b * p.H + h) * p.N + row] = (m + lg2(l)) * kLn2;
+    for (int i = 0; i < 3; ++i)
+      if (i < 2 || ct < 2)
+        reinterpret_cast<uint4*>(dst)[i] = make_uint4(
+            pack_bf16(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv),
+            pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv),
+            pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv),
+            pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv));
+    if (ct == 0) p.lse[((long long)b * p.H + h) * p.N + row] = (m + lg2(l)) * kLn2;
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p) {
   using namespace fwd;
   extern __shared__ uint8_t smem_raw[];
@@ -190,14 +220,14 @@ attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p
   const int nheads = p.B * p.H;
   const bool two = p.N > 128;  // second query tile in use
 
-  if (warp == 8) {
+  if (warp == 12) {
     if (lane == 0) {
       prefetch_tmap(&tmap_qkv);
       mbar_init(&bar[B_QK], 1); mbar_init(&bar[B_V], 1);
       mbar_init(&bar[B_S0], 1); mbar_init(&bar[B_S1], 1);
-      mbar_init(&bar[B_P0], 256); mbar_init(&bar[B_P1], 256);
+      mbar_init(&bar[B_P0], kSoftmaxThreads); mbar_init(&bar[B_P1], kSoftmaxThreads);
       mbar_init(&bar[B_O0], 1); mbar_init(&bar[B_O1], 1);
-      mbar_init(&bar[B_OFREE], 256);
+      mbar_init(&bar[B_OFREE0], kSoftmaxThreads); mbar_init(&bar[B_OFREE1], kSoftmaxThreads);
       fence_barrier_init();
     }
     __syncwarp();
@@ -208,13 +238,16 @@ attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
-    if (lane == 0) {
+  if (warp >= 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // the control warpgroup hands its registers to the softmax warps
+    if (warp == 12 && lane == 0) {
       // -------------------------------------------------------------------------- control thread
       const uint32_t sq = smem_u32(smem + OFF_Q), sk = smem_u32(smem + OFF_K), sv = smem_u32(smem + OFF_V);
       const uint32_t spp = smem_u32(smem + OFF_P);
       constexpr uint32_t idesc_s = make_idesc(1, false, false, 128, kMaxN);
       constexpr uint32_t idesc_o = make_idesc(1, false, true, 128, kHeadDim);
+      const uint64_t dq0 = make_smem_desc_sw128(sq, 0, 1024), dk0 = make_smem_desc_sw128(sk, 0, 1024);
+      const uint64_t dp0 = make_smem_desc_sw128(spp, 0, 1024), dv0 = make_smem_desc_sw128(sv, 8192, 1024);
       const int nks = (p.N + 15) / 16;  // key steps of the PV product
       auto load_qk = [&](int head) {
         const int b = head / p.H, h = head % p.H;
@@ -230,17 +263,17 @@ attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p
       if ((int)blockIdx.x < nheads) { load_qk(blockIdx.x); load_v(blockIdx.x); }
       uint32_t ph = 0;
       for (int head = blockIdx.x; head < nheads; head += gridDim.x, ph ^= 1) {
+        const bool first = head == (int)blockIdx.x;
         mbar_wait(&bar[B_QK], ph, nullptr, 1);
-        if (head != (int)blockIdx.x) mbar_wait(&bar[B_OFREE], ph ^ 1, nullptr, 2);
-        tc_fence_after();
+        // Both query tiles are always issued (tile 1 of a short sequence computes rows nobody reads): ptxas 12.9
+        // mis-schedules the descriptor moves of a predicated UTCHMMA, so the MMAs below carry no predicate.
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          if (t == 0 || two) {
+          if (!first) mbar_wait(&bar[B_OFREE0 + t], ph ^ 1, nullptr, 2);  // O_t of the previous head has been read
+          tc_fence_after();
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(tmem_base + s_col(t), make_smem_desc_sw128(sq + t * 16384 + ks * 32, 0, 1024),
-                        make_smem_desc_sw128(sk + ks * 32, 0, 1024), idesc_s, ks != 0);
-          }
+          for (int ks = 0; ks < 4; ++ks)  // descriptor address field counts 16-byte units
+            umma_bf16(tmem_base + s_col(t), dq0 + (uint64_t)(t * 1024 + ks * 2), dk0 + (uint64_t)(ks * 2), idesc_s, ks != 0);
           umma_commit(&bar[B_S0 + t]);
         }
         mbar_wait(&bar[B_S1], ph, nullptr, 3);  // both S tiles done: Q and K are free
@@ -251,11 +284,12 @@ attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p
         for (int t = 0; t < 2; ++t) {
           mbar_wait(&bar[B_P0 + t], ph, nullptr, 5);
           tc_fence_after();
-          if (t == 0 || two) {
-            for (int ks = 0; ks < nks; ++ks)
-              umma_bf16(tmem_base + s_col(t),
-                        make_smem_desc_sw128(spp + t * P_TILE + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
-                        make_smem_desc_sw128(sv + ks * 2048, 8192, 1024), idesc_o, ks != 0);
+          uint64_t da = dp0 + (uint64_t)(t * (P_TILE >> 4)), db = dv0;
+#pragma unroll 1
+          for (int ks = 0; ks < nks; ++ks) {  // rolled on purpose: the control thread lives on few registers
+            umma_bf16(tmem_base + s_col(t), da, db, idesc_o, ks != 0);
+            da += ((ks & 3) == 3) ? (uint64_t)(1024 - 6) : (uint64_t)2;  // next 32 B, or next 64-key block
+            db += 128;
           }
           umma_commit(&bar[B_O0 + t]);
         }
@@ -265,37 +299,43 @@ attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p
     }
   } else {
     // ------------------------------------------------------------------------------ softmax / epilogue warps
-    const int quarter = warp & 3, half = warp >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int quarter = warp & 3, cq = warp >> 2;  // cq: column third of the row
     uint32_t ph = 0;
     for (int head = blockIdx.x; head < nheads; head += gridDim.x, ph ^= 1) {
       const int b = head / p.H, h = head % p.H;
       float m0 = 0.f, m1 = 0.f;
+      float x[72];
+      fwd_load_bias<0>(p, h, quarter, cq, lane, x);
       mbar_wait(&bar[B_S0], ph, nullptr, 7);
       tc_fence_after();
-      fwd_softmax_tile<0>(p, smem, tmem_base, h, quarter, half, lane, m0);
+      fwd_softmax_tile<0>(p, smem, tmem_base, quarter, cq, lane, x, m0);
+      if (two) fwd_load_bias<1>(p, h, quarter, cq, lane, x);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bar[B_P0]);
       mbar_wait(&bar[B_S1], ph, nullptr, 8);
       tc_fence_after();
-      if (two) fwd_softmax_tile<1>(p, smem, tmem_base, h, quarter, half, lane, m1);
+      if (two) fwd_softmax_tile<1>(p, smem, tmem_base, quarter, cq, lane, x, m1);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&bar[B_P1]);
       mbar_wait(&bar[B_O0], ph, nullptr, 9);
       tc_fence_after();
-      fwd_out_tile<0>(p, smem, tmem_base, b, h, quarter, half, lane, m0);
+      fwd_out_tile<0>(p, smem, tmem_base, b, h, quarter, cq, lane, m0);
+      tc_fence_before();
+      mbar_arrive(&bar[B_OFREE0]);
       mbar_wait(&bar[B_O1], ph, nullptr, 10);
       tc_fence_after();
-      if (two) fwd_out_tile<1>(p, smem, tmem_base, b, h, quarter, half, lane, m1);
+      if (two) fwd_out_tile<1>(p, smem, tmem_base, b, h, quarter, cq, lane, m1);
       tc_fence_before();
-      mbar_arrive(&bar[B_OFREE]);
+      mbar_arrive(&bar[B_OFREE1]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -305,22 +345,20 @@ attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p
 namespace bwd {
 constexpr int OFF_Q = 0;                        // [208][128 B]
 constexpr int OFF_DO = kLoadBytes;              // [208][128 B]
-constexpr int OFF_K = 2 * kLoadBytes;           // [256][128 B] (rows >= 208 stale: unused S^T rows only)
-constexpr int OFF_V = OFF_K + 32768;            // [256][128 B]
-constexpr int OFF_PT = OFF_V + 32768;           // 2 query blocks x [128 keys][64 queries]
-constexpr int OFF_DST = OFF_PT + 32768;         // same shape: dS^T
-constexpr int OFF_NL = OFF_DST + 32768;         // float[208]: -lse*log2e  (-inf for q >= N)
-constexpr int OFF_DELTA = OFF_NL + 1024;        // float[208]: rowsum(dO * O)
+constexpr int OFF_K = 2 * kLoadBytes;           // [208][128 B]; tile 1 as an A operand runs 48 rows past the end into
+constexpr int OFF_V = 3 * kLoadBytes;           // the next buffer: those rows only feed S^T / dP^T rows that nobody reads
+constexpr int OFF_PT = 4 * kLoadBytes;          // 2 slots x [128 keys][64 queries] bf16
+constexpr int OFF_DST = OFF_PT + 2 * 16384;     // 4 slots (2 pairs) of the same shape: dS^T
+constexpr int OFF_NL = OFF_DST + 4 * 16384;     // float[256]: -lse*log2e  (-inf for q >= N)
+constexpr int OFF_DELTA = OFF_NL + 1024;        // float[256]: rowsum(dO * O)
 constexpr int OFF_BAR = OFF_DELTA + 1024;
 constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
-enum { B_LOAD = 0, B_S, B_PD, B_MMA2, B_ACCFREE, B_COUNT };
-constexpr int COL_ST = 0, COL_DPT = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
+enum { B_LOAD = 0, B_S0, B_S1, B_PD0, B_PD1, B_B20, B_B21, B_ACC, B_ACCFREE, B_COUNT };
+constexpr int COL_DV = 256, COL_DK = 320, COL_DQ = 384;  // S^T at 128*buf, dP^T at 128*buf + 64
 }  // namespace bwd
 
 struct BwdParams {
-  const bf16* out;
-  const bf16* dout;
-  const float* lse;
+  const float* nl_delta;  // [2][B*H*N]: -lse*log2e, rowsum(dO*O)   (attn_bwd_prep)
   const float* biasT;
   int ldb, B, N, H;
   float scale, c1;
@@ -328,36 +366,61 @@ struct BwdParams {
   int write_ds;
 };
 
-// One group of G (32 or 8) query columns of this thread's key row: S^T, dP^T -> P^T, dS^T (bf16, swizzled smem).
+// nl[b,h,q] = -lse*log2(e), delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]: one thread per (b, q, h), whole 128 B lines.
+__global__ void __launch_bounds__(256) attn_bwd_prep(const bf16* __restrict__ out, const bf16* __restrict__ dout,
+                                                     const float* __restrict__ lse, int B, int N, int H,
+                                                     float* __restrict__ nl_delta) {
+  const long long total = (long long)B * N * H;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // (b, q, h), h fastest: coalesced rows
+  if (i >= total) return;
+  const int h = (int)(i % H);
+  const long long bq = i / H;
+  const int q = (int)(bq % N), b = (int)(bq / N);
+  const uint4* o4 = reinterpret_cast<const uint4*>(out + i * kHeadDim);
+  const uint4* g4 = reinterpret_cast<const uint4*>(dout + i * kHeadDim);
+  float d = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint4 ov = __ldg(o4 + k), gv = __ldg(g4 + k);
+    const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov);
+    const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __bfloat1622float2(oh[j]), g = __bfloat1622float2(gh[j]);
+      d = fmaf(a.x, g.x, fmaf(a.y, g.y, d));
+    }
+  }
+  const long long o = ((long long)b * H + h) * N + q;
+  nl_delta[o] = -lse[o] * kLog2e;
+  nl_delta[total + o] = d;
+}
+
+// G (32 or 8) query columns of this thread's key row: S^T, dP^T -> P^T, dS^T (bf16, swizzled smem slots).
 template <int G>
-__device__ __forceinline__ void bwd_group(const BwdParams& p, uint8_t* smem, uint32_t taddr, const float4* btrow, bool kv,
-                                          int q0 /* global query index */, int cl0 /* column within the chunk */, int rl) {
+__device__ __forceinline__ void bwd_group(const BwdParams& p, uint8_t* smem, uint32_t taddr, const float4 (&breg)[8], bool kv,
+                                          int q0 /* global query index */, int cl0 /* column within the chunk */, int rl,
+                                          uint32_t spt, uint32_t sdst) {
   using namespace bwd;
   float s[G], dp[G];
   if constexpr (G == 32) {
-    tmem_ld32f(taddr + COL_ST, s);
-    tmem_ld32f(taddr + COL_DPT, dp);
+    tmem_ld32f(taddr, s);
+    tmem_ld32f(taddr + 64, dp);
   } else {
     uint32_t a[8], c[8];
-    tmem_ld8(taddr + COL_ST, a);
-    tmem_ld8(taddr + COL_DPT, c);
+    tmem_ld8(taddr, a);
+    tmem_ld8(taddr + 64, c);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] = __uint_as_float(a[i]); dp[i] = __uint_as_float(c[i]); }
   }
   tmem_ld_wait();
   const float* nl = reinterpret_cast<const float*>(smem + OFF_NL);
   const float* dl = reinterpret_cast<const float*>(smem + OFF_DELTA);
-  const uint32_t spt = smem_u32(smem + OFF_PT), sdst = smem_u32(smem + OFF_DST);
 #pragma unroll
   for (int c = 0; c < G / 8; ++c) {
     const int q = q0 + 8 * c, cl = cl0 + 8 * c;
     uint32_t pw[4] = {0u, 0u, 0u, 0u}, dw[4] = {0u, 0u, 0u, 0u};
-    if (kv && q < p.N) {
-      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-      if (btrow) {  // packed: (column group, row = key) float4s, pre-multiplied by log2(e)
-        b0 = __ldg(btrow + (q >> 2) * 256);
-        b1 = __ldg(btrow + ((q >> 2) + 1) * 256);
-      }
+    if (kv) {
+      const float4 b0 = breg[2 * c], b1 = breg[2 * c + 1];
       const float4 n0 = *reinterpret_cast<const float4*>(nl + q), n1 = *reinterpret_cast<const float4*>(nl + q + 4);
       const float4 d0 = *reinterpret_cast<const float4*>(dl + q), d1 = *reinterpret_cast<const float4*>(dl + q + 4);
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -375,9 +438,8 @@ __device__ __forceinline__ void bwd_group(const BwdParams& p, uint8_t* smem, uin
         dw[j] = pack_bf16(de[2 * j], de[2 * j + 1]);
       }
     }
-    const int blk = cl >> 6, chunk = (cl & 63) >> 3;
-    st_shared_v4(sw128(spt + blk * 16384, rl, chunk), pw[0], pw[1], pw[2], pw[3]);
-    st_shared_v4(sw128(sdst + blk * 16384, rl, chunk), dw[0], dw[1], dw[2], dw[3]);
+    st_shared_v4(sw128(spt, rl, cl >> 3), pw[0], pw[1], pw[2], pw[3]);
+    st_shared_v4(sw128(sdst, rl, cl >> 3), dw[0], dw[1], dw[2], dw[3]);
   }
 }
 
@@ -396,7 +458,24 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, float mul, bf16* d
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// NQ k-steps of 16 queries: dV_t += P^T dO_j, dK_t += dS^T Q_j.  Descriptor address fields count 16-byte units.
+template <int NQ>
+__device__ __forceinline__ void issue_dv_dk(uint32_t tmem_base, uint64_t dpt, uint64_t ddst, uint64_t ddo, uint64_t dq,
+                                            uint32_t idesc, bool first_chunk) {
+#pragma unroll
+  for (int ks = 0; ks < NQ; ++ks) {
+    umma_bf16(tmem_base + bwd::COL_DV, dpt + (uint64_t)(ks * 2), ddo + (uint64_t)(ks * 128), idesc, !(first_chunk && ks == 0));
+    umma_bf16(tmem_base + bwd::COL_DK, ddst + (uint64_t)(ks * 2), dq + (uint64_t)(ks * 128), idesc, !(first_chunk && ks == 0));
+  }
+}
+template <int NK>
+__device__ __forceinline__ void issue_dq(uint32_t tmem_d, uint64_t dds, uint64_t dk, uint32_t idesc, bool first_tile) {
+#pragma unroll
+  for (int ks = 0; ks < NK; ++ks)
+    umma_bf16(tmem_d, dds + (uint64_t)(ks * 128), dk + (uint64_t)(ks * 128), idesc, !(first_tile && ks == 0));
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attention_bwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                  const __grid_constant__ CUtensorMap tmap_ds, const BwdParams p) {
   using namespace bwd;
@@ -406,109 +485,109 @@ attention_bwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-  const int nt = p.N > 128 ? 2 : 1;  // key tiles == query chunks in use
+  const int nt = p.N > 128 ? 2 : 1;               // key tiles
+  const int nch = min(4, (p.N + 63) / 64);        // query chunks (64 wide; the 4th is 16 wide)
+  const int npair = (nch + 1) >> 1;
 
   if (warp == 8) {
     if (lane == 0) {
       prefetch_tmap(&tmap_qkv); prefetch_tmap(&tmap_do); prefetch_tmap(&tmap_ds);
       mbar_init(&bar[B_LOAD], 1);
-      mbar_init(&bar[B_S], 1);
-      mbar_init(&bar[B_PD], 256);
-      mbar_init(&bar[B_MMA2], 1);
+      mbar_init(&bar[B_S0], 1); mbar_init(&bar[B_S1], 1);
+      mbar_init(&bar[B_PD0], 256); mbar_init(&bar[B_PD1], 256);
+      mbar_init(&bar[B_B20], 1); mbar_init(&bar[B_B21], 1);
+      mbar_init(&bar[B_ACC], 1);
       mbar_init(&bar[B_ACCFREE], 256);
       fence_barrier_init();
       mbar_arrive_expect_tx(&bar[B_LOAD], 4 * kLoadBytes);
-      tma_load_2d(smem + OFF_Q, &tmap_qkv, &bar[B_LOAD], h * kHeadDim, b * p.N);
       tma_load_2d(smem + OFF_K, &tmap_qkv, &bar[B_LOAD], (p.H + h) * kHeadDim, b * p.N);
+      tma_load_2d(smem + OFF_Q, &tmap_qkv, &bar[B_LOAD], h * kHeadDim, b * p.N);
       tma_load_2d(smem + OFF_V, &tmap_qkv, &bar[B_LOAD], (2 * p.H + h) * kHeadDim, b * p.N);
       tma_load_2d(smem + OFF_DO, &tmap_do, &bar[B_LOAD], h * kHeadDim, b * p.N);
     }
     __syncwarp();
     tmem_alloc(tmem_slot, 512);
-  } else {
-    // delta[q] = sum_d dO[q,d] * O[q,d] (straight from global), -lse*log2e -> smem
+  } else if (warp < 8) {
     float* nl = reinterpret_cast<float*>(smem + OFF_NL);
     float* dl = reinterpret_cast<float*>(smem + OFF_DELTA);
-    const long long os = (long long)p.H * kHeadDim;
-    for (int q = threadIdx.x; q < kMaxN; q += 256) {
-      float d = 0.f, l = -INFINITY;
-      if (q < p.N) {
-        const uint4* o4 = reinterpret_cast<const uint4*>(p.out + ((long long)b * p.N + q) * os + h * kHeadDim);
-        const uint4* g4 = reinterpret_cast<const uint4*>(p.dout + ((long long)b * p.N + q) * os + h * kHeadDim);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 ov = __ldg(o4 + i), gv = __ldg(g4 + i);
-          const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov);
-          const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gv);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 a = __bfloat1622float2(oh[j]), g = __bfloat1622float2(gh[j]);
-            d = fmaf(a.x, g.x, fmaf(a.y, g.y, d));
-          }
-        }
-        l = -p.lse[((long long)b * p.H + h) * p.N + q] * kLog2e;
-      }
-      dl[q] = d;
-      nl[q] = l;
-    }
+    const int q = threadIdx.x;
+    const long long o = (long long)blockIdx.x * p.N + q, total = (long long)p.B * p.H * p.N;
+    nl[q] = q < p.N ? __ldg(p.nl_delta + o) : -INFINITY;
+    dl[q] = q < p.N ? __ldg(p.nl_delta + total + o) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sq = smem_u32(smem + OFF_Q), sdo = smem_u32(smem + OFF_DO), sk = smem_u32(smem + OFF_K);
+  const uint32_t sv = smem_u32(smem + OFF_V), spt = smem_u32(smem + OFF_PT), sdst = smem_u32(smem + OFF_DST);
 
   if (warp == 8) {
     if (lane == 0) {
-      // -------------------------------------------------------------------------- control thread
-      const uint32_t sq = smem_u32(smem + OFF_Q), sdo = smem_u32(smem + OFF_DO), sk = smem_u32(smem + OFF_K);
-      const uint32_t sv = smem_u32(smem + OFF_V), spt = smem_u32(smem + OFF_PT), sdst = smem_u32(smem + OFF_DST);
-      constexpr uint32_t idesc_s128 = make_idesc(1, false, false, 128, 128);
-      constexpr uint32_t idesc_s80 = make_idesc(1, false, false, 128, 80);
-      constexpr uint32_t idesc_kv = make_idesc(1, false, true, 128, kHeadDim);  // A K-major (P^T / dS^T), B MN-major
-      constexpr uint32_t idesc_dq = make_idesc(1, true, true, 128, kHeadDim);   // A MN-major (dS), B MN-major (K)
+      // ---------------------------------------------------- issuer 1: S^T = K_t Q_j^T, dP^T = V_t dO_j^T -> TMEM buffer g & 1
+      constexpr uint32_t idesc_s64 = make_idesc(1, false, false, 128, 64);
+      constexpr uint32_t idesc_s16 = make_idesc(1, false, false, 128, 16);
+      const uint64_t dk0 = make_smem_desc_sw128(sk, 0, 1024), dq0 = make_smem_desc_sw128(sq, 0, 1024);
+      const uint64_t dv0 = make_smem_desc_sw128(sv, 0, 1024), ddo0 = make_smem_desc_sw128(sdo, 0, 1024);
+      auto issue_b1 = [&](int g, int t, int j) {
+        const int buf = g & 1;
+        const uint32_t idesc = j < 3 ? idesc_s64 : idesc_s16;
+        const uint64_t a_off = (uint64_t)(t * 1024), b_off = (uint64_t)(j * 512);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem_base + 128 * buf, dk0 + a_off + (uint64_t)(ks * 2), dq0 + b_off + (uint64_t)(ks * 2), idesc, ks != 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem_base + 128 * buf + 64, dv0 + a_off + (uint64_t)(ks * 2), ddo0 + b_off + (uint64_t)(ks * 2), idesc, ks != 0);
+        umma_commit(&bar[B_S0 + buf]);
+      };
       mbar_wait(&bar[B_LOAD], 0, nullptr, 1);
       tc_fence_after();
-      uint32_t it = 0;
-      for (int t = 0; t < nt; ++t) {
-        for (int c = 0; c < nt; ++c, ++it) {
-          const uint32_t ph = it & 1;
-          // ---- S^T = K_t Q_c^T, dP^T = V_t dO_c^T
-          const uint32_t idesc_s = c ? idesc_s80 : idesc_s128;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_bf16(tmem_base + COL_ST, make_smem_desc_sw128(sk + t * 16384 + ks * 32, 0, 1024),
-                      make_smem_desc_sw128(sq + c * 16384 + ks * 32, 0, 1024), idesc_s, ks != 0);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_bf16(tmem_base + COL_DPT, make_smem_desc_sw128(sv + t * 16384 + ks * 32, 0, 1024),
-                      make_smem_desc_sw128(sdo + c * 16384 + ks * 32, 0, 1024), idesc_s, ks != 0);
-          umma_commit(&bar[B_S]);
-          mbar_wait(&bar[B_PD], ph, nullptr, 2);  // P^T, dS^T tiles written; S^T, dP^T consumed
-          tc_fence_after();
-          if (t == 1 && c == 0) mbar_wait(&bar[B_ACCFREE], 0, nullptr, 3);  // dV_0 / dK_0 read out
-          // ---- dV_t += P^T dO_c, dK_t += dS^T Q_c   (reduction over the chunk's queries)
-          const int nq = c ? 5 : 8;
-          for (int ks = 0; ks < nq; ++ks) {
-            const uint32_t aoff = (ks >> 2) * 16384 + (ks & 3) * 32, boff = (c * 128 + ks * 16) * 128;
-            umma_bf16(tmem_base + COL_DV, make_smem_desc_sw128(spt + aoff, 0, 1024),
-                      make_smem_desc_sw128(sdo + boff, 8192, 1024), idesc_kv, (c | ks) != 0);
-            umma_bf16(tmem_base + COL_DK, make_smem_desc_sw128(sdst + aoff, 0, 1024),
-                      make_smem_desc_sw128(sq + boff, 8192, 1024), idesc_kv, (c | ks) != 0);
+      int g = 0;
+      for (int t = 0; t < nt; ++t)
+        for (int j = 0; j < nch; ++j, ++g) {
+          if (g >= 2) {  // chunk g-2 has left this TMEM buffer
+            mbar_wait(&bar[B_PD0 + (g & 1)], ((g - 2) >> 1) & 1, nullptr, 2);
+            tc_fence_after();
           }
-          // ---- dQ_c += dS K_t   (reduction over the tile's keys; A = dS read MN-major out of the dS^T tile)
-          const int nk = t ? 5 : 8;
-          for (int ks = 0; ks < nk; ++ks)
-            umma_bf16(tmem_base + COL_DQ + 64 * c, make_smem_desc_sw128(sdst + ks * 2048, 16384, 1024),
-                      make_smem_desc_sw128(sk + (t * 128 + ks * 16) * 128, 8192, 1024), idesc_dq, (t | ks) != 0);
-          umma_commit(&bar[B_MMA2]);
-          if (p.write_ds) {  // dS^T[b, h, keys of tile t, queries of chunk c]  (rows >= N, columns >= ldb clipped)
-            for (int j = 0; j < 2; ++j)
-              if (c * 128 + j * 64 < p.ldb) tma_store_3d(&tmap_ds, sdst + j * 16384, c * 128 + j * 64, t * 128, blockIdx.x);
+          issue_b1(g, t, j);
+        }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      // ---------------------------------------------------- issuer 2: dV, dK, dQ accumulation + dS^T store
+      constexpr uint32_t idesc_kv = make_idesc(1, false, true, 128, kHeadDim);  // A K-major (P^T / dS^T), B MN-major
+      constexpr uint32_t idesc_dq = make_idesc(1, true, true, 128, kHeadDim);   // A MN-major (dS), B MN-major (K)
+      const uint64_t dpt0 = make_smem_desc_sw128(spt, 0, 1024), ddst0 = make_smem_desc_sw128(sdst, 0, 1024);
+      const uint64_t ddo0 = make_smem_desc_sw128(sdo, 8192, 1024), dq0 = make_smem_desc_sw128(sq, 8192, 1024);
+      const uint64_t dds0 = make_smem_desc_sw128(sdst, 16384, 1024), dk0 = make_smem_desc_sw128(sk, 8192, 1024);
+      mbar_wait(&bar[B_LOAD], 0, nullptr, 3);
+      int g = 0;
+      for (int t = 0; t < nt; ++t)
+        for (int j = 0; j < nch; ++j, ++g) {
+          const int buf = g & 1;
+          const int slot = 2 * ((t * npair + (j >> 1)) & 1) + (j & 1);
+          mbar_wait(&bar[B_PD0 + buf], (g >> 1) & 1, nullptr, 4);  // P^T, dS^T of chunk g are in smem
+          if (t == 1 && j == 0) mbar_wait(&bar[B_ACCFREE], 0, nullptr, 5);  // dV_0 / dK_0 have been read out
+          tc_fence_after();
+          const uint64_t a_pt = dpt0 + (uint64_t)(buf * 1024), a_dst = ddst0 + (uint64_t)(slot * 1024);
+          const uint64_t b_off = (uint64_t)(j * 512);
+          if (j < 3) issue_dv_dk<4>(tmem_base, a_pt, a_dst, ddo0 + b_off, dq0 + b_off, idesc_kv, j == 0);
+          else issue_dv_dk<1>(tmem_base, a_pt, a_dst, ddo0 + b_off, dq0 + b_off, idesc_kv, false);
+          if ((j & 1) || j == nch - 1) {  // a pair of chunks is complete: dQ_pair += dS K_t
+            const uint64_t a_ds = dds0 + (uint64_t)((slot & 2) * 1024), b_k = dk0 + (uint64_t)(t * 1024);
+            const uint32_t d = tmem_base + COL_DQ + 64 * (j >> 1);
+            if (t == 0) issue_dq<8>(d, a_ds, b_k, idesc_dq, true);
+            else issue_dq<5>(d, a_ds, b_k, idesc_dq, false);
+          }
+          if (p.write_ds) bulk_wait_read<0>();  // earlier dS^T stores have left smem before the commit frees slots
+          umma_commit(&bar[B_B20 + buf]);
+          if (j == nch - 1) umma_commit(&bar[B_ACC]);
+          if (p.write_ds && j * 64 < p.ldb) {  // dS^T[b, h, keys of tile t, queries of chunk j]  (clipped at N / ldb)
+            tma_store_3d(&tmap_ds, sdst + slot * 16384, j * 64, t * 128, blockIdx.x);
             bulk_commit();
-            bulk_wait_read<0>();  // the next S commit (below) then also covers "dS^T tile is reusable"
           }
         }
-      }
       if (p.write_ds) bulk_wait<0>();
     }
   } else {
@@ -518,37 +597,42 @@ attention_bwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const long long rs = 3LL * p.H * kHeadDim;
     bf16* dq_base = p.dqkv + (long long)b * p.N * rs + h * kHeadDim;
-    uint32_t it = 0;
+    int g = 0;
     for (int t = 0; t < nt; ++t) {
       const int key = t * 128 + rl;
       const bool kv = key < p.N;
-      const float4* btrow = (p.biasT && kv) ? reinterpret_cast<const float4*>(p.biasT) + (long long)h * kBiasGroups * 256 + key
-                                            : nullptr;
-      for (int c = 0; c < nt; ++c, ++it) {
-        const uint32_t ph = it & 1;
-        mbar_wait(&bar[B_S], ph, nullptr, 4);
-        tc_fence_after();
-        if (c == 0) {  // 128 queries: 64 per thread
-          bwd_group<32>(p, smem, tlane + half * 64, btrow, kv, half * 64, half * 64, rl);
-          bwd_group<32>(p, smem, tlane + half * 64 + 32, btrow, kv, half * 64 + 32, half * 64 + 32, rl);
-        } else {       // 80 queries: 40 per thread
-          bwd_group<32>(p, smem, tlane + half * 40, btrow, kv, 128 + half * 40, half * 40, rl);
-          bwd_group<8>(p, smem, tlane + half * 40 + 32, btrow, kv, 128 + half * 40 + 32, half * 40 + 32, rl);
+      for (int j = 0; j < nch; ++j, ++g) {
+        const int buf = g & 1;
+        const int slot = 2 * ((t * npair + (j >> 1)) & 1) + (j & 1);
+        const int cl0 = j < 3 ? half * 32 : half * 8;  // first column (within the chunk) of this thread
+        const int q0 = j * 64 + cl0;
+        // bias^T values of this thread's columns, issued before the wait
+        float4 breg[8];
+        {
+          const int nb = j < 3 ? 8 : 2;
+          const float4* bt = reinterpret_cast<const float4*>(p.biasT) + ((long long)h * kBiasGroups + (q0 >> 2)) * 256 + key;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            breg[i] = (p.biasT && kv && i < nb && q0 + 4 * i < p.N) ? ldg_f4(bt + i * 256) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        mbar_wait(&bar[B_S0 + buf], (g >> 1) & 1, nullptr, 6);
+        if (g >= 2) mbar_wait(&bar[B_B20 + buf], ((g - 2) >> 1) & 1, nullptr, 7);  // P^T slot (and dS^T slot) reusable
+        tc_fence_after();
+        if (j < 3) bwd_group<32>(p, smem, tlane + 128 * buf + cl0, breg, kv, q0, cl0, rl, spt + buf * 16384, sdst + slot * 16384);
+        else bwd_group<8>(p, smem, tlane + 128 * buf + cl0, breg, kv, q0, cl0, rl, spt + buf * 16384, sdst + slot * 16384);
         fence_proxy_async();
         tc_fence_before();
-        mbar_arrive(&bar[B_PD]);
-        mbar_wait(&bar[B_MMA2], ph, nullptr, 5);
-        tc_fence_after();
-        if (c == nt - 1) {  // dV_t (half 0) / dK_t (half 1) complete
-          bf16* dst = dq_base + (long long)key * rs + (half ? 1 : 2) * p.H * kHeadDim;
-          store_acc_row(tlane + (half ? COL_DK : COL_DV), half ? p.scale : 1.f, dst, kv);
-          tc_fence_before();
-          mbar_arrive(&bar[B_ACCFREE]);
-        }
+        mbar_arrive(&bar[B_PD0 + buf]);
       }
+      // tile finished: dV_t (half 0) / dK_t (half 1)
+      mbar_wait(&bar[B_ACC], t & 1, nullptr, 8);
+      tc_fence_after();
+      bf16* dst = dq_base + (long long)key * rs + (half ? 1 : 2) * p.H * kHeadDim;
+      store_acc_row(tlane + (half ? COL_DK : COL_DV), half ? p.scale : 1.f, dst, kv);
+      tc_fence_before();
+      mbar_arrive(&bar[B_ACCFREE]);
     }
-    // dQ: query tile `half`
+    // dQ: query tile `half` (the last B_ACC phase covers every MMA of issuer 2)
     if (half < nt) {
       const int q = half * 128 + rl;
       store_acc_row(tlane + COL_DQ + 64 * half, p.scale, dq_base + (long long)q * rs, q < p.N);
@@ -630,17 +714,22 @@ extern "C" int memb_attention_fwd(const void* qkv, const float* bias, int ldb, i
   }
   FwdParams p{bias, ldb, B, N, H, scale * kLog2e, (bf16*)out, lse};
   const int grid = std::min(B * H, num_sms());
-  attention_fwd_tc<<<grid, kThreads, fwd::SMEM_BYTES, s>>>(tq, p);
+  attention_fwd_tc<<<grid, kFwdThreads, fwd::SMEM_BYTES, s>>>(tq, p);
   MEMB_LAUNCH_OK("attention_fwd_tc");
   return MEMB_OK;
 }
 
+extern "C" size_t memb_attention_bwd_workspace_bytes(int B, int N, int H) {
+  return (size_t)2 * (size_t)B * (size_t)N * (size_t)H * sizeof(float);
+}
+
 extern "C" int memb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias,
                                   const float* biasT, int ldb, int B, int N, int H, int head_dim, float scale, void* dqkv,
-                                  void* dsT, memb_stream_t s) {
+                                  void* dsT, void* workspace, size_t ws_bytes, memb_stream_t s) {
   (void)bias;  // the backward reads the transposed copy only
   if (int rc = check_shape(B, N, H, head_dim, ldb, dsT != nullptr)) return rc;
-  MEMB_REQUIRE(qkv && out && dout && lse && dqkv, "attention_bwd: null pointer");
+  MEMB_REQUIRE(qkv && out && dout && lse && dqkv && workspace, "attention_bwd: null pointer");
+  MEMB_REQUIRE(ws_bytes >= memb_attention_bwd_workspace_bytes(B, N, H), "attention_bwd: workspace too small");
   MEMB_REQUIRE((bias == nullptr) == (biasT == nullptr), "attention_bwd: bias and its transpose go together");
   MEMB_REQUIRE(!biasT || (reinterpret_cast<uintptr_t>(biasT) & 15u) == 0, "attention_bwd: biasT must be 16-byte aligned");
   CUtensorMap tq, tdo, tds;
@@ -666,8 +755,12 @@ extern "C" int memb_attention_bwd(const void* qkv, const void* out, const void* 
     MEMB_CUDA_OK(cudaFuncSetAttribute(attention_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES));
     configured = true;
   }
-  BwdParams p{(const bf16*)out, (const bf16*)dout, lse, biasT, ldb, B, N, H, scale, scale * kLog2e, (bf16*)dqkv, dsT ? 1 : 0};
-  attention_bwd_tc<<<B * H, kThreads, bwd::SMEM_BYTES, s>>>(tq, tdo, tds, p);
+  const long long rows = (long long)B * N * H;
+  attn_bwd_prep<<<(unsigned)ceil_div<long long>(rows, 256), 256, 0, s>>>((const bf16*)out, (const bf16*)dout, lse, B, N, H,
+                                                                         (float*)workspace);
+  MEMB_LAUNCH_OK("attn_bwd_prep");
+  BwdParams p{(const float*)workspace, biasT, ldb, B, N, H, scale, scale * kLog2e, (bf16*)dqkv, dsT ? 1 : 0};
+  attention_bwd_tc<<<B * H, kBwdThreads, bwd::SMEM_BYTES, s>>>(tq, tdo, tds, p);
   MEMB_LAUNCH_OK("attention_bwd_tc");
   return MEMB_OK;
 }

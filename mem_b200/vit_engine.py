@@ -358,6 +358,7 @@ class VitEngine:
         dz = g("dz", (M, D), bf, dev); dh = g("dh", (M, hidden), bf, dev); dln = g("dln", (M, D), bf, dev)
         dao = g("dao", (M, D), bf, dev); dqkv = g("dqkv", (M, 3 * D), bf, dev)
         ds = g("ds", (B, H, N, ldk), bf, dev)
+        attn_ws = g("attn_ws", (int(lib.memb_attention_bwd_workspace_bytes(B, N, H)),), torch.uint8, dev)
         shared = ctx["shared_bias"] is not None
         dbias_acc = g("dbias_acc", (H, N, ldk), torch.float32, dev)
         if shared:
@@ -387,7 +388,8 @@ class VitEngine:
             _lib.check(lib.memb_attention_bwd(s["qkv"].data_ptr(), s["ao"].data_ptr(), dao.data_ptr(), s["lse"].data_ptr(),
                                               ops._ptr(bias_pair[0]) if bias_pair else None,
                                               ops._ptr(bias_pair[1]) if bias_pair else None, ldk, B, N, H, D // H, scale,
-                                              dqkv.data_ptr(), ds.data_ptr() if bias_pair else None, sp))
+                                              dqkv.data_ptr(), ds.data_ptr() if bias_pair else None,
+                                              attn_ws.data_ptr(), attn_ws.numel(), sp))
             if bias_pair is not None:
                 if not shared:
                     _lib.check(lib.memb_fill_f32(dbias_acc.data_ptr(), dbias_acc.numel(), 0.0, sp))

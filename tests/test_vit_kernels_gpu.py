@@ -116,9 +116,10 @@ def test_attention_fwd_bwd(L, B, N, H, with_bias):
     ref.backward(dout.float())
     dqkv = torch.zeros(B, N, 3 * D, device="cuda", dtype=torch.bfloat16)
     ds = torch.zeros(B, H, N, ldk, device="cuda", dtype=torch.bfloat16) if with_bias else None
+    ws = torch.empty(L.memb_attention_bwd_workspace_bytes(B, N, H), device="cuda", dtype=torch.uint8)
     ck(L.memb_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
                             bias_p.data_ptr() if with_bias else None, biasT_p.data_ptr() if with_bias else None, ldk, B, N, H, 64,
-                            scale, dqkv.data_ptr(), ds.data_ptr() if with_bias else None, sp()))
+                            scale, dqkv.data_ptr(), ds.data_ptr() if with_bias else None, ws.data_ptr(), ws.numel(), sp()))
     g = qkv_r.grad.view(B, N, 3, D)
     got = dqkv.float().view(B, N, 3, D)
     for i, name in enumerate("qkv"):

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Time the fused attention kernels at the ViT-B pretraining shape (B=128, N=197, H=12) and check them
-against a torch fp32 reference at a small batch.  `legacy` also times the mma.sync kernels if exported."""
+against a torch fp32 reference at a small batch. """
 import ctypes, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,7 +13,10 @@ for name in ("memb_attention_fwd_mma", "memb_attention_bwd_mma"):
     if hasattr(L, name):
         fn = getattr(L, name)
         fn.restype = _i32
-        fn.argtypes = _lib.SIGNATURES[name.replace("_mma", "")][1]
+        fn.argtypes = [a for a in _lib.SIGNATURES[name.replace("_mma", "")][1]]
+        if "bwd" in name:
+            del fn.argtypes  # legacy signature has no workspace pair
+            fn.argtypes = _lib.SIGNATURES["memb_attention_bwd"][1][:-3] + [_vp]
 
 
 def rel(a, b):
@@ -36,6 +39,7 @@ def run(B, N, H, check, iters=20):
     dqkv = torch.zeros(B, N, 3 * D, device="cuda", dtype=torch.bfloat16)
     ds = torch.zeros(B, H, N, ldk, device="cuda", dtype=torch.bfloat16)
     scale = 64 ** -0.5
+    ws = torch.empty(L.memb_attention_bwd_workspace_bytes(B, N, H), device="cuda", dtype=torch.uint8)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def fwd(fn):
@@ -46,7 +50,7 @@ def run(B, N, H, check, iters=20):
         legacy = fn is not L.memb_attention_bwd
         _lib.check(fn(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), (bias if legacy else bias_p).data_ptr(),
                       (biasT if legacy else biasT_p).data_ptr(), ldk,
-                      B, N, H, 64, scale, dqkv.data_ptr(), ds.data_ptr(), sp()))
+                      B, N, H, 64, scale, dqkv.data_ptr(), ds.data_ptr(), *(() if legacy else (ws.data_ptr(), ws.numel())), sp()))
 
     def timeit(f):
         f(); torch.cuda.synchronize()
@@ -60,7 +64,8 @@ def run(B, N, H, check, iters=20):
         return ts[len(ts) // 2] * 1e3
 
     res = {}
-    fwd(L.memb_attention_fwd); bwd(L.memb_attention_bwd); torch.cuda.synchronize()
+    fwd(L.memb_attention_fwd); torch.cuda.synchronize(); print("fwd ok", flush=True)
+    bwd(L.memb_attention_bwd); torch.cuda.synchronize(); print("bwd ok", flush=True)
     if check:
         q, k, v = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
         qr, kr, vr = q.clone().requires_grad_(True), k.clone().requires_grad_(True), v.clone().requires_grad_(True)
@@ -83,6 +88,9 @@ def run(B, N, H, check, iters=20):
 
 
 if __name__ == "__main__":
+    if "small" in sys.argv:
+        run(2, 197, 2, True, iters=1)
+        sys.exit(0)
     if "ncu" in sys.argv:
         run(128, 197, 12, False, iters=2)
         sys.exit(0)
