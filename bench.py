@@ -89,6 +89,14 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch of a roofline kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]["bytes"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -158,7 +166,8 @@ class HistogramWorkload:
         return {"bound": "hbm", "kernel": "hist_scatter_global (+init, finalize: whole step timed)",
                 "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
                 "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-                "algorithmic_bytes_per_launch": alg_bytes, "traffic": None}
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": ncu_traffic("hist_scatter_global_10M_640x480") if (self.n, self.W, self.H) == (10_000_000, 640, 480) else None}
 
     # --- reference's CPU path (numpy np.add.at restatement, oracle/histogram_ref.py)
     def cpu_once(self, ev):

@@ -258,10 +258,21 @@ def gemm_roofline(torch, model, B, m, measured_peaks):
     ms = float(np.mean(times))
     fl = 2.0 * M * N * K
     ach = fl / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": f"gemm_tcgen05<bf16, BIAS_GELU> fc1 [{M}x{K}]x[{N}x{K}]^T", "achieved": round(ach, 1),
+    return {"bound": "tensor", "kernel": f"gemm_pair_kernel<256, BIAS_GELU> (CTA-pair tcgen05, bf16) fc1 [{M}x{K}]x[{N}x{K}]^T", "achieved": round(ach, 1),
             "peak": tf_burst, "unit": "TFLOP/s", "frac": round(ach / tf_burst, 4), "peak_source": how + " (MEASURED_PEAKS.json bf16_tflops, burst)",
             "algorithmic_flops_per_launch": fl, "launch_ms": round(ms, 4), "l2": "flushed (256 MB memset) before every timed launch",
-            "traffic": None}
+            "traffic": _traffic("gemm_fc1_bias_gelu_B128") if (M, N, K) == (128 * 197, 3072, 768) else None}
+
+
+def _traffic(key):
+    """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json)."""
+    import json
+    import os
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        return json.load(open(os.path.join(root, "profiles", "ncu_traffic.json")))[key]["bytes"]
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------- CPU arms (oracle port)
