@@ -332,5 +332,29 @@ def main():
         dist.destroy_process_group()
 
 
+def _quiet_stdout_main():
+    """Library chatter (e.g. NCCL's version banner) goes to stderr; stdout carries the JSON line only."""
+    import builtins
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real, "w")
+    orig_print = builtins.print
+
+    def json_print(*a, **k):
+        if len(a) == 1 and isinstance(a[0], str) and a[0].startswith("{") and "file" not in k:
+            out.write(a[0] + "\n")
+            out.flush()
+        else:
+            orig_print(*a, **k)
+    builtins.print = json_print
+    try:
+        main()
+    finally:
+        builtins.print = orig_print
+        sys.stdout.flush()
+        out.flush()
+
+
 if __name__ == "__main__":
-    main()
+    _quiet_stdout_main()
