@@ -263,6 +263,17 @@ int memb_attention_bwd(const void* qkv, const void* out, const void* dout, const
                        const float* biasT, int ld_ds, int B, int N, int H, int head_dim, float scale, void* dqkv,
                        void* dsT, void* workspace, size_t ws_bytes, memb_stream_t stream);
 
+/* Classification head of ft_vit (VisionTransformer.forward_features / forward with mean pooling,
+ * modeling_finetune.py:343-352, 354-357): pooled = mean over patch tokens; small fp32 nn.Linear (D -> num_classes). */
+int memb_meanpool_fwd(const float* x /* [B*N, D] */, int B, int N, int D, float* out /* [B, D] */, memb_stream_t stream);
+int memb_meanpool_bwd(const float* dpool /* [B, D] */, int B, int N, int D, float* gres /* [B*N, D], overwritten */,
+                      memb_stream_t stream);
+int memb_linear_small_fwd(const void* z_bf16 /* [B, D] */, const float* W /* [C, D] */, const float* bias, int B, int D, int C,
+                          float* out /* [B, C] */, memb_stream_t stream);
+int memb_linear_small_bwd(const float* dl /* [B, C] */, const void* z_bf16, const float* W, int B, int D, int C,
+                          float* dW /* += */, float* db /* +=, nullable */, float* dz /* [B, D], overwritten */,
+                          memb_stream_t stream);
+
 /* Flat-buffer optimizer pass (mem/utils.py:357-371 + torch.optim.AdamW with optim_factory.py:121 betas). */
 int memb_fill_f32(float* p, int64_t n, float v, memb_stream_t stream);
 int memb_cast_bf16(const float* src, void* dst, int64_t n, memb_stream_t stream);

@@ -66,6 +66,10 @@ SIGNATURES.update({
     "memb_relpos_gather": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "memb_relpos_scatter": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     "memb_batch_reduce_bf16": (_i32, [_vp, _i32, _i64, _vp, _vp]),
+    "memb_meanpool_fwd": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "memb_meanpool_bwd": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "memb_linear_small_fwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "memb_linear_small_bwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "memb_attention_pack_bias": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "memb_attention_fwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
     "memb_attention_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32]),

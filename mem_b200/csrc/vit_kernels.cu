@@ -482,6 +482,73 @@ __global__ void __launch_bounds__(256) batch_reduce_bf16(const bf16* __restrict_
   st4(acc + i, make_float4(a.x + s.x, a.y + s.y, a.z + s.z, a.w + s.w));
 }
 
+
+// ------------------------------------------------------------------ classification head (ft_vit, config 5)
+// VisionTransformer.forward_features with mean pooling (modeling_finetune.py:343-352): pooled[b] = mean of the patch
+// tokens x[b, 1:, :]; the backward spreads dpooled / P over the patch rows (the cls row gets zero).
+__global__ void __launch_bounds__(256) meanpool_fwd(const float* __restrict__ x, int B, int N, int D, float* __restrict__ out) {
+  const int b = blockIdx.y, col = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (col >= D) return;
+  const float* xb = x + ((long long)b * N + 1) * D + col;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < N - 1; ++t) {
+    const float4 v = ld4(xb + (long long)t * D);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  const float inv = 1.f / (float)(N - 1);
+  st4(out + (long long)b * D + col, make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv));
+}
+__global__ void __launch_bounds__(256) meanpool_bwd(const float* __restrict__ dpool, int B, int N, int D, float* __restrict__ gres) {
+  const long long total = (long long)B * N * D / 4;
+  const float inv = 1.f / (float)(N - 1);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 4, row = e / D;
+    const int col = (int)(e % D), t = (int)(row % N), b = (int)(row / N);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t > 0) { v = ld4(dpool + (long long)b * D + col); v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv; }
+    st4(gres + e, v);
+  }
+}
+// Small dense head (nn.Linear D -> C, C from 2 to ~1000): fp32 CUDA-core kernels, one warp per output.
+__global__ void __launch_bounds__(256) linear_small_fwd(const bf16* __restrict__ z, const float* __restrict__ W,
+                                                        const float* __restrict__ bias, int B, int D, int C,
+                                                        float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * C) return;
+  const int b = warp / C, c = warp % C;
+  float s = 0.f;
+  for (int d = lane * 4; d < D; d += 128) {
+    const float4 a = ld4_bf16(z + (long long)b * D + d), w = ld4(W + (long long)c * D + d);
+    s += a.x * w.x + a.y * w.y + a.z * w.z + a.w * w.w;
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[(long long)b * C + c] = s + (bias ? bias[c] : 0.f);
+}
+// dW[c,d] += sum_b dl[b,c] z[b,d];  db[c] += sum_b dl[b,c];  dz[b,d] = sum_c dl[b,c] W[c,d]
+__global__ void __launch_bounds__(256) linear_small_bwd(const float* __restrict__ dl, const bf16* __restrict__ z,
+                                                        const float* __restrict__ W, int B, int D, int C,
+                                                        float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dz) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long n_w = (long long)C * D, n_z = (long long)B * D;
+  if (i < n_w) {
+    const int c = (int)(i / D), d = (int)(i % D);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dl[(long long)b * C + c] * __bfloat162float(z[(long long)b * D + d]);
+    dW[i] += s;
+    if (d == 0 && db) {
+      float t = 0.f;
+      for (int b = 0; b < B; ++b) t += dl[(long long)b * C + c];
+      db[c] += t;
+    }
+  } else if (i < n_w + n_z) {
+    const long long j = i - n_w;
+    const int b = (int)(j / D), d = (int)(j % D);
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += dl[(long long)b * C + c] * W[(long long)c * D + d];
+    dz[j] = s;
+  }
+}
+
 // ------------------------------------------------------------------ optimizer
 __global__ void __launch_bounds__(256) fill_f32(float* __restrict__ p, long long n, float v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
@@ -688,6 +755,34 @@ extern "C" int memb_batch_reduce_bf16(const void* x, int B, int64_t inner, float
   MEMB_REQUIRE(x && acc && B > 0 && inner > 0 && inner % 4 == 0, "batch_reduce: bad arguments");
   batch_reduce_bf16<<<(unsigned)ceil_div<long long>(inner / 4, 256), 256, 0, s>>>((const bf16*)x, B, inner, acc);
   MEMB_LAUNCH_OK("batch_reduce_bf16");
+  return MEMB_OK;
+}
+
+extern "C" int memb_meanpool_fwd(const float* x, int B, int N, int D, float* out, memb_stream_t s) {
+  MEMB_REQUIRE(x && out && B > 0 && N > 1 && D > 0 && D % 4 == 0, "meanpool_fwd: bad arguments");
+  meanpool_fwd<<<dim3((unsigned)ceil_div(D / 4, 256), (unsigned)B), 256, 0, s>>>(x, B, N, D, out);
+  MEMB_LAUNCH_OK("meanpool_fwd");
+  return MEMB_OK;
+}
+extern "C" int memb_meanpool_bwd(const float* dpool, int B, int N, int D, float* gres, memb_stream_t s) {
+  MEMB_REQUIRE(dpool && gres && B > 0 && N > 1 && D > 0 && D % 4 == 0, "meanpool_bwd: bad arguments");
+  meanpool_bwd<<<flat_grid((long long)B * N * D / 4), 256, 0, s>>>(dpool, B, N, D, gres);
+  MEMB_LAUNCH_OK("meanpool_bwd");
+  return MEMB_OK;
+}
+extern "C" int memb_linear_small_fwd(const void* z, const float* W, const float* bias, int B, int D, int C, float* out,
+                                     memb_stream_t s) {
+  MEMB_REQUIRE(z && W && out && B > 0 && C > 0 && D > 0 && D % 4 == 0, "linear_small_fwd: bad arguments");
+  linear_small_fwd<<<(unsigned)ceil_div<long long>((long long)B * C * 32, 256), 256, 0, s>>>((const bf16*)z, W, bias, B, D, C, out);
+  MEMB_LAUNCH_OK("linear_small_fwd");
+  return MEMB_OK;
+}
+extern "C" int memb_linear_small_bwd(const float* dl, const void* z, const float* W, int B, int D, int C, float* dW, float* db,
+                                     float* dz, memb_stream_t s) {
+  MEMB_REQUIRE(dl && z && W && dW && dz && B > 0 && C > 0 && D > 0, "linear_small_bwd: bad arguments");
+  const long long n = (long long)C * D + (long long)B * D;
+  linear_small_bwd<<<(unsigned)ceil_div<long long>(n, 256), 256, 0, s>>>(dl, (const bf16*)z, W, B, D, C, dW, db, dz);
+  MEMB_LAUNCH_OK("linear_small_bwd");
   return MEMB_OK;
 }
 

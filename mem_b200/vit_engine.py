@@ -311,6 +311,49 @@ class VitEngine:
             out.update(stats=stats, dlogits=dlogits)
         return out
 
+    # ---- classification head (ft_vit): mean pool -> fc_norm -> head --------------------------------
+    def classify_head(self, xlast, ctx):
+        lib = _lib.load()
+        m, c = self.model, ctx["cfg"]
+        dev = xlast.device
+        B, D, N = ctx["B"], c["D"], c["N"]
+        C = m.head.out_features
+        g, sp = self.bufs.get, _sp(device=dev)
+        pooled = g("pooled", (B, D), torch.float32, dev)
+        _lib.check(lib.memb_meanpool_fwd(xlast.data_ptr(), B, N, D, pooled.data_ptr(), sp))
+        z = g("z_cls", (B, D), torch.bfloat16, dev); mu = g("mu_cls", (B,), torch.float32, dev); rs = g("rs_cls", (B,), torch.float32, dev)
+        _ln_fwd(lib, pooled, m.fc_norm.weight, m.fc_norm.bias, m.fc_norm.eps, z, mu, rs, B, D)
+        logits = g("cls_logits", (B, C), torch.float32, dev)
+        _lib.check(lib.memb_linear_small_fwd(z.data_ptr(), m.head.weight.data_ptr(), ops._ptr(m.head.bias), B, D, C,
+                                             logits.data_ptr(), sp))
+        return dict(logits=logits, pooled=pooled, z=z, mu=mu, rs=rs)
+
+    def backward_classify(self, ctx, head, dlogits, bucket_hook=None):
+        """dlogits fp32 [B, num_classes] -> every parameter gradient (accumulated into flat.grad)."""
+        lib = _lib.load()
+        m, flat, c = self.model, self.flat(), ctx["cfg"]
+        B, M, D, N = ctx["B"], ctx["M"], c["D"], c["N"]
+        C = m.head.out_features
+        dev = flat.device
+        g, sp = self.bufs.get, _sp(device=dev)
+        dz = g("dz_cls", (B, D), torch.float32, dev)
+        has_bias = m.head.bias is not None
+        _lib.check(lib.memb_linear_small_bwd(dlogits.data_ptr(), head["z"].data_ptr(), m.head.weight.data_ptr(), B, D, C,
+                                             flat.g("head.weight").data_ptr(), flat.g("head.bias").data_ptr() if has_bias else None,
+                                             dz.data_ptr(), sp))
+        dpool = g("dpool", (B, D), torch.float32, dev)
+        _lib.check(lib.memb_fill_f32(dpool.data_ptr(), dpool.numel(), 0.0, sp))
+        _ln_bwd(lib, dz, head["pooled"], m.fc_norm.weight, head["mu"], head["rs"], B, D, dpool, flat.g("fc_norm.weight"),
+                flat.g("fc_norm.bias"))
+        gres = g("gres", (M, D), torch.float32, dev)
+        _lib.check(lib.memb_meanpool_bwd(dpool.data_ptr(), B, N, D, gres.data_ptr(), sp))
+        if bucket_hook:
+            bucket_hook("head")
+        self._backward_blocks(ctx, gres, bucket_hook)
+        self._backward_embed(ctx, gres)
+        if bucket_hook:
+            bucket_hook("embed")
+
     # ---- backward -----------------------------------------------------------------------------
     def backward_pretrain(self, ctx, head, grad_scale_dev, dlogits=None, bucket_hook=None):
         """Accumulates all parameter gradients into flat.grad.  dlogits (bf16 [cap,V]) defaults to the one
@@ -554,5 +597,38 @@ def pretrain_step(model, samples, bool_masked_pos, tokens, grad_scale_dev=None, 
     return head["stats"]
 
 
+class _ClassifyVitFn(torch.autograd.Function):
+    """logits[B, num_classes] = head(fc_norm(mean over patch tokens of blocks(embed(x)))) with a kernel backward
+    that accumulates into the flat gradient buffer (``VisionTransformer.forward``, modeling_finetune.py:343-357)."""
+
+    @staticmethod
+    def forward(ctx, model, x, droppath, *params):
+        eng = engine_of(model)
+        need_grad = bool(ctx.needs_input_grad and any(ctx.needs_input_grad[3:]))
+        xlast, fctx = eng.forward_features(x, None, need_grad, droppath)
+        head = eng.classify_head(xlast, fctx)
+        ctx.eng, ctx.fctx, ctx.head = eng, fctx, head
+        return head["logits"].clone()
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        eng = ctx.eng
+        flat = eng.flat()
+        bind_param_grads(flat, flat.params)
+        eng.backward_classify(ctx.fctx, ctx.head, grad_logits.contiguous().float())
+        return (None,) * (3 + len(flat.params))
+
+
 def classify_forward(model, x):
-    raise NotImplementedError("ft_vit forward: see vit_engine.classify_* (config 5)")
+    """``VisionTransformer.forward`` of ft_vit (mem/modeling_finetune.py:354-357), mean-pooling head."""
+    _lib.require_cuda()
+    if not x.is_cuda:
+        raise RuntimeError("mem_b200 models run on CUDA tensors only (no CPU path)")
+    if getattr(model, "fc_norm", None) is None:
+        raise NotImplementedError("ft_vit without mean pooling (cls-token head) is outside the MEM hot path (configs use "
+                                  "use_mean_pooling=True, run_class_finetuning.py:118)")
+    eng = engine_of(model)
+    dp = droppath_scales(model, x.shape[0], x.device, model.training)
+    flat = eng.flat()
+    params = [flat.params[n] for n in flat.names]
+    return _ClassifyVitFn.apply(model, x, dp, *params)

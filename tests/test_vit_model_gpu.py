@@ -120,3 +120,60 @@ def test_gradient_accumulates_and_zero_grad():
     opt.zero_grad()                                            # set_to_none
     vit_engine.pretrain_step(model, img, mask, tokens)
     assert rel(model.lm_head.weight.grad, g1) < 1e-2
+
+
+def test_tiny_ft_vit_matches_golden_and_oracle(golden_dir):
+    """ft_vit (modeling_finetune path, BASELINE config 5 shape family): per-block rel-pos tables, mean pooling,
+    fc_norm, 2-class head; logits / loss vs the reference golden, every gradient vs the fp32 oracle."""
+    from mem_b200 import modeling_finetune  # noqa: F401
+    gold = np.load(os.path.join(golden_dir, "vit_tiny.npz"))
+    model = registry.create_model("ft_vit", **vit_ref.TINY_FT)
+    sd = vit_ref.synth_state_dict(model.state_dict(), seed=12)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    img, _, _ = vit_ref.synth_inputs(4, 3, 112, 112, 49, 2, seed=6, n_mask=1)
+    target = torch.tensor([0, 1, 1, 0]).cuda()
+    logits = model(img.cuda())
+    g_logits = torch.from_numpy(gold["ft/logits"]).cuda()
+    assert logits.shape == g_logits.shape == (4, 2)
+    assert (logits - g_logits).abs().max().item() < 3e-2 * max(g_logits.abs().max().item(), 1e-3) + 2e-3
+    loss = torch.nn.functional.cross_entropy(logits, target)
+    assert abs(loss.item() - float(gold["ft/loss"])) < 2e-2 * float(gold["ft/loss"])
+    loss.backward()
+    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    ref_loss = torch.nn.functional.cross_entropy(vit_ref.classify_logits(img, sdr, heads=2, patch=16), target.cpu())
+    ref_loss.backward()
+    _compare_grads(model, {k: v.grad.cuda() for k, v in sdr.items() if v.is_floating_point() and v.grad is not None})
+    model.eval()
+    with torch.no_grad():
+        ev = model(img.cuda())
+    assert (ev - g_logits).abs().max().item() < 3e-2 * max(g_logits.abs().max().item(), 1e-3) + 2e-3
+
+
+def test_ft_vit_base_forward_backward_vs_oracle():
+    """BASELINE config 5: ViT-B/16 finetuning forward/backward, N-Cars-shaped 2-class synthetic histograms (C=3)."""
+    from mem_b200 import modeling_finetune  # noqa: F401
+    torch.manual_seed(0)
+    kw = dict(img_size=(224, 224), patch_size=(16, 16), in_chans=3, num_classes=2, embed_dim=768, depth=12, num_heads=12,
+              mlp_ratio=4, init_values=0.1, use_rel_pos_bias=True, use_abs_pos_emb=False, use_mean_pooling=True,
+              drop_path_rate=0.0)
+    model = registry.create_model("ft_vit", **kw)
+    sd = vit_ref.synth_state_dict(model.state_dict(), seed=4)
+    for k in sd:
+        if sd[k].is_floating_point() and sd[k].dim() >= 2 and "relative_position" not in k and not k.startswith("head"):
+            sd[k] = sd[k] * 0.4
+    model.load_state_dict(sd)
+    model.cuda().train()
+    B = 4
+    img, _, _ = vit_ref.synth_inputs(B, 3, 224, 224, 196, 2, seed=8, n_mask=1)
+    target = torch.tensor([0, 1, 1, 0]).cuda()
+    logits = model(img.cuda())
+    loss = torch.nn.functional.cross_entropy(logits, target)
+    loss.backward()
+    sdr = {k: (v.cuda().requires_grad_(True) if v.is_floating_point() else v.cuda()) for k, v in sd.items()}
+    ref_logits = vit_ref.classify_logits(img.cuda(), sdr, heads=12, patch=16)
+    ref_loss = torch.nn.functional.cross_entropy(ref_logits, target)
+    ref_loss.backward()
+    assert (logits - ref_logits).abs().max().item() < 3e-2 * ref_logits.abs().max().item() + 2e-3
+    assert abs(loss.item() - ref_loss.item()) < 2e-2 * ref_loss.item()
+    _compare_grads(model, {k: v.grad for k, v in sdr.items() if v.is_floating_point() and v.grad is not None})
