@@ -177,3 +177,26 @@ def test_ft_vit_base_forward_backward_vs_oracle():
     assert (logits - ref_logits).abs().max().item() < 3e-2 * ref_logits.abs().max().item() + 2e-3
     assert abs(loss.item() - ref_loss.item()) < 2e-2 * ref_loss.item()
     _compare_grads(model, {k: v.grad for k, v in sdr.items() if v.is_floating_point() and v.grad is not None})
+
+
+def test_vit_large_step_vs_oracle():
+    """BASELINE config 4 architecture: ViT-L/16 (D 1024, 24 blocks, 16 heads, init_values 1e-5) MEM step at batch 2."""
+    torch.manual_seed(0)
+    kw = dict(drop_path_rate=0.0, use_shared_rel_pos_bias=True, use_abs_pos_emb=False, init_values=1e-5, in_chans=2)
+    model = registry.create_model("beit_large_patch16_224_8k_vocab", **kw)
+    sd = vit_ref.synth_state_dict(model.state_dict(), seed=5)
+    for k in sd:
+        if sd[k].is_floating_point() and sd[k].dim() >= 2 and "relative_position" not in k:
+            sd[k] = sd[k] * 0.3
+        if "gamma_" in k:
+            sd[k] = sd[k] * 0.0 + 0.05   # LayerScale large enough for the branches to matter in the comparison
+    model.load_state_dict(sd)
+    model.cuda().train()
+    B = 2
+    img, mask, tokens = vit_ref.synth_inputs(B, 2, 224, 224, 196, 8192, seed=9, n_mask=75)
+    stats = vit_engine.pretrain_step(model, img.cuda(), mask.cuda(), tokens.cuda())
+    n = int(mask.sum())
+    loss = stats[0].item() / n
+    ref_loss, ref_acc, ref_logits, ref_grads = _oracle(sd, img, mask, tokens, 16, 16, "cuda")
+    assert abs(loss - ref_loss) < 2e-2 * ref_loss, (loss, ref_loss)
+    _compare_grads(model, ref_grads)
