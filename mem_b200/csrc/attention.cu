@@ -19,7 +19,7 @@
 //            registers, preloaded with the bias: x = s*scale*log2e + bias*log2e, row max exchanged through smem,
 //            p = 2^(x-m) -> bf16 P tile in swizzled smem (the A operand of the PV MMA), then the O epilogue
 //            (1/l, bf16, global) and lse.
-// Backward (one CTA per (b, h), 320 threads: 8 elementwise warps, one warp issuing batch 1, one issuing batch 2), keys on the M axis so that P^T / dS^T come out of TMEM in the
+// Backward (one CTA per (b, h), 576 threads: 16 elementwise warps, one warp issuing batch 1, one issuing batch 2), keys on the M axis so that P^T / dS^T come out of TMEM in the
 // orientation dV = P^T dO, dK = dS^T Q and dQ = dS K need; per key tile t the queries go by in chunks of 64:
 //   batch 1 (chunk g):  S^T = K_t Q_g^T, dP^T = V_t dO_g^T                    (TMEM buffer g & 1)
 //   elementwise:        p = 2^(s*c1 + b - lse2), ds = p (dp - delta) -> bf16 P^T (slot g & 1), dS^T (4 slots) in smem
@@ -44,7 +44,8 @@ constexpr int kHeadDim = 64;
 constexpr int kMaxN = 208;                    // 13 x 16
 constexpr int kLoadBytes = kMaxN * 128;       // one TMA box: [208 rows][64 bf16]
 constexpr int kFwdThreads = 512;              // 12 softmax warps + a control warpgroup (1 working warp)
-constexpr int kBwdThreads = 320;              // 8 elementwise warps + 2 MMA-issuing warps
+constexpr int kBwdThreads = 576;              // 16 elementwise warps + 2 MMA-issuing warps
+constexpr int kBwdEw = 512;                   // elementwise threads
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kBiasGroups = MEMB_ATTN_BIAS_GROUPS;  // packed bias: [H][52 column groups][256 rows][4]
@@ -242,6 +243,8 @@ attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // the control warpgroup hands its registers to the softmax warps
     if (warp == 12 && lane == 0) {
       // -------------------------------------------------------------------------- control thread
+      // (a single-thread branch: the `if (elect_one())` form makes ptxas 12.9 predicate these UTCHMMAs, the shape it
+      //  mis-schedules; the backward issuers, whose MMAs it leaves unpredicated, do use it)
       const uint32_t sq = smem_u32(smem + OFF_Q), sk = smem_u32(smem + OFF_K), sv = smem_u32(smem + OFF_V);
       const uint32_t spp = smem_u32(smem + OFF_P);
       constexpr uint32_t idesc_s = make_idesc(1, false, false, 128, kMaxN);
@@ -264,6 +267,7 @@ attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p
       uint32_t ph = 0;
       for (int head = blockIdx.x; head < nheads; head += gridDim.x, ph ^= 1) {
         const bool first = head == (int)blockIdx.x;
+        const int next = head + gridDim.x;
         mbar_wait(&bar[B_QK], ph, nullptr, 1);
         // Both query tiles are always issued (tile 1 of a short sequence computes rows nobody reads): ptxas 12.9
         // mis-schedules the descriptor moves of a predicated UTCHMMA, so the MMAs below carry no predicate.
@@ -277,7 +281,6 @@ attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p
           umma_commit(&bar[B_S0 + t]);
         }
         mbar_wait(&bar[B_S1], ph, nullptr, 3);  // both S tiles done: Q and K are free
-        const int next = head + gridDim.x;
         if (next < nheads) load_qk(next);
         mbar_wait(&bar[B_V], ph, nullptr, 4);
 #pragma unroll
@@ -342,6 +345,15 @@ attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p
 }
 
 // =========================================================================================== backward
+#ifdef MEMB_ATTN_TRACE
+// debug timeline of one CTA: three writers (elementwise thread 0, issuer 1, issuer 2), 512 slots each, no atomics
+__device__ long long g_trace[3 * 512 * 2];
+#define TRACE_DECL(role) int trace_i_ = (role) * 512
+#define TRACE(id) do { if (blockIdx.x == MEMB_ATTN_TRACE) { g_trace[2 * trace_i_] = (id); g_trace[2 * trace_i_ + 1] = clock64(); ++trace_i_; } } while (0)
+#else
+#define TRACE_DECL(role) do {} while (0)
+#define TRACE(id) do {} while (0)
+#endif
 namespace bwd {
 constexpr int OFF_Q = 0;                        // [208][128 B]
 constexpr int OFF_DO = kLoadBytes;              // [208][128 B]
@@ -395,22 +407,19 @@ __global__ void __launch_bounds__(256) attn_bwd_prep(const bf16* __restrict__ ou
   nl_delta[total + o] = d;
 }
 
-// G (32 or 8) query columns of this thread's key row: S^T, dP^T -> P^T, dS^T (bf16, swizzled smem slots).
+// G (16 or 8) query columns of this thread's key row: S^T, dP^T -> P^T, dS^T (bf16, swizzled smem slots).
 template <int G>
-__device__ __forceinline__ void bwd_group(const BwdParams& p, uint8_t* smem, uint32_t taddr, const float4 (&breg)[8], bool kv,
+__device__ __forceinline__ void bwd_group(const BwdParams& p, uint8_t* smem, uint32_t taddr, const float4 (&breg)[4], bool kv,
                                           int q0 /* global query index */, int cl0 /* column within the chunk */, int rl,
                                           uint32_t spt, uint32_t sdst) {
   using namespace bwd;
-  float s[G], dp[G];
-  if constexpr (G == 32) {
-    tmem_ld32f(taddr, s);
-    tmem_ld32f(taddr + 64, dp);
+  uint32_t sr[G], dr[G];
+  if constexpr (G == 16) {
+    tmem_ld16(taddr, sr);
+    tmem_ld16(taddr + 64, dr);
   } else {
-    uint32_t a[8], c[8];
-    tmem_ld8(taddr, a);
-    tmem_ld8(taddr + 64, c);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] = __uint_as_float(a[i]); dp[i] = __uint_as_float(c[i]); }
+    tmem_ld8(taddr, sr);
+    tmem_ld8(taddr + 64, dr);
   }
   tmem_ld_wait();
   const float* nl = reinterpret_cast<const float*>(smem + OFF_NL);
@@ -429,8 +438,8 @@ __device__ __forceinline__ void bwd_group(const BwdParams& p, uint8_t* smem, uin
       float pe[8], de[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        pe[j] = ex2(fmaf(s[8 * c + j], p.c1, bb[j] + nn[j]));  // nn = -inf for q >= N -> p = 0
-        de[j] = pe[j] * (dp[8 * c + j] - dd[j]);
+        pe[j] = ex2(fmaf(__uint_as_float(sr[8 * c + j]), p.c1, bb[j] + nn[j]));  // nn = -inf for q >= N -> p = 0
+        de[j] = pe[j] * (__uint_as_float(dr[8 * c + j]) - dd[j]);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -443,19 +452,17 @@ __device__ __forceinline__ void bwd_group(const BwdParams& p, uint8_t* smem, uin
   }
 }
 
-// 64 fp32 accumulator columns of this thread's TMEM lane -> bf16 row (128 B) in global memory
-__device__ __forceinline__ void store_acc_row(uint32_t taddr, float mul, bf16* dst, bool valid) {
-  float v[64];
+// 32 fp32 accumulator columns of this thread's TMEM lane -> bf16, four 16-byte chunks of row `rl` of a swizzled
+// [128][64] staging tile (the layout a SWIZZLE_128B TMA store expects)
+__device__ __forceinline__ void stage_acc32(uint32_t taddr, float mul, uint32_t stage, int rl, int chunk0) {
+  float v[32];
   tmem_ld32f(taddr, v);
-  tmem_ld32f(taddr + 32, v + 32);
   tmem_ld_wait();
-  if (valid) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      reinterpret_cast<uint4*>(dst)[i] =
-          make_uint4(pack_bf16(v[8 * i] * mul, v[8 * i + 1] * mul), pack_bf16(v[8 * i + 2] * mul, v[8 * i + 3] * mul),
-                     pack_bf16(v[8 * i + 4] * mul, v[8 * i + 5] * mul), pack_bf16(v[8 * i + 6] * mul, v[8 * i + 7] * mul));
-  }
+  for (int i = 0; i < 4; ++i)
+    st_shared_v4(sw128(stage, rl, chunk0 + i), pack_bf16(v[8 * i] * mul, v[8 * i + 1] * mul),
+                 pack_bf16(v[8 * i + 2] * mul, v[8 * i + 3] * mul), pack_bf16(v[8 * i + 4] * mul, v[8 * i + 5] * mul),
+                 pack_bf16(v[8 * i + 6] * mul, v[8 * i + 7] * mul));
 }
 
 // NQ k-steps of 16 queries: dV_t += P^T dO_j, dK_t += dS^T Q_j.  Descriptor address fields count 16-byte units.
@@ -477,7 +484,7 @@ __device__ __forceinline__ void issue_dq(uint32_t tmem_d, uint64_t dds, uint64_t
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attention_bwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                 const __grid_constant__ CUtensorMap tmap_ds, const BwdParams p) {
+                 const __grid_constant__ CUtensorMap tmap_ds, const __grid_constant__ CUtensorMap tmap_dqkv, const BwdParams p) {
   using namespace bwd;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -489,15 +496,15 @@ attention_bwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
   const int nch = min(4, (p.N + 63) / 64);        // query chunks (64 wide; the 4th is 16 wide)
   const int npair = (nch + 1) >> 1;
 
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0) {
-      prefetch_tmap(&tmap_qkv); prefetch_tmap(&tmap_do); prefetch_tmap(&tmap_ds);
+      prefetch_tmap(&tmap_qkv); prefetch_tmap(&tmap_do); prefetch_tmap(&tmap_ds); prefetch_tmap(&tmap_dqkv);
       mbar_init(&bar[B_LOAD], 1);
       mbar_init(&bar[B_S0], 1); mbar_init(&bar[B_S1], 1);
-      mbar_init(&bar[B_PD0], 256); mbar_init(&bar[B_PD1], 256);
+      mbar_init(&bar[B_PD0], kBwdEw / 2); mbar_init(&bar[B_PD1], kBwdEw / 2);
       mbar_init(&bar[B_B20], 1); mbar_init(&bar[B_B21], 1);
       mbar_init(&bar[B_ACC], 1);
-      mbar_init(&bar[B_ACCFREE], 256);
+      mbar_init(&bar[B_ACCFREE], kBwdEw);
       fence_barrier_init();
       mbar_arrive_expect_tx(&bar[B_LOAD], 4 * kLoadBytes);
       tma_load_2d(smem + OFF_K, &tmap_qkv, &bar[B_LOAD], (p.H + h) * kHeadDim, b * p.N);
@@ -507,7 +514,7 @@ attention_bwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
     }
     __syncwarp();
     tmem_alloc(tmem_slot, 512);
-  } else if (warp < 8) {
+  } else if (warp < 8) {  // 256 threads fill the two 256-entry vectors
     float* nl = reinterpret_cast<float*>(smem + OFF_NL);
     float* dl = reinterpret_cast<float*>(smem + OFF_DELTA);
     const int q = threadIdx.x;
@@ -522,54 +529,59 @@ attention_bwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
   const uint32_t sq = smem_u32(smem + OFF_Q), sdo = smem_u32(smem + OFF_DO), sk = smem_u32(smem + OFF_K);
   const uint32_t sv = smem_u32(smem + OFF_V), spt = smem_u32(smem + OFF_PT), sdst = smem_u32(smem + OFF_DST);
 
-  if (warp == 8) {
-    if (lane == 0) {
-      // ---------------------------------------------------- issuer 1: S^T = K_t Q_j^T, dP^T = V_t dO_j^T -> TMEM buffer g & 1
-      constexpr uint32_t idesc_s64 = make_idesc(1, false, false, 128, 64);
-      constexpr uint32_t idesc_s16 = make_idesc(1, false, false, 128, 16);
-      const uint64_t dk0 = make_smem_desc_sw128(sk, 0, 1024), dq0 = make_smem_desc_sw128(sq, 0, 1024);
-      const uint64_t dv0 = make_smem_desc_sw128(sv, 0, 1024), ddo0 = make_smem_desc_sw128(sdo, 0, 1024);
-      auto issue_b1 = [&](int g, int t, int j) {
+  if (warp == 16) {
+    // ---------------------------------------------------- issuer 1: S^T = K_t Q_j^T, dP^T = V_t dO_j^T -> TMEM buffer g & 1
+    // (the whole warp walks the loop; one elected lane issues, so ptxas emits straight-line UTCHMMA)
+    constexpr uint32_t idesc_s64 = make_idesc(1, false, false, 128, 64);
+    constexpr uint32_t idesc_s16 = make_idesc(1, false, false, 128, 16);
+    const uint64_t dk0 = make_smem_desc_sw128(sk, 0, 1024), dq0 = make_smem_desc_sw128(sq, 0, 1024);
+    const uint64_t dv0 = make_smem_desc_sw128(sv, 0, 1024), ddo0 = make_smem_desc_sw128(sdo, 0, 1024);
+    mbar_wait(&bar[B_LOAD], 0, nullptr, 1);
+    tc_fence_after();
+    TRACE_DECL(1);
+    TRACE(2);
+    int g = 0;
+    for (int t = 0; t < nt; ++t)
+      for (int j = 0; j < nch; ++j, ++g) {
         const int buf = g & 1;
-        const uint32_t idesc = j < 3 ? idesc_s64 : idesc_s16;
-        const uint64_t a_off = (uint64_t)(t * 1024), b_off = (uint64_t)(j * 512);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tmem_base + 128 * buf, dk0 + a_off + (uint64_t)(ks * 2), dq0 + b_off + (uint64_t)(ks * 2), idesc, ks != 0);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tmem_base + 128 * buf + 64, dv0 + a_off + (uint64_t)(ks * 2), ddo0 + b_off + (uint64_t)(ks * 2), idesc, ks != 0);
-        umma_commit(&bar[B_S0 + buf]);
-      };
-      mbar_wait(&bar[B_LOAD], 0, nullptr, 1);
-      tc_fence_after();
-      int g = 0;
-      for (int t = 0; t < nt; ++t)
-        for (int j = 0; j < nch; ++j, ++g) {
-          if (g >= 2) {  // chunk g-2 has left this TMEM buffer
-            mbar_wait(&bar[B_PD0 + (g & 1)], ((g - 2) >> 1) & 1, nullptr, 2);
-            tc_fence_after();
-          }
-          issue_b1(g, t, j);
-        }
-    }
-  } else if (warp == 9) {
-    if (lane == 0) {
-      // ---------------------------------------------------- issuer 2: dV, dK, dQ accumulation + dS^T store
-      constexpr uint32_t idesc_kv = make_idesc(1, false, true, 128, kHeadDim);  // A K-major (P^T / dS^T), B MN-major
-      constexpr uint32_t idesc_dq = make_idesc(1, true, true, 128, kHeadDim);   // A MN-major (dS), B MN-major (K)
-      const uint64_t dpt0 = make_smem_desc_sw128(spt, 0, 1024), ddst0 = make_smem_desc_sw128(sdst, 0, 1024);
-      const uint64_t ddo0 = make_smem_desc_sw128(sdo, 8192, 1024), dq0 = make_smem_desc_sw128(sq, 8192, 1024);
-      const uint64_t dds0 = make_smem_desc_sw128(sdst, 16384, 1024), dk0 = make_smem_desc_sw128(sk, 8192, 1024);
-      mbar_wait(&bar[B_LOAD], 0, nullptr, 3);
-      int g = 0;
-      for (int t = 0; t < nt; ++t)
-        for (int j = 0; j < nch; ++j, ++g) {
-          const int buf = g & 1;
-          const int slot = 2 * ((t * npair + (j >> 1)) & 1) + (j & 1);
-          mbar_wait(&bar[B_PD0 + buf], (g >> 1) & 1, nullptr, 4);  // P^T, dS^T of chunk g are in smem
-          if (t == 1 && j == 0) mbar_wait(&bar[B_ACCFREE], 0, nullptr, 5);  // dV_0 / dK_0 have been read out
+        if (g >= 2) {  // chunk g-2 has left this TMEM buffer
+          mbar_wait(&bar[B_PD0 + buf], ((g - 2) >> 1) & 1, nullptr, 2);
           tc_fence_after();
+        }
+        TRACE(100 + g);
+        if (elect_one()) {
+          const uint32_t idesc = j < 3 ? idesc_s64 : idesc_s16;
+          const uint64_t a_off = (uint64_t)(t * 1024), b_off = (uint64_t)(j * 512);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem_base + 128 * buf, dk0 + a_off + (uint64_t)(ks * 2), dq0 + b_off + (uint64_t)(ks * 2), idesc, ks != 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem_base + 128 * buf + 64, dv0 + a_off + (uint64_t)(ks * 2), ddo0 + b_off + (uint64_t)(ks * 2), idesc, ks != 0);
+          umma_commit(&bar[B_S0 + buf]);
+        }
+        __syncwarp();
+        TRACE(200 + g);
+      }
+  } else if (warp == 17) {
+    // ---------------------------------------------------- issuer 2: dV, dK, dQ accumulation + dS^T store
+    constexpr uint32_t idesc_kv = make_idesc(1, false, true, 128, kHeadDim);  // A K-major (P^T / dS^T), B MN-major
+    constexpr uint32_t idesc_dq = make_idesc(1, true, true, 128, kHeadDim);   // A MN-major (dS), B MN-major (K)
+    const uint64_t dpt0 = make_smem_desc_sw128(spt, 0, 1024), ddst0 = make_smem_desc_sw128(sdst, 0, 1024);
+    const uint64_t ddo0 = make_smem_desc_sw128(sdo, 8192, 1024), dq0 = make_smem_desc_sw128(sq, 8192, 1024);
+    const uint64_t dds0 = make_smem_desc_sw128(sdst, 16384, 1024), dk0 = make_smem_desc_sw128(sk, 8192, 1024);
+    mbar_wait(&bar[B_LOAD], 0, nullptr, 3);
+    TRACE_DECL(2);
+    int g = 0;
+    for (int t = 0; t < nt; ++t)
+      for (int j = 0; j < nch; ++j, ++g) {
+        const int buf = g & 1;
+        const int slot = 2 * ((t * npair + (j >> 1)) & 1) + (j & 1);
+        mbar_wait(&bar[B_PD0 + buf], (g >> 1) & 1, nullptr, 4);  // P^T, dS^T of chunk g are in smem
+        TRACE(300 + g);
+        if (t == 1 && j == 0) mbar_wait(&bar[B_ACCFREE], 0, nullptr, 5);  // dV_0 / dK_0 have been read out
+        tc_fence_after();
+        if (elect_one()) {
           const uint64_t a_pt = dpt0 + (uint64_t)(buf * 1024), a_dst = ddst0 + (uint64_t)(slot * 1024);
           const uint64_t b_off = (uint64_t)(j * 512);
           if (j < 3) issue_dv_dk<4>(tmem_base, a_pt, a_dst, ddo0 + b_off, dq0 + b_off, idesc_kv, j == 0);
@@ -588,60 +600,97 @@ attention_bwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
             bulk_commit();
           }
         }
-      if (p.write_ds) bulk_wait<0>();
-    }
-  } else {
+        __syncwarp();
+        TRACE(400 + g);
+      }
+    if (p.write_ds && elect_one()) bulk_wait_read<0>();
+    __syncwarp();
+  } else if (warp < 16) {
     // ------------------------------------------------------------------------------ elementwise / epilogue warps
-    const int quarter = warp & 3, half = warp >> 2;
+    // two groups of 8 warps take the even / odd chunks (each on its own TMEM buffer and P^T slot), so that one
+    // group's barrier round trips hide behind the other group's math
+    const int grp = warp >> 3, w8 = warp & 7;
+    const int quarter = warp & 3, half = w8 >> 2;
+    const int part = warp >> 2;  // epilogue role: 4 x (tile half / 32-column half)
     const int rl = quarter * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const long long rs = 3LL * p.H * kHeadDim;
-    bf16* dq_base = p.dqkv + (long long)b * p.N * rs + h * kHeadDim;
+    TRACE_DECL(0);
     int g = 0;
     for (int t = 0; t < nt; ++t) {
       const int key = t * 128 + rl;
       const bool kv = key < p.N;
       for (int j = 0; j < nch; ++j, ++g) {
+        if ((g & 1) != grp) continue;
         const int buf = g & 1;
         const int slot = 2 * ((t * npair + (j >> 1)) & 1) + (j & 1);
-        const int cl0 = j < 3 ? half * 32 : half * 8;  // first column (within the chunk) of this thread
+        const bool wide = j < 3;                       // 64-query chunk: 32 columns per thread; last chunk: 8
+        const int cl0 = wide ? half * 32 : half * 8;   // first column (within the chunk) of this thread
         const int q0 = j * 64 + cl0;
-        // bias^T values of this thread's columns, issued before the wait
-        float4 breg[8];
+        // bias^T values of this thread's columns, issued before the waits
+        float4 br0[4], br1[4];
         {
-          const int nb = j < 3 ? 8 : 2;
           const float4* bt = reinterpret_cast<const float4*>(p.biasT) + ((long long)h * kBiasGroups + (q0 >> 2)) * 256 + key;
+          const bool on = p.biasT && kv;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            breg[i] = (p.biasT && kv && i < nb && q0 + 4 * i < p.N) ? ldg_f4(bt + i * 256) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 4; ++i) {
+            br0[i] = (on && (wide || i < 2) && q0 + 4 * i < p.N) ? ldg_f4(bt + i * 256) : make_float4(0.f, 0.f, 0.f, 0.f);
+            br1[i] = (on && wide && q0 + 16 + 4 * i < p.N) ? ldg_f4(bt + (4 + i) * 256) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
+        if (warp == 0 && lane == 0) TRACE(500 + g);
         mbar_wait(&bar[B_S0 + buf], (g >> 1) & 1, nullptr, 6);
         if (g >= 2) mbar_wait(&bar[B_B20 + buf], ((g - 2) >> 1) & 1, nullptr, 7);  // P^T slot (and dS^T slot) reusable
         tc_fence_after();
-        if (j < 3) bwd_group<32>(p, smem, tlane + 128 * buf + cl0, breg, kv, q0, cl0, rl, spt + buf * 16384, sdst + slot * 16384);
-        else bwd_group<8>(p, smem, tlane + 128 * buf + cl0, breg, kv, q0, cl0, rl, spt + buf * 16384, sdst + slot * 16384);
+        if (warp == 0 && lane == 0) TRACE(700 + g);
+        const uint32_t ta = tlane + 128 * buf + cl0, s_pt = spt + buf * 16384, s_ds = sdst + slot * 16384;
+        if (wide) {
+          bwd_group<16>(p, smem, ta, br0, kv, q0, cl0, rl, s_pt, s_ds);
+          bwd_group<16>(p, smem, ta + 16, br1, kv, q0 + 16, cl0 + 16, rl, s_pt, s_ds);
+        } else {
+          bwd_group<8>(p, smem, ta, br0, kv, q0, cl0, rl, s_pt, s_ds);
+        }
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(&bar[B_PD0 + buf]);
+        if (warp == 0 && lane == 0) TRACE(800 + g);
       }
-      // tile finished: dV_t (half 0) / dK_t (half 1)
+      // tile finished: dV_t (parts 0, 1) / dK_t (parts 2, 3), 32 columns each -> staging tiles in the two (now idle)
+      // P^T slots -> coalesced TMA stores, clipped at the sequence end
       mbar_wait(&bar[B_ACC], t & 1, nullptr, 8);
       tc_fence_after();
-      bf16* dst = dq_base + (long long)key * rs + (half ? 1 : 2) * p.H * kHeadDim;
-      store_acc_row(tlane + (half ? COL_DK : COL_DV), half ? p.scale : 1.f, dst, kv);
-      tc_fence_before();
-      mbar_arrive(&bar[B_ACCFREE]);
+      if (threadIdx.x == 0) TRACE(900 + t);
+      {
+        const bool is_k = part >= 2;
+        stage_acc32(tlane + (is_k ? COL_DK : COL_DV) + (part & 1) * 32, is_k ? p.scale : 1.f, spt + (is_k ? 16384 : 0), rl,
+                    (part & 1) * 4);
+        tc_fence_before();
+        mbar_arrive(&bar[B_ACCFREE]);
+        fence_proxy_async();
+        named_bar_sync(2, kBwdEw);
+        if (threadIdx.x == 0) {
+          tma_store_3d(&tmap_dqkv, spt, (2 * p.H + h) * kHeadDim, t * 128, b);
+          tma_store_3d(&tmap_dqkv, spt + 16384, (p.H + h) * kHeadDim, t * 128, b);
+          bulk_commit();
+          bulk_wait_read<0>();
+        }
+        named_bar_sync(2, kBwdEw);  // the P^T slots are writable again
+      }
     }
-    // dQ: query tile `half` (the last B_ACC phase covers every MMA of issuer 2)
-    if (half < nt) {
-      const int q = half * 128 + rl;
-      store_acc_row(tlane + COL_DQ + 64 * half, p.scale, dq_base + (long long)q * rs, q < p.N);
+    // dQ: query tile (part >> 1), column half (part & 1)   (the last B_ACC phase covers every MMA of issuer 2)
+    if ((part >> 1) < nt)
+      stage_acc32(tlane + COL_DQ + 64 * (part >> 1) + (part & 1) * 32, p.scale, spt + (part >> 1) * 16384, rl, (part & 1) * 4);
+    fence_proxy_async();
+    named_bar_sync(2, kBwdEw);
+    if (threadIdx.x == 0) {
+      for (int t = 0; t < nt; ++t) tma_store_3d(&tmap_dqkv, spt + t * 16384, h * kHeadDim, t * 128, b);
+      bulk_commit();
+      bulk_wait_read<0>();  // smem may be released once the TMA unit has read it; the writes land before the grid ends
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -719,6 +768,16 @@ extern "C" int memb_attention_fwd(const void* qkv, const float* bias, int ldb, i
   return MEMB_OK;
 }
 
+#ifdef MEMB_ATTN_TRACE
+extern "C" int memb_attention_trace_dump(long long* host, int max_pairs) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * 2 * 1536);
+  static long long zeros[2 * 1536];
+  cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros));
+  return 1536;
+}
+#endif
+
 extern "C" size_t memb_attention_bwd_workspace_bytes(int B, int N, int H) {
   return (size_t)2 * (size_t)B * (size_t)N * (size_t)H * sizeof(float);
 }
@@ -732,7 +791,12 @@ extern "C" int memb_attention_bwd(const void* qkv, const void* out, const void* 
   MEMB_REQUIRE(ws_bytes >= memb_attention_bwd_workspace_bytes(B, N, H), "attention_bwd: workspace too small");
   MEMB_REQUIRE((bias == nullptr) == (biasT == nullptr), "attention_bwd: bias and its transpose go together");
   MEMB_REQUIRE(!biasT || (reinterpret_cast<uintptr_t>(biasT) & 15u) == 0, "attention_bwd: biasT must be 16-byte aligned");
-  CUtensorMap tq, tdo, tds;
+  CUtensorMap tq, tdo, tds, tdq;
+  {
+    const long long dims[3] = {3LL * H * kHeadDim, N, B}, str[2] = {3LL * H * kHeadDim, (long long)N * 3 * H * kHeadDim};
+    const int box[3] = {64, 128, 1};
+    if (int rc = make_tmap_bf16(&tdq, dqkv, 3, dims, str, box)) return rc;
+  }
   {
     const long long dims[2] = {3LL * H * kHeadDim, (long long)B * N}, str[1] = {3LL * H * kHeadDim};
     const int box[2] = {64, kMaxN};
@@ -760,7 +824,7 @@ extern "C" int memb_attention_bwd(const void* qkv, const void* out, const void* 
                                                                          (float*)workspace);
   MEMB_LAUNCH_OK("attn_bwd_prep");
   BwdParams p{(const float*)workspace, biasT, ldb, B, N, H, scale, scale * kLog2e, (bf16*)dqkv, dsT ? 1 : 0};
-  attention_bwd_tc<<<B * H, kBwdThreads, bwd::SMEM_BYTES, s>>>(tq, tdo, tds, p);
+  attention_bwd_tc<<<B * H, kBwdThreads, bwd::SMEM_BYTES, s>>>(tq, tdo, tds, tdq, p);
   MEMB_LAUNCH_OK("attention_bwd_tc");
   return MEMB_OK;
 }
