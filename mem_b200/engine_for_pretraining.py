@@ -63,6 +63,48 @@ class _StepStats:
         return self.host.tolist()
 
 
+class _PrefetchToDevice:
+    """Iterates ``data_loader`` yielding ``((samples, images, mask, n_masked), rest...)`` with the tensors already on
+    ``device``: the host->device copies of batch k+1 run on a side stream while step k computes (the reference copies
+    inside the step, engine_for_pretraining.py:136-138; with pinned DataLoader memory the copy time leaves the step)."""
+
+    def __init__(self, data_loader, device):
+        self.loader, self.device = data_loader, device
+        self.side = torch.cuda.Stream(device=device)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _load(self, item):
+        batch, rest = item[0], item[1:]
+        samples, images, mask = batch
+        # masked-patch count from the host copy of the mask: sizes the lm_head / CE kernels without a device sync
+        n_masked = int(mask.ne(0).sum()) if not mask.is_cuda else None
+        with torch.cuda.stream(self.side):
+            moved = tuple(t.to(self.device, non_blocking=True) for t in (samples, images, mask))
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        return moved, n_masked, ev, rest
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._load(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            (samples, images, mask), n_masked, ev, rest = nxt
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            for t in (samples, images, mask):
+                t.record_stream(cur)
+            try:
+                nxt = self._load(next(it))
+            except StopIteration:
+                nxt = None
+            yield ((samples, images, mask, n_masked),) + tuple(rest)
+
+
 def train_one_epoch(model: torch.nn.Module, d_vae: torch.nn.Module, data_loader: Iterable,
                     optimizer: torch.optim.Optimizer, device: torch.device, epoch: int, loss_scaler, max_norm: float = 0,
                     log_writer=None, lr_scheduler=None, start_steps=None, lr_schedule_values=None,
@@ -82,7 +124,7 @@ def train_one_epoch(model: torch.nn.Module, d_vae: torch.nn.Module, data_loader:
         optimizer.grad_divisor = float(utils.get_world_size())
     hand_off = _StepStats(device)
 
-    for step, (batch, _) in enumerate(metric_logger.log_every(data_loader, 10, header)):
+    for step, (batch, _) in enumerate(metric_logger.log_every(_PrefetchToDevice(data_loader, device), 10, header)):
         it = start_steps + step
         if lr_schedule_values is not None or wd_schedule_values is not None:
             for group in optimizer.param_groups:
@@ -91,12 +133,7 @@ def train_one_epoch(model: torch.nn.Module, d_vae: torch.nn.Module, data_loader:
                 if wd_schedule_values is not None and group["weight_decay"] > 0:
                     group["weight_decay"] = wd_schedule_values[it]
 
-        samples, images, bool_masked_pos = batch
-        # masked-patch count from the host copy of the mask: sizes the lm_head / CE kernels without a device sync
-        n_masked = int(bool_masked_pos.ne(0).sum()) if not bool_masked_pos.is_cuda else None
-        images = images.to(device, non_blocking=True)
-        samples = samples.to(device, non_blocking=True)
-        bool_masked_pos = bool_masked_pos.to(device, non_blocking=True)
+        samples, images, bool_masked_pos, n_masked = batch   # already on the device (prefetched on a side stream)
 
         with torch.no_grad():
             input_ids = d_vae.get_codebook_indices(images).flatten(1)      # [B, P] int64

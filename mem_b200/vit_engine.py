@@ -480,18 +480,23 @@ def droppath_scales(model, B, device, training):
     generator in the order the reference would draw them (attention branch, then MLP branch)."""
     if not training:
         return None
-    out, any_dp = [], False
-    for blk in model.blocks:
-        p = float(getattr(blk.drop_path, "drop_prob", 0.0) or 0.0)
-        if p > 0.0:
-            keep = 1.0 - p
-            s1 = (torch.rand(B, device=device) + keep).floor_().div_(keep)
-            s2 = (torch.rand(B, device=device) + keep).floor_().div_(keep)
-            out.append((s1, s2))
-            any_dp = True
-        else:
-            out.append((None, None))
-    return out if any_dp else None
+    probs = [float(getattr(blk.drop_path, "drop_prob", 0.0) or 0.0) for blk in model.blocks]
+    idx = [i for i, p in enumerate(probs) if p > 0.0]
+    if not idx:
+        return None
+    # one batched draw for all blocks (3 launches instead of 8 per block); the per-block keep probabilities live on the
+    # device once per (model, device)
+    cache = getattr(model, "_memb_dp_keep", None)
+    if cache is None or cache[0] != (tuple(probs), str(device)):
+        keep = torch.tensor([1.0 - probs[i] for i in idx], dtype=torch.float32).view(-1, 1, 1).to(device)
+        cache = ((tuple(probs), str(device)), keep)
+        object.__setattr__(model, "_memb_dp_keep", cache)
+    keep = cache[1]
+    scales = (torch.rand(len(idx), 2, B, device=device) + keep).floor_().div_(keep)
+    out = [(None, None)] * len(probs)
+    for k, i in enumerate(idx):
+        out[i] = (scales[k, 0], scales[k, 1])
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
