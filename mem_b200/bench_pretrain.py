@@ -67,7 +67,8 @@ def synth_batch(torch, B, seed, device, cfg=CFG):
     random.seed(seed)
     gen = MaskingGenerator((H // cfg["patch"],) * 2, cfg["num_mask"], min_num_patches=cfg["min_mask"])
     masks = torch.from_numpy(np.stack([gen() for _ in range(B)])).long()
-    return img.contiguous(), img.clone(), masks
+    img = img.contiguous()   # NCHW-contiguous, what a DataLoader's default collate hands the engine
+    return img, img.clone(), masks
 
 
 class Step:

@@ -63,28 +63,55 @@ class _StepStats:
         return self.host.tolist()
 
 
+_STAGING = {}   # device index -> two slots of {position in the batch tuple: device buffer}
+
+
 class _PrefetchToDevice:
     """Iterates ``data_loader`` yielding ``((samples, images, mask, n_masked), rest...)`` with the tensors already on
     ``device``: the host->device copies of batch k+1 run on a side stream while step k computes (the reference copies
-    inside the step, engine_for_pretraining.py:136-138; with pinned DataLoader memory the copy time leaves the step)."""
+    inside the step, engine_for_pretraining.py:136-138; with pinned DataLoader memory the copy time leaves the step).
+
+    The copies land in two persistent staging slots per device (batch k in slot k % 2), allocated once and reused by
+    every epoch: a fresh ``.to(device)`` per step costs a ``cudaMalloc`` (tens of ms) whenever the caching allocator
+    has no free block on the side stream, which was the first one or two steps of every epoch.  The yielded tensors
+    are views of a slot and stay valid until the batch after next is loaded."""
 
     def __init__(self, data_loader, device):
         self.loader, self.device = data_loader, device
         self.side = torch.cuda.Stream(device=device)
+        self.slots = _STAGING.setdefault(torch.device(device).index or 0, [{}, {}])
+        self.k = 0
 
     def __len__(self):
         return len(self.loader)
+
+    def _stage(self, slot, pos, t):
+        # same shape, dtype AND strides as the source, so that the copy is one plain memcpy (a layout change would
+        # make ``copy_`` restage the tensor on the host, synchronously)
+        buf = slot.get(pos)
+        if buf is None or buf.dtype != t.dtype or buf.shape != t.shape or buf.stride() != t.stride():
+            buf = slot[pos] = torch.empty_like(t, device=self.device)   # on the compute stream; a short last batch
+        return buf                                                       # re-allocates once, which is harmless
 
     def _load(self, item):
         batch, rest = item[0], item[1:]
         samples, images, mask = batch
         # masked-patch count from the host copy of the mask: sizes the lm_head / CE kernels without a device sync
         n_masked = int(mask.ne(0).sum()) if not mask.is_cuda else None
+        slot = self.slots[self.k % 2]
+        self.k += 1
+        cur = torch.cuda.current_stream(self.device)
+        dst = tuple(self._stage(slot, i, t) for i, t in enumerate((samples, images, mask)))
+        # the slot's previous batch (two loads ago) was consumed by work already enqueued on the compute stream
+        free = torch.cuda.Event()
+        free.record(cur)
         with torch.cuda.stream(self.side):
-            moved = tuple(t.to(self.device, non_blocking=True) for t in (samples, images, mask))
+            self.side.wait_event(free)
+            for d, t in zip(dst, (samples, images, mask)):
+                d.copy_(t, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.side)
-        return moved, n_masked, ev, rest
+        return dst, n_masked, ev, rest
 
     def __iter__(self):
         it = iter(self.loader)
@@ -94,10 +121,7 @@ class _PrefetchToDevice:
             return
         while nxt is not None:
             (samples, images, mask), n_masked, ev, rest = nxt
-            cur = torch.cuda.current_stream(self.device)
-            cur.wait_event(ev)
-            for t in (samples, images, mask):
-                t.record_stream(cur)
+            torch.cuda.current_stream(self.device).wait_event(ev)
             try:
                 nxt = self._load(next(it))
             except StopIteration:
