@@ -78,6 +78,52 @@ int memb_hist_status(const void* ws, memb_stream_t stream);
 int memb_hist_extent(const double* ev, int64_t n, int64_t* max_xy_host, void* ws, size_t ws_bytes,
                      memb_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Event-space augmentations fused into the rasteriser, and the post-raster
+ * tensor transforms.  Replaces, for one batch in one pass,
+ * the per-sample numpy chain of build_transformNPY (mem/datasets.py:611-660):
+ *   ReshapeScaleXandY (:464-485)  x *= scale_x, y *= scale_y
+ *   SliceRandomMaxEvs (:488-498)  rows [start, start+count) of the stream
+ *   RandomTimeFlip    (:598-608)  p = -p (row order and t only matter to the time surface)
+ *   Aug_FlipEvsAlongX (:501-521)  x = flip_w - 1 - x
+ *   Aug_RandomShiftEvs(:524-549)  x += shift_x, y += shift_y, rows outside [0,cull_w)x[0,cull_h) dropped
+ *   EventArrToImg     (:552-595)  -> uint8 counts
+ * and then ToTensor (/255), RandomCrop(pad_if_needed), RemoveTimesurface, RemoveHotPixels(num_stds),
+ * NormalizeEvent (mem/transforms.py:225-275) -> float32 [B,C,outH,outW].
+ * The random draws stay on the host (they consume Python's / numpy's / torch's global generators in the
+ * reference's order, mem_b200/event_pipeline.py); the device applies them.  All float64 event arithmetic
+ * is done with single correctly rounded operations in the reference's order, so the counts are bit-exact.
+ * ---------------------------------------------------------------------- */
+typedef struct memb_event_aug {   /* one per stream, 64 bytes, device memory */
+  double scale_x, scale_y;        /* 1.0 = off */
+  int64_t start, count;           /* window inside the stream; count < 0: to the end of the stream */
+  int32_t time_flip;              /* != 0: polarity inverted */
+  int32_t flip_x, flip_w;         /* != 0: x = (flip_w - 1) - x */
+  int32_t cull;                   /* != 0: shift, then drop rows outside the cull window */
+  int32_t shift_x, shift_y, cull_w, cull_h;
+} memb_event_aug;
+
+/* As memb_hist_u8 (same workspace size, strategies AUTO / GLOBAL / GLOBAL_AGG / TILE, no time surface),
+ * with stream b transformed by aug[b] on the fly.  aug: device array [B]. */
+int memb_hist_aug_u8(const double* ev, int64_t n, const int64_t* offsets, int B, int64_t max_stream_len,
+                     const memb_event_aug* aug, int H, int W, int C, int strategy, uint8_t* out,
+                     void* ws, size_t ws_bytes, memb_stream_t stream);
+
+/* hist    : uint8 [B,H,W,C] counts, C == 3 [pos, ts, neg] or C == 2 [pos, neg].
+ * crop_tl : device int32 [B,2] (top, left) of the outH x outW window in the (virtually) padded image, or NULL
+ *           for (0,0); pad_t / pad_l: rows / columns of zero padding torchvision's RandomCrop(pad_if_needed)
+ *           put before the image (the window may also run past the bottom / right edge into padding).
+ * remove_ts     : zero the middle channel (RemoveTimesurface; C == 3 only).
+ * hot_num_stds  : < 0 off; else zero, in both polarity channels, every pixel where either exceeds
+ *                 mean + num_stds * std (unbiased) of the cropped polarity channels (RemoveHotPixels).
+ * normalize     : divide the polarity channels by their maximum when it is not 0 (NormalizeEvent).
+ * out     : float32 [B,C,outH,outW].  Workspace: memb_raster_post_workspace_bytes(B). */
+size_t memb_raster_post_workspace_bytes(int B);
+int memb_raster_post_f32(const uint8_t* hist, int B, int H, int W, int C, const int32_t* crop_tl, int pad_t,
+                         int pad_l, int outH, int outW, int remove_ts, float hot_num_stds, int normalize,
+                         float* out, void* ws, size_t ws_bytes, memb_stream_t stream);
+
+
 
 /* ------------------------------------------------------------------------
  * tcgen05 GEMM with fused epilogues:  D[M,N] = epi( A[M,K] * B[N,K]^T ).

@@ -31,6 +31,7 @@ struct Header {
 };
 
 struct Event { double x, y, t, p; };
+static_assert(sizeof(memb_event_aug) == 64, "memb_event_aug is part of the ABI: 64 bytes");
 
 template <bool kAligned>
 __device__ __forceinline__ Event load_event(const double* __restrict__ ev, long long row) {
@@ -63,6 +64,29 @@ __device__ __forceinline__ unsigned long long order_key(double v) {
 __device__ __forceinline__ double key_value(unsigned long long k) {
   unsigned long long b = (k >> 63) ? (k ^ 0x8000000000000000ull) : ~k;
   return __longlong_as_double((long long)b);
+}
+
+// ---------------------------------------------------------------- fused event-space augmentation
+// One correctly rounded float64 operation per reference statement, in the reference's order
+// (datasets.py:482-484 scale, :603-606 time flip, :518-519 x flip, :541-546 shift + cull).
+// Returns false for a row the shift stage drops.
+__device__ __forceinline__ bool apply_aug(Event& e, const memb_event_aug& a) {
+  e.x = __dmul_rn(e.x, a.scale_x);
+  e.y = __dmul_rn(e.y, a.scale_y);
+  if (a.time_flip) e.p = -e.p;
+  if (a.flip_x) e.x = __dsub_rn((double)(a.flip_w - 1), e.x);
+  if (a.cull) {
+    e.x = __dadd_rn(e.x, (double)a.shift_x);
+    e.y = __dadd_rn(e.y, (double)a.shift_y);
+    return e.x >= 0.0 && e.x < (double)a.cull_w && e.y >= 0.0 && e.y < (double)a.cull_h;
+  }
+  return true;
+}
+
+// Row range of stream b after the SliceRandomMaxEvs window (datasets.py:494-497).
+__device__ __forceinline__ void aug_window(const memb_event_aug& a, long long& begin, long long& end) {
+  begin = min(end, begin + max((long long)a.start, 0LL));
+  if (a.count >= 0) end = min(end, begin + (long long)a.count);
 }
 
 // ---------------------------------------------------------------- init
@@ -110,9 +134,15 @@ template <bool kAligned, bool kAggregate, bool kTss>
 __global__ void __launch_bounds__(kThreads) hist_scatter_global(
     const double* __restrict__ ev, const long long* __restrict__ offsets, long long n_total, int W,
     long long npix, unsigned int* __restrict__ acc, unsigned long long* __restrict__ last,
-    Header* __restrict__ hdr) {
+    Header* __restrict__ hdr, const memb_event_aug* __restrict__ aug) {
   const int b = blockIdx.y;
-  const long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
+  long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
+  memb_event_aug a;
+  const bool has_aug = aug != nullptr;
+  if (has_aug) {
+    a = aug[b];
+    aug_window(a, begin, end);
+  }
   unsigned int* acc_b = acc + (long long)b * 2 * npix;
   unsigned long long* last_b = kTss ? last + (long long)b * npix : nullptr;
   bool bad = false;
@@ -130,6 +160,7 @@ __global__ void __launch_bounds__(kThreads) hist_scatter_global(
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
+      if (has_aug && live[u]) live[u] = apply_aug(e[u], a);
       long long idx = 0;
       const bool pos = live[u] && e[u].p == 1.0, neg = live[u] && e[u].p == -1.0;
       const bool need = kTss ? live[u] : (pos || neg);
@@ -204,10 +235,17 @@ __global__ void __launch_bounds__(256) hist_finalize(const unsigned int* __restr
 template <bool kAligned>
 __global__ void __launch_bounds__(kTileThreads, 1) hist_tile_smem(
     const double* __restrict__ ev, const long long* __restrict__ offsets, long long n_total, int W,
-    long long npix, int tile_pix, int C, uint8_t* __restrict__ out, Header* __restrict__ hdr) {
+    long long npix, int tile_pix, int C, uint8_t* __restrict__ out, Header* __restrict__ hdr,
+    const memb_event_aug* __restrict__ aug) {
   extern __shared__ unsigned int tile[];
   const int b = blockIdx.y;
-  const long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
+  long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
+  memb_event_aug a;
+  const bool has_aug = aug != nullptr;
+  if (has_aug) {
+    a = aug[b];
+    aug_window(a, begin, end);
+  }
   const long long lo = (long long)blockIdx.x * tile_pix;
   const int mine = (int)min((long long)tile_pix, npix - lo);
   for (int i = threadIdx.x; i < tile_pix; i += kTileThreads) tile[i] = 0u;
@@ -227,6 +265,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) hist_tile_smem(
       }
 #pragma unroll
       for (int u = 0; u < kTileUnroll; ++u) {
+        if (has_aug && live[u]) live[u] = apply_aug(e[u], a);
         const bool pos = live[u] && e[u].p == 1.0, neg = live[u] && e[u].p == -1.0;
         if (pos || neg) {
           long long idx;
@@ -363,9 +402,9 @@ extern "C" size_t memb_hist_workspace_bytes(int B, int64_t n, int H, int W, int 
   return make_plan(B, n, H, W, timesurface, strategy).ws_bytes;
 }
 
-extern "C" int memb_hist_u8(const double* ev, int64_t n, const int64_t* offsets, int B,
-                            int64_t max_stream_len, int H, int W, int C, int timesurface, int strategy,
-                            uint8_t* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
+static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, int64_t max_stream_len,
+                    const memb_event_aug* aug, int H, int W, int C, int timesurface, int strategy,
+                    uint8_t* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
   MEMB_REQUIRE(B >= 1 && H >= 1 && W >= 1, "hist: B, H, W must be positive (B=%d H=%d W=%d)", B, H, W);
   MEMB_REQUIRE(C == 2 || C == 3, "hist: C must be 2 or 3, got %d", C);
   MEMB_REQUIRE(!(timesurface && C != 3), "hist: the time surface needs C == 3");
@@ -405,7 +444,7 @@ extern "C" int memb_hist_u8(const double* ev, int64_t n, const int64_t* offsets,
       MEMB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxWords * 4));
       attr_set[aligned] = true;
     }
-    kern<<<dim3(p.tiles, B), kTileThreads, smem, stream>>>(ev, offs, n, W, npix, p.tile_pix, C, out, hdr);
+    kern<<<dim3(p.tiles, B), kTileThreads, smem, stream>>>(ev, offs, n, W, npix, p.tile_pix, C, out, hdr, aug);
     MEMB_LAUNCH_OK("hist_tile_smem");
     return MEMB_OK;
   }
@@ -425,7 +464,7 @@ extern "C" int memb_hist_u8(const double* ev, int64_t n, const int64_t* offsets,
   if (n > 0) {
     const bool agg = p.strategy == MEMB_HIST_GLOBAL_AGG;
 #define MEMB_SCATTER(A, G, T)                                                                        \
-  hist_scatter_global<A, G, T><<<grid, kThreads, 0, stream>>>(ev, offs, n, W, npix, acc, last, hdr)
+  hist_scatter_global<A, G, T><<<grid, kThreads, 0, stream>>>(ev, offs, n, W, npix, acc, last, hdr, aug)
     if (timesurface) {
       if (aligned) { if (agg) MEMB_SCATTER(true, true, true); else MEMB_SCATTER(true, false, true); }
       else { if (agg) MEMB_SCATTER(false, true, true); else MEMB_SCATTER(false, false, true); }
@@ -444,6 +483,21 @@ extern "C" int memb_hist_u8(const double* ev, int64_t n, const int64_t* offsets,
     MEMB_LAUNCH_OK("hist_finalize");
   }
   return MEMB_OK;
+}
+
+extern "C" int memb_hist_u8(const double* ev, int64_t n, const int64_t* offsets, int B,
+                            int64_t max_stream_len, int H, int W, int C, int timesurface, int strategy,
+                            uint8_t* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
+  return run_hist(ev, n, offsets, B, max_stream_len, nullptr, H, W, C, timesurface, strategy, out, ws, ws_bytes,
+                  stream);
+}
+
+extern "C" int memb_hist_aug_u8(const double* ev, int64_t n, const int64_t* offsets, int B,
+                                int64_t max_stream_len, const memb_event_aug* aug, int H, int W, int C,
+                                int strategy, uint8_t* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
+  MEMB_REQUIRE(aug != nullptr, "hist_aug: null augmentation array");
+  MEMB_REQUIRE((((uintptr_t)aug) & 7u) == 0, "hist_aug: misaligned augmentation array");
+  return run_hist(ev, n, offsets, B, max_stream_len, aug, H, W, C, 0, strategy, out, ws, ws_bytes, stream);
 }
 
 extern "C" int memb_hist_status(const void* ws, memb_stream_t stream) {

@@ -1,0 +1,225 @@
+"""Events -> model input for a whole batch on the GPU: event-space augmentations fused into the rasteriser,
+then the post-raster tensor transforms.
+
+Drop-in for what ``build_transformNPY`` composes per sample on the CPU (reference ``mem/datasets.py:611-660``,
+fixed-sensor N-ImageNet path): ``ReshapeScaleXandY`` -> ``SliceRandomMaxEvs`` -> ``RandomTimeFlip`` ->
+``Aug_FlipEvsAlongX`` -> ``Aug_RandomShiftEvs`` -> ``EventArrToImg`` -> ``ToTensor`` -> ``RandomCrop`` ->
+``RemoveTimesurface`` -> ``RemoveHotPixels`` -> ``NormalizeEvent``.
+
+Division of labour: the random draws stay on the host and consume Python's ``random``, ``numpy.random`` and
+``torch``'s global generators exactly like the reference chain does, sample by sample (``draw_params``; same idea as
+``MaskingGenerator``); the arithmetic runs on the device for the whole batch: ``memb_hist_aug_u8`` (one pass over the
+raw float64 rows, bit-exact counts) and ``memb_raster_post_f32`` (uint8 counts -> float32 [B,C,h,w]).
+
+Not covered (raise / documented in DESIGN.md): variable sensor size (``H = W = None``, N-Caltech101 / N-Cars paths and
+their bilinear ``Resize``), the time surface together with augmentations, ``LogTransform`` / ``GammaTransform``,
+``ColorJitter`` and ``EventRandAugment``.
+"""
+from __future__ import annotations
+
+import ctypes
+import random
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["PipelineConfig", "EventAug", "draw_params", "pack_params", "rasterise_augmented", "post_raster",
+           "EventBatchPipeline"]
+
+
+class EventAug(ctypes.Structure):
+    """``memb_event_aug`` (include/memb.h), 64 bytes."""
+    _fields_ = [("scale_x", ctypes.c_double), ("scale_y", ctypes.c_double), ("start", ctypes.c_int64),
+                ("count", ctypes.c_int64), ("time_flip", ctypes.c_int32), ("flip_x", ctypes.c_int32),
+                ("flip_w", ctypes.c_int32), ("cull", ctypes.c_int32), ("shift_x", ctypes.c_int32),
+                ("shift_y", ctypes.c_int32), ("cull_w", ctypes.c_int32), ("cull_h", ctypes.c_int32)]
+
+
+AUG_DTYPE = np.dtype([("scale_x", "<f8"), ("scale_y", "<f8"), ("start", "<i8"), ("count", "<i8"), ("time_flip", "<i4"),
+                      ("flip_x", "<i4"), ("flip_w", "<i4"), ("cull", "<i4"), ("shift_x", "<i4"), ("shift_y", "<i4"),
+                      ("cull_w", "<i4"), ("cull_h", "<i4")])
+assert AUG_DTYPE.itemsize == ctypes.sizeof(EventAug) == 64
+
+
+@dataclass
+class PipelineConfig:
+    """The ``args`` fields ``build_transformNPY`` reads (run_mem_pretraining.py:48-57,80-81), fixed sensor."""
+    is_train: bool = True
+    sensor_H: int = 480
+    sensor_W: int = 640
+    input_H: int = 224
+    input_W: int = 224
+    slice_max_evs: int = 30000
+    max_random_shift_evs: int = 15
+    timesurface: bool = False
+    hotpixfilter: bool = True
+    hotpix_num_stds: float = 10
+    normalize_events: bool = False
+
+    def __post_init__(self):
+        # the reference's own range checks (datasets.py:466-469, 491, 530)
+        assert 100 <= self.input_H <= 640 and 100 <= self.input_W <= 640
+        assert 100 <= self.sensor_H <= 640 and 100 <= self.sensor_W <= 640
+        assert 5000 <= self.slice_max_evs < 200000
+        assert 0 <= self.max_random_shift_evs <= 200
+
+    def scales(self):
+        """(scale_x, scale_y) of ReshapeScaleXandY (datasets.py:472-480)."""
+        if self.is_train:
+            hw = [self.sensor_H, self.sensor_W]
+            s = 256 / hw[int(np.argmin(hw))]
+            return s, s
+        return self.input_W / self.sensor_W, self.input_H / self.sensor_H
+
+    def raster_hw(self):
+        """(H, W) the rasteriser runs at (datasets.py:616-621)."""
+        if self.is_train:
+            scale = 256 / 480
+            return int(480 * scale), int(640 * scale)
+        return self.input_H, self.input_W
+
+
+def draw_params(n_events: int, cfg: PipelineConfig) -> dict:
+    """One sample's random draws, consuming the global generators in the reference's order:
+    ``random.choice`` (slice start, only when the stream is longer than ``slice_max_evs``, datasets.py:495-496),
+    ``np.random.random`` (time flip, :603), ``np.random.random`` (x flip, :518), ``np.random.randint(size=(2,))``
+    (shift, :541), ``torch.randint`` twice (torchvision ``RandomCrop.get_params``: top, then left)."""
+    import torch
+    H, W = cfg.raster_hw()
+    sx, sy = cfg.scales()
+    p = dict(scale_x=sx, scale_y=sy, start=0, count=n_events, time_flip=False, flip_x=False, flip_w=W, cull=False,
+             shift_x=0, shift_y=0, cull_w=W, cull_h=H, top=0, left=0)
+    if n_events > cfg.slice_max_evs:
+        p["start"] = random.choice(range(n_events - cfg.slice_max_evs + 1))
+        p["count"] = cfg.slice_max_evs
+    if cfg.is_train:
+        p["time_flip"] = bool(np.random.random() < 0.5)
+        p["flip_x"] = bool(np.random.random() < 0.5)
+        xs, ys = np.random.randint(-cfg.max_random_shift_evs, cfg.max_random_shift_evs + 1, size=(2,))
+        p["shift_x"], p["shift_y"], p["cull"] = int(xs), int(ys), True
+        ph = H + 2 * max(cfg.input_H - H, 0)        # RandomCrop pads both sides when the image is smaller
+        pw = W + 2 * max(cfg.input_W - W, 0)
+        if not (ph == cfg.input_H and pw == cfg.input_W):
+            p["top"] = int(torch.randint(0, ph - cfg.input_H + 1, size=(1,)).item())
+            p["left"] = int(torch.randint(0, pw - cfg.input_W + 1, size=(1,)).item())
+    return p
+
+
+def pack_params(params) -> tuple[np.ndarray, np.ndarray]:
+    """List of ``draw_params`` dicts -> (``memb_event_aug`` records [B], crop (top, left) int32 [B,2])."""
+    aug = np.zeros(len(params), dtype=AUG_DTYPE)
+    crop = np.zeros((len(params), 2), dtype=np.int32)
+    for i, p in enumerate(params):
+        aug[i] = (p["scale_x"], p["scale_y"], p["start"], p["count"], int(p["time_flip"]), int(p["flip_x"]), p["flip_w"],
+                  int(p["cull"]), p["shift_x"], p["shift_y"], p["cull_w"], p["cull_h"])
+        crop[i] = (p["top"], p["left"])
+    return aug, crop
+
+
+def rasterise_augmented(events, offsets, aug, H, W, channels=3, *, max_stream_len=None, strategy=_lib.HIST_AUTO,
+                        check=True, out=None):
+    """Ragged batch of raw streams + per-stream ``memb_event_aug`` records -> ``uint8 (B,H,W,channels)`` on the device.
+
+    events ``float64 (sum N_b, 4)`` CUDA tensor (or numpy / CPU tensor: copied), offsets ``int64 (B+1,)``,
+    aug: numpy structured array (``AUG_DTYPE``) or a ``uint8 (B*64,)`` / ``(B,64)`` CUDA tensor holding the records."""
+    torch = _lib.require_cuda()
+    from .process_data import _as_device_events
+    device = torch.device(events.device if (isinstance(events, torch.Tensor) and events.is_cuda) else "cuda")
+    with torch.cuda.device(device):
+        ev, _ = _as_device_events(torch, events, device)
+        off = offsets if isinstance(offsets, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64))
+        off = off.to(device=device, dtype=torch.int64).contiguous()
+        B = int(off.numel()) - 1
+        if B < 1:
+            raise ValueError("offsets must have B+1 >= 2 entries")
+        if isinstance(aug, np.ndarray):
+            if aug.dtype != AUG_DTYPE or aug.shape != (B,):
+                raise ValueError(f"aug must be a ({B},) array of memb_event_aug records")
+            aug_dev = torch.from_numpy(aug.view(np.uint8).reshape(B, 64)).to(device)
+        else:
+            aug_dev = aug.to(device).contiguous()
+            if aug_dev.dtype != torch.uint8 or aug_dev.numel() != B * 64:
+                raise ValueError("aug tensor must hold B 64-byte memb_event_aug records (uint8)")
+        if out is None:
+            out = torch.empty((B, H, W, channels), dtype=torch.uint8, device=device)
+        n = int(ev.shape[0])
+        lib = _lib.load()
+        need = lib.memb_hist_workspace_bytes(B, n, H, W, 0, strategy)
+        ws = _lib.workspace.get(torch, need, device, "hist")
+        stream = _lib.stream_ptr(torch, device)
+        _lib.check(lib.memb_hist_aug_u8(ev.data_ptr() if n else None, n, off.data_ptr(), B,
+                                        int(max_stream_len if max_stream_len is not None else n), aug_dev.data_ptr(),
+                                        H, W, channels, strategy, out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        if check:
+            _lib.check(lib.memb_hist_status(ws.data_ptr(), stream))
+    return out
+
+
+def post_raster(hist, crop_tl=None, out_hw=None, *, remove_timesurface=True, hot_num_stds=10.0, normalize=False,
+                out=None):
+    """``uint8 (B,H,W,C)`` counts -> ``float32 (B,C,outH,outW)``: /255, crop (zero padding like
+    ``RandomCrop(pad_if_needed=True)``), RemoveTimesurface, RemoveHotPixels (``hot_num_stds=None`` = off), NormalizeEvent.
+
+    crop_tl: ``int32 (B,2)`` (top, left) in the padded image (numpy or tensor) or None for (0,0)."""
+    torch = _lib.require_cuda()
+    if not (isinstance(hist, torch.Tensor) and hist.is_cuda and hist.dtype == torch.uint8 and hist.ndim == 4):
+        raise ValueError("hist must be a uint8 CUDA tensor (B,H,W,C)")
+    hist = hist.contiguous()
+    B, H, W, C = (int(v) for v in hist.shape)
+    outH, outW = (H, W) if out_hw is None else (int(out_hw[0]), int(out_hw[1]))
+    pad_t, pad_l = max(outH - H, 0), max(outW - W, 0)
+    device = hist.device
+    with torch.cuda.device(device):
+        crop = None
+        if crop_tl is not None:
+            crop = crop_tl if isinstance(crop_tl, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(crop_tl, dtype=np.int32))
+            crop = crop.to(device=device, dtype=torch.int32).contiguous()
+            if tuple(crop.shape) != (B, 2):
+                raise ValueError(f"crop_tl must be ({B}, 2)")
+        if out is None:
+            out = torch.empty((B, C, outH, outW), dtype=torch.float32, device=device)
+        lib = _lib.load()
+        ws = _lib.workspace.get(torch, max(lib.memb_raster_post_workspace_bytes(B), 16), device, "raster_post")
+        _lib.check(lib.memb_raster_post_f32(hist.data_ptr(), B, H, W, C, crop.data_ptr() if crop is not None else None,
+                                            pad_t, pad_l, outH, outW, int(bool(remove_timesurface)),
+                                            float(hot_num_stds) if hot_num_stds is not None else -1.0, int(bool(normalize)),
+                                            out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch, device)))
+    return out
+
+
+class EventBatchPipeline:
+    """Batched GPU replacement of ``build_transformNPY(is_train, args)`` for fixed-sensor data.
+
+    ``pipe(streams)`` with ``streams`` a list of ``(N_b, 4)`` float64 arrays (or ``(events, offsets)`` already
+    concatenated) returns ``float32 (B, C, input_H, input_W)`` on the device, equal to stacking the reference
+    transform's outputs when the generators start from the same state and samples are drawn in order."""
+
+    def __init__(self, cfg: PipelineConfig, channels: int = 3, device="cuda"):
+        if cfg.timesurface:
+            raise NotImplementedError("the fused augmentation path rasterises polarity counts only (no time surface)")
+        self.cfg, self.channels, self.device = cfg, channels, device
+
+    def __call__(self, streams, offsets=None, params=None):
+        torch = _lib.require_cuda()
+        if offsets is None:
+            lens = [len(s) for s in streams]
+            offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            events = np.concatenate([np.asarray(s, dtype=np.float64).reshape(-1, 4) for s in streams], axis=0) \
+                if sum(lens) else np.zeros((0, 4))
+        else:
+            events = streams
+            off_host = offsets.cpu().numpy() if isinstance(offsets, torch.Tensor) else np.asarray(offsets)
+            lens = np.diff(off_host).tolist()
+        cfg = self.cfg
+        if params is None:
+            params = [draw_params(int(n), cfg) for n in lens]
+        aug, crop = pack_params(params)
+        H, W = cfg.raster_hw()
+        hist = rasterise_augmented(events, offsets, aug, H, W, self.channels,
+                                   max_stream_len=int(max(p["count"] for p in params)) if params else 0,
+                                   check=not cfg.is_train)   # after the cull every row is inside the sensor
+        return post_raster(hist, crop if cfg.is_train else None, (cfg.input_H, cfg.input_W) if cfg.is_train else None,
+                           remove_timesurface=not cfg.timesurface,
+                           hot_num_stds=cfg.hotpix_num_stds if cfg.hotpixfilter else None, normalize=cfg.normalize_events)

@@ -221,8 +221,39 @@ def golden_engine():
     np.savez_compressed(os.path.join(GOLD, "engine_tiny.npz"), **out)
 
 
+def golden_event_pipeline():
+    """Reference build_transformNPY (mem/datasets.py:611-660) on seeded synthetic N-ImageNet-shaped streams.
+
+    Inputs are regenerated from the stored seeds (``synth_events``), outputs are stored: the (3,h,w) float32 tensor
+    the reference chain returns, plus the RNG seeds it ran under."""
+    import torch
+    from types import SimpleNamespace
+    ds = ref_shims.ref_module("datasets")
+    out = {}
+    cases = [  # name, is_train, n_events, kind, normalize, seed
+        ("train_a", True, 45000, "edge", 1, 11), ("train_b", True, 45000, "hot", 1, 12), ("train_c", True, 20000, "uniform", 0, 13),
+        ("train_d", True, 45000, "edge", 0, 14), ("eval_a", False, 45000, "edge", 1, 15), ("eval_b", False, 12000, "hot", 0, 16),
+    ]
+    for name, is_train, n, kind, norm, seed in cases:
+        args = SimpleNamespace(data_path="/data/N_imagenet", input_H=224, input_W=224, slice_max_evs=30000,
+                               max_random_shift_evs=15, timesurface=0, hotpixfilter=1, hotpix_num_stds=10, logtrafo=0,
+                               gammatrafo=0, gamma=0.5, normalize_events=norm, rand_aug=0)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            tf = ds.build_transformNPY(is_train, args)
+        ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
+        random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+        res = tf(ev.copy())
+        out[name + "_out"] = res.numpy()
+        out[name + "_meta"] = np.array([int(is_train), n, norm, seed], dtype=np.int64)
+        out[name + "_kind"] = np.array(kind)
+        print(f"event_pipeline {name}: out {tuple(res.shape)} nnz {int((res != 0).sum())} max {float(res.max()):.4f}")
+    np.savez_compressed(os.path.join(GOLD, "event_pipeline.npz"), **out)
+
+
+
 SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit, "dvae": golden_dvae,
-            "engine": golden_engine}
+            "engine": golden_engine, "event_pipeline": golden_event_pipeline}
 
 
 def main(argv):

@@ -1,0 +1,170 @@
+"""GPU parity: fused event augmentation + rasteriser + post-raster transforms (through the C ABI) against
+the reference's own build_transformNPY outputs (tests/golden/event_pipeline.npz) and the oracle.  Bit-exact."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle.event_pipeline_ref import PipelineCfg, apply_event_aug, apply_post_raster, pipeline_ref
+from oracle.histogram_ref import event_hist_ref
+from oracle.make_golden import synth_events
+
+STRATS = [0, 1, 2, 3]
+
+
+def seed_all(seed):
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def product_cfg(cfg: PipelineCfg):
+    from mem_b200.event_pipeline import PipelineConfig
+    return PipelineConfig(**cfg.__dict__)
+
+
+def golden_cases(golden_dir):
+    z = np.load(os.path.join(golden_dir, "event_pipeline.npz"))
+    for name in sorted(k[:-4] for k in z.files if k.endswith("_out")):
+        is_train, n, norm, seed = (int(v) for v in z[name + "_meta"])
+        kind = str(z[name + "_kind"])
+        ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
+        yield name, ev, PipelineCfg(is_train=bool(is_train), normalize_events=bool(norm)), seed, z[name + "_out"]
+
+
+def test_reference_golden_single_streams(golden_dir):
+    """Same generator seeds as the reference run -> same draws -> identical float32 tensors."""
+    from mem_b200.event_pipeline import EventBatchPipeline
+    seen = 0
+    for name, ev, cfg, seed, want in golden_cases(golden_dir):
+        seed_all(seed)
+        got = EventBatchPipeline(product_cfg(cfg))([ev])
+        assert got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == (1,) + want.shape, name
+        assert np.array_equal(got[0].cpu().numpy(), want), (name, float(np.abs(got[0].cpu().numpy() - want).max()))
+        seen += 1
+    assert seen >= 6
+
+
+def test_draws_match_oracle_draws():
+    from mem_b200 import event_pipeline as ep
+    from oracle import event_pipeline_ref as ref
+    for is_train in (True, False):
+        for n in (100, 30000, 30001, 45000):
+            seed_all(n + is_train)
+            a = ep.draw_params(n, ep.PipelineConfig(is_train=is_train))
+            seed_all(n + is_train)
+            b = ref.draw_params(n, ref.PipelineCfg(is_train=is_train))
+            assert a == b
+
+
+@pytest.mark.parametrize("channels", [2, 3])
+def test_batch_against_oracle_all_strategies(channels):
+    """Ragged batch (one empty stream, one fully culled, streams shorter and longer than the slice window)."""
+    from mem_b200.event_pipeline import PipelineConfig, draw_params, pack_params, post_raster, rasterise_augmented
+    rng = np.random.default_rng(3)
+    cfg = PipelineCfg(is_train=True, normalize_events=True)
+    pcfg = product_cfg(cfg)
+    H, W = cfg.raster_hw()
+    lens = [45000, 0, 7, 30001, 12345, 60000, 1000]
+    streams = [synth_events(rng, n, 480, 640, kind, frac=True) if n else np.zeros((0, 4))
+               for n, kind in zip(lens, ["edge", "uniform", "uniform", "hot", "edge", "uniform", "uniform"])]
+    seed_all(17)
+    params = [draw_params(n, pcfg) for n in lens]
+    params[6].update(shift_x=400)       # every row of stream 6 leaves the sensor: an all-zero image
+    aug, crop = pack_params(params)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    events = np.concatenate(streams, axis=0)
+    def raster(s, p):
+        # an empty stream makes the reference's time flip raise (x[0, 2] of nothing); the batched path returns zeros
+        a = apply_event_aug(s, p) if len(s) else s
+        return event_hist_ref(a, H, W) if len(a) else np.zeros((H, W, 3), np.uint8)
+    want_hist = np.stack([raster(s, p) for s, p in zip(streams, params)])
+    assert want_hist[6].sum() == 0 and want_hist[0].sum() > 0
+    for strat in STRATS:
+        got = rasterise_augmented(torch.from_numpy(events).cuda(), offsets, aug, H, W, channels, strategy=strat,
+                                  max_stream_len=30000)
+        want = want_hist if channels == 3 else want_hist[..., 0::2]
+        assert np.array_equal(got.cpu().numpy(), want), (strat, int((got.cpu().numpy() != want).sum()))
+    out = post_raster(got, crop, (224, 224), hot_num_stds=10.0, normalize=True)
+    for b, p in enumerate(params):
+        w = apply_post_raster(want_hist[b], p, cfg).numpy()
+        w = w if channels == 3 else w[0::2]
+        assert np.array_equal(out[b].cpu().numpy(), w), b
+
+
+@pytest.mark.parametrize("H,W", [(200, 180), (224, 300), (256, 341)])
+@pytest.mark.parametrize("hot,norm", [(None, False), (10.0, False), (3.0, True), (None, True)])
+def test_post_raster_padding_and_switches(H, W, hot, norm):
+    """RandomCrop(pad_if_needed) geometry: the image is padded on both sides by the missing amount."""
+    from mem_b200.event_pipeline import post_raster
+    rng = np.random.default_rng(H * W)
+    B = 5
+    hist = (rng.random((B, H, W, 3)) < 0.05).astype(np.uint8) * rng.integers(1, 6, (B, H, W, 3)).astype(np.uint8)
+    hist[:, 10, 10, 0] = 255
+    hist[:, 150, 100, 2] = 200
+    hist[4] = 0                                             # all-zero image: max == 0 -> NormalizeEvent leaves it
+    ph, pw = H + 2 * max(224 - H, 0), W + 2 * max(224 - W, 0)
+    tl = np.stack([rng.integers(0, ph - 224 + 1, B), rng.integers(0, pw - 224 + 1, B)], axis=1).astype(np.int32)
+    cfg = PipelineCfg(is_train=True, hotpixfilter=hot is not None, hotpix_num_stds=hot if hot is not None else 10,
+                      normalize_events=norm)
+    got = post_raster(torch.from_numpy(hist).cuda(), tl, (224, 224), hot_num_stds=hot, normalize=norm)
+    for b in range(B):
+        want = apply_post_raster(hist[b], dict(top=int(tl[b, 0]), left=int(tl[b, 1])), cfg).numpy()
+        assert np.array_equal(got[b].cpu().numpy(), want), (b, float(np.abs(got[b].cpu().numpy() - want).max()))
+
+
+def test_full_size_properties():
+    """B = 128 streams x 30000 events (the training batch of BASELINE config 3), checked through properties:
+    an x flip mirrors the image, a time flip swaps the polarity channels, a shift translates it."""
+    from mem_b200.event_pipeline import AUG_DTYPE, rasterise_augmented
+    from mem_b200.process_data import histogram_batch
+    B, n, H, W = 128, 30000, 256, 341
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ev = torch.empty(B * n, 4, dtype=torch.float64, device="cuda")
+    ev[:, 0] = torch.randint(0, W, (B * n,), generator=g, device="cuda").double()
+    ev[:, 1] = torch.randint(0, H, (B * n,), generator=g, device="cuda").double()
+    ev[:, 2] = torch.rand(B * n, generator=g, device="cuda", dtype=torch.float64)
+    ev[:, 3] = torch.randint(0, 2, (B * n,), generator=g, device="cuda").double() * 2 - 1
+    off = torch.arange(B + 1, device="cuda", dtype=torch.int64) * n
+    base = histogram_batch(ev, off, H, W, channels=2, max_stream_len=n)
+    aug = np.zeros(B, dtype=AUG_DTYPE)
+    aug["scale_x"] = aug["scale_y"] = 1.0
+    aug["count"] = -1
+    aug["flip_w"], aug["cull_w"], aug["cull_h"] = W, W, H
+    ident = rasterise_augmented(ev, off, aug, H, W, 2, max_stream_len=n)
+    assert torch.equal(ident, base)
+    a = aug.copy(); a["flip_x"] = 1
+    assert torch.equal(rasterise_augmented(ev, off, a, H, W, 2, max_stream_len=n), base.flip(2))
+    a = aug.copy(); a["time_flip"] = 1
+    assert torch.equal(rasterise_augmented(ev, off, a, H, W, 2, max_stream_len=n), base.flip(3))
+    a = aug.copy(); a["cull"] = 1; a["shift_x"] = 7; a["shift_y"] = -5
+    got = rasterise_augmented(ev, off, a, H, W, 2, max_stream_len=n)
+    want = torch.zeros_like(base)
+    want[:, :H - 5, 7:] = base[:, 5:, :W - 7]
+    assert torch.equal(got, want)
+    a = aug.copy(); a["start"] = 1000; a["count"] = 5000
+    got = rasterise_augmented(ev, off, a, H, W, 2, max_stream_len=5000)
+    win = ev.view(B, n, 4)[:, 1000:6000].reshape(-1, 4).contiguous()
+    want = histogram_batch(win, torch.arange(B + 1, device="cuda", dtype=torch.int64) * 5000, H, W, channels=2)
+    assert torch.equal(got, want)
+
+
+def test_bad_arguments_fail_loudly():
+    from mem_b200 import _lib
+    from mem_b200.event_pipeline import AUG_DTYPE, EventBatchPipeline, PipelineConfig, post_raster, rasterise_augmented
+    with pytest.raises(NotImplementedError):
+        EventBatchPipeline(PipelineConfig(timesurface=True))
+    ev = np.zeros((4, 4))
+    with pytest.raises(ValueError):
+        rasterise_augmented(ev, np.array([0, 4]), np.zeros(2, dtype=AUG_DTYPE), 100, 100)
+    with pytest.raises(ValueError):
+        post_raster(torch.zeros(1, 8, 8, 3), None)
+    # an eval-path stream that indexes outside the sensor raises like the reference's np.add.at
+    aug = np.zeros(1, dtype=AUG_DTYPE); aug["scale_x"] = aug["scale_y"] = 1.0; aug["count"] = -1
+    bad = np.array([[100.0, 100.0, 0.0, 1.0]])
+    with pytest.raises((IndexError, _lib.MembError)):
+        rasterise_augmented(bad, np.array([0, 1]), aug, 100, 100)

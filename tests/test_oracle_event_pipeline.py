@@ -1,0 +1,80 @@
+"""CPU: the event-pipeline oracle (oracle/event_pipeline_ref.py) against golden tensors produced by the reference's own
+``build_transformNPY`` chain (tests/golden/event_pipeline.npz, made by oracle/make_golden.py::golden_event_pipeline
+from mem/datasets.py:611-660 + mem/transforms.py:225-275), under the same generator seeds."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.event_pipeline_ref import PipelineCfg, apply_event_aug, draw_params, pipeline_ref
+from oracle.make_golden import synth_events
+
+
+def golden_cases(golden_dir):
+    z = np.load(os.path.join(golden_dir, "event_pipeline.npz"))
+    for name in sorted(k[:-4] for k in z.files if k.endswith("_out")):
+        is_train, n, norm, seed = (int(v) for v in z[name + "_meta"])
+        kind = str(z[name + "_kind"])
+        ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
+        cfg = PipelineCfg(is_train=bool(is_train), normalize_events=bool(norm))
+        yield name, ev, cfg, seed, z[name + "_out"]
+
+
+def seed_all(seed):
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def test_oracle_matches_reference_golden(golden_dir):
+    seen = 0
+    for name, ev, cfg, seed, want in golden_cases(golden_dir):
+        seed_all(seed)
+        got = pipeline_ref(ev, cfg).numpy()
+        assert got.shape == want.shape and got.dtype == np.float32, name
+        assert np.array_equal(got, want), f"{name}: {np.abs(got - want).max()}"
+        seen += 1
+    assert seen >= 6
+
+
+def test_draws_follow_the_reference_order():
+    cfg = PipelineCfg()
+    seed_all(5)
+    p = draw_params(45000, cfg)
+    seed_all(5)
+    start = random.choice(range(45000 - 30000 + 1))
+    tf, fx = np.random.random() < 0.5, np.random.random() < 0.5
+    sx, sy = np.random.randint(-15, 16, size=(2,))
+    top = int(torch.randint(0, 256 - 224 + 1, size=(1,)).item())
+    left = int(torch.randint(0, 341 - 224 + 1, size=(1,)).item())
+    assert (p["start"], p["count"], p["time_flip"], p["flip_x"], p["shift_x"], p["shift_y"], p["top"], p["left"]) == \
+        (start, 30000, tf, fx, int(sx), int(sy), top, left)
+    # short streams do not consume Python's generator (datasets.py:495)
+    seed_all(5)
+    state = random.getstate()
+    draw_params(100, cfg)
+    assert random.getstate() == state
+
+
+def test_eval_path_has_no_random_draws():
+    cfg = PipelineCfg(is_train=False)
+    seed_all(9)
+    s0, s1, s2 = random.getstate(), np.random.get_state()[1].copy(), torch.get_rng_state().clone()
+    p = draw_params(1000, cfg)
+    assert random.getstate() == s0 and np.array_equal(np.random.get_state()[1], s1) and torch.equal(torch.get_rng_state(), s2)
+    assert not p["cull"] and p["scale_x"] == 224 / 640 and p["scale_y"] == 224 / 480
+
+
+def test_cull_and_flip_semantics():
+    ev = np.array([[0.0, 0.0, 1.0, 1.0], [639.0, 479.0, 2.0, -1.0], [320.4, 100.7, 3.0, 1.0]])
+    p = dict(scale_x=256 / 480, scale_y=256 / 480, start=0, count=3, time_flip=True, flip_x=True, flip_w=341, cull=True,
+             shift_x=-1, shift_y=2, cull_w=341, cull_h=256)
+    out = apply_event_aug(ev, p)
+    # rows reversed, polarity inverted, x mirrored about W-1 then shifted; the mirrored first pixel (x=340-1) stays,
+    # the mirrored last pixel (340 - 340.8 - 1 < 0) is culled
+    assert out.shape == (2, 4)
+    assert np.array_equal(out[:, 3], [-1.0, -1.0])
+    assert np.array_equal(out[:, 2], [0.0, 2.0])
+    assert out[1, 0] == 341 - 1 - 0.0 - 1 and out[1, 1] == 2.0
