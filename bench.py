@@ -9,6 +9,8 @@ Prints ONE JSON line on rank 0.  Workloads:
 
   histogram  event -> polarity histogram rasterisation, 10M uniform events at the
              N-ImageNet 640x480 sensor (largest single-GPU case of BASELINE config 2)
+  event_pipeline  one training batch of raw streams -> model input: fused event
+             augmentations + rasteriser + crop / hot-pixel filter / normalise
   pretrain   ViT-B/16 MEM pretraining step, batch 128/GPU (BASELINE config 3)
 
 `--workload auto` picks `pretrain` when the training-step kernels are built in,
@@ -34,7 +36,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "histogram", "pretrain"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "histogram", "pretrain", "event_pipeline"])
     ap.add_argument("--events", type=int, default=10_000_000)
     ap.add_argument("--sensor", default="640x480")
     ap.add_argument("--batch", type=int, default=128)
@@ -190,6 +192,169 @@ class HistogramWorkload:
                           f"(np.add.at is serial: 1 thread)"}
 
 
+# ----------------------------------------------------------------------------- event pipeline workload
+class EventPipelineWorkload:
+    """One training batch of raw streams -> model input: augment + rasterise + crop / hot-pixel filter / normalise.
+    128 streams x 45000 raw events at 640x480 (N-ImageNet), 30000-event windows, 256x341 raster, 224x224 crops."""
+    metric = "Gevents/s event pipeline (augment+rasterise+post)"
+    unit = "Gevents/s"
+    dtype = "f64->u8->f32"
+
+    def __init__(self, args):
+        self.B, self.n_raw, self.C = args.batch, 45000, 3
+        self.config = {"workload": f"build_transformNPY(train) on the GPU: {self.B} streams x {self.n_raw} raw events (640x480), "
+                                   "scale 256/480, 30000-event window, time/x flips, shift+cull, 256x341 raster, 224x224 crop, "
+                                   "hot-pixel filter (10 sigma), normalise -> float32 [B,3,224,224]",
+                       "batch": self.B, "raw_events_per_stream": self.n_raw, "window": 30000,
+                       "l2_policy": "raw batch (184 MB) larger than the 126 MB L2; 4 resident batches rotate",
+                       "parallelism": "independent batches per GPU (no collective)"}
+
+    def make_stream(self, rng, n=None):
+        import numpy as np
+        n = n or self.n_raw
+        ev = np.empty((n, 4), dtype=np.float64)
+        seg = rng.integers(0, 12, n)
+        x0, y0 = rng.uniform(0, 640, 12), rng.uniform(0, 480, 12)
+        dx, dy = rng.uniform(-1, 1, 12), rng.uniform(-1, 1, 12)
+        sgm = rng.uniform(0, 240, n)
+        ev[:, 0] = np.clip(x0[seg] + dx[seg] * sgm + rng.normal(0, 1.5, n), 0, 639.99)
+        ev[:, 1] = np.clip(y0[seg] + dy[seg] * sgm + rng.normal(0, 1.5, n), 0, 479.99)
+        noise = rng.random(n) < 0.2
+        ev[noise, 0] = rng.uniform(0, 639.99, int(noise.sum()))
+        ev[noise, 1] = rng.uniform(0, 479.99, int(noise.sum()))
+        ev[:, 2] = np.sort(rng.uniform(0, 3e5, n))
+        ev[:, 3] = rng.integers(0, 2, n) * 2.0 - 1.0
+        return ev
+
+    def setup(self, torch, rank):
+        import numpy as np
+        from mem_b200 import _lib, event_pipeline as ep
+        self.torch, self._lib, self.ep = torch, _lib, ep
+        self.cfg = ep.PipelineConfig(is_train=True, normalize_events=True)
+        self.pipe = ep.EventBatchPipeline(self.cfg, channels=self.C)
+        rng = np.random.default_rng(100 + rank)
+        base = [self.make_stream(rng) for _ in range(8)]
+        self.host, self.dev = [], []
+        for k in range(4):                      # 4 resident batches, streams drawn from 8 templates with a per-slot jitter
+            ev = np.concatenate([base[(i + k) % 8] for i in range(self.B)], axis=0)
+            ev[:, 0] = np.clip(ev[:, 0] + rng.uniform(-20, 20, len(ev)), 0, 639.99)
+            h = torch.from_numpy(ev).pin_memory()
+            self.host.append(h)
+            self.dev.append(h.cuda())
+        self.off_host = np.arange(self.B + 1, dtype=np.int64) * self.n_raw
+        self.off_dev = torch.from_numpy(self.off_host).cuda()
+        # device-resident arm: the per-sample augmentation records are inputs too (drawn once per resident batch)
+        self.resident = []
+        for k in range(4):
+            aug, crop = ep.pack_params([ep.draw_params(self.n_raw, self.cfg) for _ in range(self.B)])
+            self.resident.append((torch.from_numpy(aug.view(np.uint8).reshape(self.B, 64)).cuda(), torch.from_numpy(crop).cuda()))
+        self.hw = self.cfg.raster_hw()
+        self.out_host = None
+        self.first_stream = base[0]
+        self.k = 0
+        self.units_per_step = self.B * self.cfg.slice_max_evs
+        self.h2d, self.d2h = self.B * self.n_raw * 32, self.B * self.C * 224 * 224 * 4
+        self.out = None
+
+    def _run(self, events):
+        lens = [self.n_raw] * self.B
+        params = [self.ep.draw_params(n, self.cfg) for n in lens]     # host draws, reference generator order
+        return self.pipe(events, self.off_dev, params=params)
+
+    def step_device(self):
+        self.k += 1
+        aug, crop = self.resident[self.k % 4]
+        self.out = self.ep.pipeline_fused(self.dev[self.k % 4], self.off_dev, aug, crop, self.hw[0], self.hw[1], (224, 224),
+                                          self.C, hot_num_stds=10.0, normalize=True, check=False, out=self.out)
+
+    def step_e2e(self):
+        # public API from HOST buffers: generator draws, H2D of the raw batch, the kernel, D2H of the model input
+        self.k += 1
+        dev = self.host[self.k % 4].to("cuda", non_blocking=True)
+        res = self._run(dev)
+        if self.out_host is None:
+            self.out_host = self.torch.empty(res.shape, dtype=res.dtype).pin_memory()
+        self.out_host.copy_(res, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        return self.out_host
+
+    def verify(self):
+        import random
+        import numpy as np
+        from oracle.event_pipeline_ref import PipelineCfg, pipeline_ref
+        torch = self.torch
+        ok = True
+        for b in (0, 5):
+            ev = self.host[0][b * self.n_raw:(b + 1) * self.n_raw].numpy()
+            for g in (random, np.random, torch):
+                (g.seed if g is not torch else g.manual_seed)(7 + b)
+            want = pipeline_ref(ev, PipelineCfg(is_train=True, normalize_events=True)).numpy()
+            for g in (random, np.random, torch):
+                (g.seed if g is not torch else g.manual_seed)(7 + b)
+            got = self.pipe([ev])[0].cpu().numpy()
+            ok = ok and bool(np.array_equal(got, want))
+        return ok
+
+    def roofline(self, ms_per_step):
+        hbm, _, _, how = measured_peaks()
+        alg_bytes = 32.0 * self.units_per_step + self.d2h
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "event_pipeline_fused (one CTA per stream: augment + rasterise + crop + hot-pixel filter "
+                                          "+ normalise in shared memory)",
+                "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
+                "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                "algorithmic_bytes_per_launch": alg_bytes, "traffic": None}
+
+    def cpu_baseline(self):
+        import numpy as np
+        from oracle.event_pipeline_ref import PipelineCfg, pipeline_ref
+        cfg = PipelineCfg(is_train=True, normalize_events=True)
+        ev = self.first_stream
+        pipeline_ref(ev, cfg)
+        reps, t0 = 0, time.perf_counter()
+        while reps < 8 or time.perf_counter() - t0 < 4.0:
+            pipeline_ref(ev, cfg)
+            reps += 1
+            if time.perf_counter() - t0 > 25:
+                break
+        dt = (time.perf_counter() - t0) / reps
+        return {"value": round(cfg.slice_max_evs / dt / 1e9, 6), "unit": self.unit, "cores": 1, "kind": "port",
+                "sample": f"{reps} samples of {self.n_raw} raw events through oracle/event_pipeline_ref.py "
+                          f"(the reference's numpy/torch chain, 1 thread; {dt * 1e3:.1f} ms per sample)"}
+
+
+def _ref_pipe_init(n_raw):
+    global _REF_EV
+    import numpy as np
+    _REF_EV = EventPipelineWorkload.make_stream(None, np.random.default_rng(os.getpid()), n_raw)
+
+
+def _ref_pipe_worker(k):
+    import torch
+    from oracle.event_pipeline_ref import PipelineCfg, pipeline_ref
+    torch.set_num_threads(1)
+    cfg = PipelineCfg(is_train=True, normalize_events=True)
+    return float(sum(pipeline_ref(_REF_EV, cfg).sum() for _ in range(k)))
+
+
+def run_reference_event_pipeline(args, wl):
+    """Reference CPU arm: every host core runs the per-sample chain on its own resident stream (DataLoader workers)."""
+    import multiprocessing as mp
+    workers = max(1, min(os.cpu_count() or 1, 64))
+    per_worker = 8
+    steps, warm = args.steps or 5, args.warmup if args.warmup is not None else 1
+    with mp.get_context("fork").Pool(workers, initializer=_ref_pipe_init, initargs=(wl.n_raw,)) as pool:
+        for _ in range(max(1, warm)):
+            pool.map(_ref_pipe_worker, [per_worker] * workers, chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_ref_pipe_worker, [per_worker] * workers, chunksize=1)
+        dt = time.perf_counter() - t0
+    value = workers * per_worker * 30000 * steps / dt / 1e9
+    return value, dt / steps * 1e3, workers, (f"{workers} worker processes (all host cores, capped at 64), each running the "
+                                              f"per-sample chain on {per_worker} samples of {wl.n_raw} raw events per step")
+
+
 _REF_EV = None
 
 
@@ -247,12 +412,12 @@ def main():
         from mem_b200 import bench_pretrain
         return bench_pretrain.main(args, rank, local_rank, world, ClockSampler, measured_peaks)
 
-    wl = HistogramWorkload(args)
+    wl = EventPipelineWorkload(args) if workload == "event_pipeline" else HistogramWorkload(args)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        value, ms, workers, sample = run_reference_histogram(args, wl)
+        value, ms, workers, sample = (run_reference_event_pipeline if workload == "event_pipeline" else run_reference_histogram)(args, wl)
         line = {"impl": "reference", "metric": wl.metric, "value": round(value, 6), "unit": wl.unit,
                 "n_gpus": args.gpus, "steps": args.steps or 10, "warmup": args.warmup if args.warmup is not None else 3,
                 "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

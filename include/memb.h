@@ -118,6 +118,17 @@ int memb_hist_aug_u8(const double* ev, int64_t n, const int64_t* offsets, int B,
  *                 mean + num_stds * std (unbiased) of the cropped polarity channels (RemoveHotPixels).
  * normalize     : divide the polarity channels by their maximum when it is not 0 (NormalizeEvent).
  * out     : float32 [B,C,outH,outW].  Workspace: memb_raster_post_workspace_bytes(B). */
+/* The whole chain in ONE kernel, one CTA per stream, for output rasters that fit a shared-memory tile
+ * (outH * outW <= 51200 pixels, e.g. the 224 x 224 training crop): augment -> rasterise at H x W -> crop ->
+ * /255 -> RemoveTimesurface -> RemoveHotPixels -> NormalizeEvent -> float32 [B,C,outH,outW].  The uint8 image
+ * never reaches HBM.  Arguments as memb_hist_aug_u8 / memb_raster_post_f32 (the middle channel of C == 3 is
+ * always zero: no time surface on this path).  ws: >= 256 bytes (status header for memb_hist_status).
+ * Returns MEMB_EINVAL when the output raster is too large: use the two calls above instead. */
+int memb_event_pipeline_f32(const double* ev, int64_t n, const int64_t* offsets, int B, const memb_event_aug* aug,
+                            const int32_t* crop_tl, int H, int W, int pad_t, int pad_l, int outH, int outW, int C,
+                            float hot_num_stds, int normalize, float* out, void* ws, size_t ws_bytes,
+                            memb_stream_t stream);
+
 size_t memb_raster_post_workspace_bytes(int B);
 int memb_raster_post_f32(const uint8_t* hist, int B, int H, int W, int C, const int32_t* crop_tl, int pad_t,
                          int pad_l, int outH, int outW, int remove_ts, float hot_num_stds, int normalize,

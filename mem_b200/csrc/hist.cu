@@ -335,6 +335,154 @@ __global__ void __launch_bounds__(kTileThreads, 1) hist_tile_smem(
   }
 }
 
+// ---------------------------------------------------------------- fused event pipeline
+// One CTA per stream does the whole per-sample chain of build_transformNPY(train) (datasets.py:611-660):
+// augment -> rasterise -> crop -> ToTensor -> RemoveTimesurface -> RemoveHotPixels -> NormalizeEvent.
+// The cropped outH x outW raster (<= kTileMaxWords pixels, e.g. 224 x 224) lives in shared memory as one packed
+// word per pixel, so the uint8 image never exists in HBM: the stream window is read once (32 B / event) and the
+// float32 planes are written once.  Crop is applied to the integer pixel index (after numpy's truncation and
+// negative wrap), which is what cropping the rasterised image does.
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* scratch) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned long long t = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += scratch[w];
+  return t;
+}
+
+template <bool kAligned>
+__global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
+    const double* __restrict__ ev, const long long* __restrict__ offsets, long long n_total,
+    const memb_event_aug* __restrict__ aug, const int* __restrict__ crop_tl, int H, int W, int pad_t, int pad_l,
+    int outH, int outW, int C, float hot_num_stds, int normalize, float* __restrict__ out, Header* __restrict__ hdr) {
+  extern __shared__ unsigned int tile[];
+  __shared__ unsigned long long red[kTileThreads / 32];
+  __shared__ float lut[256];
+  __shared__ int params[2];
+  const int b = blockIdx.x;
+  long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
+  const memb_event_aug a = aug[b];
+  if (threadIdx.x == 0) params[1] = 0;
+  aug_window(a, begin, end);
+  const long long npix = (long long)H * W;
+  const int npx = outH * outW;
+  const int y0 = (crop_tl ? crop_tl[2 * b] : 0) - pad_t, x0 = (crop_tl ? crop_tl[2 * b + 1] : 0) - pad_l;
+  for (int i = threadIdx.x; i < npx; i += kTileThreads) tile[i] = 0u;
+  __syncthreads();
+
+  bool bad = false;
+  for (long long chunk = begin; chunk < end; chunk += kTileChunk) {
+    const long long stop = min(end, chunk + (long long)kTileChunk);
+    for (long long base = chunk; base < stop; base += kTileThreads * kTileUnroll) {
+      Event e[kTileUnroll];
+      bool live[kTileUnroll];
+#pragma unroll
+      for (int u = 0; u < kTileUnroll; ++u) {
+        long long r = base + u * kTileThreads + threadIdx.x;
+        live[u] = r < stop;
+        if (live[u]) e[u] = load_event<kAligned>(ev, r);
+      }
+#pragma unroll
+      for (int u = 0; u < kTileUnroll; ++u) {
+        if (live[u]) live[u] = apply_aug(e[u], a);
+        const bool pos = live[u] && e[u].p == 1.0, neg = live[u] && e[u].p == -1.0;
+        if (pos || neg) {
+          long long idx;
+          if (!pixel_index(e[u].x, e[u].y, W, npix, idx)) {
+            bad = true;
+          } else {
+            const int y = (int)(idx / W) - y0, x = (int)(idx % W) - x0;
+            if (y >= 0 && y < outH && x >= 0 && x < outW) atomicAdd(&tile[y * outW + x], pos ? 1u : 0x10000u);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npx; i += kTileThreads) tile[i] &= 0x00ff00ffu;   // counts mod 256 (uint8 wrap)
+    __syncthreads();
+  }
+  if (bad) hdr->oob = 1;
+
+  // ---- value table: lut[c] = fl32(c / 255), the ToTensor value of count c (one division per entry, not per pixel)
+  if (threadIdx.x < 256) lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+  // ---- RemoveHotPixels: threshold from exact integer sums (see raster_post.cu for the rounding argument),
+  //      turned into the largest count that is NOT hot so that the passes below compare integers
+  const bool filter = hot_num_stds >= 0.0f;
+  if (filter) {
+    unsigned long long s1 = 0, s2 = 0;
+    for (int i = threadIdx.x; i < npx; i += kTileThreads) {
+      const unsigned int w = tile[i], cp = w & 0xffu, cn = w >> 16;
+      s1 += cp + cn;
+      s2 += cp * cp + cn * cn;
+    }
+    s1 = block_sum_u64(s1, red);
+    s2 = block_sum_u64(s2, red);
+    const double n = 2.0 * (double)npx;
+    const double mean = (double)s1 / (255.0 * n);
+    double var = ((double)s2 - (double)s1 * (double)s1 / n) / ((n - 1.0) * 255.0 * 255.0);
+    var = var > 0.0 ? var : 0.0;
+    const float thr = (float)(mean + (double)hot_num_stds * sqrt(var));
+    // lut is monotone: count the entries that are not above the threshold
+    const bool cold = threadIdx.x < 256 && !(lut[threadIdx.x] > thr);   // own entry, written by this thread
+    const int n_cold = __syncthreads_count(cold);
+    if (threadIdx.x == 0) params[0] = n_cold - 1;          // counts 0 .. params[0] survive (-1: everything is hot)
+  } else {
+    if (threadIdx.x == 0) params[0] = 255;
+  }
+  __syncthreads();
+  const int c_keep = params[0];
+  // ---- NormalizeEvent factor from the maximum surviving count
+  float factor = 1.0f;
+  bool scale = false;
+  if (normalize) {
+    unsigned int m = 0;
+    for (int i = threadIdx.x; i < npx; i += kTileThreads) {
+      const unsigned int w = tile[i];
+      const int cp = (int)(w & 0xffu), cn = (int)(w >> 16);
+      if (cp <= c_keep && cn <= c_keep) m = max(m, (unsigned int)max(cp, cn));
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&params[1], (int)m);
+    __syncthreads();
+    m = (unsigned int)params[1];
+    if (m != 0) {
+      factor = __fdiv_rn(1.0f, lut[m]);
+      scale = true;
+    }
+  }
+  // ---- float32 planes, 4 pixels (16 B) per thread per plane
+  float* o = out + (long long)b * C * npx;
+  float* o_neg = o + (long long)(C - 1) * npx;
+  for (int i = threadIdx.x * 4; i < npx; i += kTileThreads * 4) {
+    float vp[4], vn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned int w = (i + j < npx) ? tile[i + j] : 0u;
+      const int cp = (int)(w & 0xffu), cn = (int)(w >> 16);
+      const bool hot = cp > c_keep || cn > c_keep;
+      vp[j] = hot ? 0.0f : lut[cp];
+      vn[j] = hot ? 0.0f : lut[cn];
+      if (scale) {
+        vp[j] = __fmul_rn(vp[j], factor);
+        vn[j] = __fmul_rn(vn[j], factor);
+      }
+    }
+    if (i + 3 < npx && (npx & 3) == 0) {
+      __stcs(reinterpret_cast<float4*>(o + i), make_float4(vp[0], vp[1], vp[2], vp[3]));
+      __stcs(reinterpret_cast<float4*>(o_neg + i), make_float4(vn[0], vn[1], vn[2], vn[3]));
+      if (C == 3) __stcs(reinterpret_cast<float4*>(o + npx + i), make_float4(0.f, 0.f, 0.f, 0.f));
+    } else {
+      for (int j = 0; j < 4 && i + j < npx; ++j) {
+        o[i + j] = vp[j];
+        o_neg[i + j] = vn[j];
+        if (C == 3) o[npx + i + j] = 0.0f;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- extent (H/W = None)
 template <bool kAligned>
 __global__ void __launch_bounds__(kThreads) hist_extent(const double* __restrict__ ev, long long n,
@@ -498,6 +646,38 @@ extern "C" int memb_hist_aug_u8(const double* ev, int64_t n, const int64_t* offs
   MEMB_REQUIRE(aug != nullptr, "hist_aug: null augmentation array");
   MEMB_REQUIRE((((uintptr_t)aug) & 7u) == 0, "hist_aug: misaligned augmentation array");
   return run_hist(ev, n, offsets, B, max_stream_len, aug, H, W, C, 0, strategy, out, ws, ws_bytes, stream);
+}
+
+extern "C" int memb_event_pipeline_f32(const double* ev, int64_t n, const int64_t* offsets, int B,
+                                       const memb_event_aug* aug, const int32_t* crop_tl, int H, int W, int pad_t,
+                                       int pad_l, int outH, int outW, int C, float hot_num_stds, int normalize,
+                                       float* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
+  MEMB_REQUIRE(B >= 1 && H >= 1 && W >= 1 && outH >= 1 && outW >= 1, "event_pipeline: bad shape");
+  MEMB_REQUIRE(C == 2 || C == 3, "event_pipeline: C must be 2 or 3, got %d", C);
+  MEMB_REQUIRE((long long)outH * outW <= kTileMaxWords,
+               "event_pipeline: the %dx%d output raster does not fit one shared-memory tile (%d pixels); use "
+               "memb_hist_aug_u8 + memb_raster_post_f32", outH, outW, kTileMaxWords);
+  MEMB_REQUIRE(n >= 0 && (n == 0 || ev != nullptr), "event_pipeline: null event pointer");
+  MEMB_REQUIRE(offsets != nullptr || B == 1, "event_pipeline: a batch needs row offsets");
+  MEMB_REQUIRE(aug != nullptr && (((uintptr_t)aug) & 7u) == 0, "event_pipeline: null / misaligned augmentation array");
+  MEMB_REQUIRE(out != nullptr && (((uintptr_t)out) & 15u) == 0, "event_pipeline: null / misaligned output");
+  MEMB_REQUIRE(ws != nullptr && (((uintptr_t)ws) & 15u) == 0 && ws_bytes >= (size_t)kHeaderBytes,
+               "event_pipeline: workspace must hold the %d-byte status header", kHeaderBytes);
+  MEMB_REQUIRE((((uintptr_t)ev) & 7u) == 0 && pad_t >= 0 && pad_l >= 0, "event_pipeline: misaligned pointer / bad padding");
+  MEMB_CUDA_OK(cudaMemsetAsync(ws, 0, kHeaderBytes, stream));
+  const bool aligned = (((uintptr_t)ev) & 31u) == 0;
+  auto kern = aligned ? event_pipeline_fused<true> : event_pipeline_fused<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[aligned]) {
+    MEMB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxWords * 4));
+    attr_set[aligned] = true;
+  }
+  const size_t smem = (size_t)round_up<long long>((long long)outH * outW, 4) * 4;
+  kern<<<B, kTileThreads, smem, stream>>>(ev, reinterpret_cast<const long long*>(offsets), n, aug, crop_tl, H, W, pad_t,
+                                          pad_l, outH, outW, C, hot_num_stds, normalize, out,
+                                          reinterpret_cast<Header*>(ws));
+  MEMB_LAUNCH_OK("event_pipeline_fused");
+  return MEMB_OK;
 }
 
 extern "C" int memb_hist_status(const void* ws, memb_stream_t stream) {

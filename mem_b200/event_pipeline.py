@@ -26,7 +26,9 @@ import numpy as np
 from . import _lib
 
 __all__ = ["PipelineConfig", "EventAug", "draw_params", "pack_params", "rasterise_augmented", "post_raster",
-           "EventBatchPipeline"]
+           "pipeline_fused", "EventBatchPipeline"]
+
+FUSED_MAX_PIXELS = 50 * 1024      # one shared-memory tile (csrc/hist.cu kTileMaxWords)
 
 
 class EventAug(ctypes.Structure):
@@ -64,21 +66,22 @@ class PipelineConfig:
         assert 100 <= self.sensor_H <= 640 and 100 <= self.sensor_W <= 640
         assert 5000 <= self.slice_max_evs < 200000
         assert 0 <= self.max_random_shift_evs <= 200
-
-    def scales(self):
-        """(scale_x, scale_y) of ReshapeScaleXandY (datasets.py:472-480)."""
         if self.is_train:
             hw = [self.sensor_H, self.sensor_W]
             s = 256 / hw[int(np.argmin(hw))]
-            return s, s
-        return self.input_W / self.sensor_W, self.input_H / self.sensor_H
+            scale = 256 / 480
+            self._scales, self._raster = (s, s), (int(480 * scale), int(640 * scale))
+        else:
+            self._scales = (self.input_W / self.sensor_W, self.input_H / self.sensor_H)
+            self._raster = (self.input_H, self.input_W)
+
+    def scales(self):
+        """(scale_x, scale_y) of ReshapeScaleXandY (datasets.py:472-480)."""
+        return self._scales
 
     def raster_hw(self):
         """(H, W) the rasteriser runs at (datasets.py:616-621)."""
-        if self.is_train:
-            scale = 256 / 480
-            return int(480 * scale), int(640 * scale)
-        return self.input_H, self.input_W
+        return self._raster
 
 
 def draw_params(n_events: int, cfg: PipelineConfig) -> dict:
@@ -134,14 +137,7 @@ def rasterise_augmented(events, offsets, aug, H, W, channels=3, *, max_stream_le
         B = int(off.numel()) - 1
         if B < 1:
             raise ValueError("offsets must have B+1 >= 2 entries")
-        if isinstance(aug, np.ndarray):
-            if aug.dtype != AUG_DTYPE or aug.shape != (B,):
-                raise ValueError(f"aug must be a ({B},) array of memb_event_aug records")
-            aug_dev = torch.from_numpy(aug.view(np.uint8).reshape(B, 64)).to(device)
-        else:
-            aug_dev = aug.to(device).contiguous()
-            if aug_dev.dtype != torch.uint8 or aug_dev.numel() != B * 64:
-                raise ValueError("aug tensor must hold B 64-byte memb_event_aug records (uint8)")
+        aug_dev = _aug_to_device(torch, aug, B, device)
         if out is None:
             out = torch.empty((B, H, W, channels), dtype=torch.uint8, device=device)
         n = int(ev.shape[0])
@@ -152,6 +148,55 @@ def rasterise_augmented(events, offsets, aug, H, W, channels=3, *, max_stream_le
         _lib.check(lib.memb_hist_aug_u8(ev.data_ptr() if n else None, n, off.data_ptr(), B,
                                         int(max_stream_len if max_stream_len is not None else n), aug_dev.data_ptr(),
                                         H, W, channels, strategy, out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        if check:
+            _lib.check(lib.memb_hist_status(ws.data_ptr(), stream))
+    return out
+
+
+def _aug_to_device(torch, aug, B, device):
+    if isinstance(aug, np.ndarray):
+        if aug.dtype != AUG_DTYPE or aug.shape != (B,):
+            raise ValueError(f"aug must be a ({B},) array of memb_event_aug records")
+        return torch.from_numpy(aug.view(np.uint8).reshape(B, 64)).to(device)
+    aug_dev = aug.to(device).contiguous()
+    if aug_dev.dtype != torch.uint8 or aug_dev.numel() != B * 64:
+        raise ValueError("aug tensor must hold B 64-byte memb_event_aug records (uint8)")
+    return aug_dev
+
+
+def pipeline_fused(events, offsets, aug, crop_tl, H, W, out_hw, channels=3, *, hot_num_stds=10.0, normalize=False,
+                   check=True, out=None):
+    """The whole chain in one kernel (``memb_event_pipeline_f32``): raw ragged batch -> ``float32 (B,C,outH,outW)``.
+    Needs ``outH * outW <= FUSED_MAX_PIXELS``; arguments as ``rasterise_augmented`` + ``post_raster``."""
+    torch = _lib.require_cuda()
+    from .process_data import _as_device_events
+    device = torch.device(events.device if (isinstance(events, torch.Tensor) and events.is_cuda) else "cuda")
+    outH, outW = int(out_hw[0]), int(out_hw[1])
+    with torch.cuda.device(device):
+        ev, _ = _as_device_events(torch, events, device)
+        off = offsets if isinstance(offsets, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64))
+        off = off.to(device=device, dtype=torch.int64).contiguous()
+        B = int(off.numel()) - 1
+        if B < 1:
+            raise ValueError("offsets must have B+1 >= 2 entries")
+        aug_dev = _aug_to_device(torch, aug, B, device)
+        crop = None
+        if crop_tl is not None:
+            crop = crop_tl if isinstance(crop_tl, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(crop_tl, dtype=np.int32))
+            crop = crop.to(device=device, dtype=torch.int32).contiguous()
+            if tuple(crop.shape) != (B, 2):
+                raise ValueError(f"crop_tl must be ({B}, 2)")
+        if out is None:
+            out = torch.empty((B, channels, outH, outW), dtype=torch.float32, device=device)
+        lib = _lib.load()
+        ws = _lib.workspace.get(torch, 256, device, "hist")
+        stream = _lib.stream_ptr(torch, device)
+        n = int(ev.shape[0])
+        _lib.check(lib.memb_event_pipeline_f32(
+            ev.data_ptr() if n else None, n, off.data_ptr(), B, aug_dev.data_ptr(),
+            crop.data_ptr() if crop is not None else None, H, W, max(outH - H, 0), max(outW - W, 0), outH, outW, channels,
+            float(hot_num_stds) if hot_num_stds is not None else -1.0, int(bool(normalize)), out.data_ptr(),
+            ws.data_ptr(), ws.numel(), stream))
         if check:
             _lib.check(lib.memb_hist_status(ws.data_ptr(), stream))
     return out
@@ -196,10 +241,14 @@ class EventBatchPipeline:
     concatenated) returns ``float32 (B, C, input_H, input_W)`` on the device, equal to stacking the reference
     transform's outputs when the generators start from the same state and samples are drawn in order."""
 
-    def __init__(self, cfg: PipelineConfig, channels: int = 3, device="cuda"):
+    def __init__(self, cfg: PipelineConfig, channels: int = 3, device="cuda", fused=None):
         if cfg.timesurface:
             raise NotImplementedError("the fused augmentation path rasterises polarity counts only (no time surface)")
         self.cfg, self.channels, self.device = cfg, channels, device
+        fits = cfg.input_H * cfg.input_W <= FUSED_MAX_PIXELS
+        if fused and not fits:
+            raise ValueError("the output raster does not fit one shared-memory tile; use fused=False")
+        self.fused = fits if fused is None else bool(fused)   # one kernel when the crop fits a shared-memory tile
 
     def __call__(self, streams, offsets=None, params=None):
         torch = _lib.require_cuda()
@@ -217,6 +266,11 @@ class EventBatchPipeline:
             params = [draw_params(int(n), cfg) for n in lens]
         aug, crop = pack_params(params)
         H, W = cfg.raster_hw()
+        hot = cfg.hotpix_num_stds if cfg.hotpixfilter else None
+        if self.fused:
+            return pipeline_fused(events, offsets, aug, crop if cfg.is_train else None, H, W,
+                                  (cfg.input_H, cfg.input_W) if cfg.is_train else (H, W), self.channels,
+                                  hot_num_stds=hot, normalize=cfg.normalize_events, check=not cfg.is_train)
         hist = rasterise_augmented(events, offsets, aug, H, W, self.channels,
                                    max_stream_len=int(max(p["count"] for p in params)) if params else 0,
                                    check=not cfg.is_train)   # after the cull every row is inside the sensor

@@ -41,10 +41,11 @@ def test_reference_golden_single_streams(golden_dir):
     from mem_b200.event_pipeline import EventBatchPipeline
     seen = 0
     for name, ev, cfg, seed, want in golden_cases(golden_dir):
-        seed_all(seed)
-        got = EventBatchPipeline(product_cfg(cfg))([ev])
-        assert got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == (1,) + want.shape, name
-        assert np.array_equal(got[0].cpu().numpy(), want), (name, float(np.abs(got[0].cpu().numpy() - want).max()))
+        for fused in (True, False):       # one-kernel path and rasterise + post-raster path
+            seed_all(seed)
+            got = EventBatchPipeline(product_cfg(cfg), fused=fused)([ev])
+            assert got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == (1,) + want.shape, name
+            assert np.array_equal(got[0].cpu().numpy(), want), (name, fused, float(np.abs(got[0].cpu().numpy() - want).max()))
         seen += 1
     assert seen >= 6
 
@@ -64,7 +65,8 @@ def test_draws_match_oracle_draws():
 @pytest.mark.parametrize("channels", [2, 3])
 def test_batch_against_oracle_all_strategies(channels):
     """Ragged batch (one empty stream, one fully culled, streams shorter and longer than the slice window)."""
-    from mem_b200.event_pipeline import PipelineConfig, draw_params, pack_params, post_raster, rasterise_augmented
+    from mem_b200.event_pipeline import (PipelineConfig, draw_params, pack_params, pipeline_fused, post_raster,
+                                         rasterise_augmented)
     rng = np.random.default_rng(3)
     cfg = PipelineCfg(is_train=True, normalize_events=True)
     pcfg = product_cfg(cfg)
@@ -90,10 +92,13 @@ def test_batch_against_oracle_all_strategies(channels):
         want = want_hist if channels == 3 else want_hist[..., 0::2]
         assert np.array_equal(got.cpu().numpy(), want), (strat, int((got.cpu().numpy() != want).sum()))
     out = post_raster(got, crop, (224, 224), hot_num_stds=10.0, normalize=True)
+    one = pipeline_fused(torch.from_numpy(events).cuda(), offsets, aug, crop, H, W, (224, 224), channels,
+                         hot_num_stds=10.0, normalize=True)
     for b, p in enumerate(params):
         w = apply_post_raster(want_hist[b], p, cfg).numpy()
         w = w if channels == 3 else w[0::2]
         assert np.array_equal(out[b].cpu().numpy(), w), b
+        assert np.array_equal(one[b].cpu().numpy(), w), ("fused", b)
 
 
 @pytest.mark.parametrize("H,W", [(200, 180), (224, 300), (256, 341)])
@@ -115,6 +120,25 @@ def test_post_raster_padding_and_switches(H, W, hot, norm):
     for b in range(B):
         want = apply_post_raster(hist[b], dict(top=int(tl[b, 0]), left=int(tl[b, 1])), cfg).numpy()
         assert np.array_equal(got[b].cpu().numpy(), want), (b, float(np.abs(got[b].cpu().numpy() - want).max()))
+
+
+def test_fused_padding_small_raster():
+    """Raster smaller than the crop (RandomCrop pads both sides): one-kernel path vs rasterise + oracle post."""
+    from mem_b200.event_pipeline import AUG_DTYPE, pipeline_fused
+    rng = np.random.default_rng(8)
+    H, W, B, n = 200, 180, 3, 20000
+    ev = np.concatenate([synth_events(rng, n, H, W, "hot") for _ in range(B)], axis=0)
+    off = np.arange(B + 1, dtype=np.int64) * n
+    aug = np.zeros(B, dtype=AUG_DTYPE)
+    aug["scale_x"] = aug["scale_y"] = 1.0
+    aug["count"] = -1
+    tl = np.array([[0, 0], [24, 44], [12, 20]], dtype=np.int32)     # padded image is 248 x 268
+    cfg = PipelineCfg(is_train=True, normalize_events=True, hotpix_num_stds=5)
+    got = pipeline_fused(ev, off, aug, tl, H, W, (224, 224), 3, hot_num_stds=5.0, normalize=True)
+    for b in range(B):
+        hist = event_hist_ref(ev[off[b]:off[b + 1]], H, W)
+        want = apply_post_raster(hist, dict(top=int(tl[b, 0]), left=int(tl[b, 1])), cfg).numpy()
+        assert np.array_equal(got[b].cpu().numpy(), want), b
 
 
 def test_full_size_properties():
