@@ -342,15 +342,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) hist_tile_smem(
 // word per pixel, so the uint8 image never exists in HBM: the stream window is read once (32 B / event) and the
 // float32 planes are written once.  Crop is applied to the integer pixel index (after numpy's truncation and
 // negative wrap), which is what cropping the rasterised image does.
-__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* scratch) {
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-  __syncthreads();
-  unsigned long long t = 0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += scratch[w];
-  return t;
+constexpr int kFuseUnroll = 2;                                   // rows per thread per iteration (double-buffered)
+constexpr int kFuseAhead = 4;                                    // iterations (64 KB each) the L2 prefetch runs ahead
+
+// Ask the copy engine to pull [p, p + bytes) into L2: no registers, no shared memory, nothing to wait on.
+__device__ __forceinline__ void prefetch_l2(const void* p, unsigned int bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+constexpr int kFuseFold = kTileChunk / (kTileThreads * kFuseUnroll);   // iterations between mod-256 folds
 
 template <bool kAligned>
 __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
@@ -358,126 +357,188 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
     const memb_event_aug* __restrict__ aug, const int* __restrict__ crop_tl, int H, int W, int pad_t, int pad_l,
     int outH, int outW, int C, float hot_num_stds, int normalize, float* __restrict__ out, Header* __restrict__ hdr) {
   extern __shared__ unsigned int tile[];
-  __shared__ unsigned long long red[kTileThreads / 32];
+  __shared__ unsigned long long red[2];
+  __shared__ unsigned int present[8];
   __shared__ float lut[256];
-  __shared__ int params[2];
+  __shared__ int params[3];
   const int b = blockIdx.x;
   long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
   const memb_event_aug a = aug[b];
-  if (threadIdx.x == 0) params[1] = 0;
   aug_window(a, begin, end);
   const long long npix = (long long)H * W;
-  const int npx = outH * outW;
+  const int npx = outH * outW, npx4 = (npx + 3) & ~3;
   const int y0 = (crop_tl ? crop_tl[2 * b] : 0) - pad_t, x0 = (crop_tl ? crop_tl[2 * b + 1] : 0) - pad_l;
-  for (int i = threadIdx.x; i < npx; i += kTileThreads) tile[i] = 0u;
+  // After the shift stage's cull every surviving row lies inside [0,cull_w) x [0,cull_h); when that window is
+  // inside the raster the truncated coordinates ARE the pixel (no wrap, no range test, 32-bit conversions).
+  const bool fast = a.cull && a.cull_w <= W && a.cull_h <= H;
+
+  // The register double buffer below keeps only ~64 KB per SM in flight, too little to cover HBM latency at
+  // full bandwidth; a bulk L2 prefetch running kFuseAhead iterations ahead turns the loads into L2 hits.
+  constexpr int kStep = kTileThreads * kFuseUnroll;
+  if (kAligned && threadIdx.x == 0 && begin < end)
+    prefetch_l2(ev + 4 * begin, (unsigned int)(min((long long)kFuseAhead * kStep, end - begin) * 32));
+  // first rows are requested before the tile is cleared: the clear overlaps their latency
+  Event nxt[kFuseUnroll];
+#pragma unroll
+  for (int u = 0; u < kFuseUnroll; ++u) {
+    const long long r = begin + u * kTileThreads + threadIdx.x;
+    if (r < end) nxt[u] = load_event<kAligned>(ev, r);
+  }
+  if (threadIdx.x < 2) red[threadIdx.x] = 0ull;
+  if (threadIdx.x < 8) present[threadIdx.x] = 0u;
+  if (threadIdx.x < 256) lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);   // ToTensor value of count c
+  for (int i = threadIdx.x * 4; i < npx4; i += kTileThreads * 4) *reinterpret_cast<uint4*>(tile + i) = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
 
   bool bad = false;
-  for (long long chunk = begin; chunk < end; chunk += kTileChunk) {
-    const long long stop = min(end, chunk + (long long)kTileChunk);
-    for (long long base = chunk; base < stop; base += kTileThreads * kTileUnroll) {
-      Event e[kTileUnroll];
-      bool live[kTileUnroll];
+  int it = 0;
+  for (long long base = begin; base < end; base += kStep, ++it) {
+    Event cur[kFuseUnroll];
+    bool live[kFuseUnroll];
 #pragma unroll
-      for (int u = 0; u < kTileUnroll; ++u) {
-        long long r = base + u * kTileThreads + threadIdx.x;
-        live[u] = r < stop;
-        if (live[u]) e[u] = load_event<kAligned>(ev, r);
+    for (int u = 0; u < kFuseUnroll; ++u) {
+      cur[u] = nxt[u];
+      live[u] = base + u * kTileThreads + threadIdx.x < end;
+    }
+    if (kAligned && threadIdx.x == 0) {
+      const long long far = base + (long long)kFuseAhead * kStep;
+      if (far < end) prefetch_l2(ev + 4 * far, (unsigned int)(min((long long)kStep, end - far) * 32));
+    }
+#pragma unroll
+    for (int u = 0; u < kFuseUnroll; ++u) {            // next iteration's rows into registers
+      const long long r = base + kStep + u * kTileThreads + threadIdx.x;
+      if (r < end) nxt[u] = load_event<kAligned>(ev, r);
+    }
+#pragma unroll
+    for (int u = 0; u < kFuseUnroll; ++u) {
+      if (live[u]) live[u] = apply_aug(cur[u], a);
+      const bool pos = live[u] && cur[u].p == 1.0, neg = live[u] && cur[u].p == -1.0;
+      if (pos || neg) {
+        int x, y;
+        bool ok = true;
+        if (fast) {
+          x = __double2int_rz(cur[u].x);
+          y = __double2int_rz(cur[u].y);
+        } else {
+          long long idx = 0;
+          ok = pixel_index(cur[u].x, cur[u].y, W, npix, idx);
+          y = (int)(idx / W);
+          x = (int)(idx - (long long)y * W);
+        }
+        if (!ok) {
+          bad = true;
+        } else {
+          y -= y0;
+          x -= x0;
+          if ((unsigned)y < (unsigned)outH && (unsigned)x < (unsigned)outW)
+            atomicAdd(&tile[y * outW + x], pos ? 1u : 0x10000u);
+        }
       }
+    }
+    if ((it + 1) % kFuseFold == 0 && base + kStep < end) {     // halves can never carry: fold them mod 256
+      __syncthreads();
+      for (int i = threadIdx.x; i < npx4; i += kTileThreads) tile[i] &= 0x00ff00ffu;
+      __syncthreads();
+    }
+  }
+  if (bad) hdr->oob = 1;
+  __syncthreads();
+
+  // ---- pass 1: counts mod 256 (uint8 wrap) in place, exact integer sums for RemoveHotPixels, and a 256-bit
+  //      presence map of max(pos, neg) per pixel (what NormalizeEvent's maximum is read from once the hot
+  //      threshold is known -- no second scan).  Event images are sparse: all-zero quads cost one 16-byte read.
+  const bool filter = hot_num_stds >= 0.0f;
+  {
+    unsigned long long s1 = 0, s2 = 0;
+    unsigned int seen0 = 0u;                            // counts < 32 (nearly all of them); larger ones go to smem
+    for (int i = threadIdx.x * 4; i < npx4; i += kTileThreads * 4) {
+      uint4 q = *reinterpret_cast<uint4*>(tile + i);
+      if ((q.x | q.y | q.z | q.w) == 0u) continue;
+      q.x &= 0x00ff00ffu; q.y &= 0x00ff00ffu; q.z &= 0x00ff00ffu; q.w &= 0x00ff00ffu;
+      *reinterpret_cast<uint4*>(tile + i) = q;
+      const unsigned int w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-      for (int u = 0; u < kTileUnroll; ++u) {
-        if (live[u]) live[u] = apply_aug(e[u], a);
-        const bool pos = live[u] && e[u].p == 1.0, neg = live[u] && e[u].p == -1.0;
-        if (pos || neg) {
-          long long idx;
-          if (!pixel_index(e[u].x, e[u].y, W, npix, idx)) {
-            bad = true;
-          } else {
-            const int y = (int)(idx / W) - y0, x = (int)(idx % W) - x0;
-            if (y >= 0 && y < outH && x >= 0 && x < outW) atomicAdd(&tile[y * outW + x], pos ? 1u : 0x10000u);
+      for (int k = 0; k < 4; ++k) {
+        const unsigned int cp = w[k] & 0xffu, cn = w[k] >> 16, m = max(cp, cn);
+        s1 += cp + cn;
+        s2 += cp * cp + cn * cn;
+        if (m < 32u) seen0 |= 1u << m;
+        else atomicOr(&present[m >> 5], 1u << (m & 31u));
+      }
+    }
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    seen0 = __reduce_or_sync(0xffffffffu, seen0);
+    if ((threadIdx.x & 31) == 0) {
+      if (s1) atomicAdd(&red[0], s1);
+      if (s2) atomicAdd(&red[1], s2);
+      if (seen0) atomicOr(&present[0], seen0);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // warp 0: threshold -> largest count that is NOT hot -> maximum surviving count -> scale factor
+    int c_keep = 255;
+    if (filter) {
+      // exact sums, one rounding to float32 (see raster_post.cu for the rounding argument)
+      const double s1 = (double)red[0], s2 = (double)red[1], n = 2.0 * (double)npx;
+      const double mean = s1 / (255.0 * n);
+      double var = (s2 - s1 * s1 / n) / ((n - 1.0) * 255.0 * 255.0);
+      var = var > 0.0 ? var : 0.0;
+      const float thr = (float)(mean + (double)hot_num_stds * sqrt(var));
+      int cold = 0;                                     // lut is monotone: count the entries not above thr
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cold += !(lut[threadIdx.x * 8 + k] > thr);
+      cold = __reduce_add_sync(0xffffffffu, cold);
+      c_keep = cold - 1;                                // counts 0 .. c_keep survive (-1: everything is hot)
+    }
+    if (threadIdx.x == 0) {
+      int m = 0;
+      for (int c = min(c_keep, 255); c > 0 && m == 0; --c)
+        if (present[c >> 5] >> (c & 31) & 1u) m = c;
+      params[0] = c_keep;
+      params[1] = (normalize && m != 0) ? 1 : 0;
+      // factor = 1.0 / x.max(), x.max() = fl32(cmax / 255)   (transforms.py:234-236)
+      params[2] = __float_as_int((normalize && m != 0) ? __fdiv_rn(1.0f, lut[m]) : 1.0f);
+    }
+  }
+  __syncthreads();
+  const int c_keep = params[0];
+  const bool scale = params[1] != 0;
+  const float factor = __int_as_float(params[2]);
+  // ---- pass 3: float32 planes, 4 pixels (16 B) per thread per plane, streaming stores
+  float* o = out + (long long)b * C * npx;
+  float* o_neg = o + (long long)(C - 1) * npx;
+  const bool vec = (npx & 3) == 0;
+  for (int i = threadIdx.x * 4; i < npx4; i += kTileThreads * 4) {
+    const uint4 q = *reinterpret_cast<const uint4*>(tile + i);
+    float vp[4] = {0.f, 0.f, 0.f, 0.f}, vn[4] = {0.f, 0.f, 0.f, 0.f};
+    if ((q.x | q.y | q.z | q.w) != 0u) {
+      const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cp = (int)(w[k] & 0xffu), cn = (int)(w[k] >> 16);
+        if (w[k] != 0u && cp <= c_keep && cn <= c_keep) {
+          vp[k] = lut[cp];
+          vn[k] = lut[cn];
+          if (scale) {
+            vp[k] = __fmul_rn(vp[k], factor);
+            vn[k] = __fmul_rn(vn[k], factor);
           }
         }
       }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < npx; i += kTileThreads) tile[i] &= 0x00ff00ffu;   // counts mod 256 (uint8 wrap)
-    __syncthreads();
-  }
-  if (bad) hdr->oob = 1;
-
-  // ---- value table: lut[c] = fl32(c / 255), the ToTensor value of count c (one division per entry, not per pixel)
-  if (threadIdx.x < 256) lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
-  // ---- RemoveHotPixels: threshold from exact integer sums (see raster_post.cu for the rounding argument),
-  //      turned into the largest count that is NOT hot so that the passes below compare integers
-  const bool filter = hot_num_stds >= 0.0f;
-  if (filter) {
-    unsigned long long s1 = 0, s2 = 0;
-    for (int i = threadIdx.x; i < npx; i += kTileThreads) {
-      const unsigned int w = tile[i], cp = w & 0xffu, cn = w >> 16;
-      s1 += cp + cn;
-      s2 += cp * cp + cn * cn;
-    }
-    s1 = block_sum_u64(s1, red);
-    s2 = block_sum_u64(s2, red);
-    const double n = 2.0 * (double)npx;
-    const double mean = (double)s1 / (255.0 * n);
-    double var = ((double)s2 - (double)s1 * (double)s1 / n) / ((n - 1.0) * 255.0 * 255.0);
-    var = var > 0.0 ? var : 0.0;
-    const float thr = (float)(mean + (double)hot_num_stds * sqrt(var));
-    // lut is monotone: count the entries that are not above the threshold
-    const bool cold = threadIdx.x < 256 && !(lut[threadIdx.x] > thr);   // own entry, written by this thread
-    const int n_cold = __syncthreads_count(cold);
-    if (threadIdx.x == 0) params[0] = n_cold - 1;          // counts 0 .. params[0] survive (-1: everything is hot)
-  } else {
-    if (threadIdx.x == 0) params[0] = 255;
-  }
-  __syncthreads();
-  const int c_keep = params[0];
-  // ---- NormalizeEvent factor from the maximum surviving count
-  float factor = 1.0f;
-  bool scale = false;
-  if (normalize) {
-    unsigned int m = 0;
-    for (int i = threadIdx.x; i < npx; i += kTileThreads) {
-      const unsigned int w = tile[i];
-      const int cp = (int)(w & 0xffu), cn = (int)(w >> 16);
-      if (cp <= c_keep && cn <= c_keep) m = max(m, (unsigned int)max(cp, cn));
-    }
-    m = __reduce_max_sync(0xffffffffu, m);
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(&params[1], (int)m);
-    __syncthreads();
-    m = (unsigned int)params[1];
-    if (m != 0) {
-      factor = __fdiv_rn(1.0f, lut[m]);
-      scale = true;
-    }
-  }
-  // ---- float32 planes, 4 pixels (16 B) per thread per plane
-  float* o = out + (long long)b * C * npx;
-  float* o_neg = o + (long long)(C - 1) * npx;
-  for (int i = threadIdx.x * 4; i < npx; i += kTileThreads * 4) {
-    float vp[4], vn[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const unsigned int w = (i + j < npx) ? tile[i + j] : 0u;
-      const int cp = (int)(w & 0xffu), cn = (int)(w >> 16);
-      const bool hot = cp > c_keep || cn > c_keep;
-      vp[j] = hot ? 0.0f : lut[cp];
-      vn[j] = hot ? 0.0f : lut[cn];
-      if (scale) {
-        vp[j] = __fmul_rn(vp[j], factor);
-        vn[j] = __fmul_rn(vn[j], factor);
-      }
-    }
-    if (i + 3 < npx && (npx & 3) == 0) {
+    if (vec) {
       __stcs(reinterpret_cast<float4*>(o + i), make_float4(vp[0], vp[1], vp[2], vp[3]));
       __stcs(reinterpret_cast<float4*>(o_neg + i), make_float4(vn[0], vn[1], vn[2], vn[3]));
       if (C == 3) __stcs(reinterpret_cast<float4*>(o + npx + i), make_float4(0.f, 0.f, 0.f, 0.f));
     } else {
-      for (int j = 0; j < 4 && i + j < npx; ++j) {
-        o[i + j] = vp[j];
-        o_neg[i + j] = vn[j];
-        if (C == 3) o[npx + i + j] = 0.0f;
+      for (int k = 0; k < 4 && i + k < npx; ++k) {
+        o[i + k] = vp[k];
+        o_neg[i + k] = vn[k];
+        if (C == 3) o[npx + i + k] = 0.0f;
       }
     }
   }

@@ -167,38 +167,59 @@ def _aug_to_device(torch, aug, B, device):
 def pipeline_fused(events, offsets, aug, crop_tl, H, W, out_hw, channels=3, *, hot_num_stds=10.0, normalize=False,
                    check=True, out=None):
     """The whole chain in one kernel (``memb_event_pipeline_f32``): raw ragged batch -> ``float32 (B,C,outH,outW)``.
-    Needs ``outH * outW <= FUSED_MAX_PIXELS``; arguments as ``rasterise_augmented`` + ``post_raster``."""
+    Needs ``outH * outW <= FUSED_MAX_PIXELS``; arguments as ``rasterise_augmented`` + ``post_raster``.
+    Inputs that already are contiguous CUDA tensors of the right dtype are used as they are (no copies)."""
     torch = _lib.require_cuda()
-    from .process_data import _as_device_events
-    device = torch.device(events.device if (isinstance(events, torch.Tensor) and events.is_cuda) else "cuda")
     outH, outW = int(out_hw[0]), int(out_hw[1])
-    with torch.cuda.device(device):
+    ready = (isinstance(events, torch.Tensor) and events.is_cuda and events.dtype == torch.float64 and events.is_contiguous()
+             and events.ndim == 2 and events.shape[1] == 4)
+    device = events.device if ready else torch.device(
+        events.device if (isinstance(events, torch.Tensor) and events.is_cuda) else "cuda")
+    if device.index is not None and device.index != torch.cuda.current_device():
+        with torch.cuda.device(device):
+            return pipeline_fused(events, offsets, aug, crop_tl, H, W, out_hw, channels, hot_num_stds=hot_num_stds,
+                                  normalize=normalize, check=check, out=out)
+    if ready:
+        ev = events
+    else:
+        from .process_data import _as_device_events
         ev, _ = _as_device_events(torch, events, device)
+    if isinstance(offsets, torch.Tensor) and offsets.is_cuda and offsets.dtype == torch.int64 and offsets.is_contiguous():
+        off = offsets
+    else:
         off = offsets if isinstance(offsets, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64))
         off = off.to(device=device, dtype=torch.int64).contiguous()
-        B = int(off.numel()) - 1
-        if B < 1:
-            raise ValueError("offsets must have B+1 >= 2 entries")
+    B = off.numel() - 1
+    if B < 1:
+        raise ValueError("offsets must have B+1 >= 2 entries")
+    if isinstance(aug, torch.Tensor) and aug.is_cuda and aug.dtype == torch.uint8 and aug.is_contiguous() and aug.numel() == B * 64:
+        aug_dev = aug
+    else:
         aug_dev = _aug_to_device(torch, aug, B, device)
-        crop = None
-        if crop_tl is not None:
+    crop = None
+    if crop_tl is not None:
+        if isinstance(crop_tl, torch.Tensor) and crop_tl.is_cuda and crop_tl.dtype == torch.int32 and crop_tl.is_contiguous():
+            crop = crop_tl
+        else:
             crop = crop_tl if isinstance(crop_tl, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(crop_tl, dtype=np.int32))
             crop = crop.to(device=device, dtype=torch.int32).contiguous()
-            if tuple(crop.shape) != (B, 2):
-                raise ValueError(f"crop_tl must be ({B}, 2)")
-        if out is None:
-            out = torch.empty((B, channels, outH, outW), dtype=torch.float32, device=device)
-        lib = _lib.load()
-        ws = _lib.workspace.get(torch, 256, device, "hist")
-        stream = _lib.stream_ptr(torch, device)
-        n = int(ev.shape[0])
-        _lib.check(lib.memb_event_pipeline_f32(
-            ev.data_ptr() if n else None, n, off.data_ptr(), B, aug_dev.data_ptr(),
-            crop.data_ptr() if crop is not None else None, H, W, max(outH - H, 0), max(outW - W, 0), outH, outW, channels,
-            float(hot_num_stds) if hot_num_stds is not None else -1.0, int(bool(normalize)), out.data_ptr(),
-            ws.data_ptr(), ws.numel(), stream))
-        if check:
-            _lib.check(lib.memb_hist_status(ws.data_ptr(), stream))
+        if tuple(crop.shape) != (B, 2):
+            raise ValueError(f"crop_tl must be ({B}, 2)")
+    if out is None:
+        out = torch.empty((B, channels, outH, outW), dtype=torch.float32, device=device)
+    elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, channels, outH, outW)):
+        raise ValueError("out must be a contiguous float32 CUDA tensor (B, channels, outH, outW)")
+    lib = _lib.load()
+    ws = _lib.workspace.get(torch, 256, device, "hist")
+    stream = _lib.stream_ptr(torch, device)
+    n = ev.shape[0]
+    _lib.check(lib.memb_event_pipeline_f32(
+        ev.data_ptr() if n else None, n, off.data_ptr(), B, aug_dev.data_ptr(),
+        crop.data_ptr() if crop is not None else None, H, W, max(outH - H, 0), max(outW - W, 0), outH, outW, channels,
+        float(hot_num_stds) if hot_num_stds is not None else -1.0, int(bool(normalize)), out.data_ptr(),
+        ws.data_ptr(), ws.numel(), stream))
+    if check:
+        _lib.check(lib.memb_hist_status(ws.data_ptr(), stream))
     return out
 
 
