@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
     const memb_event_aug* __restrict__ aug, const int* __restrict__ crop_tl, int H, int W, int pad_t, int pad_l,
     int outH, int outW, int C, float hot_num_stds, int normalize, float* __restrict__ out, Header* __restrict__ hdr) {
   extern __shared__ unsigned int tile[];
-  __shared__ unsigned long long red[2];
+  __shared__ unsigned long long red[2][kTileThreads / 32];   // per-warp partial sums (no 64-bit smem atomics)
   __shared__ unsigned int present[8];
   __shared__ float lut[256];
   __shared__ int params[3];
@@ -384,7 +384,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
     const long long r = begin + u * kTileThreads + threadIdx.x;
     if (r < end) nxt[u] = load_event<kAligned>(ev, r);
   }
-  if (threadIdx.x < 2) red[threadIdx.x] = 0ull;
   if (threadIdx.x < 8) present[threadIdx.x] = 0u;
   if (threadIdx.x < 256) lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);   // ToTensor value of count c
   for (int i = threadIdx.x * 4; i < npx4; i += kTileThreads * 4) *reinterpret_cast<uint4*>(tile + i) = make_uint4(0u, 0u, 0u, 0u);
@@ -472,8 +471,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
     }
     seen0 = __reduce_or_sync(0xffffffffu, seen0);
     if ((threadIdx.x & 31) == 0) {
-      if (s1) atomicAdd(&red[0], s1);
-      if (s2) atomicAdd(&red[1], s2);
+      red[0][threadIdx.x >> 5] = s1;
+      red[1][threadIdx.x >> 5] = s2;
       if (seen0) atomicOr(&present[0], seen0);
     }
   }
@@ -483,7 +482,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
     int c_keep = 255;
     if (filter) {
       // exact sums, one rounding to float32 (see raster_post.cu for the rounding argument)
-      const double s1 = (double)red[0], s2 = (double)red[1], n = 2.0 * (double)npx;
+      unsigned long long t1 = red[0][threadIdx.x], t2 = red[1][threadIdx.x];
+      for (int o = 16; o; o >>= 1) {
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+      }
+      const double s1 = (double)t1, s2 = (double)t2, n = 2.0 * (double)npx;
       const double mean = s1 / (255.0 * n);
       double var = (s2 - s1 * s1 / n) / ((n - 1.0) * 255.0 * 255.0);
       var = var > 0.0 ? var : 0.0;
