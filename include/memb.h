@@ -137,6 +137,25 @@ int memb_raster_post_f32(const uint8_t* hist, int B, int H, int W, int C, const 
 
 
 /* ------------------------------------------------------------------------
+ * Raw recording formats.  Replaces the byte-by-byte Python decoders of
+ * process_data/process_dataset.py: ncaltech101 (:24-63, 40-bit big-endian records) and ncars (:66-103,
+ * Prophesee .dat: uint32 timestamp + uint32 data, little endian; the '%' header lines and the two
+ * type/size bytes are skipped by the caller, mem_b200/process_data.py).
+ * ---------------------------------------------------------------------- */
+#define MEMB_RAW_NCALTECH101 1 /* 5 bytes: col0 = b0, col1 = b1, p = 2*(b2>>7)-1, t = ((b2&0x7f)<<16)|(b3<<8)|b4 */
+#define MEMB_RAW_NCARS 2       /* 8 bytes: t = u32, d = u32: col0 = d&0x3fff, col1 = (d>>14)&0x3fff, p = (d>>28)&1 */
+
+/* raw: device bytes, 16-byte aligned, n_records records.  out: float64 [n_records,4] rows exactly as the
+ * reference's .npy files hold them ([col0, col1, t, p]), 32-byte aligned. */
+int memb_decode_events_f64(const uint8_t* raw, int64_t n_records, int format, double* out, memb_stream_t stream);
+
+/* Rasterise one recording straight from its raw records (no float64 rows in HBM): identical to
+ * memb_hist_u8(decode(raw)) with strategy GLOBAL, no time surface.  Workspace:
+ * memb_hist_workspace_bytes(1, n_records, H, W, 0, MEMB_HIST_GLOBAL); status via memb_hist_status. */
+int memb_hist_raw_u8(const uint8_t* raw, int64_t n_records, int format, int H, int W, int C, uint8_t* out,
+                     void* ws, size_t ws_bytes, memb_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * tcgen05 GEMM with fused epilogues:  D[M,N] = epi( A[M,K] * B[N,K]^T ).
  * Replaces the cuBLASLt / cuDNN calls behind nn.Linear / nn.Conv2d on the hot
  * path: mem/modeling_finetune.py:61-71 (Mlp), :130-155 (qkv, proj), :203-209

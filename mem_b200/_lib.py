@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("MEMB_LIB_PATH") or os.path.join(_HERE, "libmemb.so") 
 MEMB_OK, MEMB_EINVAL, MEMB_EOOB, MEMB_ECUDA, MEMB_EWORKSPACE = 0, -1, -2, -3, -4
 
 HIST_AUTO, HIST_GLOBAL, HIST_GLOBAL_AGG, HIST_TILE = 0, 1, 2, 3
+RAW_NCALTECH101, RAW_NCARS = 1, 2
 
 _c = ctypes
 _vp, _i32, _i64, _sz, _f32 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_size_t, _c.c_float
@@ -30,6 +31,8 @@ SIGNATURES = {
     "memb_hist_u8": (_i32, [_vp, _i64, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "memb_hist_status": (_i32, [_vp, _vp]),
     "memb_hist_extent": (_i32, [_vp, _i64, _vp, _vp, _sz, _vp]),
+    "memb_decode_events_f64": (_i32, [_vp, _i64, _i32, _vp, _vp]),
+    "memb_hist_raw_u8": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "memb_hist_aug_u8": (_i32, [_vp, _i64, _vp, _i32, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "memb_event_pipeline_f32": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32,
                                        _vp, _vp, _sz, _vp]),

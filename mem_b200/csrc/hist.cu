@@ -548,6 +548,92 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
   }
 }
 
+// ---------------------------------------------------------------- raw record formats
+// The reference turns raw recordings into float64 [N,4] .npy files with byte-by-byte Python loops
+// (process_data/process_dataset.py): N-Caltech101 40-bit big-endian records (:47-60) and N-Cars / Prophesee
+// .dat 64-bit little-endian records (:85-99).  decode_record restates the bit fields; the decoder kernel
+// writes the reference's rows, the raw rasteriser feeds the same fields straight into the scatter so that a
+// recording costs 5 or 8 bytes per event of HBM (and PCIe) traffic instead of 32.
+template <int kFmt>
+__device__ __forceinline__ Event decode_record(const uint8_t* __restrict__ rec) {
+  Event e;
+  if constexpr (kFmt == MEMB_RAW_NCALTECH101) {
+    // column 0 = byte 0, column 1 = byte 1, p = bit 7 of byte 2 -> {-1,+1}, t = low 23 bits, big endian
+    e.x = (double)rec[0];
+    e.y = (double)rec[1];
+    e.p = (rec[2] & 0x80u) ? 1.0 : -1.0;
+    e.t = (double)(((unsigned int)(rec[2] & 0x7fu) << 16) | ((unsigned int)rec[3] << 8) | (unsigned int)rec[4]);
+  } else {
+    // uint32 timestamp, then uint32 data: column 0 = bits 0-13, column 1 = bits 14-27, p = bit 28 -> {0,1}
+    const unsigned int t = *reinterpret_cast<const unsigned int*>(rec);
+    const unsigned int d = *reinterpret_cast<const unsigned int*>(rec + 4);
+    e.x = (double)(d & 0x3fffu);
+    e.y = (double)((d & 0x0fffc000u) >> 14);
+    e.t = (double)t;
+    e.p = (d & 0x10000000u) ? 1.0 : 0.0;
+  }
+  return e;
+}
+
+constexpr int kRawRecords = 4096;   // records staged per CTA iteration (20 KB of 5-byte records)
+
+// Stage `count` records starting at record `first` into shared memory with 16-byte loads (raw is 16-byte
+// aligned; the first / last partial vectors are read bytewise so nothing outside the buffer is touched).
+template <int kBytes>
+__device__ __forceinline__ const uint8_t* stage_records(const uint8_t* __restrict__ raw, long long first, int count,
+                                                        long long n_total, uint8_t* smem) {
+  const long long b0 = first * kBytes, b1 = (first + count) * kBytes;
+  const long long v0 = b0 & ~15LL;                       // aligned start (>= 0, inside the buffer)
+  const long long v1 = min((b1 + 15) & ~15LL, (n_total * kBytes) & ~15LL);   // last full vector boundary inside the buffer
+  for (long long v = v0 + 16LL * threadIdx.x; v < v1; v += 16LL * blockDim.x)
+    *reinterpret_cast<uint4*>(smem + (v - v0)) = __ldg(reinterpret_cast<const uint4*>(raw + v));
+  for (long long q = max(v1, v0) + threadIdx.x; q < b1; q += blockDim.x) smem[q - v0] = raw[q];   // tail bytes
+  __syncthreads();
+  return smem + (b0 - v0);
+}
+
+template <int kFmt>
+__global__ void __launch_bounds__(kThreads) decode_events_kernel(const uint8_t* __restrict__ raw, long long n,
+                                                                 double* __restrict__ out) {
+  constexpr int kBytes = kFmt == MEMB_RAW_NCALTECH101 ? 5 : 8;
+  __shared__ __align__(16) uint8_t stage[kRawRecords * kBytes + 32];
+  for (long long first = (long long)blockIdx.x * kRawRecords; first < n; first += (long long)gridDim.x * kRawRecords) {
+    const int count = (int)min((long long)kRawRecords, n - first);
+    const uint8_t* rec = stage_records<kBytes>(raw, first, count, n, stage);
+    for (int r = threadIdx.x; r < count; r += kThreads) {
+      const Event e = decode_record<kFmt>(rec + r * kBytes);
+      double* o = out + 4 * (first + r);
+      asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(o), "d"(e.x), "d"(e.y), "d"(e.t), "d"(e.p) : "memory");
+    }
+    __syncthreads();
+  }
+}
+
+// GLOBAL strategy straight from raw records: acc u32 [2][npix] as in hist_scatter_global.
+template <int kFmt>
+__global__ void __launch_bounds__(kThreads) hist_scatter_raw(const uint8_t* __restrict__ raw, long long n, int W,
+                                                             long long npix, unsigned int* __restrict__ acc,
+                                                             Header* __restrict__ hdr) {
+  constexpr int kBytes = kFmt == MEMB_RAW_NCALTECH101 ? 5 : 8;
+  __shared__ __align__(16) uint8_t stage[kRawRecords * kBytes + 32];
+  bool bad = false;
+  for (long long first = (long long)blockIdx.x * kRawRecords; first < n; first += (long long)gridDim.x * kRawRecords) {
+    const int count = (int)min((long long)kRawRecords, n - first);
+    const uint8_t* rec = stage_records<kBytes>(raw, first, count, n, stage);
+    for (int r = threadIdx.x; r < count; r += kThreads) {
+      const Event e = decode_record<kFmt>(rec + r * kBytes);
+      const bool pos = e.p == 1.0, neg = e.p == -1.0;
+      if (pos || neg) {
+        long long idx;
+        if (!pixel_index(e.x, e.y, W, npix, idx)) bad = true;
+        else atomicAdd(acc + (neg ? npix : 0) + idx, 1u);
+      }
+    }
+    __syncthreads();
+  }
+  if (bad) hdr->oob = 1;
+}
+
 // ---------------------------------------------------------------- extent (H/W = None)
 template <bool kAligned>
 __global__ void __launch_bounds__(kThreads) hist_extent(const double* __restrict__ ev, long long n,
@@ -742,6 +828,59 @@ extern "C" int memb_event_pipeline_f32(const double* ev, int64_t n, const int64_
                                           pad_l, outH, outW, C, hot_num_stds, normalize, out,
                                           reinterpret_cast<Header*>(ws));
   MEMB_LAUNCH_OK("event_pipeline_fused");
+  return MEMB_OK;
+}
+
+extern "C" int memb_decode_events_f64(const uint8_t* raw, int64_t n_records, int format, double* out,
+                                      memb_stream_t stream) {
+  MEMB_REQUIRE(format == MEMB_RAW_NCALTECH101 || format == MEMB_RAW_NCARS, "decode: unknown record format %d", format);
+  MEMB_REQUIRE(n_records >= 0, "decode: negative record count");
+  if (n_records == 0) return MEMB_OK;
+  MEMB_REQUIRE(raw != nullptr && out != nullptr, "decode: null pointer");
+  MEMB_REQUIRE((((uintptr_t)raw) & 15u) == 0 && (((uintptr_t)out) & 31u) == 0,
+               "decode: raw records must be 16-byte aligned and the output 32-byte aligned");
+  const int blocks = (int)std::min<long long>(ceil_div<long long>(n_records, kRawRecords), (long long)num_sms() * 8);
+  if (format == MEMB_RAW_NCALTECH101) decode_events_kernel<MEMB_RAW_NCALTECH101><<<blocks, kThreads, 0, stream>>>(raw, n_records, out);
+  else decode_events_kernel<MEMB_RAW_NCARS><<<blocks, kThreads, 0, stream>>>(raw, n_records, out);
+  MEMB_LAUNCH_OK("decode_events_kernel");
+  return MEMB_OK;
+}
+
+extern "C" int memb_hist_raw_u8(const uint8_t* raw, int64_t n_records, int format, int H, int W, int C, uint8_t* out,
+                                void* ws, size_t ws_bytes, memb_stream_t stream) {
+  MEMB_REQUIRE(format == MEMB_RAW_NCALTECH101 || format == MEMB_RAW_NCARS, "hist_raw: unknown record format %d", format);
+  MEMB_REQUIRE(H >= 1 && W >= 1 && (C == 2 || C == 3), "hist_raw: bad shape (H=%d W=%d C=%d)", H, W, C);
+  MEMB_REQUIRE(n_records >= 0 && (n_records == 0 || raw != nullptr), "hist_raw: null record pointer");
+  MEMB_REQUIRE(out != nullptr && ws != nullptr, "hist_raw: null output / workspace");
+  MEMB_REQUIRE((((uintptr_t)raw) & 15u) == 0 && (((uintptr_t)ws) & 15u) == 0, "hist_raw: misaligned pointer");
+  const long long npix = (long long)H * W;
+  const Plan p = make_plan(1, n_records, H, W, 0, MEMB_HIST_GLOBAL);
+  if (ws_bytes < p.ws_bytes)
+    return fail(MEMB_EWORKSPACE, "hist_raw: workspace %zu B < required %zu B", ws_bytes, p.ws_bytes);
+  char* wsb = static_cast<char*>(ws);
+  Header* hdr = reinterpret_cast<Header*>(wsb);
+  unsigned int* acc = reinterpret_cast<unsigned int*>(wsb + p.off_acc);
+  const int sms = num_sms();
+  {
+    const long long n_vec = (long long)(p.ws_bytes / 16);
+    const int blocks = (int)std::min<long long>(ceil_div<long long>(n_vec, 256), (long long)sms * 8);
+    hist_init<<<blocks, 256, 0, stream>>>(reinterpret_cast<uint4*>(wsb), n_vec, -1LL, 1);
+    MEMB_LAUNCH_OK("hist_init");
+  }
+  if (n_records > 0) {
+    const int blocks = (int)std::min<long long>(ceil_div<long long>(n_records, kRawRecords), (long long)sms * 8);
+    if (format == MEMB_RAW_NCALTECH101)
+      hist_scatter_raw<MEMB_RAW_NCALTECH101><<<blocks, kThreads, 0, stream>>>(raw, n_records, W, npix, acc, hdr);
+    else
+      hist_scatter_raw<MEMB_RAW_NCARS><<<blocks, kThreads, 0, stream>>>(raw, n_records, W, npix, acc, hdr);
+    MEMB_LAUNCH_OK("hist_scatter_raw");
+  }
+  {
+    const long long fx = std::min<long long>(ceil_div<long long>(npix, 256), (long long)sms * 8);
+    hist_finalize<false><<<(unsigned)std::max<long long>(1, fx), 256, 0, stream>>>(acc, nullptr, nullptr, nullptr, nullptr,
+                                                                                  npix, C, out);
+    MEMB_LAUNCH_OK("hist_finalize");
+  }
   return MEMB_OK;
 }
 

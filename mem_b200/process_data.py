@@ -16,7 +16,11 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["histogram", "histogram_batch"]
+__all__ = ["histogram", "histogram_batch", "decode_events", "histogram_raw", "read_ncaltech101_bin", "read_ncars_dat",
+           "RAW_NCALTECH101", "RAW_NCARS"]
+
+RAW_NCALTECH101, RAW_NCARS = _lib.RAW_NCALTECH101, _lib.RAW_NCARS
+_RECORD_BYTES = {RAW_NCALTECH101: 5, RAW_NCARS: 8}
 
 
 def _as_device_events(torch, events, device):
@@ -117,4 +121,83 @@ def histogram_batch(events, offsets, H, W, channels=3, timesurface=False, *, max
         if out is None:
             out = torch.empty((B, H, W, channels), dtype=torch.uint8, device=device)
         _launch(torch, ev, off, B, int(max_stream_len or 0), H, W, channels, timesurface, strategy, out, check)
+    return out.cpu().numpy() if numpy_in else out
+
+
+# ----------------------------------------------------------------------------- raw recordings
+def read_ncaltech101_bin(path) -> np.ndarray:
+    """Raw bytes of an N-Caltech101 ``.bin`` recording: a sequence of 5-byte records, no header
+    (reference ``process_data/process_dataset.py:47-51`` reads them with ``file.read(5)`` until EOF; a trailing
+    partial record would make the reference raise ``IndexError`` -- here it raises ``ValueError``)."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    if raw.size % 5:
+        raise ValueError(f"{path}: {raw.size} bytes is not a whole number of 5-byte records")
+    return raw
+
+
+def read_ncars_dat(path) -> np.ndarray:
+    """Raw record bytes of an N-Cars / Prophesee ``.dat`` file: skips the ``%`` header lines and the two
+    type / size bytes like the reference (``process_data/process_dataset.py:77-85``), returns the 8-byte records.
+    A trailing partial record makes the reference's ``struct.unpack`` raise; here it raises ``ValueError``."""
+    with open(path, "rb") as f:
+        while True:
+            pos = f.tell()
+            line = f.readline(256)
+            if not line or line[0] != 37:
+                f.seek(pos)
+                break
+        f.read(2)
+        raw = np.frombuffer(f.read(), dtype=np.uint8)
+    if raw.size % 8:
+        raise ValueError(f"{path}: {raw.size} payload bytes is not a whole number of 8-byte records")
+    return raw
+
+
+def _raw_on_device(torch, raw, fmt, device):
+    if fmt not in _RECORD_BYTES:
+        raise ValueError(f"unknown raw record format {fmt}")
+    t = raw if isinstance(raw, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(raw), dtype=np.uint8))
+    if t.dtype != torch.uint8 or t.ndim != 1:
+        raise ValueError("raw records must be a flat uint8 buffer")
+    if t.numel() % _RECORD_BYTES[fmt]:
+        raise ValueError(f"{t.numel()} bytes is not a whole number of {_RECORD_BYTES[fmt]}-byte records")
+    t = t.to(device).contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()        # a slice of a larger buffer: the kernels want 16-byte aligned records
+    return t, t.numel() // _RECORD_BYTES[fmt]
+
+
+def decode_events(raw, fmt, *, device=None):
+    """Raw record bytes -> ``float64 (N, 4)`` rows ``[col0, col1, t, p]``, the array the reference's
+    ``process_dataset.py`` stores as ``.npy`` (N-Caltech101: p in {-1,+1}; N-Cars: p in {0,1}).
+    numpy in -> numpy out; tensor in -> CUDA tensor out."""
+    torch = _lib.require_cuda()
+    numpy_in = not isinstance(raw, torch.Tensor)
+    device = torch.device(device if device is not None else (raw.device if (not numpy_in and raw.is_cuda) else "cuda"))
+    with torch.cuda.device(device):
+        t, n = _raw_on_device(torch, raw, fmt, device)
+        out = torch.empty((n, 4), dtype=torch.float64, device=device)
+        _lib.check(_lib.load().memb_decode_events_f64(t.data_ptr() if n else None, n, fmt, out.data_ptr() if n else None,
+                                                      _lib.stream_ptr(torch, device)))
+    return out.cpu().numpy() if numpy_in else out
+
+
+def histogram_raw(raw, fmt, H, W, channels=3, *, device=None, check=True):
+    """Rasterise a recording straight from its raw records: equal to ``histogram(decode_events(raw, fmt), H, W)``
+    without the float64 rows ever existing (5 or 8 bytes per event of PCIe / HBM traffic instead of 32)."""
+    torch = _lib.require_cuda()
+    if channels not in (2, 3):
+        raise ValueError("channels must be 2 or 3")
+    numpy_in = not isinstance(raw, torch.Tensor)
+    device = torch.device(device if device is not None else (raw.device if (not numpy_in and raw.is_cuda) else "cuda"))
+    with torch.cuda.device(device):
+        t, n = _raw_on_device(torch, raw, fmt, device)
+        lib = _lib.load()
+        out = torch.empty((H, W, channels), dtype=torch.uint8, device=device)
+        ws = _lib.workspace.get(torch, lib.memb_hist_workspace_bytes(1, n, H, W, 0, _lib.HIST_GLOBAL), device, "hist")
+        stream = _lib.stream_ptr(torch, device)
+        _lib.check(lib.memb_hist_raw_u8(t.data_ptr() if n else None, n, fmt, H, W, channels, out.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), stream))
+        if check:
+            _lib.check(lib.memb_hist_status(ws.data_ptr(), stream))
     return out.cpu().numpy() if numpy_in else out

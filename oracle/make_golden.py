@@ -252,8 +252,63 @@ def golden_event_pipeline():
 
 
 
+def golden_decode():
+    """Reference process_data/process_dataset.py decoders (ncaltech101 :24-63, ncars :66-103) run on synthetic
+    recordings written to a temporary dataset tree; stores the raw file bytes and the .npy arrays they produced."""
+    import importlib.util
+    import tempfile
+    import contextlib, io
+    from types import SimpleNamespace
+    from oracle import decode_ref
+    ref_shims.install()
+    pd_dir = os.path.join(ref_shims.REFERENCE_ROOT, "process_data")
+    saved = sys.modules.pop("utils", None)          # process_dataset.py does `from utils import *` (its own utils.py)
+    sys.path.insert(0, pd_dir)
+    try:
+        spec = importlib.util.spec_from_file_location("ref_process_dataset", os.path.join(pd_dir, "process_dataset.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(pd_dir)
+        sys.modules.pop("utils", None)
+        if saved is not None:
+            sys.modules["utils"] = saved
+    rng = np.random.default_rng(21)
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        # N-Caltech101: <input>/<class>/<file>.bin + a split file naming train / val members
+        src, dst = os.path.join(tmp, "ncal_in"), os.path.join(tmp, "ncal_out")
+        os.makedirs(os.path.join(src, "airplanes"))
+        raws = {"image_0001": decode_ref.synth_ncaltech101(rng, 1500), "image_0002": decode_ref.synth_ncaltech101(rng, 1)}
+        for k, v in raws.items():
+            open(os.path.join(src, "airplanes", k + ".bin"), "wb").write(v)
+        split = os.path.join(tmp, "split.txt")
+        # (the reference's split parser keeps names up to ".bin\\n" and, its filter iterator being consumed by the
+        # "val" pass, only ever finds "val" members -- both recordings are listed as such)
+        open(split, "w").write("val/airplanes/image_0001.bin\nval/airplanes/image_0002.bin\n")
+        with contextlib.redirect_stdout(io.StringIO()):
+            mod.ncaltech101("airplanes", SimpleNamespace(input=src, output=dst, split=split))
+        for k, part in (("image_0001", "val"), ("image_0002", "val")):
+            out["ncaltech101_" + k + "_raw"] = np.frombuffer(raws[k], dtype=np.uint8)
+            out["ncaltech101_" + k + "_npy"] = np.load(os.path.join(dst, part, "airplanes", k + ".npy"))
+        # N-Cars: <input>/n-cars_train/<class>/<file>.dat and n-cars_test/...
+        src, dst = os.path.join(tmp, "ncars_in"), os.path.join(tmp, "ncars_out")
+        raws = {"obj_000001_td": decode_ref.synth_ncars(rng, 1200), "obj_000002_td": decode_ref.synth_ncars(rng, 3)}
+        for sub, k in (("n-cars_train", "obj_000001_td"), ("n-cars_test", "obj_000002_td")):
+            os.makedirs(os.path.join(src, sub, "cars"))
+            open(os.path.join(src, sub, "cars", k + ".dat"), "wb").write(raws[k])
+        with contextlib.redirect_stdout(io.StringIO()):
+            mod.ncars("cars", SimpleNamespace(input=src, output=dst))
+        for k, part in (("obj_000001_td", "train"), ("obj_000002_td", "val")):
+            out["ncars_" + k + "_raw"] = np.frombuffer(raws[k], dtype=np.uint8)
+            out["ncars_" + k + "_npy"] = np.load(os.path.join(dst, part, "cars", k + ".npy"))
+    for k, v in out.items():
+        print("decode", k, v.shape, v.dtype)
+    np.savez_compressed(os.path.join(GOLD, "decode.npz"), **out)
+
+
 SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit, "dvae": golden_dvae,
-            "engine": golden_engine, "event_pipeline": golden_event_pipeline}
+            "engine": golden_engine, "event_pipeline": golden_event_pipeline, "decode": golden_decode}
 
 
 def main(argv):
