@@ -36,7 +36,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "histogram", "pretrain", "event_pipeline"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "histogram", "pretrain", "event_pipeline", "raw_histogram"])
     ap.add_argument("--events", type=int, default=10_000_000)
     ap.add_argument("--sensor", default="640x480")
     ap.add_argument("--batch", type=int, default=128)
@@ -165,7 +165,9 @@ class HistogramWorkload:
         hbm, _, _, how = measured_peaks()
         alg_bytes = 32.0 * self.n + self.C * self.H * self.W
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-        return {"bound": "hbm", "kernel": "hist_scatter_global (+init, finalize: whole step timed)",
+        private = self.H * self.W <= 51200 and self.n >= (1 << 18)     # what MEMB_HIST_AUTO picks (csrc/hist.cu make_plan)
+        return {"bound": "hbm", "kernel": ("hist_private (+hist_private_finalize: whole step timed)" if private else
+                                           "hist_scatter_global (+init, finalize: whole step timed)"),
                 "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
                 "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "algorithmic_bytes_per_launch": alg_bytes,
@@ -190,6 +192,73 @@ class HistogramWorkload:
         return {"value": round(n / dt / 1e9, 6), "unit": self.unit, "cores": 1, "kind": "port",
                 "sample": f"{reps} passes of {n} events ({self.W}x{self.H}) through oracle/histogram_ref.py "
                           f"(np.add.at is serial: 1 thread)"}
+
+
+# ----------------------------------------------------------------------------- raw recording workload
+class RawHistogramWorkload(HistogramWorkload):
+    """N-Caltech101 raw 5-byte records -> polarity histogram without float64 rows (decode fused into the scatter)."""
+    metric = "Gevents/s raw-record rasterise (N-Caltech101 5-byte records)"
+
+    def __init__(self, args):
+        self.H, self.W, self.n, self.C = 180, 240, args.events, 3
+        self.config = {"workload": f"N-Caltech101 .bin records (5 B/event) -> uint8[180,240,3], uniform synthetic recording, "
+                                   f"{self.n} events; decode fused into the rasteriser",
+                       "events": self.n, "sensor_wxh": [240, 180], "channels": 3,
+                       "l2_policy": "256 MB L2 flush (memset) is NOT used: 4 resident recordings rotate (200 MB > 126 MB L2)",
+                       "parallelism": "independent recordings per GPU (no collective)"}
+
+    def setup(self, torch, rank):
+        import numpy as np
+        from mem_b200 import _lib
+        from mem_b200.process_data import RAW_NCALTECH101, histogram_raw
+        from oracle import decode_ref
+        self.torch, self._lib, self.fmt, self.histogram_raw, self.decode_ref = torch, _lib, RAW_NCALTECH101, histogram_raw, decode_ref
+        self.host = [torch.frombuffer(bytearray(decode_ref.synth_ncaltech101(np.random.default_rng(10 * rank + k), self.n)),
+                                      dtype=torch.uint8).pin_memory() for k in range(4)]
+        self.dev = [h.cuda() for h in self.host]
+        self.k, self.out = 0, None
+        self.units_per_step = self.n
+        self.h2d, self.d2h = self.n * 5, self.H * self.W * self.C
+
+    def step_device(self):
+        self.k += 1
+        self.out = self.histogram_raw(self.dev[self.k % 4], self.fmt, self.H, self.W, channels=self.C, check=False)
+
+    def step_e2e(self):
+        self.k += 1
+        dev = self.host[self.k % 4].to("cuda", non_blocking=True)
+        return self.histogram_raw(dev, self.fmt, self.H, self.W, channels=self.C, check=True).cpu()
+
+    def verify(self):
+        import numpy as np
+        from oracle.histogram_ref import event_hist_ref
+        n = min(self.n, 2_000_000)
+        raw = self.host[0][:5 * n]
+        got = self.histogram_raw(raw.cuda(), self.fmt, self.H, self.W, channels=self.C).cpu().numpy()
+        return bool(np.array_equal(got, event_hist_ref(self.decode_ref.ncaltech101_np(raw.numpy().tobytes()), self.H, self.W)))
+
+    def roofline(self, ms_per_step):
+        hbm, _, _, how = measured_peaks()
+        alg_bytes = 5.0 * self.n + self.C * self.H * self.W
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "hist_scatter_raw<NCALTECH101> (+init, finalize: whole step timed); note: at 5 B/event "
+                                          "the step is bound by the L2 RED rate (one atomic per event), not by HBM bytes",
+                "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
+                "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": None}
+
+    def cpu_baseline(self):
+        import numpy as np
+        n = 200_000
+        raw = self.decode_ref.synth_ncaltech101(np.random.default_rng(0), n)
+        t0 = time.perf_counter()
+        ev = self.decode_ref.ncaltech101_loop(raw)           # the reference's byte-by-byte Python decoder
+        t1 = time.perf_counter()
+        self.cpu_once(ev)                                    # + np.add.at rasteriser
+        t2 = time.perf_counter()
+        return {"value": round(n / (t2 - t0) / 1e9, 6), "unit": self.unit, "cores": 1, "kind": "port",
+                "sample": f"{n} records: oracle/decode_ref.py ncaltech101_loop ({(t1 - t0):.2f} s) + oracle/histogram_ref.py "
+                          f"({(t2 - t1) * 1e3:.0f} ms), 1 thread"}
 
 
 # ----------------------------------------------------------------------------- event pipeline workload (SURVEY 8f N1)
@@ -412,10 +481,20 @@ def main():
         from mem_b200 import bench_pretrain
         return bench_pretrain.main(args, rank, local_rank, world, ClockSampler, measured_peaks)
 
-    wl = EventPipelineWorkload(args) if workload == "event_pipeline" else HistogramWorkload(args)
+    wl = {"event_pipeline": EventPipelineWorkload, "raw_histogram": RawHistogramWorkload}.get(workload, HistogramWorkload)(args)
 
     if args.impl == "reference":
         if rank != 0:
+            return
+        if workload == "raw_histogram":
+            from oracle import decode_ref
+            wl.decode_ref = decode_ref
+            cb = RawHistogramWorkload.cpu_baseline(wl)
+            print(json.dumps({"impl": "reference", "metric": wl.metric, "value": cb["value"], "unit": wl.unit, "n_gpus": args.gpus,
+                              "steps": 1, "warmup": 0, "ms_per_step": round(200_000 / cb["value"] / 1e6, 3), "higher_is_better": True,
+                              "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config,
+                              "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": wl.unit, "h2d_bytes_per_step": 0,
+                                                          "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
             return
         value, ms, workers, sample = (run_reference_event_pipeline if workload == "event_pipeline" else run_reference_histogram)(args, wl)
         line = {"impl": "reference", "metric": wl.metric, "value": round(value, 6), "unit": wl.unit,

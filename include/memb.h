@@ -56,6 +56,8 @@ int64_t memb_launch_count(void);
 #define MEMB_HIST_GLOBAL 1      /* L2-resident u32 accumulators + RED            */
 #define MEMB_HIST_GLOBAL_AGG 2  /* same, duplicates merged per warp (match.any)  */
 #define MEMB_HIST_TILE 3        /* shared-memory privatised sensor tiles         */
+#define MEMB_HIST_PRIVATE 4     /* one stream, sensor <= 51200 px: a whole-sensor copy per SM in shared      */
+                                /* memory, copies summed from per-CTA slices (else falls back to GLOBAL)    */
 
 /* Bytes memb_hist_u8 needs for this problem (n = total rows; same strategy value as the call). */
 size_t memb_hist_workspace_bytes(int B, int64_t n, int H, int W, int timesurface, int strategy);

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <climits>
 
+
 #include "common.cuh"
 
 namespace memb {
@@ -55,6 +56,18 @@ __device__ __forceinline__ bool pixel_index(double x, double y, int W, long long
   if (i < -npix || i >= npix) return false;
   idx = i < 0 ? i + npix : i;
   return true;
+}
+
+// Same result, common case first: a row inside the sensor needs four compares and two 32-bit conversions.
+__device__ __forceinline__ bool pixel_index_fast(double x, double y, int W, int H, long long npix, int& idx) {
+  if (x >= 0.0 && x < (double)W && y >= 0.0 && y < (double)H) {
+    idx = __double2int_rz(x) + W * __double2int_rz(y);
+    return true;
+  }
+  long long i = 0;
+  const bool ok = pixel_index(x, y, W, npix, i);
+  idx = (int)i;
+  return ok;
 }
 
 __device__ __forceinline__ unsigned long long order_key(double v) {
@@ -419,10 +432,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
           x = __double2int_rz(cur[u].x);
           y = __double2int_rz(cur[u].y);
         } else {
-          long long idx = 0;
-          ok = pixel_index(cur[u].x, cur[u].y, W, npix, idx);
-          y = (int)(idx / W);
-          x = (int)(idx - (long long)y * W);
+          int idx = 0;
+          ok = pixel_index_fast(cur[u].x, cur[u].y, W, H, npix, idx);
+          y = idx / W;
+          x = idx - y * W;
         }
         if (!ok) {
           bad = true;
@@ -544,6 +557,138 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
         o_neg[i + k] = vn[k];
         if (C == 3) o[npx + i + k] = 0.0f;
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- strategy PRIVATE (one long stream, small sensor)
+// Every CTA (one per SM) keeps a private copy of the WHOLE sensor in shared memory (one packed word per pixel,
+// <= kTileMaxWords pixels: N-Caltech101 240x180, N-Cars 120x100) and rasterises a strided share of the stream into
+// it: hot pixels and edges cost shared-memory atomics instead of same-address L2 REDs, and nothing needs a zero-fill.
+// Each CTA then stores its copy, already reduced mod 256, as one u16 per pixel (pos | neg << 8) into its own slice
+// of the workspace with plain coalesced stores; hist_private_finalize adds the slices up.  (A first version summed
+// the copies of a thread-block cluster through distributed shared memory: the DSMEM reads (~20 B/clk/SM) and the
+// gpu-scope fences of cluster.sync cost more than writing 86 KB per CTA, and clusters left 28 SMs idle.)
+constexpr int kPrivMaxCtas = 160;      // upper bound of the grid the workspace is sized for (>= SM count)
+
+template <bool kAligned>
+__global__ void __launch_bounds__(kTileThreads, 1) hist_private(
+    const double* __restrict__ ev, long long n, int W, int H, long long npix, unsigned short* __restrict__ slices,
+    int* __restrict__ flags) {
+  extern __shared__ unsigned int tile[];
+  const int words = ((int)npix + 7) & ~7;
+  constexpr int kStep = kTileThreads * kFuseUnroll;
+  const long long stride = (long long)gridDim.x * kStep;
+  const long long first = (long long)blockIdx.x * kStep;
+
+  if (kAligned && threadIdx.x == 0) {          // the copy engine pulls this CTA's next chunks into L2
+    for (int k = 0; k < kFuseAhead; ++k) {
+      const long long far = first + k * stride;
+      if (far < n) prefetch_l2(ev + 4 * far, (unsigned int)(min((long long)kStep, n - far) * 32));
+    }
+  }
+  Event nxt[kFuseUnroll];
+#pragma unroll
+  for (int u = 0; u < kFuseUnroll; ++u) {
+    const long long r = first + u * kTileThreads + threadIdx.x;
+    if (r < n) nxt[u] = load_event<kAligned>(ev, r);
+  }
+  for (int i = threadIdx.x * 4; i < words; i += kTileThreads * 4) *reinterpret_cast<uint4*>(tile + i) = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+
+  bool bad = false;
+  int it = 0;
+  for (long long base = first; base < n; base += stride, ++it) {
+    Event cur[kFuseUnroll];
+    bool live[kFuseUnroll];
+#pragma unroll
+    for (int u = 0; u < kFuseUnroll; ++u) {
+      cur[u] = nxt[u];
+      live[u] = base + u * kTileThreads + threadIdx.x < n;
+    }
+    if (kAligned && threadIdx.x == 0) {
+      const long long far = base + (long long)kFuseAhead * stride;
+      if (far < n) prefetch_l2(ev + 4 * far, (unsigned int)(min((long long)kStep, n - far) * 32));
+    }
+#pragma unroll
+    for (int u = 0; u < kFuseUnroll; ++u) {
+      const long long r = base + stride + u * kTileThreads + threadIdx.x;
+      if (r < n) nxt[u] = load_event<kAligned>(ev, r);
+    }
+#pragma unroll
+    for (int u = 0; u < kFuseUnroll; ++u) {
+      const bool pos = live[u] && cur[u].p == 1.0, neg = live[u] && cur[u].p == -1.0;
+      if (pos || neg) {
+        int idx;
+        if (!pixel_index_fast(cur[u].x, cur[u].y, W, H, npix, idx)) bad = true;
+        else atomicAdd(&tile[idx], pos ? 1u : 0x10000u);
+      }
+    }
+    if ((it + 1) % kFuseFold == 0 && base + stride < n) {     // halves can never carry: fold them mod 256
+      __syncthreads();
+      for (int i = threadIdx.x; i < words; i += kTileThreads) tile[i] &= 0x00ff00ffu;
+      __syncthreads();
+    }
+  }
+  const int any_bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) flags[blockIdx.x] = any_bad;           // plain store: nothing to initialise beforehand
+  // this CTA's slice: 8 pixels -> 8 x u16 (pos | neg << 8) -> one 16-byte store
+  uint4* slice = reinterpret_cast<uint4*>(slices + (long long)blockIdx.x * words);
+  for (int i = threadIdx.x * 8; i < words; i += kTileThreads * 8) {
+    const uint4 a = *reinterpret_cast<const uint4*>(tile + i), b = *reinterpret_cast<const uint4*>(tile + i + 4);
+    auto pack = [](unsigned int lo, unsigned int hi) {
+      return (lo & 0xffu) | ((lo >> 8) & 0xff00u) | ((hi & 0xffu) << 16) | ((hi << 8) & 0xff000000u);
+    };
+    slice[i >> 3] = make_uint4(pack(a.x, a.y), pack(a.z, a.w), pack(b.x, b.y), pack(b.z, b.w));
+  }
+}
+
+// out[px] = (sum over the CTA slices) mod 256; also publishes the out-of-range flag.  blockDim = (32, kFinRows): lane x
+// owns 8 consecutive pixels, row y sums slices y, y + kFinRows, ... (all its loads in flight at once); the partial sums
+// meet in shared memory.
+constexpr int kFinRows = 32;
+__global__ void __launch_bounds__(32 * kFinRows) hist_private_finalize(const unsigned short* __restrict__ slices, int n_slices, int words,
+                                                             const int* __restrict__ flags, long long npix, int C,
+                                                             uint8_t* __restrict__ out, Header* __restrict__ hdr) {
+  __shared__ unsigned int part[kFinRows][32][8];      // [slice group][lane][pixel]: pos | neg << 16 (sums < 65536)
+  if (blockIdx.x == 0 && threadIdx.y == 0) {
+    int f = 0;
+    for (int i = threadIdx.x; i < n_slices; i += 32) f |= flags[i];
+    f = (int)__reduce_or_sync(0xffffffffu, (unsigned)f);
+    if (threadIdx.x == 0) hdr->oob = f ? 1 : 0;
+  }
+  const long long oct = (long long)blockIdx.x * 32 + threadIdx.x;       // pixel octet
+  unsigned int acc[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  if (oct * 8 < words) {
+#pragma unroll 5
+    for (int k = threadIdx.y; k < n_slices; k += kFinRows) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(slices + (long long)k * words) + oct);
+      const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc[2 * q] += (w[q] & 0xffu) | ((w[q] & 0xff00u) << 8);
+        acc[2 * q + 1] += ((w[q] >> 16) & 0xffu) | ((w[q] >> 8) & 0xff0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) part[threadIdx.y][threadIdx.x][q] = acc[q];
+  __syncthreads();
+  // the first 256 threads -> the block's 256 pixels
+  const int lane = threadIdx.y * 4 + (threadIdx.x >> 3), q = threadIdx.x & 7;   // (octet in block, pixel in octet)
+  const long long px = ((long long)blockIdx.x * 32 + lane) * 8 + q;
+  if (threadIdx.y < 8 && px < npix) {
+    unsigned int w = 0;
+#pragma unroll
+    for (int g = 0; g < kFinRows; ++g) w += part[g][lane][q];
+    const uint8_t cp = (uint8_t)(w & 0xffu), cn = (uint8_t)((w >> 16) & 0xffu);
+    if (C == 2) {
+      out[2 * px] = cp;
+      out[2 * px + 1] = cn;
+    } else {
+      out[3 * px] = cp;
+      out[3 * px + 1] = 0;
+      out[3 * px + 2] = cn;
     }
   }
 }
@@ -678,13 +823,18 @@ static Plan make_plan(int B, int64_t n, int H, int W, int timesurface, int strat
     // One long stream: every SM streams its share and REDs into L2.
     const long long per_stream = B > 0 ? n / B : n;
     strategy = (B >= 16 && per_stream <= (1 << 20)) ? MEMB_HIST_TILE : MEMB_HIST_GLOBAL;
+    // one long stream on a sensor that fits a shared-memory tile: a privatised copy per SM (immune to hot pixels)
+    if (B == 1 && npix <= kTileMaxWords && n >= (1 << 18)) strategy = MEMB_HIST_PRIVATE;
   }
+  if (strategy == MEMB_HIST_PRIVATE && (B != 1 || npix > kTileMaxWords)) strategy = MEMB_HIST_GLOBAL;
   p.strategy = strategy;
   p.tiles = (int)ceil_div<long long>(npix, kTileMaxWords);
   p.tile_pix = (int)round_up<long long>(ceil_div<long long>(npix, p.tiles), 4);
   p.off_tkeys = kHeaderBytes;
   p.off_acc = p.off_tkeys + (timesurface ? round_up<size_t>((size_t)B * 16, 256) : 0);
   p.off_last = p.off_acc + (strategy == MEMB_HIST_TILE ? 0 : (size_t)B * 2 * npix * 4);
+  if (strategy == MEMB_HIST_PRIVATE)   // CTA slices [kPrivMaxCtas][words] u16 + one flag per CTA
+    p.off_last = p.off_acc + (size_t)kPrivMaxCtas * round_up<size_t>((size_t)npix, 8) * 2 + kPrivMaxCtas * 4;
   p.off_last = round_up<size_t>(p.off_last, 16);
   p.ws_bytes = round_up<size_t>(p.off_last + (timesurface ? (size_t)B * npix * 8 : 0), 16);
   return p;
@@ -711,7 +861,7 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
   MEMB_REQUIRE(offsets != nullptr || B == 1, "hist: a batch needs row offsets");
   MEMB_REQUIRE(out != nullptr && ws != nullptr, "hist: null output / workspace");
   MEMB_REQUIRE((((uintptr_t)ev) & 7u) == 0 && (((uintptr_t)ws) & 15u) == 0, "hist: misaligned pointer");
-  MEMB_REQUIRE(strategy >= MEMB_HIST_AUTO && strategy <= MEMB_HIST_TILE, "hist: unknown strategy %d", strategy);
+  MEMB_REQUIRE(strategy >= MEMB_HIST_AUTO && strategy <= MEMB_HIST_PRIVATE, "hist: unknown strategy %d", strategy);
   const long long npix = (long long)H * W;
   const Plan p = make_plan(B, n, H, W, timesurface, strategy);
   if (ws_bytes < p.ws_bytes)
@@ -727,7 +877,8 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
   const long long* offs = reinterpret_cast<const long long*>(offsets);
   const int sms = num_sms();
 
-  {  // zero the header (+ accumulators) and seed the min/max keys
+  const bool use_private = n > 0 && p.strategy == MEMB_HIST_PRIVATE && aug == nullptr && !timesurface;
+  if (!use_private) {  // zero the header (+ accumulators) and seed the min/max keys
     const long long n_vec = (long long)((p.strategy == MEMB_HIST_TILE ? (size_t)kHeaderBytes : p.ws_bytes) / 16);
     const int blocks = (int)std::min<long long>(ceil_div<long long>(n_vec, 256), (long long)sms * 8);
     hist_init<<<blocks, 256, 0, stream>>>(reinterpret_cast<uint4*>(wsb), n_vec,
@@ -760,7 +911,26 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
     else hist_time_range<false><<<grid, kThreads, 0, stream>>>(ev, offs, n, tkeys);
     MEMB_LAUNCH_OK("hist_time_range");
   }
-  if (n > 0) {
+  if (use_private) {
+    auto kern = aligned ? hist_private<true> : hist_private<false>;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[aligned]) {
+      MEMB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxWords * 4));
+      attr_set[aligned] = true;
+    }
+    const int words = (int)round_up<long long>(npix, 8);
+    // one CTA per SM; fewer when the stream is short (every CTA costs one sensor's worth of slice traffic)
+    const long long want = ceil_div<long long>(n, (long long)kTileThreads * kFuseUnroll * 4);
+    const int ctas = (int)std::max<long long>(1, std::min<long long>(std::min(sms, kPrivMaxCtas), want));
+    unsigned short* slices = reinterpret_cast<unsigned short*>(acc);
+    int* flags = reinterpret_cast<int*>(slices + (size_t)kPrivMaxCtas * words);
+    kern<<<ctas, kTileThreads, (size_t)words * 4, stream>>>(ev, n, W, H, npix, slices, flags);
+    MEMB_LAUNCH_OK("hist_private");
+    const int fblocks = (int)ceil_div<long long>(words / 8, 32);
+    hist_private_finalize<<<fblocks, dim3(32, kFinRows), 0, stream>>>(slices, ctas, words, flags, npix, C, out, hdr);
+    MEMB_LAUNCH_OK("hist_private_finalize");
+    return MEMB_OK;
+  } else if (n > 0) {
     const bool agg = p.strategy == MEMB_HIST_GLOBAL_AGG;
 #define MEMB_SCATTER(A, G, T)                                                                        \
   hist_scatter_global<A, G, T><<<grid, kThreads, 0, stream>>>(ev, offs, n, W, npix, acc, last, hdr, aug)

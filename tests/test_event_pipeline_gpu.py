@@ -13,7 +13,7 @@ from oracle.event_pipeline_ref import PipelineCfg, apply_event_aug, apply_post_r
 from oracle.histogram_ref import event_hist_ref
 from oracle.make_golden import synth_events
 
-STRATS = [0, 1, 2, 3]
+STRATS = [0, 1, 2, 3, 4]
 
 
 def seed_all(seed):

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 from mem_b200.process_data import histogram, histogram_batch  # noqa: E402
 from oracle.make_golden import synth_events  # noqa: E402
 
-NAMES = {0: "auto", 1: "global", 2: "global_agg", 3: "tile"}
+NAMES = {1: "global", 2: "global_agg", 3: "tile", 4: "private"}
 
 
 def timeit(fn, iters=20, warm=3):
@@ -41,6 +41,9 @@ def hot_pixel_events(rng, n, H, W):
     return ev
 
 
+ONLY = [int(v) for v in os.environ.get("SWEEP_STRATEGIES", "").split(",") if v]
+
+
 def main():
     rng = np.random.default_rng(0)
     rows = []
@@ -49,8 +52,12 @@ def main():
             for n in [10_000, 30_000, 100_000, 1_000_000, 10_000_000]:
                 ev = hot_pixel_events(rng, n, H, W) if kind == "hot" else synth_events(rng, n, H, W, kind)
                 d = torch.from_numpy(ev).cuda()
-                for s in (1, 2, 3):
+                for s in (1, 2, 3, 4):
                     if s == 3 and n > 1_000_000 and W == 640:
+                        continue
+                    if s == 4 and W == 640:            # sensor does not fit a tile: PRIVATE is GLOBAL there
+                        continue
+                    if ONLY and s not in ONLY:
                         continue
                     ms = timeit(lambda: histogram(d, H, W, strategy=s, check=False))
                     rows.append({"sensor": f"{W}x{H}", "kind": kind, "n": n, "strategy": NAMES[s], "ms": ms,
