@@ -213,18 +213,56 @@ __global__ void __launch_bounds__(kRowThreads) branch_bwd(const float* __restric
   block_column_atomic<2, CH>(acc, D, dst, smem);
 }
 
-// out[n] += sum_rows x[row, n]   (bias gradients of fc1 / qkv); N % 4 == 0.
-__global__ void __launch_bounds__(256) colsum_bf16(const bf16* __restrict__ x, long long ld, int rows, int N,
-                                                   int rows_per_block, float* __restrict__ out) {
-  const int col = (blockIdx.x * 256 + threadIdx.x) * 4;
-  if (col >= N) return;
+// out[n] += sum_rows x[row, n]   (bias gradients of fc1 / qkv); N % 8 == 0, rows 16-byte aligned.
+// Block = 32 column lanes (8 columns = one 16-byte load each) x 8 row phases; every thread keeps 8 independent loads
+// in flight, the 8 phases meet in shared memory and one atomic per column leaves the block.
+constexpr int kColsumRows = 8;
+__global__ void __launch_bounds__(32 * kColsumRows) colsum_bf16(const bf16* __restrict__ x, long long ld, int rows, int N,
+                                                                int rows_per_block, float* __restrict__ out) {
+  __shared__ float part[kColsumRows][32][8];
+  const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = r0; r < r1; ++r) {
-    const float4 v = ld4_bf16(x + (long long)r * ld + col);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < N) {
+    const bf16* p = x + col;
+    int r = r0 + threadIdx.y;
+    for (; r + 7 * kColsumRows < r1; r += 8 * kColsumRows) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const uint4*>(p + (long long)(r + u * kColsumRows) * ld));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(h[k]);
+          s[2 * k] += f.x;
+          s[2 * k + 1] += f.y;
+        }
+      }
+    }
+    for (; r < r1; r += kColsumRows) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p + (long long)r * ld));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        s[2 * k] += f.x;
+        s[2 * k + 1] += f.y;
+      }
+    }
   }
-  atomicAdd(out + col, s.x); atomicAdd(out + col + 1, s.y); atomicAdd(out + col + 2, s.z); atomicAdd(out + col + 3, s.w);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[threadIdx.y][threadIdx.x][k] = s[k];
+  __syncthreads();
+  // 256 threads -> the block's 256 columns
+  const int t = threadIdx.y * 32 + threadIdx.x, c = blockIdx.x * 256 + t;
+  if (c < N) {
+    float a = 0.f;
+#pragma unroll
+    for (int g = 0; g < kColsumRows; ++g) a += part[g][t >> 3][t & 7];
+    atomicAdd(out + c, a);
+  }
 }
 
 // ------------------------------------------------------------------ patch embedding helpers
@@ -677,11 +715,13 @@ extern "C" int memb_branch_bwd(const float* gout, int64_t ldg, const void* branc
 }
 
 extern "C" int memb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float* out, memb_stream_t s) {
-  MEMB_REQUIRE(x && out && rows > 0 && N > 0 && N % 4 == 0, "colsum: bad arguments");
-  const int gx = ceil_div(N, 1024);
-  const int gy = std::max(1, std::min(ceil_div(rows, 64), (num_sms() * 8) / gx));
+  MEMB_REQUIRE(x && out && rows > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0 && (((uintptr_t)x) & 15u) == 0,
+               "colsum: N and ld must be multiples of 8 and x 16-byte aligned");
+  const int gx = ceil_div(N, 256);
+  // about 8 resident blocks per SM over the whole grid, at least 64 rows (8 loads per thread) per block
+  const int gy = std::max(1, std::min(ceil_div(rows, 64), ceil_div(num_sms() * 8, gx)));
   const int rpb = ceil_div(rows, gy);
-  colsum_bf16<<<dim3(gx, ceil_div(rows, rpb)), 256, 0, s>>>((const bf16*)x, ld, rows, N, rpb, out);
+  colsum_bf16<<<dim3(gx, ceil_div(rows, rpb)), dim3(32, kColsumRows), 0, s>>>((const bf16*)x, ld, rows, N, rpb, out);
   MEMB_LAUNCH_OK("colsum_bf16");
   return MEMB_OK;
 }
