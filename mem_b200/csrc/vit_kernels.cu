@@ -115,64 +115,80 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd(const float* __rest
 
 // ------------------------------------------------------------------ LayerNorm backward
 // dx[target row] += LNbwd(dy);  dgamma += sum dy*xhat;  dbeta += sum dy.   dy is bf16 or fp32.
+// The column sums live in per-warp shared-memory rows (plain read-modify-write, a lane owns its columns), not in
+// registers: 48 fewer registers per thread lets two blocks share an SM, which is what this HBM-bound kernel needs
+// (16 warps x ~4.5 KB of loads in flight instead of 8).
 template <typename DyT, int CH>
-__global__ void __launch_bounds__(kRowThreads) layernorm_bwd(const DyT* __restrict__ dy, long long lddy,
-                                                             const float* __restrict__ x, long long ldx,
-                                                             const float* __restrict__ gamma,
-                                                             const float* __restrict__ mean,
-                                                             const float* __restrict__ rstd, int rows, int D,
-                                                             float* __restrict__ dx, long long lddx,
-                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                             const int* __restrict__ row_index,
-                                                             const int* __restrict__ count) {
-  extern __shared__ float smem[];
+__global__ void __launch_bounds__(kRowThreads, 2) layernorm_bwd(const DyT* __restrict__ dy, long long lddy,
+                                                                const float* __restrict__ x, long long ldx,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, int rows, int D,
+                                                                float* __restrict__ dx, long long lddx,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                const int* __restrict__ row_index,
+                                                                const int* __restrict__ count) {
+  extern __shared__ float smem[];                 // [2][kRowWarps][D]: dgamma partials, dbeta partials
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int live = count ? min(rows, *count) : rows;
-  float acc[2][CH][4];
+  float* sg = smem + (size_t)warp * D;
+  float* sb = smem + (size_t)(kRowWarps + warp) * D;
 #pragma unroll
-  for (int c = 0; c < CH; ++c)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[0][c][j] = acc[1][c][j] = 0.f;
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 4;
+    st4(sg + col, make_float4(0.f, 0.f, 0.f, 0.f));
+    st4(sb + col, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
 
   for (int r = blockIdx.x * kRowWarps + warp; r < live; r += gridDim.x * kRowWarps) {
     const long long src = row_index ? row_index[r] : r;
     const float* xr = x + src * ldx;
     const DyT* dyr = dy + (long long)r * lddy;
+    float* dxr = dx + src * lddx;
     const float mu = mean[r], rs = rstd[r];
-    float4 xh[CH], dg[CH];
+    float4 xh[CH], dg[CH], o[CH];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < CH; ++c)
-      {
-        const int col = (c * 32 + lane) * 4;
-        float4 d;
-        if constexpr (sizeof(DyT) == 2) d = ld4_bf16(reinterpret_cast<const bf16*>(dyr) + col);
-        else d = ld4(reinterpret_cast<const float*>(dyr) + col);
-        const float4 xv = ld4(xr + col), g = ld4(gamma + col);
-        xh[c] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        acc[0][c][0] += d.x * xh[c].x; acc[0][c][1] += d.y * xh[c].y; acc[0][c][2] += d.z * xh[c].z; acc[0][c][3] += d.w * xh[c].w;
-        acc[1][c][0] += d.x; acc[1][c][1] += d.y; acc[1][c][2] += d.z; acc[1][c][3] += d.w;
-        dg[c] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-        s1 += dg[c].x + dg[c].y + dg[c].z + dg[c].w;
-        s2 += dg[c].x * xh[c].x + dg[c].y * xh[c].y + dg[c].z * xh[c].z + dg[c].w * xh[c].w;
-      }
+    for (int c = 0; c < CH; ++c) {
+      const int col = (c * 32 + lane) * 4;
+      float4 d;
+      if constexpr (sizeof(DyT) == 2) d = ld4_bf16(reinterpret_cast<const bf16*>(dyr) + col);
+      else d = ld4(reinterpret_cast<const float*>(dyr) + col);
+      const float4 xv = ld4(xr + col), g = ld4(gamma + col);
+      o[c] = ld4(dxr + col);                      // requested early: only needed after the two warp sums
+      xh[c] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      float4 a = ld4(sg + col), b = ld4(sb + col);
+      a.x += d.x * xh[c].x; a.y += d.y * xh[c].y; a.z += d.z * xh[c].z; a.w += d.w * xh[c].w;
+      b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+      st4(sg + col, a);
+      st4(sb + col, b);
+      dg[c] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+      s1 += dg[c].x + dg[c].y + dg[c].z + dg[c].w;
+      s2 += dg[c].x * xh[c].x + dg[c].y * xh[c].y + dg[c].z * xh[c].z + dg[c].w * xh[c].w;
+    }
     s1 = warp_sum(s1) / D;
     s2 = warp_sum(s2) / D;
-    float* dxr = dx + src * lddx;
 #pragma unroll
-    for (int c = 0; c < CH; ++c)
-      {
-        const int col = (c * 32 + lane) * 4;
-        float4 o = ld4(dxr + col);
-        o.x += rs * (dg[c].x - s1 - xh[c].x * s2);
-        o.y += rs * (dg[c].y - s1 - xh[c].y * s2);
-        o.z += rs * (dg[c].z - s1 - xh[c].z * s2);
-        o.w += rs * (dg[c].w - s1 - xh[c].w * s2);
-        st4(dxr + col, o);
-      }
+    for (int c = 0; c < CH; ++c) {
+      const int col = (c * 32 + lane) * 4;
+      o[c].x += rs * (dg[c].x - s1 - xh[c].x * s2);
+      o[c].y += rs * (dg[c].y - s1 - xh[c].y * s2);
+      o[c].z += rs * (dg[c].z - s1 - xh[c].z * s2);
+      o[c].w += rs * (dg[c].w - s1 - xh[c].w * s2);
+      st4(dxr + col, o[c]);
+    }
   }
-  float* const dst[2] = {dgamma, dbeta};
-  block_column_atomic<2, CH>(acc, D, dst, smem);
+  __syncthreads();
+  for (int col = threadIdx.x; col < D; col += kRowThreads) {
+    float g = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRowWarps; ++w) {
+      g += smem[(size_t)w * D + col];
+      b += smem[(size_t)(kRowWarps + w) * D + col];
+    }
+    if (dgamma) atomicAdd(dgamma + col, g);
+    if (dbeta) atomicAdd(dbeta + col, b);
+  }
 }
 
 // ------------------------------------------------------------------ branch backward
@@ -692,11 +708,12 @@ extern "C" int memb_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, co
                                   const int32_t* count, memb_stream_t s) {
   MEMB_REQ_D(D);
   MEMB_REQUIRE(dy && x && gamma && mean && rstd && dx && rows > 0, "layernorm_bwd: bad arguments");
-  const size_t smem = (size_t)kRowWarps * D * sizeof(float);
+  const size_t smem = (size_t)2 * kRowWarps * D * sizeof(float);
+  const int grid = std::max(1, std::min(ceil_div(rows, kRowWarps), num_sms() * 2));   // persistent: 2 blocks per SM
   if (dy_dtype == MEMB_DT_BF16) {
-    MEMB_CH_DISPATCH(D, (layernorm_bwd<bf16, CH><<<row_grid(rows), kRowThreads, smem, s>>>((const bf16*)dy, lddy, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dgamma, dbeta, row_index, count)));
+    MEMB_CH_DISPATCH(D, (cudaFuncSetAttribute(layernorm_bwd<bf16, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), layernorm_bwd<bf16, CH><<<grid, kRowThreads, smem, s>>>((const bf16*)dy, lddy, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dgamma, dbeta, row_index, count)));
   } else {
-    MEMB_CH_DISPATCH(D, (layernorm_bwd<float, CH><<<row_grid(rows), kRowThreads, smem, s>>>((const float*)dy, lddy, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dgamma, dbeta, row_index, count)));
+    MEMB_CH_DISPATCH(D, (cudaFuncSetAttribute(layernorm_bwd<float, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), layernorm_bwd<float, CH><<<grid, kRowThreads, smem, s>>>((const float*)dy, lddy, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dgamma, dbeta, row_index, count)));
   }
   MEMB_LAUNCH_OK("layernorm_bwd");
   return MEMB_OK;
