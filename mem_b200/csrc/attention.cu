@@ -378,22 +378,20 @@ struct BwdParams {
   int write_ds;
 };
 
-// nl[b,h,q] = -lse*log2(e), delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]: one thread per (b, q, h), whole 128 B lines.
+// nl[b,h,q] = -lse*log2(e), delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]: eight lanes per (b, q, h) row of 64, one
+// 16-byte load of O and of dO each (a warp reads 512 contiguous bytes per instruction), 3 shuffles, lane 0 writes.
 __global__ void __launch_bounds__(256) attn_bwd_prep(const bf16* __restrict__ out, const bf16* __restrict__ dout,
                                                      const float* __restrict__ lse, int B, int N, int H,
                                                      float* __restrict__ nl_delta) {
+  static_assert(kHeadDim == 64, "eight 16-byte loads cover one head row");
   const long long total = (long long)B * N * H;
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // (b, q, h), h fastest: coalesced rows
-  if (i >= total) return;
-  const int h = (int)(i % H);
-  const long long bq = i / H;
-  const int q = (int)(bq % N), b = (int)(bq / N);
-  const uint4* o4 = reinterpret_cast<const uint4*>(out + i * kHeadDim);
-  const uint4* g4 = reinterpret_cast<const uint4*>(dout + i * kHeadDim);
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long i = t >> 3;                                            // (b, q, h), h fastest
+  const int part = (int)(t & 7);
   float d = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const uint4 ov = __ldg(o4 + k), gv = __ldg(g4 + k);
+  if (i < total) {
+    const uint4 ov = __ldcs(reinterpret_cast<const uint4*>(out + i * kHeadDim) + part);
+    const uint4 gv = __ldcs(reinterpret_cast<const uint4*>(dout + i * kHeadDim) + part);
     const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov);
     const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gv);
 #pragma unroll
@@ -402,9 +400,17 @@ __global__ void __launch_bounds__(256) attn_bwd_prep(const bf16* __restrict__ ou
       d = fmaf(a.x, g.x, fmaf(a.y, g.y, d));
     }
   }
-  const long long o = ((long long)b * H + h) * N + q;
-  nl_delta[o] = -lse[o] * kLog2e;
-  nl_delta[total + o] = d;
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  d += __shfl_xor_sync(0xffffffffu, d, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 4);
+  if (i < total && part == 0) {
+    const int h = (int)(i % H);
+    const long long bq = i / H;
+    const int q = (int)(bq % N), b = (int)(bq / N);
+    const long long o = ((long long)b * H + h) * N + q;
+    nl_delta[o] = -lse[o] * kLog2e;
+    nl_delta[total + o] = d;
+  }
 }
 
 // G (16 or 8) query columns of this thread's key row: S^T, dP^T -> P^T, dS^T (bf16, swizzled smem slots).
@@ -820,7 +826,7 @@ extern "C" int memb_attention_bwd(const void* qkv, const void* out, const void* 
     configured = true;
   }
   const long long rows = (long long)B * N * H;
-  attn_bwd_prep<<<(unsigned)ceil_div<long long>(rows, 256), 256, 0, s>>>((const bf16*)out, (const bf16*)dout, lse, B, N, H,
+  attn_bwd_prep<<<(unsigned)ceil_div<long long>(rows * 8, 256), 256, 0, s>>>((const bf16*)out, (const bf16*)dout, lse, B, N, H,
                                                                          (float*)workspace);
   MEMB_LAUNCH_OK("attn_bwd_prep");
   BwdParams p{(const float*)workspace, biasT, ldb, B, N, H, scale, scale * kLog2e, (bf16*)dqkv, dsT ? 1 : 0};
