@@ -9,6 +9,7 @@ Prints ONE JSON line on rank 0.  Workloads:
 
   histogram  event -> polarity histogram rasterisation, 10M uniform events at the
              N-ImageNet 640x480 sensor (largest single-GPU case of BASELINE config 2)
+  finetune   ViT-B/16 ft_vit classification step, batch 128/GPU (BASELINE config 5)
   event_pipeline  one training batch of raw streams -> model input: fused event
              augmentations + rasteriser + crop / hot-pixel filter / normalise
   pretrain   ViT-B/16 MEM pretraining step, batch 128/GPU (BASELINE config 3)
@@ -36,7 +37,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "histogram", "pretrain", "event_pipeline", "raw_histogram"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "histogram", "pretrain", "event_pipeline", "raw_histogram", "finetune"])
     ap.add_argument("--events", type=int, default=10_000_000)
     ap.add_argument("--sensor", default="640x480")
     ap.add_argument("--batch", type=int, default=128)
@@ -480,6 +481,9 @@ def main():
     if workload == "pretrain":
         from mem_b200 import bench_pretrain
         return bench_pretrain.main(args, rank, local_rank, world, ClockSampler, measured_peaks)
+    if workload == "finetune":
+        from mem_b200 import bench_finetune
+        return bench_finetune.main(args, rank, local_rank, world, ClockSampler, measured_peaks)
 
     wl = {"event_pipeline": EventPipelineWorkload, "raw_histogram": RawHistogramWorkload}.get(workload, HistogramWorkload)(args)
 

@@ -67,3 +67,50 @@ def run_steps(vit_sd, vae_sd, batches, heads=2, patch=16, vae_layers=4, vae_res=
         opt.step()
         out.append({"loss": loss.item(), "mlm_acc": acc.item(), "grad_norm": norm.item()})
     return out, {k: v.detach() for k, v in sd.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+# Finetuning loop (mem/engine_for_finetuning.py:42-205): seeded case shared by make_golden.py and the tests
+# ---------------------------------------------------------------------------------------------
+FT_LR = [1e-3, 2e-3]
+FT_WD = [0.05, 0.04]
+FT_UPDATE_FREQ = 2
+
+
+def synth_class_batches(n=4, B=6, seed=91):
+    """[(samples float32 [B,3,112,112], targets int64 [B])]: ``n`` micro-batches (``n / FT_UPDATE_FREQ`` optimizer steps)."""
+    out = []
+    for s in range(n):
+        img = dvae_ref.synth_images(B, 3, 112, 112, seed + s)
+        g = torch.Generator().manual_seed(seed + 100 + s)
+        out.append((img, torch.randint(0, 2, (B,), generator=g)))
+    return out
+
+
+def run_finetune(vit_sd, batches, heads=2, patch=16, update_freq=FT_UPDATE_FREQ):
+    """The finetuning loop restated: CE on ft_vit logits, loss / update_freq, accumulate, clip + AdamW every
+    ``update_freq`` micro-steps with the schedule value of the optimizer step (engine_for_finetuning.py:77-129).
+    Returns (global-average stats like the reference's MetricLogger, final weights)."""
+    names = [k for k, v in vit_sd.items() if v.is_floating_point()]
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in vit_sd.items()}
+    groups = [g for g in param_groups([(n, sd[n]) for n in names], FT_WD[0]) if g["params"]]
+    opt = torch.optim.AdamW(groups, lr=FT_LR[0], betas=(0.9, 0.95), eps=1e-8)
+    opt.zero_grad()
+    losses, accs, norms = [], [], []
+    for i, (samples, targets) in enumerate(batches):
+        it = i // update_freq
+        for g in opt.param_groups:
+            g["lr"] = FT_LR[it] * g["lr_scale"]
+            if g["weight_decay"] > 0:
+                g["weight_decay"] = FT_WD[it]
+        logits = vit_ref.classify_logits(samples, sd, heads, patch)
+        loss = torch.nn.functional.cross_entropy(logits, targets)
+        losses.append(loss.item())
+        accs.append((logits.max(-1)[1] == targets).float().mean().item())
+        (loss / update_freq).backward()
+        if (i + 1) % update_freq == 0:
+            norms.append(torch.nn.utils.clip_grad_norm_([sd[n] for n in names], MAX_NORM).item())
+            opt.step()
+            opt.zero_grad()
+    mean = lambda v: sum(v) / len(v)  # noqa: E731
+    return {"loss": mean(losses), "class_acc": mean(accs), "grad_norm": mean(norms)}, {k: v.detach() for k, v in sd.items()}

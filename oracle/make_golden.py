@@ -307,8 +307,48 @@ def golden_decode():
     np.savez_compressed(os.path.join(GOLD, "decode.npz"), **out)
 
 
+def golden_engine_ft():
+    """The UNMODIFIED reference finetuning loop (mem/engine_for_finetuning.py:42-205) on CPU fp32: tiny ft_vit, four
+    micro-batches with update_freq 2 (two AdamW steps, per-step lr / wd schedule, clip 1.0), CrossEntropyLoss."""
+    import torch
+    from types import SimpleNamespace
+    from oracle import engine_ref, vit_ref
+    eng = ref_shims.ref_module("engine_for_finetuning")
+    rutils = ref_shims.ref_module("utils")
+    optf = ref_shims.ref_module("optim_factory")
+    torch.cuda.synchronize = lambda *a, **k: None
+    rutils.is_main_process = lambda: False
+
+    class Scaler(rutils.NativeScalerWithGradNormCount):
+        def state_dict(self):
+            return {"scale": 1.0}
+
+    torch.manual_seed(0)
+    model = ref_shims.ref_create_model("ft_vit", **vit_ref.TINY_FT)
+    model.load_state_dict(vit_ref.synth_state_dict(model.state_dict(), seed=41))
+    groups = optf.get_parameter_groups(model, engine_ref.FT_WD[0], model.no_weight_decay())
+    opt = torch.optim.AdamW(groups, lr=engine_ref.FT_LR[0], betas=(0.9, 0.95), eps=1e-8)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        stats = eng.train_one_epoch(SimpleNamespace(), model, torch.nn.CrossEntropyLoss(), engine_ref.synth_class_batches(), opt,
+                                    torch.device("cpu"), 0, Scaler(), engine_ref.MAX_NORM, start_steps=0,
+                                    lr_schedule_values=engine_ref.FT_LR, wd_schedule_values=engine_ref.FT_WD,
+                                    num_training_steps_per_epoch=2, update_freq=engine_ref.FT_UPDATE_FREQ)
+    out = {"stat/" + k: np.array(v) for k, v in stats.items()}
+    out["keys"] = np.array(sorted(stats.keys()))
+    print({k: round(float(v), 6) for k, v in stats.items()})
+    sd = model.state_dict()
+    for k in ("head.weight", "head.bias", "fc_norm.weight", "blocks.0.attn.qkv.weight", "blocks.1.attn.relative_position_bias_table",
+              "cls_token", "patch_embed.proj.bias", "blocks.1.gamma_2", "blocks.0.mlp.fc1.bias"):
+        out["final/" + k] = sd[k].detach().numpy().reshape(-1)[:512]
+    model.eval()
+    with torch.no_grad():
+        out["eval_logits"] = model(engine_ref.synth_class_batches()[0][0]).numpy()
+    np.savez_compressed(os.path.join(GOLD, "engine_ft_tiny.npz"), **out)
+
+
 SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit, "dvae": golden_dvae,
-            "engine": golden_engine, "event_pipeline": golden_event_pipeline, "decode": golden_decode}
+            "engine": golden_engine, "event_pipeline": golden_event_pipeline, "decode": golden_decode, "engine_ft": golden_engine_ft}
 
 
 def main(argv):

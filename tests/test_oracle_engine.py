@@ -28,6 +28,40 @@ def test_engine_oracle_matches_reference_golden(golden_dir):
     assert sorted(gold["keys"].tolist()) == ["grad_norm", "loss", "loss_scale", "lr", "min_lr", "mlm_acc", "weight_decay"]
 
 
+def test_finetune_oracle_matches_reference_golden(golden_dir):
+    """oracle/engine_ref.run_finetune vs the unmodified reference finetuning loop (tests/golden/engine_ft_tiny.npz)."""
+    from mem_b200 import modeling_finetune  # noqa: F401
+    gold = np.load(os.path.join(golden_dir, "engine_ft_tiny.npz"))
+    model = registry.create_model("ft_vit", **vit_ref.TINY_FT)
+    sd = vit_ref.synth_state_dict(model.state_dict(), seed=41)
+    stats, final = engine_ref.run_finetune(sd, engine_ref.synth_class_batches())
+    assert abs(stats["loss"] - float(gold["stat/loss"])) < 2e-5
+    assert abs(stats["class_acc"] - float(gold["stat/class_acc"])) < 1e-6
+    assert abs(stats["grad_norm"] - float(gold["stat/grad_norm"])) < 5e-4
+    for k in gold.files:
+        if k.startswith("final/"):
+            np.testing.assert_allclose(final[k[6:]].numpy().reshape(-1)[:512], gold[k], rtol=1e-4, atol=2e-6)
+    with torch.no_grad():
+        logits = vit_ref.classify_logits(engine_ref.synth_class_batches()[0][0], final, 2, 16).numpy()
+    np.testing.assert_allclose(logits, gold["eval_logits"], rtol=1e-4, atol=1e-5)
+    assert sorted(gold["keys"].tolist()) == ["class_acc", "grad_norm", "loss", "loss_scale", "lr", "min_lr", "weight_decay"]
+
+
+def test_finetune_losses_and_accuracy_helpers():
+    from mem_b200.engine_for_finetuning import LabelSmoothingCrossEntropy, SoftTargetCrossEntropy, accuracy
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(7, 5, generator=g)
+    t = torch.randint(0, 5, (7,), generator=g)
+    want = torch.nn.functional.cross_entropy(x, t, label_smoothing=0.1)
+    assert abs(LabelSmoothingCrossEntropy(0.1)(x, t).item() - want.item()) < 1e-6
+    soft = torch.nn.functional.one_hot(t, 5).float()
+    assert abs(SoftTargetCrossEntropy()(x, soft).item() - torch.nn.functional.cross_entropy(x, t).item()) < 1e-6
+    a1, a3 = accuracy(x, t, topk=(1, 3))
+    top3 = x.topk(3, dim=1).indices
+    assert abs(a1.item() - 100.0 * (x.argmax(1) == t).float().mean().item()) < 1e-4
+    assert abs(a3.item() - 100.0 * (top3 == t[:, None]).any(1).float().mean().item()) < 1e-4
+
+
 def test_cosine_scheduler_and_meters():
     import math
     s = utils.cosine_scheduler(1e-3, 1e-5, epochs=4, niter_per_ep=10, warmup_epochs=1, start_warmup_value=1e-6)
