@@ -70,6 +70,26 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
+// In every group of four lanes, lane r holds quarters q[0..3] of its own row; afterwards lane r holds quarter r of the
+// rows of lanes 4g, 4g+1, 4g+2, 4g+3 (q[j] = old q[r] of lane 4g+j): two butterfly steps of 2 x 16-byte exchanges.
+__device__ __forceinline__ uint4 shfl_xor_u4(uint4 v, int m) {
+  return make_uint4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                    __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+__device__ __forceinline__ void transpose4x4_quarters(uint4 (&q)[4], int lane) {
+  const bool odd = lane & 1, up = lane & 2;
+#pragma unroll
+  for (int k = 0; k < 4; k += 2) {          // 2x2 blocks: (r, k..k+1) x (r^1)
+    const uint4 recv = shfl_xor_u4(odd ? q[k] : q[k + 1], 1);
+    if (odd) q[k] = recv; else q[k + 1] = recv;
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {             // blocks of 2: (r, k / k+2) x (r^2)
+    const uint4 recv = shfl_xor_u4(up ? q[k] : q[k + 2], 2);
+    if (up) q[k] = recv; else q[k + 2] = recv;
+  }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
            const __grid_constant__ CUtensorMap tmap_w, const Params p) {
@@ -208,10 +228,22 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
       }
       // ---- fused epilogue from registers
       unsigned long long best = 0ull;
+      // hi / lo rows leave through a 4x4 transpose of 16-byte quarters inside each group of four lanes: one store
+      // instruction then writes 64 contiguous bytes of each of 8 rows (8 lines, full sectors) instead of 16 bytes of
+      // each of 32 rows (32 lines, half sectors).  Row bases / liveness of the group's four rows:
+      long long off_g[4];
+      bool live_g[4];
+      if (p.d_hi) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          off_g[j] = __shfl_sync(0xffffffffu, off, (lane & ~3) + j);
+          live_g[j] = __shfl_sync(0xffffffffu, (int)live, (lane & ~3) + j) != 0;
+        }
+      }
 #pragma unroll
       for (int c = 0; c < kEpiCols / 32; ++c) {
         const int col0 = n_tile * BLOCK_N + half * kEpiCols + c * 32;
-        if (live && col0 < p.Cout) {  // Cout % 32 == 0
+        if (col0 < p.Cout) {  // warp-uniform (Cout % 32 == 0); rows that are not live compute on zeros and store nothing
           float v[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -221,7 +253,7 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
             v[4 * j + 2] = fmaf(sum[c * 32 + 4 * j + 2], p.acc_scale, bq.z);
             v[4 * j + 3] = fmaf(sum[c * 32 + 4 * j + 3], p.acc_scale, bq.w);
           }
-          if (p.aux) {
+          if (p.aux && live) {
             const float4* a4 = reinterpret_cast<const float4*>(p.aux + plain * p.Cout + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -233,14 +265,16 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
+          if (live) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(v[j]));
-          if (p.d_full) {
+            for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(v[j]));
+          }
+          if (p.d_full && live) {
             float4* dst = reinterpret_cast<float4*>(p.d_full + plain * p.Cout + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-          if (p.keys) {
+          if (p.keys && live) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const unsigned long long key = argmax_key(v[j], col0 + j);
@@ -248,20 +282,31 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
             }
           }
           if (p.d_hi) {
-            uint32_t hh[16], ll[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float s0 = v[2 * j] * p.out_scale, s1 = v[2 * j + 1] * p.out_scale;
-              const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
-              hh[j] = pack_h2(h0, h1);
-              ll[j] = pack_h2(__float2half_rn(s0 - __half2float(h0)), __float2half_rn(s1 - __half2float(h1)));
-            }
-            uint4* dh = reinterpret_cast<uint4*>(p.d_hi + off + col0);
-            uint4* dl = reinterpret_cast<uint4*>(p.d_lo + off + col0);
+            uint4 qh[4], ql[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              dh[j] = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
-              dl[j] = make_uint4(ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float s0 = v[8 * j + 2 * k] * p.out_scale, s1 = v[8 * j + 2 * k + 1] * p.out_scale;
+                const __half2 h = __floats2half2_rn(s0, s1);            // one cvt.rn.f16x2.f32
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+                hw[k] = *reinterpret_cast<const uint32_t*>(&h);
+                lw[k] = *reinterpret_cast<const uint32_t*>(&l);
+              }
+              qh[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              ql[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+            transpose4x4_quarters(qh, lane);
+            transpose4x4_quarters(ql, lane);
+            const int q = lane & 3;     // this lane now holds quarter q of rows 4g .. 4g+3
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (live_g[j]) {
+                *reinterpret_cast<uint4*>(p.d_hi + off_g[j] + col0 + 8 * q) = qh[j];
+                *reinterpret_cast<uint4*>(p.d_lo + off_g[j] + col0 + 8 * q) = ql[j];
+              }
             }
           }
         }
