@@ -336,12 +336,13 @@ __global__ void __launch_bounds__(256) im2col_l1_f16(const float* __restrict__ i
                                                      __half* __restrict__ a_hi, __half* __restrict__ a_lo,
                                                      unsigned int* __restrict__ absmax) {
   const int OH = H / 2, OW = W / 2, kq = Kpad / 4;
-  const long long total = (long long)B * OH * OW * kq;
+  const unsigned int total = (unsigned int)B * OH * OW * kq;   // < 2^31 (checked by the launcher): 32-bit index math
   float amax = 0.f;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(t % kq);
-    const long long pix = t / kq;
-    const int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH), b = (int)(pix / ((long long)OW * OH));
+  for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int q = (int)(t % (unsigned int)kq);
+    const unsigned int pix = t / (unsigned int)kq;
+    const unsigned int rowi = pix / (unsigned int)OW;            // b * OH + oy
+    const int ox = (int)(pix - rowi * OW), oy = (int)(rowi % (unsigned int)OH), b = (int)(rowi / (unsigned int)OH);
     const int k0 = q * 4, c = k0 / 16, ky = (k0 % 16) / 4;  // the 4 k's share (c, ky); kx = 0..3
     __half hi[4], lo[4];
 #pragma unroll
@@ -363,8 +364,8 @@ __global__ void __launch_bounds__(256) im2col_l1_f16(const float* __restrict__ i
         }
       }
     }
-    *reinterpret_cast<uint2*>(a_hi + pix * Kpad + k0) = make_uint2(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]));
-    *reinterpret_cast<uint2*>(a_lo + pix * Kpad + k0) = make_uint2(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]));
+    *reinterpret_cast<uint2*>(a_hi + (long long)pix * Kpad + k0) = make_uint2(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]));
+    *reinterpret_cast<uint2*>(a_lo + (long long)pix * Kpad + k0) = make_uint2(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]));
   }
   if (absmax) {
 #pragma unroll
@@ -486,6 +487,7 @@ extern "C" int memb_dvae_im2col_l1_f16(const float* img, int B, int C, int H, in
   MEMB_REQUIRE(Kpad % 64 == 0 && Kpad >= 16 * C, "im2col_l1_f16: Kpad must be a multiple of 64 and >= 16*C");
   MEMB_REQUIRE((mean == nullptr) == (stdv == nullptr), "im2col_l1_f16: mean and std go together");
   const long long total = (long long)B * (H / 2) * (W / 2) * (Kpad / 4);
+  MEMB_REQUIRE(total < (1LL << 31), "im2col_l1_f16: %lld work items do not fit 32-bit indexing (tokenise in smaller chunks)", total);
   const int grid = (int)std::min<long long>(ceil_div<long long>(total, 256), (long long)num_sms() * 32);
   im2col_l1_f16<<<grid, 256, 0, s>>>(img, B, C, H, W, Kpad, mean, stdv, ldexpf(1.0f, exp2), reinterpret_cast<__half*>(a_hi),
                                      reinterpret_cast<__half*>(a_lo), absmax);
