@@ -404,9 +404,9 @@ __global__ void __launch_bounds__(256) attn_bwd_prep(const bf16* __restrict__ ou
   d += __shfl_xor_sync(0xffffffffu, d, 2);
   d += __shfl_xor_sync(0xffffffffu, d, 4);
   if (i < total && part == 0) {
-    const int h = (int)(i % H);
-    const long long bq = i / H;
-    const int q = (int)(bq % N), b = (int)(bq / N);
+    const unsigned int iu = (unsigned int)i;                           // B*N*H < 2^31 (checked by the launcher)
+    const unsigned int bq = iu / (unsigned int)H, h = iu - bq * H;
+    const unsigned int b = bq / (unsigned int)N, q = bq - b * N;
     const long long o = ((long long)b * H + h) * N + q;
     nl_delta[o] = -lse[o] * kLog2e;
     nl_delta[total + o] = d;
@@ -826,6 +826,7 @@ extern "C" int memb_attention_bwd(const void* qkv, const void* out, const void* 
     configured = true;
   }
   const long long rows = (long long)B * N * H;
+  MEMB_REQUIRE(rows < (1LL << 28), "attention_bwd: B*N*H = %lld is beyond the 32-bit row indexing of the prep kernel", rows);
   attn_bwd_prep<<<(unsigned)ceil_div<long long>(rows * 8, 256), 256, 0, s>>>((const bf16*)out, (const bf16*)dout, lse, B, N, H,
                                                                          (float*)workspace);
   MEMB_LAUNCH_OK("attn_bwd_prep");
