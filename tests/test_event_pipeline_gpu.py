@@ -192,3 +192,45 @@ def test_bad_arguments_fail_loudly():
     bad = np.array([[100.0, 100.0, 0.0, 1.0]])
     with pytest.raises((IndexError, _lib.MembError)):
         rasterise_augmented(bad, np.array([0, 1]), aug, 100, 100)
+
+
+def test_randomised_parameters_fused_vs_oracle():
+    """40 random parameter sets (windows, scales, flips, shifts beyond the reference's range, cull on / off with
+    fractional and slightly negative coordinates that exercise numpy's truncation and negative-index wrap) through the
+    one-kernel path and the two-stage path, against the oracle chain."""
+    from mem_b200.event_pipeline import pack_params, pipeline_fused, post_raster, rasterise_augmented
+    rng = np.random.default_rng(2024)
+    H, W, oh, ow = 200, 230, 160, 176
+    for case in range(40):
+        B = int(rng.integers(1, 5))
+        lens = [int(rng.integers(0, 4000)) for _ in range(B)]
+        streams, params = [], []
+        for n in lens:
+            cull = bool(rng.integers(0, 2))
+            sx, sy = (float(rng.uniform(0.3, 1.0)), float(rng.uniform(0.3, 1.0))) if rng.integers(0, 2) else (1.0, 1.0)
+            ev = np.stack([rng.uniform(-0.9 if not cull else -30, (W - 1) / sx if not cull else W / sx + 30, n),
+                           rng.uniform(0.0 if not cull else -30, (H - 1) / sy if not cull else H / sy + 30, n),
+                           np.sort(rng.uniform(0, 1e5, n)), rng.choice([-1.0, 1.0, 0.0], n, p=[0.45, 0.45, 0.1])], axis=1)
+            start = int(rng.integers(0, max(1, n)))
+            p = dict(scale_x=sx, scale_y=sy, start=start, count=int(rng.integers(0, n - start + 1)) if n else 0,
+                     time_flip=bool(rng.integers(0, 2)), flip_x=bool(rng.integers(0, 2)) and cull, flip_w=W, cull=cull,
+                     shift_x=int(rng.integers(-40, 41)) if cull else 0, shift_y=int(rng.integers(-40, 41)) if cull else 0,
+                     cull_w=W, cull_h=H, top=int(rng.integers(0, H - oh + 1)), left=int(rng.integers(0, W - ow + 1)))
+            streams.append(ev)
+            params.append(p)
+        aug, crop = pack_params(params)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        events = np.concatenate(streams, axis=0) if sum(lens) else np.zeros((0, 4))
+        hot = [None, 10.0, 2.5][case % 3]
+        norm = bool(case % 2)
+        cfg = PipelineCfg(is_train=True, input_H=oh, input_W=ow, hotpixfilter=hot is not None,
+                          hotpix_num_stds=hot if hot is not None else 10, normalize_events=norm)
+        one = pipeline_fused(events, off, aug, crop, H, W, (oh, ow), 3, hot_num_stds=hot, normalize=norm)
+        two = post_raster(rasterise_augmented(events, off, aug, H, W, 3), crop, (oh, ow), hot_num_stds=hot, normalize=norm)
+        for b, (s, p) in enumerate(zip(streams, params)):
+            win = s[p["start"]:p["start"] + p["count"]]
+            a = apply_event_aug(s, p) if len(win) else win
+            hist = event_hist_ref(a, H, W) if len(a) else np.zeros((H, W, 3), np.uint8)
+            want = apply_post_raster(hist, p, cfg).numpy()
+            assert np.array_equal(one[b].cpu().numpy(), want), (case, b, "fused")
+            assert np.array_equal(two[b].cpu().numpy(), want), (case, b, "two-stage")
