@@ -159,29 +159,20 @@ def train_one_epoch(args, model: torch.nn.Module, criterion: torch.nn.Module, da
         loss_scale_value = loss_scaler.state_dict()["scale"]
         torch.cuda.synchronize()
 
-        class_acc = (output.max(-1)[-1] == targets).float().mean() if mixup_fn is None else None
-        metric_logger.update(loss=loss_value)
-        metric_logger.update(class_acc=class_acc)
-        metric_logger.update(loss_scale=loss_scale_value)
         lrs = [g["lr"] for g in optimizer.param_groups]
-        min_lr, max_lr = min([10.0] + lrs), max([0.0] + lrs)
-        metric_logger.update(lr=max_lr)
-        metric_logger.update(min_lr=min_lr)
-        weight_decay_value = None
-        for g in optimizer.param_groups:
-            if g["weight_decay"] > 0:
-                weight_decay_value = g["weight_decay"]
-        metric_logger.update(weight_decay=weight_decay_value)
-        metric_logger.update(grad_norm=grad_norm)
-
+        decays = [g["weight_decay"] for g in optimizer.param_groups if g["weight_decay"] > 0]
+        # one record per micro-step, in the reference's meter order; None entries (accuracy under mixup, the norm of a
+        # non-updating micro-step, no decayed group) are skipped by the logger exactly like the reference's
+        record = {"loss": loss_value,
+                  "class_acc": (output.max(-1)[-1] == targets).float().mean() if mixup_fn is None else None,
+                  "loss_scale": loss_scale_value, "lr": max([0.0] + lrs), "min_lr": min([10.0] + lrs),
+                  "weight_decay": decays[-1] if decays else None, "grad_norm": grad_norm}
+        for name, value in record.items():
+            metric_logger.update(**{name: value})
         if log_writer is not None:
-            log_writer.update(loss=loss_value, head="loss")
-            log_writer.update(class_acc=class_acc, head="loss")
-            log_writer.update(loss_scale=loss_scale_value, head="opt")
-            log_writer.update(lr=max_lr, head="opt")
-            log_writer.update(min_lr=min_lr, head="opt")
-            log_writer.update(weight_decay=weight_decay_value, head="opt")
-            log_writer.update(grad_norm=grad_norm, head="opt")
+            heads = {"loss": "loss", "class_acc": "loss"}
+            for name, value in record.items():
+                log_writer.update(head=heads.get(name, "opt"), **{name: value})
             log_writer.set_step()
 
     metric_logger.synchronize_between_processes()
