@@ -242,8 +242,9 @@ class RawHistogramWorkload(HistogramWorkload):
         hbm, _, _, how = measured_peaks()
         alg_bytes = 5.0 * self.n + self.C * self.H * self.W
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-        return {"bound": "hbm", "kernel": "hist_scatter_raw<NCALTECH101> (+init, finalize: whole step timed); note: at 5 B/event "
-                                          "the step is bound by the L2 RED rate (one atomic per event), not by HBM bytes",
+        return {"bound": "hbm", "kernel": "hist_private<NCALTECH101> (records decoded inside the privatised rasteriser) + "
+                                          "hist_private_finalize: whole step timed; at 5 B/event the step is bound by per-event "
+                                          "instructions / shared-memory atomics and by the host call, not by HBM bytes",
                 "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
                 "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "algorithmic_bytes_per_launch": alg_bytes,
                 "traffic": None}

@@ -152,8 +152,9 @@ int memb_raster_post_f32(const uint8_t* hist, int B, int H, int W, int C, const 
 int memb_decode_events_f64(const uint8_t* raw, int64_t n_records, int format, double* out, memb_stream_t stream);
 
 /* Rasterise one recording straight from its raw records (no float64 rows in HBM): identical to
- * memb_hist_u8(decode(raw)) with strategy GLOBAL, no time surface.  Workspace:
- * memb_hist_workspace_bytes(1, n_records, H, W, 0, MEMB_HIST_GLOBAL); status via memb_hist_status. */
+ * memb_hist_u8(decode(raw)), no time surface.  Workspace: at least
+ * memb_hist_workspace_bytes(1, n_records, H, W, 0, MEMB_HIST_GLOBAL); with the MEMB_HIST_AUTO size a long recording
+ * on a sensor of <= 51200 pixels takes the PRIVATE strategy (records decoded inside it).  Status via memb_hist_status. */
 int memb_hist_raw_u8(const uint8_t* raw, int64_t n_records, int format, int H, int W, int C, uint8_t* out,
                      void* ws, size_t ws_bytes, memb_stream_t stream);
 

@@ -561,6 +561,54 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
   }
 }
 
+// ---------------------------------------------------------------- row sources for the PRIVATE strategy
+// kSrc: 0 = float64 rows, 32-byte aligned; -1 = float64 rows, 8-byte aligned; MEMB_RAW_NCALTECH101 / MEMB_RAW_NCARS =
+// raw records decoded on the fly (bit fields as in decode_record below, process_dataset.py:52-60, :88-99).
+template <int kSrc>
+struct RowSource {
+  static constexpr int kBytes = kSrc == 1 ? 5 : (kSrc == 2 ? 8 : 32);
+  static constexpr bool kPrefetch = kSrc != -1;
+  __device__ __forceinline__ static Event fetch(const void* __restrict__ base, long long r, long long n) {
+    if constexpr (kSrc == 0) {
+      return load_event<true>(static_cast<const double*>(base), r);
+    } else if constexpr (kSrc == -1) {
+      return load_event<false>(static_cast<const double*>(base), r);
+    } else if constexpr (kSrc == 2) {
+      const uint2 w = __ldg(static_cast<const uint2*>(base) + r);       // records are 8-byte aligned
+      Event e;
+      e.x = (double)(w.y & 0x3fffu);
+      e.y = (double)((w.y & 0x0fffc000u) >> 14);
+      e.t = (double)w.x;
+      e.p = (w.y & 0x10000000u) ? 1.0 : 0.0;
+      return e;
+    } else {
+      // 5-byte record at byte 5r: the two aligned words around it, or single bytes at the very end of the buffer
+      const long long at = 5 * r, wi = at >> 2, bytes = 5 * n;
+      unsigned long long v;
+      if ((wi + 2) * 4 <= bytes) {
+        const unsigned int* w = static_cast<const unsigned int*>(base) + wi;
+        v = (((unsigned long long)__ldg(w + 1) << 32) | __ldg(w)) >> ((at & 3) * 8);
+      } else {
+        const uint8_t* b = static_cast<const uint8_t*>(base) + at;
+        v = (unsigned long long)b[0] | ((unsigned long long)b[1] << 8) | ((unsigned long long)b[2] << 16) |
+            ((unsigned long long)b[3] << 24) | ((unsigned long long)b[4] << 32);
+      }
+      const unsigned int b2 = (unsigned int)(v >> 16) & 0xffu;
+      Event e;
+      e.x = (double)((unsigned int)v & 0xffu);
+      e.y = (double)((unsigned int)(v >> 8) & 0xffu);
+      e.p = (b2 & 0x80u) ? 1.0 : -1.0;
+      e.t = (double)(((b2 & 0x7fu) << 16) | (((unsigned int)(v >> 24) & 0xffu) << 8) | ((unsigned int)(v >> 32) & 0xffu));
+      return e;
+    }
+  }
+  // copy-engine prefetch of rows [r, r + rows) into L2 (16-byte aligned start for every chunk this kernel uses)
+  __device__ __forceinline__ static void prefetch(const void* __restrict__ base, long long r, long long rows) {
+    const unsigned int bytes = (unsigned int)(rows * kBytes) & ~15u;
+    if (bytes) prefetch_l2(static_cast<const char*>(base) + r * kBytes, bytes);
+  }
+};
+
 // ---------------------------------------------------------------- strategy PRIVATE (one long stream, small sensor)
 // Every CTA (one per SM) keeps a private copy of the WHOLE sensor in shared memory (one packed word per pixel,
 // <= kTileMaxWords pixels: N-Caltech101 240x180, N-Cars 120x100) and rasterises a strided share of the stream into
@@ -571,9 +619,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
 // gpu-scope fences of cluster.sync cost more than writing 86 KB per CTA, and clusters left 28 SMs idle.)
 constexpr int kPrivMaxCtas = 160;      // upper bound of the grid the workspace is sized for (>= SM count)
 
-template <bool kAligned>
+template <int kSrc>
 __global__ void __launch_bounds__(kTileThreads, 1) hist_private(
-    const double* __restrict__ ev, long long n, int W, int H, long long npix, unsigned short* __restrict__ slices,
+    const void* __restrict__ ev, long long n, int W, int H, long long npix, unsigned short* __restrict__ slices,
     int* __restrict__ flags) {
   extern __shared__ unsigned int tile[];
   const int words = ((int)npix + 7) & ~7;
@@ -581,17 +629,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) hist_private(
   const long long stride = (long long)gridDim.x * kStep;
   const long long first = (long long)blockIdx.x * kStep;
 
-  if (kAligned && threadIdx.x == 0) {          // the copy engine pulls this CTA's next chunks into L2
+  if (RowSource<kSrc>::kPrefetch && threadIdx.x == 0) {          // the copy engine pulls this CTA's next chunks into L2
     for (int k = 0; k < kFuseAhead; ++k) {
       const long long far = first + k * stride;
-      if (far < n) prefetch_l2(ev + 4 * far, (unsigned int)(min((long long)kStep, n - far) * 32));
+      if (far < n) RowSource<kSrc>::prefetch(ev, far, min((long long)kStep, n - far));
     }
   }
   Event nxt[kFuseUnroll];
 #pragma unroll
   for (int u = 0; u < kFuseUnroll; ++u) {
     const long long r = first + u * kTileThreads + threadIdx.x;
-    if (r < n) nxt[u] = load_event<kAligned>(ev, r);
+    if (r < n) nxt[u] = RowSource<kSrc>::fetch(ev, r, n);
   }
   for (int i = threadIdx.x * 4; i < words; i += kTileThreads * 4) *reinterpret_cast<uint4*>(tile + i) = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
@@ -606,14 +654,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) hist_private(
       cur[u] = nxt[u];
       live[u] = base + u * kTileThreads + threadIdx.x < n;
     }
-    if (kAligned && threadIdx.x == 0) {
+    if (RowSource<kSrc>::kPrefetch && threadIdx.x == 0) {
       const long long far = base + (long long)kFuseAhead * stride;
-      if (far < n) prefetch_l2(ev + 4 * far, (unsigned int)(min((long long)kStep, n - far) * 32));
+      if (far < n) RowSource<kSrc>::prefetch(ev, far, min((long long)kStep, n - far));
     }
 #pragma unroll
     for (int u = 0; u < kFuseUnroll; ++u) {
       const long long r = base + stride + u * kTileThreads + threadIdx.x;
-      if (r < n) nxt[u] = load_event<kAligned>(ev, r);
+      if (r < n) nxt[u] = RowSource<kSrc>::fetch(ev, r, n);
     }
 #pragma unroll
     for (int u = 0; u < kFuseUnroll; ++u) {
@@ -851,6 +899,31 @@ extern "C" size_t memb_hist_workspace_bytes(int B, int64_t n, int H, int W, int 
   return make_plan(B, n, H, W, timesurface, strategy).ws_bytes;
 }
 
+// PRIVATE strategy: rasterise + finalize (two launches, no initialisation of the workspace needed).
+template <int kSrc>
+static int run_private(const void* rows, long long n, int W, int H, int C, unsigned int* acc, Header* hdr, uint8_t* out,
+                       memb_stream_t stream) {
+  const long long npix = (long long)H * W;
+  auto kern = hist_private<kSrc>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MEMB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxWords * 4));
+    attr_set = true;
+  }
+  const int words = (int)round_up<long long>(npix, 8);
+  // one CTA per SM; fewer when the stream is short (every CTA costs one sensor's worth of slice traffic)
+  const long long want = ceil_div<long long>(n, (long long)kTileThreads * kFuseUnroll * 4);
+  const int ctas = (int)std::max<long long>(1, std::min<long long>(std::min(num_sms(), kPrivMaxCtas), want));
+  unsigned short* slices = reinterpret_cast<unsigned short*>(acc);
+  int* flags = reinterpret_cast<int*>(slices + (size_t)kPrivMaxCtas * words);
+  kern<<<ctas, kTileThreads, (size_t)words * 4, stream>>>(rows, n, W, H, npix, slices, flags);
+  MEMB_LAUNCH_OK("hist_private");
+  const int fblocks = (int)ceil_div<long long>(words / 8, 32);
+  hist_private_finalize<<<fblocks, dim3(32, kFinRows), 0, stream>>>(slices, ctas, words, flags, npix, C, out, hdr);
+  MEMB_LAUNCH_OK("hist_private_finalize");
+  return MEMB_OK;
+}
+
 static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, int64_t max_stream_len,
                     const memb_event_aug* aug, int H, int W, int C, int timesurface, int strategy,
                     uint8_t* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
@@ -912,24 +985,7 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
     MEMB_LAUNCH_OK("hist_time_range");
   }
   if (use_private) {
-    auto kern = aligned ? hist_private<true> : hist_private<false>;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[aligned]) {
-      MEMB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxWords * 4));
-      attr_set[aligned] = true;
-    }
-    const int words = (int)round_up<long long>(npix, 8);
-    // one CTA per SM; fewer when the stream is short (every CTA costs one sensor's worth of slice traffic)
-    const long long want = ceil_div<long long>(n, (long long)kTileThreads * kFuseUnroll * 4);
-    const int ctas = (int)std::max<long long>(1, std::min<long long>(std::min(sms, kPrivMaxCtas), want));
-    unsigned short* slices = reinterpret_cast<unsigned short*>(acc);
-    int* flags = reinterpret_cast<int*>(slices + (size_t)kPrivMaxCtas * words);
-    kern<<<ctas, kTileThreads, (size_t)words * 4, stream>>>(ev, n, W, H, npix, slices, flags);
-    MEMB_LAUNCH_OK("hist_private");
-    const int fblocks = (int)ceil_div<long long>(words / 8, 32);
-    hist_private_finalize<<<fblocks, dim3(32, kFinRows), 0, stream>>>(slices, ctas, words, flags, npix, C, out, hdr);
-    MEMB_LAUNCH_OK("hist_private_finalize");
-    return MEMB_OK;
+    return aligned ? run_private<0>(ev, n, W, H, C, acc, hdr, out, stream) : run_private<-1>(ev, n, W, H, C, acc, hdr, out, stream);
   } else if (n > 0) {
     const bool agg = p.strategy == MEMB_HIST_GLOBAL_AGG;
 #define MEMB_SCATTER(A, G, T)                                                                        \
@@ -1030,6 +1086,13 @@ extern "C" int memb_hist_raw_u8(const uint8_t* raw, int64_t n_records, int forma
   char* wsb = static_cast<char*>(ws);
   Header* hdr = reinterpret_cast<Header*>(wsb);
   unsigned int* acc = reinterpret_cast<unsigned int*>(wsb + p.off_acc);
+  // small sensor + long recording + a workspace sized with MEMB_HIST_AUTO: the privatised strategy, decoding on the fly
+  const Plan pa = make_plan(1, n_records, H, W, 0, MEMB_HIST_AUTO);
+  if (pa.strategy == MEMB_HIST_PRIVATE && ws_bytes >= pa.ws_bytes && n_records > 0) {
+    unsigned int* acc_p = reinterpret_cast<unsigned int*>(wsb + pa.off_acc);
+    return format == MEMB_RAW_NCALTECH101 ? run_private<MEMB_RAW_NCALTECH101>(raw, n_records, W, H, C, acc_p, hdr, out, stream)
+                                          : run_private<MEMB_RAW_NCARS>(raw, n_records, W, H, C, acc_p, hdr, out, stream);
+  }
   const int sms = num_sms();
   {
     const long long n_vec = (long long)(p.ws_bytes / 16);

@@ -194,7 +194,7 @@ def histogram_raw(raw, fmt, H, W, channels=3, *, device=None, check=True):
         t, n = _raw_on_device(torch, raw, fmt, device)
         lib = _lib.load()
         out = torch.empty((H, W, channels), dtype=torch.uint8, device=device)
-        ws = _lib.workspace.get(torch, lib.memb_hist_workspace_bytes(1, n, H, W, 0, _lib.HIST_GLOBAL), device, "hist")
+        ws = _lib.workspace.get(torch, lib.memb_hist_workspace_bytes(1, n, H, W, 0, _lib.HIST_AUTO), device, "hist")
         stream = _lib.stream_ptr(torch, device)
         _lib.check(lib.memb_hist_raw_u8(t.data_ptr() if n else None, n, fmt, H, W, channels, out.data_ptr(), ws.data_ptr(),
                                         ws.numel(), stream))
