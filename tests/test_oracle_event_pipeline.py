@@ -78,3 +78,32 @@ def test_cull_and_flip_semantics():
     assert np.array_equal(out[:, 3], [-1.0, -1.0])
     assert np.array_equal(out[:, 2], [0.0, 2.0])
     assert out[1, 0] == 341 - 1 - 0.0 - 1 and out[1, 1] == 2.0
+
+
+def test_product_draws_and_record_layout_match_the_oracle_and_the_header():
+    """Host side of mem_b200.event_pipeline (no GPU needed): same generator consumption as the oracle, and the packed
+    memb_event_aug records have the layout include/memb.h declares (64 bytes, field order / offsets)."""
+    import ctypes
+    import re
+    from mem_b200 import event_pipeline as ep
+    from oracle import event_pipeline_ref as ref
+    for is_train in (True, False):
+        for n in (100, 30000, 30001, 45000):
+            seed_all(n + is_train)
+            a = ep.draw_params(n, ep.PipelineConfig(is_train=is_train))
+            seed_all(n + is_train)
+            b = ref.draw_params(n, ref.PipelineCfg(is_train=is_train))
+            assert a == b
+    aug, crop = ep.pack_params([a, dict(a, start=7, count=9, time_flip=True, flip_x=True, shift_x=-3, shift_y=4, top=5, left=6)])
+    assert aug.dtype.itemsize == ctypes.sizeof(ep.EventAug) == 64 and crop.tolist()[1] == [5, 6]
+    rec = ep.EventAug.from_buffer_copy(aug[1].tobytes())
+    assert (rec.start, rec.count, rec.time_flip, rec.flip_x, rec.shift_x, rec.shift_y) == (7, 9, 1, 1, -3, 4)
+    assert rec.scale_x == a["scale_x"] and rec.flip_w == a["flip_w"] and rec.cull_w == a["cull_w"] and rec.cull_h == a["cull_h"]
+    # field order in the header == field order of the ctypes structure
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "memb.h")).read()
+    body = hdr[hdr.index("typedef struct memb_event_aug"):hdr.index("} memb_event_aug;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n.strip() for decl in re.findall(r"(?:double|int64_t|int32_t)\s+([^;]+);", body) for n in decl.split(",")]
+    assert names == [f[0] for f in ep.EventAug._fields_]
+    with pytest.raises(AssertionError):
+        ep.PipelineConfig(slice_max_evs=100)          # the reference's own range check (datasets.py:491)
