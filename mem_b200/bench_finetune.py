@@ -181,6 +181,8 @@ def main(args, rank, local_rank, world, ClockSampler, measured_peaks):
                                  "peak_tflops_sustained": tf_sust, "frac": round(fl * B / (ms_step * 1e-3) / 1e12 / tf_sust, 4)},
             "loss_last": round(float(loss.item()), 4), "e2e_stats": {k: round(float(v), 5) for k, v in out_stats.items()},
             "clocks": clocks, "roofline": roof}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = _cpu_line(2, 1)[2]
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
