@@ -32,6 +32,13 @@ struct Header {
 };
 
 struct Event { double x, y, t, p; };
+
+// Programmatic dependent launch (init -> scatter -> finalize of the GLOBAL strategy): a kernel launched with the
+// programmatic-serialisation attribute may start while its predecessor drains; pdl_wait() blocks until the predecessor
+// has completed and its writes are visible (a no-op for an ordinary launch), pdl_launch_dependents() lets the successor
+// start as soon as every CTA of this grid has passed the call.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 static_assert(sizeof(memb_event_aug) == 64, "memb_event_aug is part of the ABI: 64 bytes");
 
 template <bool kAligned>
@@ -106,6 +113,7 @@ __device__ __forceinline__ void aug_window(const memb_event_aug& a, long long& b
 __global__ void __launch_bounds__(256) hist_init(uint4* __restrict__ ws, long long n_vec,
                                                  long long tkeys_vec, int B) {
   // One 16-byte vector per stream holds {min key, max key}; everything else starts at zero.
+  pdl_launch_dependents();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n_vec; i += stride) {
@@ -159,6 +167,8 @@ __global__ void __launch_bounds__(kThreads) hist_scatter_global(
   unsigned int* acc_b = acc + (long long)b * 2 * npix;
   unsigned long long* last_b = kTss ? last + (long long)b * npix : nullptr;
   bool bad = false;
+  bool first = true;
+  pdl_launch_dependents();      // the finalize grid may take the SM slots this grid's tail leaves free
 
   const long long step = (long long)gridDim.x * kThreads * kUnroll;
   // Whole-warp iterations so that match.any sees a converged warp.
@@ -170,6 +180,10 @@ __global__ void __launch_bounds__(kThreads) hist_scatter_global(
       long long r = base + u * kThreads + threadIdx.x;
       live[u] = r < end;
       if (live[u]) e[u] = load_event<kAligned>(ev, r);
+    }
+    if (first) {                // the first rows were requested while the zero-fill kernel was still draining
+      pdl_wait();
+      first = false;
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -195,6 +209,7 @@ __global__ void __launch_bounds__(kThreads) hist_scatter_global(
       }
     }
   }
+  if (first) pdl_wait();         // no rows for this CTA: still order the flag write after the zero-fill
   if (bad) hdr->oob = 1;
 }
 
@@ -210,6 +225,7 @@ __global__ void __launch_bounds__(256) hist_finalize(const unsigned int* __restr
   const unsigned int* pos = acc + (long long)b * 2 * npix;
   const unsigned int* neg = pos + npix;
   uint8_t* o = out + (long long)b * npix * C;
+  pdl_wait();
   double tmin = 0.0, span = 0.0;
   const double* ev_b = nullptr;
   if constexpr (kTss) {
@@ -899,6 +915,21 @@ extern "C" size_t memb_hist_workspace_bytes(int B, int64_t n, int H, int W, int 
   return make_plan(B, n, H, W, timesurface, strategy).ws_bytes;
 }
 
+// Launch with the programmatic-stream-serialisation attribute (see pdl_wait above).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, memb_stream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // PRIVATE strategy: rasterise + finalize (two launches, no initialisation of the workspace needed).
 template <int kSrc>
 static int run_private(const void* rows, long long n, int W, int H, int C, unsigned int* acc, Header* hdr, uint8_t* out,
@@ -989,7 +1020,8 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
   } else if (n > 0) {
     const bool agg = p.strategy == MEMB_HIST_GLOBAL_AGG;
 #define MEMB_SCATTER(A, G, T)                                                                        \
-  hist_scatter_global<A, G, T><<<grid, kThreads, 0, stream>>>(ev, offs, n, W, npix, acc, last, hdr, aug)
+  MEMB_CUDA_OK(launch_pdl(hist_scatter_global<A, G, T>, grid, dim3(kThreads), stream, ev, offs, (long long)n, W, npix, acc, \
+                          last, hdr, aug))
     if (timesurface) {
       if (aligned) { if (agg) MEMB_SCATTER(true, true, true); else MEMB_SCATTER(true, false, true); }
       else { if (agg) MEMB_SCATTER(false, true, true); else MEMB_SCATTER(false, false, true); }
@@ -1003,8 +1035,10 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
   {
     long long fx = std::min<long long>(ceil_div<long long>(npix, 256), std::max<long long>(1, (long long)sms * 8 / B));
     const dim3 fgrid((unsigned)std::max<long long>(1, fx), (unsigned)B);
-    if (timesurface) hist_finalize<true><<<fgrid, 256, 0, stream>>>(acc, last, tkeys, ev, offs, npix, C, out);
-    else hist_finalize<false><<<fgrid, 256, 0, stream>>>(acc, nullptr, nullptr, ev, offs, npix, C, out);
+    if (timesurface)
+      MEMB_CUDA_OK(launch_pdl(hist_finalize<true>, fgrid, dim3(256), stream, acc, last, tkeys, ev, offs, npix, C, out));
+    else
+      MEMB_CUDA_OK(launch_pdl(hist_finalize<false>, fgrid, dim3(256), stream, acc, nullptr, nullptr, ev, offs, npix, C, out));
     MEMB_LAUNCH_OK("hist_finalize");
   }
   return MEMB_OK;
