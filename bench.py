@@ -208,13 +208,25 @@ class RawHistogramWorkload(HistogramWorkload):
                        "l2_policy": "256 MB L2 flush (memset) is NOT used: 4 resident recordings rotate (200 MB > 126 MB L2)",
                        "parallelism": "independent recordings per GPU (no collective)"}
 
+    @staticmethod
+    def synth_recording(rng, n, W=240, H=180):
+        """n synthetic N-Caltech101 records (5 bytes each: x, y, polarity bit + 23-bit big-endian timestamp)."""
+        import numpy as np
+        b = np.zeros((n, 5), dtype=np.uint8)
+        b[:, 0] = rng.integers(0, W, n)
+        b[:, 1] = rng.integers(0, H, n)
+        t = np.sort(rng.integers(0, 1 << 23, n))
+        b[:, 2] = ((t >> 16) & 0x7f) | (rng.integers(0, 2, n) << 7)
+        b[:, 3] = (t >> 8) & 0xff
+        b[:, 4] = t & 0xff
+        return b.tobytes()
+
     def setup(self, torch, rank):
         import numpy as np
         from mem_b200 import _lib
         from mem_b200.process_data import RAW_NCALTECH101, histogram_raw
-        from oracle import decode_ref
-        self.torch, self._lib, self.fmt, self.histogram_raw, self.decode_ref = torch, _lib, RAW_NCALTECH101, histogram_raw, decode_ref
-        self.host = [torch.frombuffer(bytearray(decode_ref.synth_ncaltech101(np.random.default_rng(10 * rank + k), self.n)),
+        self.torch, self._lib, self.fmt, self.histogram_raw = torch, _lib, RAW_NCALTECH101, histogram_raw
+        self.host = [torch.frombuffer(bytearray(self.synth_recording(np.random.default_rng(10 * rank + k), self.n)),
                                       dtype=torch.uint8).pin_memory() for k in range(4)]
         self.dev = [h.cuda() for h in self.host]
         self.k, self.out = 0, None
@@ -232,11 +244,12 @@ class RawHistogramWorkload(HistogramWorkload):
 
     def verify(self):
         import numpy as np
+        from oracle import decode_ref                       # the checker, not the thing measured
         from oracle.histogram_ref import event_hist_ref
         n = min(self.n, 2_000_000)
         raw = self.host[0][:5 * n]
         got = self.histogram_raw(raw.cuda(), self.fmt, self.H, self.W, channels=self.C).cpu().numpy()
-        return bool(np.array_equal(got, event_hist_ref(self.decode_ref.ncaltech101_np(raw.numpy().tobytes()), self.H, self.W)))
+        return bool(np.array_equal(got, event_hist_ref(decode_ref.ncaltech101_np(raw.numpy().tobytes()), self.H, self.W)))
 
     def roofline(self, ms_per_step):
         hbm, _, _, how = measured_peaks()
@@ -251,10 +264,11 @@ class RawHistogramWorkload(HistogramWorkload):
 
     def cpu_baseline(self):
         import numpy as np
+        from oracle import decode_ref
         n = 200_000
-        raw = self.decode_ref.synth_ncaltech101(np.random.default_rng(0), n)
+        raw = self.synth_recording(np.random.default_rng(0), n)
         t0 = time.perf_counter()
-        ev = self.decode_ref.ncaltech101_loop(raw)           # the reference's byte-by-byte Python decoder
+        ev = decode_ref.ncaltech101_loop(raw)                # the reference's byte-by-byte Python decoder
         t1 = time.perf_counter()
         self.cpu_once(ev)                                    # + np.add.at rasteriser
         t2 = time.perf_counter()
@@ -493,8 +507,6 @@ def main():
             return
         if workload == "raw_histogram":
             # the reference decodes byte by byte in one Python process per recording: a single-core sample is the arm
-            from oracle import decode_ref
-            wl.decode_ref = decode_ref
             cb = wl.cpu_baseline()
             records = 200_000                                 # what RawHistogramWorkload.cpu_baseline decodes
             print(json.dumps({"impl": "reference", "metric": wl.metric, "value": cb["value"], "unit": wl.unit, "n_gpus": args.gpus,
