@@ -40,6 +40,10 @@ def parse_args():
     ap.add_argument("--workload", default="auto", choices=["auto", "histogram", "pretrain", "event_pipeline", "raw_histogram", "finetune"])
     ap.add_argument("--events", type=int, default=10_000_000)
     ap.add_argument("--sensor", default="640x480")
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "edge8", "edge50", "hot"],
+                    help="histogram workload: spatial distribution of the synthetic stream")
+    ap.add_argument("--no-histogram", action="store_true",
+                    help="pretrain workload: skip the `histogram` sub-record (the second metric of BASELINE.json)")
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--model", default="base", choices=["base", "large"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -117,19 +121,38 @@ class HistogramWorkload:
     def __init__(self, args):
         w, h = (int(v) for v in args.sensor.split("x"))
         self.H, self.W, self.n, self.C = h, w, args.events, 3
-        self.config = {"workload": f"event->histogram rasterise, uniform synthetic stream, {self.n} events, "
+        self.kind = getattr(args, "dist", "uniform")
+        self.config = {"workload": f"event->histogram rasterise, {self.kind} synthetic stream, {self.n} events, "
                                    f"{w}x{h} sensor (N-ImageNet), float64[N,4] rows -> uint8[H,W,3]",
                        "events": self.n, "sensor_wxh": [w, h], "channels": self.C,
                        "l2_policy": "input (32 B/event, %.0f MB) larger than the 126 MB L2" % (self.n * 32 / 1e6),
                        "parallelism": "independent streams per GPU (no collective)"}
 
-    def make_events(self, seed, n=None):
+    def make_events(self, seed, n=None, kind=None):
+        """SURVEY.md 8(d) streams: uniform; edge-like (events on `segments` random line segments, sigma = 1 px:
+        "edge8" is the concentrated case of tools/hist_sweep.py, "edge50" the survey's); hot-pixel (1 % of the events
+        on 16 fixed pixels).  t sorted ascending, p = +-1."""
         import numpy as np
         n = n or self.n
+        kind = kind or self.kind
         rng = np.random.default_rng(seed)
         ev = np.empty((n, 4), dtype=np.float64)
-        ev[:, 0] = rng.integers(0, self.W, n)
-        ev[:, 1] = rng.integers(0, self.H, n)
+        if kind.startswith("edge"):
+            k = int(kind[4:] or 8)
+            seg = rng.integers(0, k, n)
+            x0, y0 = rng.uniform(0, self.W, k), rng.uniform(0, self.H, k)
+            dx, dy = rng.uniform(-1, 1, k), rng.uniform(-1, 1, k)
+            s = rng.uniform(0, min(self.H, self.W) / 2, n)
+            ev[:, 0] = np.floor(np.clip(x0[seg] + dx[seg] * s + rng.normal(0, 1, n), 0, self.W - 1))
+            ev[:, 1] = np.floor(np.clip(y0[seg] + dy[seg] * s + rng.normal(0, 1, n), 0, self.H - 1))
+        else:
+            ev[:, 0] = rng.integers(0, self.W, n)
+            ev[:, 1] = rng.integers(0, self.H, n)
+            if kind == "hot":
+                hot = rng.random(n) < 0.01
+                hx, hy = rng.integers(0, self.W, 16), rng.integers(0, self.H, 16)
+                pick = rng.integers(0, 16, n)
+                ev[hot, 0], ev[hot, 1] = hx[pick[hot]], hy[pick[hot]]
         ev[:, 2] = np.sort(rng.uniform(0, 3e5, n))
         ev[:, 3] = rng.integers(0, 2, n) * 2.0 - 1.0
         return ev
@@ -479,6 +502,51 @@ def run_reference_histogram(args, wl):
                                               f"rasterising a resident {n_each}-event stream per step")
 
 
+def _time_steps(torch, fn, steps, warm):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def histogram_record(args):
+    """`Gevents/s histogram rasterise` (BASELINE.json's second metric) at the top size of config 2 -- 10 M events on the
+    640x480 N-ImageNet sensor -- for every spatial distribution of SURVEY.md 8(d), each checked against the oracle."""
+    import torch
+    rec = {"metric": HistogramWorkload.metric, "unit": HistogramWorkload.unit, "dtype": HistogramWorkload.dtype,
+           "config": {"workload": "event->histogram rasterise, 10000000 events, 640x480 sensor, float64[N,4] rows -> uint8[H,W,3]",
+                      "l2_policy": "input (320 MB) larger than the 126 MB L2", "steps": 20, "warmup": 3}, "streams": {}}
+    for kind in ("uniform", "edge8", "edge50", "hot"):
+        wl = HistogramWorkload(argparse.Namespace(sensor="640x480", events=10_000_000, dist=kind))
+        wl.setup(torch, 0)
+        ok = wl.verify()
+        l0 = wl._lib.launch_count()
+        ms = _time_steps(torch, wl.step_device, 20, 3)
+        launches = (wl._lib.launch_count() - l0) // 23
+        roof = wl.roofline(ms)
+        rec["streams"][kind] = {"value": round(wl.n / (ms * 1e-3) / 1e9, 2), "us_per_step": round(ms * 1e3, 2), "gpu_launches_per_step": int(launches),
+                                "parity_vs_oracle": ok, "roofline": roof}
+        if kind == "uniform":
+            ms_e2e = _time_steps(torch, wl.step_e2e, 5, 2)
+            rec["e2e"] = {"value": round(wl.n / (ms_e2e * 1e-3) / 1e9, 4), "unit": wl.unit, "h2d_bytes_per_step": wl.h2d,
+                          "d2h_bytes_per_step": wl.d2h, "ms_per_step": round(ms_e2e, 3), "api": "process_data.histogram (pinned host rows in, host image out)"}
+            if not args.no_cpu_baseline:
+                rec["cpu_baseline"] = wl.cpu_baseline()
+        del wl
+        torch.cuda.empty_cache()
+    vals = [v["value"] for v in rec["streams"].values()]
+    rec["value"] = rec["streams"]["uniform"]["value"]
+    rec["worst_stream_value"] = min(vals)
+    rec["roofline"] = rec["streams"]["uniform"]["roofline"]
+    return rec
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     args = parse_args()
@@ -488,17 +556,19 @@ def main():
 
     workload = args.workload
     if workload == "auto":
-        try:
-            from mem_b200 import bench_pretrain  # noqa: F401
-            workload = "pretrain"
-        except Exception:
-            workload = "histogram"
+        workload = "pretrain"
     if workload == "pretrain":
-        from mem_b200 import bench_pretrain
-        return bench_pretrain.main(args, rank, local_rank, world, ClockSampler, measured_peaks)
+        from benchmarks import pretrain
+        line = pretrain.main(args, rank, local_rank, world, ClockSampler, measured_peaks)
+        if line is not None:
+            # the second metric BASELINE.json names rides on the same line (single-GPU runs: rasterisation has no collective)
+            if args.impl != "reference" and world == 1 and not args.no_histogram:
+                line["histogram"] = histogram_record(args)
+            print(json.dumps(line))
+        return
     if workload == "finetune":
-        from mem_b200 import bench_finetune
-        return bench_finetune.main(args, rank, local_rank, world, ClockSampler, measured_peaks)
+        from benchmarks import finetune
+        return finetune.main(args, rank, local_rank, world, ClockSampler, measured_peaks)
 
     wl = {"event_pipeline": EventPipelineWorkload, "raw_histogram": RawHistogramWorkload}.get(workload, HistogramWorkload)(args)
 

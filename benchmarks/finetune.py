@@ -13,7 +13,7 @@ import time
 
 import numpy as np
 
-from . import bench_pretrain as bp
+from . import pretrain as bp
 
 FT = dict(img_size=(224, 224), patch_size=(16, 16), in_chans=3, num_classes=2, embed_dim=768, depth=12, num_heads=12,
           mlp_ratio=4, init_values=0.1, use_rel_pos_bias=True, use_abs_pos_emb=False, use_mean_pooling=True, drop_path_rate=0.1)

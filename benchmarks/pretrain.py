@@ -8,13 +8,18 @@ then normalised by the per-image maximum like the reference's NormalizeEvent, tr
 `value`  : samples/s with the batch already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same through engine_for_pretraining.train_one_epoch with a HOST (pinned) data loader:
            H2D copies of samples / images / masks and the D2H read of the step statistics are inside.
-`roofline`: the dominant GEMM launch (fc1: [B*197, 768] x [3072, 768]^T, bf16 tcgen05) timed alone with CUDA
-           events; `step_tensor_util` is ViT bf16 FLOPs / whole step time / measured bf16 peak (dVAE time is
-           inside the step, its FLOPs are not counted: SURVEY.md 8d).
+`roofline`: the dominant kernel of the step, `conv16::conv_f16x2` (the dVAE tokenizer's convolutions: 16 launches
+           per step, ~40 % of the step's launch time, profiles/r02_pretrain_launch_shares_*.txt).  Every conv launch of
+           the timed region is bracketed by CUDA events on the launching stream; achieved = algorithmic FLOPs
+           (2*B*OH*OW*Cout*K per launch, 3.1 TFLOP per 128-image step) / summed launch time.  The kernel carries every
+           fp32 operand as an fp16 hi/lo pair and issues three tensor-core MMAs per algorithmic product, so its
+           ceiling is peak / 3 (`frac_of_scheme_ceiling`); `frac` is the plain achieved / peak the contract defines.
+`gemm_fc1`: the largest ViT GEMM launch (fc1: [B*197, 768] x [3072, 768]^T, bf16 tcgen05) timed alone, cold L2.
+`step_tensor_util`: ViT bf16 FLOPs / whole step time / measured sustained bf16 peak (dVAE time is inside the
+           step, its FLOPs are not counted: SURVEY.md 8d).
 """
 from __future__ import annotations
 
-import json
 import os
 import random
 import time
@@ -164,6 +169,8 @@ def main(args, rank, local_rank, world, ClockSampler, measured_peaks):
         sampler.start()
     # ---- device-resident timed region
     marks = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    conv_launches = []
+    vae._tokenizer().launch_timer = conv_launches       # (layer, FLOPs, start, end) per conv_f16x2 launch
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -173,6 +180,7 @@ def main(args, rank, local_rank, world, ClockSampler, measured_peaks):
     e1.record()
     barrier()
     launches = _lib.launch_count() - l0
+    vae._tokenizer().launch_timer = None
     ms_step = maxreduce(e0.elapsed_time(e1)) / steps
     seg = np.array([[mk[j].elapsed_time(mk[j + 1]) for j in range(3)] for mk in marks]).mean(0)
     n_masked = float(stats[2].item()) / B
@@ -192,8 +200,9 @@ def main(args, rank, local_rank, world, ClockSampler, measured_peaks):
         barrier()
     ms_e2e = maxreduce(e0.elapsed_time(e1)) / e2e_steps
     clocks = sampler.stop() if rank == 0 else None
-    # ---- dominant GEMM launch alone (fc1 of one block)
-    roof = gemm_roofline(torch, model, B, m, measured_peaks) if rank == 0 else None
+    # ---- dominant kernel (tokenizer convolutions, timed inside the steps above) and the largest ViT GEMM alone
+    roof = conv_roofline(conv_launches, steps, measured_peaks) if rank == 0 else None
+    fc1 = gemm_roofline(torch, model, B, m, measured_peaks) if rank == 0 else None
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -222,12 +231,42 @@ def main(args, rank, local_rank, world, ClockSampler, measured_peaks):
                                  "peak_tflops_sustained": tf_sust, "frac": round(flops * B / (ms_step * 1e-3) / 1e12 / tf_sust, 4)},
             "masked_per_sample": round(n_masked, 2), "loss_last": round(loss_last, 4),
             "e2e_stats": {k: round(float(v), 5) for k, v in out_stats.items()},
-            "clocks": clocks, "roofline": roof}
+            "clocks": clocks, "roofline": roof, "gemm_fc1": fc1}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(sample_steps=2)
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line
+
+
+def conv_roofline(conv_launches, steps, measured_peaks):
+    """Roofline record of conv16::conv_f16x2 from the per-launch CUDA events of the timed region."""
+    hbm, tf_burst, tf_sust, how = measured_peaks()
+    per_layer = {}
+    for layer, fl, e0, e1 in conv_launches:
+        acc = per_layer.setdefault(layer, [0.0, 0.0, 0])
+        acc[0] += fl; acc[1] += e0.elapsed_time(e1); acc[2] += 1
+    n = sum(v[2] for v in per_layer.values())
+    if n == 0:
+        return None
+    fl_total = sum(v[0] for v in per_layer.values())
+    ms_total = sum(v[1] for v in per_layer.values())
+    ach = fl_total / (ms_total * 1e-3) / 1e12
+    layers = {k: {"launches_per_step": v[2] // steps, "us": round(v[1] / v[2] * 1e3, 1),
+                  "tflops": round(v[0] / (v[1] * 1e-3) / 1e12, 1)} for k, v in per_layer.items()}
+    return {"bound": "tensor", "kernel": "conv16::conv_f16x2 (dVAE tokenizer convolutions: implicit GEMM on CTA-pair tcgen05, fp16 hi/lo "
+                                         "operand pairs, 3 MMAs per fp32-faithful product)",
+            "achieved": round(ach, 1), "peak": tf_sust, "unit": "TFLOP/s", "frac": round(ach / tf_sust, 4),
+            "frac_of_scheme_ceiling": round(3.0 * ach / tf_sust, 4),
+            "peak_source": how + " (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel is timed inside the long step; fp16 and bf16 "
+                                 "share the tensor-pipe rate)",
+            "scheme_ceiling": "peak / 3: lo*hi + hi*lo + hi*hi per product (22 significand bits per operand)",
+            "algorithmic_flops_per_launch": fl_total / n, "launch_ms": round(ms_total / n, 4),
+            "launches_per_step": n // steps, "step_share_ms": round(ms_total / steps, 3),
+            "timing": "CUDA events around every conv_f16x2 launch of the timed region, on the launching stream",
+            "per_layer": layers, "traffic": _traffic("conv_f16x2_B128_mean"),
+            "traffic_note": "mean DRAM read+write bytes per launch over the 16 launches of one 128-image tokenizer pass, "
+                            "ncu --set full capture (profiles/ncu_traffic.json names the commit)"}
 
 
 def gemm_roofline(torch, model, B, m, measured_peaks):
@@ -268,7 +307,6 @@ def gemm_roofline(torch, model, B, m, measured_peaks):
 def _traffic(key):
     """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json)."""
     import json
-    import os
     try:
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         return json.load(open(os.path.join(root, "profiles", "ncu_traffic.json")))[key]["bytes"]
@@ -348,4 +386,4 @@ def reference_arm(args, rank):
             "cpu_baseline": {"value": round(value, 3), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    return line

@@ -58,6 +58,9 @@ int64_t memb_launch_count(void);
 #define MEMB_HIST_TILE 3        /* shared-memory privatised sensor tiles         */
 #define MEMB_HIST_PRIVATE 4     /* one stream, sensor <= 51200 px: a whole-sensor copy per SM in shared      */
                                 /* memory, copies summed from per-CTA slices (else falls back to GLOBAL)    */
+#define MEMB_HIST_GLOBAL_REPL 5 /* GLOBAL with 8 copies of the accumulator planes (one stream only): warps RED */
+                                /* into different copies so that a concentrated stream (edges, hot pixels)    */
+                                /* does not serialise on a few L2 sectors; the finalize pass adds the copies  */
 
 /* Bytes memb_hist_u8 needs for this problem (n = total rows; same strategy value as the call). */
 size_t memb_hist_workspace_bytes(int B, int64_t n, int H, int W, int timesurface, int strategy);
@@ -357,8 +360,14 @@ int memb_linear_small_bwd(const float* dl /* [B, C] */, const void* z_bf16, cons
 int memb_fill_f32(float* p, int64_t n, float v, memb_stream_t stream);
 int memb_cast_bf16(const float* src, void* dst, int64_t n, memb_stream_t stream);
 int memb_sqnorm(const float* g, int64_t n, float scale, float* out, memb_stream_t stream);
+/* out[0] += sum (g * scale)^2 over the 1024-element chunks whose chunk_group is not 255 (255 = padding or a
+ * requires_grad = False tensor: get_grad_norm_ / clip_grad_norm_ only see trainable tensors, mem/utils.py:380-392). */
+int memb_sqnorm_groups(const float* g, int64_t n, float scale, const uint8_t* chunk_group, float* out,
+                       memb_stream_t stream);
 /* One pass over the flat parameter buffer; tensors start on 1024-element boundaries and
- * chunk_group[i/1024] (device uint8, 255 = skip) selects (group_lr_host[g], group_wd_host[g]). */
+ * chunk_group[i/1024] (device uint8, >= 64 = never updated) selects (group_lr_host[g], group_wd_host[g]).
+ * When sqnorm_dev is given and *sqnorm_dev is not finite the step is skipped (nothing is written): the
+ * reference's GradScaler.step skips inf / NaN gradients (mem/utils.py:357-371). */
 int memb_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, const uint8_t* chunk_group,
                const float* group_lr_host, const float* group_wd_host, int ngroups, float beta1, float beta2, float eps,
                int step, float grad_scale, float max_norm, const float* sqnorm_dev, memb_stream_t stream);

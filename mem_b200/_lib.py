@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("MEMB_LIB_PATH") or os.path.join(_HERE, "libmemb.so") 
 
 MEMB_OK, MEMB_EINVAL, MEMB_EOOB, MEMB_ECUDA, MEMB_EWORKSPACE = 0, -1, -2, -3, -4
 
-HIST_AUTO, HIST_GLOBAL, HIST_GLOBAL_AGG, HIST_TILE, HIST_PRIVATE = 0, 1, 2, 3, 4
+HIST_AUTO, HIST_GLOBAL, HIST_GLOBAL_AGG, HIST_TILE, HIST_PRIVATE, HIST_GLOBAL_REPL = 0, 1, 2, 3, 4, 5
 RAW_NCALTECH101, RAW_NCARS = 1, 2
 
 _c = ctypes
@@ -86,6 +86,7 @@ SIGNATURES.update({
     "memb_fill_f32": (_i32, [_vp, _i64, _f32, _vp]),
     "memb_cast_bf16": (_i32, [_vp, _vp, _i64, _vp]),
     "memb_sqnorm": (_i32, [_vp, _i64, _f32, _vp, _vp]),
+    "memb_sqnorm_groups": (_i32, [_vp, _i64, _f32, _vp, _vp, _vp]),
     "memb_adamw": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _i32, _f32, _f32, _vp, _vp]),
 })
 

@@ -9,6 +9,7 @@
 // at the end, which is exactly numpy's uint8 wrap.
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 
 #include "common.cuh"
@@ -155,7 +156,7 @@ template <bool kAligned, bool kAggregate, bool kTss>
 __global__ void __launch_bounds__(kThreads) hist_scatter_global(
     const double* __restrict__ ev, const long long* __restrict__ offsets, long long n_total, int W,
     long long npix, unsigned int* __restrict__ acc, unsigned long long* __restrict__ last,
-    Header* __restrict__ hdr, const memb_event_aug* __restrict__ aug) {
+    Header* __restrict__ hdr, const memb_event_aug* __restrict__ aug, int replicas) {
   const int b = blockIdx.y;
   long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
   memb_event_aug a;
@@ -164,7 +165,10 @@ __global__ void __launch_bounds__(kThreads) hist_scatter_global(
     a = aug[b];
     aug_window(a, begin, end);
   }
-  unsigned int* acc_b = acc + (long long)b * 2 * npix;
+  // GLOBAL_REPL: every warp adds into one of `replicas` copies of the planes (neighbouring warps use different
+  // copies), so that REDs to one hot sector are spread over `replicas` sectors; hist_finalize adds the copies.
+  const int rep = replicas > 1 ? (int)((blockIdx.x * (unsigned)(kThreads / 32) + (threadIdx.x >> 5)) % (unsigned)replicas) : 0;
+  unsigned int* acc_b = acc + ((long long)b * replicas + rep) * 2 * npix;
   unsigned long long* last_b = kTss ? last + (long long)b * npix : nullptr;
   bool bad = false;
   bool first = true;
@@ -220,9 +224,9 @@ __global__ void __launch_bounds__(256) hist_finalize(const unsigned int* __restr
                                                      const unsigned long long* __restrict__ tkeys,
                                                      const double* __restrict__ ev,
                                                      const long long* __restrict__ offsets,
-                                                     long long npix, int C, uint8_t* __restrict__ out) {
+                                                     long long npix, int C, uint8_t* __restrict__ out, int replicas) {
   const int b = blockIdx.y;
-  const unsigned int* pos = acc + (long long)b * 2 * npix;
+  const unsigned int* pos = acc + (long long)b * replicas * 2 * npix;
   const unsigned int* neg = pos + npix;
   uint8_t* o = out + (long long)b * npix * C;
   pdl_wait();
@@ -235,7 +239,12 @@ __global__ void __launch_bounds__(256) hist_finalize(const unsigned int* __restr
   }
   for (long long px = blockIdx.x * (long long)blockDim.x + threadIdx.x; px < npix;
        px += (long long)gridDim.x * blockDim.x) {
-    const uint8_t cp = (uint8_t)(pos[px] & 0xffu), cn = (uint8_t)(neg[px] & 0xffu);
+    unsigned int sp = pos[px], sn = neg[px];
+    for (int k = 1; k < replicas; ++k) {
+      sp += pos[(long long)k * 2 * npix + px];
+      sn += neg[(long long)k * 2 * npix + px];
+    }
+    const uint8_t cp = (uint8_t)(sp & 0xffu), cn = (uint8_t)(sn & 0xffu);
     if (C == 2) {
       o[2 * px] = cp;
       o[2 * px + 1] = cn;
@@ -871,8 +880,20 @@ __global__ void hist_extent_init(Header* hdr) {
 }
 
 // ---------------------------------------------------------------- host side
+constexpr int kReplDefault = 8;
+// copies of the accumulator planes the GLOBAL_REPL strategy keeps (MEMB_HIST_REPLICAS overrides: tuning only)
+static int repl_count() {
+  static const int k = [] {
+    const char* e = getenv("MEMB_HIST_REPLICAS");
+    const int v = e ? atoi(e) : kReplDefault;
+    return std::max(1, std::min(v, 64));
+  }();
+  return k;
+}
+
 struct Plan {
   int strategy;
+  int replicas;
   int tiles, tile_pix;
   size_t ws_bytes;
   size_t off_tkeys, off_acc, off_last;
@@ -891,12 +912,17 @@ static Plan make_plan(int B, int64_t n, int H, int W, int timesurface, int strat
     if (B == 1 && npix <= kTileMaxWords && n >= (1 << 18)) strategy = MEMB_HIST_PRIVATE;
   }
   if (strategy == MEMB_HIST_PRIVATE && (B != 1 || npix > kTileMaxWords)) strategy = MEMB_HIST_GLOBAL;
+  p.replicas = 1;
+  if (strategy == MEMB_HIST_GLOBAL_REPL) {   // the copies only pay for one long stream
+    strategy = MEMB_HIST_GLOBAL;
+    if (B == 1) p.replicas = repl_count();
+  }
   p.strategy = strategy;
   p.tiles = (int)ceil_div<long long>(npix, kTileMaxWords);
   p.tile_pix = (int)round_up<long long>(ceil_div<long long>(npix, p.tiles), 4);
   p.off_tkeys = kHeaderBytes;
   p.off_acc = p.off_tkeys + (timesurface ? round_up<size_t>((size_t)B * 16, 256) : 0);
-  p.off_last = p.off_acc + (strategy == MEMB_HIST_TILE ? 0 : (size_t)B * 2 * npix * 4);
+  p.off_last = p.off_acc + (strategy == MEMB_HIST_TILE ? 0 : (size_t)B * p.replicas * 2 * npix * 4);
   if (strategy == MEMB_HIST_PRIVATE)   // CTA slices [kPrivMaxCtas][words] u16 + one flag per CTA
     p.off_last = p.off_acc + (size_t)kPrivMaxCtas * round_up<size_t>((size_t)npix, 8) * 2 + kPrivMaxCtas * 4;
   p.off_last = round_up<size_t>(p.off_last, 16);
@@ -965,7 +991,7 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
   MEMB_REQUIRE(offsets != nullptr || B == 1, "hist: a batch needs row offsets");
   MEMB_REQUIRE(out != nullptr && ws != nullptr, "hist: null output / workspace");
   MEMB_REQUIRE((((uintptr_t)ev) & 7u) == 0 && (((uintptr_t)ws) & 15u) == 0, "hist: misaligned pointer");
-  MEMB_REQUIRE(strategy >= MEMB_HIST_AUTO && strategy <= MEMB_HIST_PRIVATE, "hist: unknown strategy %d", strategy);
+  MEMB_REQUIRE(strategy >= MEMB_HIST_AUTO && strategy <= MEMB_HIST_GLOBAL_REPL, "hist: unknown strategy %d", strategy);
   const long long npix = (long long)H * W;
   const Plan p = make_plan(B, n, H, W, timesurface, strategy);
   if (ws_bytes < p.ws_bytes)
@@ -1021,7 +1047,7 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
     const bool agg = p.strategy == MEMB_HIST_GLOBAL_AGG;
 #define MEMB_SCATTER(A, G, T)                                                                        \
   MEMB_CUDA_OK(launch_pdl(hist_scatter_global<A, G, T>, grid, dim3(kThreads), stream, ev, offs, (long long)n, W, npix, acc, \
-                          last, hdr, aug))
+                          last, hdr, aug, p.replicas))
     if (timesurface) {
       if (aligned) { if (agg) MEMB_SCATTER(true, true, true); else MEMB_SCATTER(true, false, true); }
       else { if (agg) MEMB_SCATTER(false, true, true); else MEMB_SCATTER(false, false, true); }
@@ -1036,9 +1062,9 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
     long long fx = std::min<long long>(ceil_div<long long>(npix, 256), std::max<long long>(1, (long long)sms * 8 / B));
     const dim3 fgrid((unsigned)std::max<long long>(1, fx), (unsigned)B);
     if (timesurface)
-      MEMB_CUDA_OK(launch_pdl(hist_finalize<true>, fgrid, dim3(256), stream, acc, last, tkeys, ev, offs, npix, C, out));
+      MEMB_CUDA_OK(launch_pdl(hist_finalize<true>, fgrid, dim3(256), stream, acc, last, tkeys, ev, offs, npix, C, out, p.replicas));
     else
-      MEMB_CUDA_OK(launch_pdl(hist_finalize<false>, fgrid, dim3(256), stream, acc, nullptr, nullptr, ev, offs, npix, C, out));
+      MEMB_CUDA_OK(launch_pdl(hist_finalize<false>, fgrid, dim3(256), stream, acc, nullptr, nullptr, ev, offs, npix, C, out, p.replicas));
     MEMB_LAUNCH_OK("hist_finalize");
   }
   return MEMB_OK;
@@ -1145,7 +1171,7 @@ extern "C" int memb_hist_raw_u8(const uint8_t* raw, int64_t n_records, int forma
   {
     const long long fx = std::min<long long>(ceil_div<long long>(npix, 256), (long long)sms * 8);
     hist_finalize<false><<<(unsigned)std::max<long long>(1, fx), 256, 0, stream>>>(acc, nullptr, nullptr, nullptr, nullptr,
-                                                                                  npix, C, out);
+                                                                                  npix, C, out, 1);
     MEMB_LAUNCH_OK("hist_finalize");
   }
   return MEMB_OK;

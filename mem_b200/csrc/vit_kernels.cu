@@ -628,10 +628,35 @@ __global__ void __launch_bounds__(256) sqnorm(const float* __restrict__ g, long 
     atomicAdd(out, t);
   }
 }
+// Same over a flat parameter-gradient buffer laid out in 1024-element chunks, skipping chunks whose group is 255
+// (padding / requires_grad = False parameters: clip_grad_norm_ only sees trainable tensors, mem/utils.py:380-392).
+__global__ void __launch_bounds__(256) sqnorm_groups(const float* __restrict__ g, long long n, float scale,
+                                                     const unsigned char* __restrict__ chunk_group, float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  const long long nchunks = (n + 1023) / 1024;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    if (chunk_group[ch] == 255) continue;
+    const long long i = ch * 1024 + threadIdx.x * 4;
+    if (i >= n) continue;
+    const float4 v = ld4(g + i);
+    s += (v.x * scale) * (v.x * scale) + (v.y * scale) * (v.y * scale) + (v.z * scale) * (v.z * scale) + (v.w * scale) * (v.w * scale);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out, t);
+  }
+}
 // AdamW over the whole flat parameter buffer (torch.optim.AdamW semantics).  Tensors are laid out on
-// 1024-element boundaries; chunk_group[i / 1024] selects the parameter group (lr, weight decay), 255 =
-// padding / frozen.  The global-norm clip coefficient is applied on the fly and the bf16 shadow copy of
-// the weights is refreshed in the same pass.
+// 1024-element boundaries; chunk_group[i / 1024] selects the parameter group (lr, weight decay), >= 64 =
+// never updated (255: padding / frozen, 254: the status chunk, counted by sqnorm_groups).  The global-norm clip
+// coefficient is applied on the fly and the bf16 shadow copy of the weights is refreshed in the same pass.
+// A step whose gradient norm is not finite is skipped entirely (parameters and moments untouched): what the
+// reference's GradScaler.step does with inf / NaN gradients (mem/utils.py:357-371).
 struct AdamGroups { float lr[64]; float wd[64]; };
 __global__ void __launch_bounds__(256) adamw(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                              float* __restrict__ v, bf16* __restrict__ shadow, long long n,
@@ -639,9 +664,10 @@ __global__ void __launch_bounds__(256) adamw(float* __restrict__ p, const float*
                                              float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
                                              float grad_scale, float max_norm, const float* __restrict__ sq) {
   float coef = grad_scale;
-  if (max_norm > 0.f && sq) {
+  if (sq) {
     const float norm = sqrtf(*sq);
-    coef *= fminf(1.f, max_norm / (norm + 1e-6f));
+    if (!isfinite(norm)) return;
+    if (max_norm > 0.f) coef *= fminf(1.f, max_norm / (norm + 1e-6f));
   }
   const long long nchunks = (n + 1023) / 1024;
   for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
@@ -859,6 +885,13 @@ extern "C" int memb_sqnorm(const float* g, int64_t n, float scale, float* out, m
   MEMB_REQUIRE(g && out && n > 0, "sqnorm: bad arguments");
   sqnorm<<<flat_grid(n, 8), 256, 0, s>>>(g, n, scale, out);
   MEMB_LAUNCH_OK("sqnorm");
+  return MEMB_OK;
+}
+extern "C" int memb_sqnorm_groups(const float* g, int64_t n, float scale, const uint8_t* chunk_group, float* out, memb_stream_t s) {
+  MEMB_REQUIRE(g && out && chunk_group && n > 0 && n % 4 == 0, "sqnorm_groups: bad arguments");
+  const long long nchunks = (n + 1023) / 1024;
+  sqnorm_groups<<<(int)std::min<long long>(nchunks, (long long)num_sms() * 16), 256, 0, s>>>(g, n, scale, chunk_group, out);
+  MEMB_LAUNCH_OK("sqnorm_groups");
   return MEMB_OK;
 }
 extern "C" int memb_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n,

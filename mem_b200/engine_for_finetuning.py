@@ -83,6 +83,16 @@ class ModelEma:
         return {n: self.shadow[self.flat.offsets[n]:self.flat.offsets[n] + p.numel()].view_as(p)
                 for n, p in self.flat.params.items()}
 
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        """Restore the EMA weights from a checkpoint's ``model_ema`` entry (mem/utils.py:521-522)."""
+        mine = self.state_dict()
+        missing = [n for n in mine if n not in state_dict]
+        if missing:
+            raise KeyError(f"model_ema checkpoint lacks {missing[:3]}{'...' if len(missing) > 3 else ''}")
+        for n, dst in mine.items():
+            dst.copy_(state_dict[n].to(dst.device, dst.dtype))
+
 
 def _unwrap(model):
     return model.module if hasattr(model, "module") else model
@@ -92,6 +102,17 @@ def train_class_batch(model, samples, target, criterion):
     outputs = model(samples)
     loss = criterion(outputs, target)
     return loss, outputs
+
+
+def _sync_replicas(core):
+    """Once per model: broadcast rank 0's parameters.  The reference seeds each rank with ``args.seed + rank``
+    (run_class_finetuning.py:355) and gets identical replicas from the DistributedDataParallel constructor (:487)."""
+    if utils.get_world_size() > 1 and not getattr(core, "_memb_replicas_synced", False):
+        flat = engine_of(core).flat()
+        torch.distributed.broadcast(flat.data, src=0)
+        if flat.data.is_cuda:
+            flat.refresh_shadow(force=True)
+        object.__setattr__(core, "_memb_replicas_synced", True)
 
 
 def _all_reduce_grads(core, optimizer):
@@ -119,6 +140,7 @@ def train_one_epoch(args, model: torch.nn.Module, criterion: torch.nn.Module, da
     start_steps = start_steps or 0
     if num_training_steps_per_epoch is None:
         num_training_steps_per_epoch = math.inf
+    _sync_replicas(core)
     optimizer.zero_grad()
 
     for data_iter_step, (samples, targets) in enumerate(metric_logger.log_every(data_loader, 10, header)):

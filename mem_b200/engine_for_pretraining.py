@@ -34,13 +34,18 @@ def _unwrap(model):
 
 
 def _reducer_for(core):
-    """One GradReducer per model (rebuilt if the process group or the flat buffer changes)."""
+    """One GradReducer per model (rebuilt if the process group or the flat buffer changes).
+
+    Building it also makes the replicas identical: the reference seeds every rank with ``args.seed + rank``
+    (run_mem_pretraining.py:255) and relies on the DistributedDataParallel constructor's broadcast of rank 0's
+    parameters (:365-367); here that broadcast is one NCCL call over the flat parameter buffer."""
     if utils.get_world_size() == 1:
         return None
     flat = engine_of(core).flat()
     red = getattr(core, "_memb_reducer", None)
     if red is None or red.grad is not flat.grad:
         red = GradReducer(flat.grad, bucket_ranges(flat, len(core.blocks)))
+        red.sync_parameters(flat)
         object.__setattr__(core, "_memb_reducer", red)
     return red
 
@@ -163,6 +168,14 @@ def train_one_epoch(model: torch.nn.Module, d_vae: torch.nn.Module, data_loader:
             input_ids = d_vae.get_codebook_indices(images).flatten(1)      # [B, P] int64
 
         optimizer.zero_grad()
+        # fp16-pair tokenizer: if an activation left its calibrated range the tokens are invalid.  The check is a device
+        # scalar (NaN / 0) dropped into a padding element of the flat gradient: it rides the gradient all-reduce to
+        # every rank, makes the global norm non-finite, and FlatAdamW skips a step whose norm is not finite (what the
+        # reference's GradScaler does with inf / NaN gradients, utils.py:357-371) -- no update from bad tokens, no
+        # extra host sync, no extra collective.
+        poison = d_vae.overflow_poison() if hasattr(d_vae, "overflow_poison") else None
+        if poison is not None:
+            engine_of(core).flat().poison_grad(poison)
         stats = pretrain_step(core, samples, bool_masked_pos.flatten(1), input_ids, cap=n_masked,
                               bucket_hook=reducer.hook if reducer is not None else None)
         if reducer is not None:
@@ -174,8 +187,12 @@ def train_one_epoch(model: torch.nn.Module, d_vae: torch.nn.Module, data_loader:
         loss_scale_value = loss_scaler.state_dict()["scale"]
 
         loss_value, mlm_acc, grad_norm_value, _ = hand_off.read(stats, grad_norm)
-        if hasattr(d_vae, "verify_range"):
-            d_vae.verify_range()   # fp16-pair tokenizer: activation maxima of this step vs its calibrated exponents
+        if hasattr(d_vae, "verify_range") and not d_vae.verify_range(raise_on_overflow=False):
+            # this rank's tokens were invalid: the step was skipped on every rank (see above); the tokenizer
+            # re-calibrates on its next call
+            print("WARNING: dVAE tokenizer left its calibrated fp16 range; step {} skipped, re-calibrating".format(it))
+        if not math.isfinite(grad_norm_value) and hasattr(optimizer, "step_skipped"):
+            optimizer.step_skipped()          # the update did not happen: keep the bias-correction step count in line
         if not math.isfinite(loss_value):
             print("Loss is {}, stopping training".format(loss_value))
             print("INFO:", "samples", samples.shape, "bool_masked_pos", bool_masked_pos.shape, "images", images.shape)
@@ -228,9 +245,13 @@ def evaluate(data_loader, model, d_vae, device, args, plotting=False, MAE=False)
         images = images.to(device, non_blocking=True)
         samples = samples.to(device, non_blocking=True)
         bool_masked_pos = bool_masked_pos.to(device, non_blocking=True)
-        input_ids = d_vae.get_codebook_indices(images).flatten(1)
-        stats = pretrain_step(core, samples, bool_masked_pos.flatten(1), input_ids, backward=False, cap=n_masked)
-        loss_value, mlm_acc, _, _ = hand_off.read(stats, None)
+        for attempt in range(2):
+            input_ids = d_vae.get_codebook_indices(images).flatten(1)
+            stats = pretrain_step(core, samples, bool_masked_pos.flatten(1), input_ids, backward=False, cap=n_masked)
+            loss_value, mlm_acc, _, _ = hand_off.read(stats, None)
+            # fp16-pair tokenizer left its calibrated range: tokens invalid -> tokenise again (it re-calibrates)
+            if not hasattr(d_vae, "verify_range") or d_vae.verify_range(raise_on_overflow=attempt == 1):
+                break
         metric_logger.update(loss=loss_value)
         metric_logger.meters["mlm_acc"].update(mlm_acc)
     metric_logger.synchronize_between_processes()

@@ -63,6 +63,7 @@ class FlatAdamW(torch.optim.Optimizer):
                 assert n is not None, "FlatAdamW: parameter does not live in the model's flat buffer"
                 c0 = flat.offsets[n] // CHUNK
                 groups[c0: c0 + (flat.sizes[n] + CHUNK - 1) // CHUNK] = gi
+        groups[nchunks - 1] = 254          # the status chunk (FlatParams.poison_grad): in the norm, never updated
         self.chunk_group = groups.to(flat.device)
         self.exp_avg = torch.zeros_like(flat.data)
         self.exp_avg_sq = torch.zeros_like(flat.data)
@@ -79,7 +80,9 @@ class FlatAdamW(torch.optim.Optimizer):
         self.step_count += 1
         gs = 1.0 / self.grad_divisor
         self.sqnorm.zero_()
-        _lib.check(lib.memb_sqnorm(flat.grad.data_ptr(), flat.numel, gs, self.sqnorm.data_ptr(), sp))
+        # chunks of requires_grad = False tensors (group 255) stay out of the norm, like clip_grad_norm_(parameters)
+        _lib.check(lib.memb_sqnorm_groups(flat.grad.data_ptr(), flat.numel, gs, self.chunk_group.data_ptr(),
+                                          self.sqnorm.data_ptr(), sp))
         ng = len(self.param_groups)
         lr = (ctypes.c_float * ng)(*[float(g["lr"]) for g in self.param_groups])
         wd = (ctypes.c_float * ng)(*[float(g["weight_decay"]) for g in self.param_groups])
@@ -90,6 +93,11 @@ class FlatAdamW(torch.optim.Optimizer):
                                   self.sqnorm.data_ptr(), sp))
         torch.sqrt(self.sqnorm, out=self.norm)
         return self.norm[0]
+
+    def step_skipped(self):
+        """The kernel leaves parameters and moments untouched when the gradient norm is not finite (the reference's
+        GradScaler skips such steps, utils.py:357-371); the caller reports it once it has read the norm."""
+        self.step_count = max(0, self.step_count - 1)
 
     def zero_grad(self, set_to_none: bool = True):
         # gradients live in the flat buffer: one fill kernel; p.grad stay bound views

@@ -63,6 +63,15 @@ class GradReducer:
         self.pending = []
         self.launched = 0
 
+    def sync_parameters(self, flat, src=0):
+        """Broadcast rank ``src``'s parameters (what DistributedDataParallel's constructor does) and refresh the bf16
+        shadow the GEMMs read.  ``flat``: the model's ``FlatParams``."""
+        if self.world == 1:
+            return
+        dist.broadcast(flat.data, src=src, group=self.group)
+        if flat.data.is_cuda:
+            flat.refresh_shadow(force=True)
+
     def hook(self, tag):
         r = self.by_tag.get(tag)
         if r is None or self.world == 1:

@@ -271,10 +271,13 @@ def cosine_scheduler(base_value, final_value, epochs, niter_per_ep, warmup_epoch
 
 # ----------------------------------------------------------------------------------- checkpoints
 def save_model(args, epoch, model, model_without_ddp, optimizer, loss_scaler, model_ema=None):
-    """``checkpoint-{epoch}.pth`` = {model, optimizer, epoch, scaler, args} on rank 0 (reference format)."""
+    """``checkpoint-{epoch}.pth`` = {model, optimizer, epoch, scaler, args[, model_ema]} on rank 0 (reference
+    format, mem/utils.py:425-442; ``epoch`` may be the string ``"best"``)."""
     path = os.path.join(args.output_dir, f"checkpoint-{epoch}.pth")
     to_save = {"model": model_without_ddp.state_dict(), "optimizer": optimizer.state_dict(), "epoch": epoch,
                "scaler": loss_scaler.state_dict() if loss_scaler is not None else None, "args": args}
+    if model_ema is not None:
+        to_save["model_ema"] = {k: v.detach().clone() for k, v in model_ema.state_dict().items()}
     save_on_master(to_save, path)
 
 
@@ -293,7 +296,10 @@ def auto_load_model(args, model, model_without_ddp, optimizer, loss_scaler, mode
     print("Resume checkpoint %s" % args.resume)
     if "optimizer" in ckpt and "epoch" in ckpt:
         optimizer.load_state_dict(ckpt["optimizer"])
-        args.start_epoch = ckpt["epoch"] + 1
+        epoch = ckpt["epoch"] if ckpt["epoch"] != "best" else args.epochs      # mem/utils.py:519
+        args.start_epoch = epoch + 1
+        if getattr(args, "model_ema", False) and model_ema is not None:        # mem/utils.py:521-522
+            model_ema.load_state_dict(ckpt["model_ema"])
         if loss_scaler is not None and ckpt.get("scaler") is not None:
             loss_scaler.load_state_dict(ckpt["scaler"])
         print("With optim & sched!")

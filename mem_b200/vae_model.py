@@ -99,11 +99,21 @@ class DiscreteVAE(nn.Module):
             object.__setattr__(self, "_tok", _Tokenizer(self, precision=getattr(self, "tokenizer_precision", "auto")))
         return self._tok
 
-    def verify_range(self):
-        """fp16-pair tokenizer only: raise if an activation overflowed its calibrated range in the last call
-        (engine_for_pretraining calls this at its per-step sync)."""
+    def verify_range(self, raise_on_overflow=True):
+        """fp16-pair tokenizer only: did every activation of the last call stay inside its calibrated range?
+        Returns True if so; otherwise raises (default) or returns False, and the tokenizer re-calibrates on its
+        next call.  engine_for_pretraining calls this at its per-step sync; the optimizer step of an overflowed
+        batch has already been suppressed on the device through ``overflow_poison``."""
         if self._tok is not None and self._tok.f16:
-            self._tok.verify(block=True)
+            return self._tok.verify(block=True, raise_on_overflow=raise_on_overflow)
+        return True
+
+    def overflow_poison(self):
+        """Device scalar, NaN if the last ``get_codebook_indices`` call overflowed its fp16 range, else 0 (None for
+        the TF32 tokenizer, which has no range to leave).  No host synchronisation."""
+        if self._tok is not None and self._tok.f16:
+            return self._tok.poison
+        return None
 
 
 def _out_layout(kind, C, OH, OW):
@@ -147,6 +157,11 @@ class _Tokenizer:
         self.bufs = {}
         self.exps = None           # layer name -> exponent of its fp16 output (None: calibrate on the next run)
         self._pending = None       # (event, host maxima, exponents used) of the last run
+        # measurement hook (bench.py): when a list, every convolution launch appends
+        # (layer, algorithmic FLOPs, start event, end event) recorded on the launching stream
+        self.launch_timer = None
+        self.poison = None         # device scalar: NaN if the last run overflowed, else 0 (see DiscreteVAE.overflow_poison)
+        self._limit_key, self._limit = None, None
 
     @property
     def f16(self):
@@ -251,13 +266,13 @@ class _Tokenizer:
         self.exps[name] = e
         return e
 
-    def verify(self, block=True):
-        """Check the activation maxima recorded by the last run against the exponents it used."""
+    def verify(self, block=True, raise_on_overflow=True):
+        """Check the activation maxima recorded by the last run against the exponents it used.  True: in range."""
         if self._pending is None:
-            return
+            return True
         ev, used = self._pending
         if not block and not ev.query():
-            return
+            return True
         ev.synchronize()
         self._pending = None
         for name, e in used.items():
@@ -266,14 +281,28 @@ class _Tokenizer:
                 continue                                   # logits are never stored as fp16
             if not math.isfinite(m) or m * 2.0 ** e >= 65504.0:
                 self.exps = None
-                raise RuntimeError(f"dVAE tokenizer: fp16 operand overflow in layer {name} (|x| max {m:g}, exponent {e}); the "
-                                   "tokens of the last batch are invalid -- re-run it (the tokenizer re-calibrates)")
+                if raise_on_overflow:
+                    raise RuntimeError(f"dVAE tokenizer: fp16 operand overflow in layer {name} (|x| max {m:g}, exponent {e}); the "
+                                       "tokens of the last batch are invalid -- re-run it (the tokenizer re-calibrates)")
+                return False
             if m * 2.0 ** e >= 32768.0:                    # half of the margin used: move the exponents
                 self.exps = None
+        return True
+
+    def _update_poison(self, device):
+        """poison = NaN if any stored activation reached the fp16 overflow threshold in this run (device-side twin of
+        ``verify``): |x| max per layer against 65504 / 2^exp."""
+        key = tuple(sorted(self.exps.items()))
+        if key != self._limit_key:
+            lim = [65504.0 * 2.0 ** -self.exps.get(n, 0) if n != "head" else float("inf") for n in self.layer_names]
+            self._limit = torch.tensor(lim, dtype=torch.float32, device=device)
+            self._limit_key = key
+        bad = (~(self.absmax < self._limit)).any()          # also catches NaN maxima
+        self.poison = torch.where(bad, float("nan"), 0.0).float()
 
     # ---- one convolution ------------------------------------------------------------------------
     def _conv(self, lib, a, geom, w, bias, B, OH, OW, relu, out_kind, out_name, device, aux=None, full=None, keys=None,
-              layer=None, calibrating=False):
+              layer=None, calibrating=False, alg_k=None):
         """a = (hi, lo, exp) tensors [B*rows_per_img, x_slots, inner]; geom = (taps_y, taps_x, tap_y0, tap_x0).
         out_kind: slot layout of the hi/lo result for its consumer, or None (only ``full`` / ``keys`` outputs)."""
         w, w_exp = w
@@ -313,7 +342,15 @@ class _Tokenizer:
             if snapshot is not None:
                 aux.copy_(snapshot)
             d.out_exp = out_exp
+            timer = self.launch_timer
+            if timer is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(torch.cuda.current_stream(device))
             _lib.check(lib.memb_conv_f16x2(ctypes.byref(d), sp))
+            if timer is not None:
+                e1.record(torch.cuda.current_stream(device))
+                k_alg = alg_k if alg_k is not None else geom[0] * geom[1] * a[0].shape[2]
+                timer.append((layer, 2.0 * B * OH * OW * Cout * k_alg, e0, e1))
 
         if out is None:
             launch(0)
@@ -347,6 +384,7 @@ class _Tokenizer:
             b1 = min(Btot, b0 + self.chunk)
             self._run_chunk(images[b0:b1], tokens[b0:b1], logits[b0:b1] if want_logits else None)
         if self.f16:
+            self._update_poison(device)
             self.absmax_host.copy_(self.absmax, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(device))
@@ -384,7 +422,7 @@ class _Tokenizer:
 
         x_full = self._buf(tag + "x_full", (B * (H >> L) * (W >> L), Hd), device) if R > 0 else None
         cur = self._conv(lib, (a_hi, a_lo, e_in), (1, 1, 0, 0), self.w[0], self.b[0], B, OH, OW, True, consumer(0), tag + "act0",
-                         device, full=x_full if (L == 1 and R > 0) else None, layer="act0", **cal)
+                         device, full=x_full if (L == 1 and R > 0) else None, layer="act0", alg_k=16 * C, **cal)
         for i in range(1, L):
             OH, OW = OH // 2, OW // 2
             cur = self._conv(lib, cur, (2, 2, 0, 0), self.w[i], self.b[i], B, OH, OW, True, consumer(i), tag + f"act{i}", device,

@@ -44,6 +44,7 @@ class FlatParams:
             self.offsets[n] = off
             self.sizes[n] = params[n].numel()
             off += (params[n].numel() + CHUNK - 1) // CHUNK * CHUNK
+        off += CHUNK       # one status chunk at the end: no tensor lives there (see poison_grad)
         self.numel = off
         self.device = dev
         self.data = torch.zeros(off, dtype=torch.float32, device=dev)
@@ -85,6 +86,11 @@ class FlatParams:
     def zero_grad(self):
         lib = _lib.load()
         _lib.check(lib.memb_fill_f32(self.grad.data_ptr(), self.numel, 0.0, _sp(device=self.device)))
+
+    def poison_grad(self, value):
+        """Store a device scalar (0 or NaN) in the status chunk at the end of the gradient buffer: no kernel writes
+        there, the DP all-reduce and the global norm read it (see engine_for_pretraining.train_one_epoch)."""
+        self.grad[self.numel - 1: self.numel].copy_(value.reshape(1))
 
 
 def get_flat(model, order_fn):

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 from oracle.histogram_ref import event_hist_batched_ref, event_hist_ref
 from oracle.make_golden import synth_events
 
-STRATS = [0, 1, 2, 3, 4]  # auto, global RED, global RED + warp aggregation, smem tile, cluster-privatised
+STRATS = [0, 1, 2, 3, 4, 5]  # auto, global RED, + warp aggregation, smem tile, per-SM private copy, replicated global planes
 
 
 def _golden(golden_dir):

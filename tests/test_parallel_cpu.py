@@ -92,3 +92,42 @@ def test_grad_reducer_and_meters_world2_gloo():
         out = mgr.dict()
         mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def _sync_worker(rank, world, port, out):
+    """Replicas built from rank-dependent seeds (the reference seeds with args.seed + rank and lets the
+    DistributedDataParallel constructor broadcast rank 0's weights, run_mem_pretraining.py:255, :365-367)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mem_b200 import engine_for_finetuning, engine_for_pretraining
+        torch.manual_seed(1234 + rank)
+        model = registry.create_model("pt_vit", **vit_ref.TINY)
+        before = engine_of(model).flat().data.clone()
+        red = engine_for_pretraining._reducer_for(model)          # builds the reducer -> broadcasts rank 0's weights
+        after = engine_of(model).flat().data
+        gathered = [torch.empty_like(after) for _ in range(world)]
+        dist.all_gather(gathered, after)
+        same = all(torch.equal(gathered[0], g) for g in gathered)
+        moved = (rank == 0 and torch.equal(before, after)) or (rank != 0 and not torch.equal(before, after))
+        # parameters seen through the module are the broadcast ones (views of the flat buffer)
+        views = torch.equal(dict(model.named_parameters())["lm_head.weight"].detach().flatten(),
+                            after[engine_of(model).flat().offsets["lm_head.weight"]:][:model.lm_head.weight.numel()])
+        # the finetuning loop's one-time sync
+        torch.manual_seed(99 + rank)
+        ft = registry.create_model("ft_vit", **vit_ref.TINY_FT)
+        engine_for_finetuning._sync_replicas(ft)
+        f = engine_of(ft).flat().data
+        g2 = [torch.empty_like(f) for _ in range(world)]
+        dist.all_gather(g2, f)
+        out[rank] = bool(same and moved and views and red is not None and torch.equal(g2[0], g2[1]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicas_are_broadcast_from_rank0_world2_gloo():
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_sync_worker, args=(2, port, out), nprocs=2, join=True)
+        assert dict(out) == {0: True, 1: True}

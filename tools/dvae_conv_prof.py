@@ -7,7 +7,7 @@ from oracle import dvae_ref
 cfg = dict(input_H=224, input_W=224, num_tokens=8192, codebook_dim=32, num_layers=4, num_resnet_blocks=3, hidden_dim=384, channels=2)
 torch.manual_seed(0)
 vae = DiscreteVAE(**cfg).cuda()
-img = dvae_ref.synth_images(64, 2, 224, 224, seed=6).cuda()
+img = dvae_ref.synth_images(int(sys.argv[1]) if len(sys.argv) > 1 else 64, 2, 224, 224, seed=6).cuda()
 for _ in range(3):
     vae.get_codebook_indices(img)
 torch.cuda.synchronize()

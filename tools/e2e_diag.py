@@ -3,7 +3,8 @@ bandwidth, and per-step wall times of train_one_epoch.  python tools/e2e_diag.py
 import os, sys, time, io, contextlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from mem_b200 import bench_pretrain as bp, engine_for_pretraining, utils, _lib
+from benchmarks import pretrain as bp
+from mem_b200 import engine_for_pretraining, utils, _lib
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)

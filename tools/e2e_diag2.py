@@ -2,7 +2,8 @@
 import os, sys, time, io, contextlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from mem_b200 import bench_pretrain as bp, engine_for_pretraining as eng, utils
+from benchmarks import pretrain as bp
+from mem_b200 import engine_for_pretraining as eng, utils
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
