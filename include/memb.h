@@ -356,6 +356,13 @@ int memb_linear_small_bwd(const float* dl /* [B, C] */, const void* z_bf16, cons
                           float* dW /* += */, float* db /* +=, nullable */, float* dz /* [B, D], overwritten */,
                           memb_stream_t stream);
 
+/* Classification criteria of the finetuning loop on [B, C] fp32 logits (mem/run_class_finetuning.py:551-559 picks
+ * timm's SoftTargetCrossEntropy under mixup, LabelSmoothingCrossEntropy for smoothing > 0, else CrossEntropyLoss):
+ * loss_out[0] += mean_i sum_c t_ic * (logsumexp_i - x_ic), dlogits (nullable) = d(mean loss)/d logits.
+ * Exactly one of labels (int64 [B], t = (1 - smoothing) * onehot + smoothing / C) and soft_targets (fp32 [B, C]). */
+int memb_soft_ce(const float* logits, int B, int C, const int64_t* labels, const float* soft_targets, float smoothing,
+                 float* loss_out, float* dlogits, memb_stream_t stream);
+
 /* Flat-buffer optimizer pass (mem/utils.py:357-371 + torch.optim.AdamW with optim_factory.py:121 betas). */
 int memb_fill_f32(float* p, int64_t n, float v, memb_stream_t stream);
 int memb_cast_bf16(const float* src, void* dst, int64_t n, memb_stream_t stream);

@@ -87,6 +87,7 @@ SIGNATURES.update({
     "memb_cast_bf16": (_i32, [_vp, _vp, _i64, _vp]),
     "memb_sqnorm": (_i32, [_vp, _i64, _f32, _vp, _vp]),
     "memb_sqnorm_groups": (_i32, [_vp, _i64, _f32, _vp, _vp, _vp]),
+    "memb_soft_ce": (_i32, [_vp, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp]),
     "memb_adamw": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _i32, _f32, _f32, _vp, _vp]),
 })
 

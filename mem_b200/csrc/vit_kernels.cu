@@ -628,6 +628,46 @@ __global__ void __launch_bounds__(256) sqnorm(const float* __restrict__ g, long 
     atomicAdd(out, t);
   }
 }
+// ------------------------------------------------------------------ classification criteria (finetuning)
+// Soft-target cross entropy on [B, C] logits, one warp per row: loss_i = sum_c t_c * (lse_i - x_ic) with
+//   t = soft[i, :]                                            (timm SoftTargetCrossEntropy: mixup / cutmix targets)
+//   t = (1 - eps) * onehot(label_i) + eps / C                 (timm LabelSmoothingCrossEntropy; eps = 0: CrossEntropyLoss)
+// (the criteria mem/run_class_finetuning.py:551-559 picks).  Accumulates loss_out[0] += mean_i loss_i and writes
+// dlogits[i, c] = (softmax_ic * sum_c t_c - t_c) / B, the gradient of that mean.
+__global__ void __launch_bounds__(128) soft_ce(const float* __restrict__ logits, int B, int C, const long long* __restrict__ labels,
+                                               const float* __restrict__ soft, float eps, float* __restrict__ loss_out,
+                                               float* __restrict__ dlogits) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* x = logits + (long long)row * C;
+  const float* t = soft ? soft + (long long)row * C : nullptr;
+  const int label = labels ? (int)labels[row] : -1;
+  const float base = eps / (float)C;
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, x[c]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = 0.f, st = 0.f, stx = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float xv = x[c];
+    const float tv = t ? t[c] : (base + (c == label ? 1.f - eps : 0.f));
+    se += expf(xv - mx);
+    st += tv;
+    stx += tv * (xv - mx);
+  }
+  se = warp_sum(se); st = warp_sum(st); stx = warp_sum(stx);
+  const float lse = logf(se);
+  const float inv_b = 1.f / (float)B;
+  if (lane == 0) atomicAdd(loss_out, (st * lse - stx) * inv_b);
+  if (dlogits) {
+    float* d = dlogits + (long long)row * C;
+    for (int c = lane; c < C; c += 32) {
+      const float tv = t ? t[c] : (base + (c == label ? 1.f - eps : 0.f));
+      d[c] = (expf(x[c] - mx - lse) * st - tv) * inv_b;
+    }
+  }
+}
+
 // Same over a flat parameter-gradient buffer laid out in 1024-element chunks, skipping chunks whose group is 255
 // (padding / requires_grad = False parameters: clip_grad_norm_ only sees trainable tensors, mem/utils.py:380-392).
 __global__ void __launch_bounds__(256) sqnorm_groups(const float* __restrict__ g, long long n, float scale,
@@ -885,6 +925,15 @@ extern "C" int memb_sqnorm(const float* g, int64_t n, float scale, float* out, m
   MEMB_REQUIRE(g && out && n > 0, "sqnorm: bad arguments");
   sqnorm<<<flat_grid(n, 8), 256, 0, s>>>(g, n, scale, out);
   MEMB_LAUNCH_OK("sqnorm");
+  return MEMB_OK;
+}
+extern "C" int memb_soft_ce(const float* logits, int B, int C, const int64_t* labels, const float* soft_targets, float smoothing,
+                            float* loss_out, float* dlogits, memb_stream_t s) {
+  MEMB_REQUIRE(logits && loss_out && B > 0 && C > 0, "soft_ce: bad arguments");
+  MEMB_REQUIRE((labels != nullptr) != (soft_targets != nullptr), "soft_ce: give integer labels or soft targets, not both");
+  MEMB_REQUIRE(smoothing >= 0.f && smoothing < 1.f, "soft_ce: smoothing must be in [0, 1)");
+  soft_ce<<<ceil_div(B, 4), 128, 0, s>>>(logits, B, C, reinterpret_cast<const long long*>(labels), soft_targets, smoothing, loss_out, dlogits);
+  MEMB_LAUNCH_OK("soft_ce");
   return MEMB_OK;
 }
 extern "C" int memb_sqnorm_groups(const float* g, int64_t n, float scale, const uint8_t* chunk_group, float* out, memb_stream_t s) {

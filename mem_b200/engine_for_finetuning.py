@@ -34,8 +34,41 @@ __all__ = ["train_class_batch", "train_one_epoch", "evaluate", "accuracy", "Labe
            "SoftTargetCrossEntropy", "ModelEma"]
 
 
+class _SoftCE(torch.autograd.Function):
+    """mean_i sum_c t_ic * (logsumexp_i - x_ic) on libmemb (``memb_soft_ce``): loss and d loss / d logits in one
+    launch; backward scales the saved gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, soft, smoothing):
+        from . import _lib
+        _lib.require_cuda()
+        if not logits.is_cuda:
+            raise RuntimeError("mem_b200 criteria run on CUDA tensors only (no CPU path)")
+        lib = _lib.load()
+        x = logits.detach().contiguous().float()
+        B, C = x.shape
+        loss = torch.zeros((), dtype=torch.float32, device=x.device)
+        dl = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        if soft is not None:
+            soft = soft.detach().contiguous().float()
+            assert soft.shape == x.shape, "soft targets must have the shape of the logits"
+        else:
+            labels = labels.detach().contiguous().long()
+            assert labels.shape == (B,), "integer targets must be [B]"
+        _lib.check(lib.memb_soft_ce(x.data_ptr(), B, C, labels.data_ptr() if soft is None else None,
+                                    soft.data_ptr() if soft is not None else None, float(smoothing), loss.data_ptr(),
+                                    dl.data_ptr() if dl is not None else None, _lib.stream_ptr(torch, x.device)))
+        ctx.dl, ctx.dtype = dl, logits.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        return (ctx.dl * grad_loss).to(ctx.dtype), None, None, None
+
+
 class LabelSmoothingCrossEntropy(torch.nn.Module):
-    """timm 0.4.12 ``timm.loss.LabelSmoothingCrossEntropy`` (what run_class_finetuning.py picks for ``smoothing > 0``)."""
+    """timm 0.4.12 ``timm.loss.LabelSmoothingCrossEntropy`` (what run_class_finetuning.py:555-556 picks for
+    ``smoothing > 0``): ``(1 - s) * nll + s * mean_c(-log p_c)``, batch mean."""
 
     def __init__(self, smoothing=0.1):
         super().__init__()
@@ -43,16 +76,15 @@ class LabelSmoothingCrossEntropy(torch.nn.Module):
         self.smoothing, self.confidence = smoothing, 1.0 - smoothing
 
     def forward(self, x, target):
-        logprobs = F.log_softmax(x.float(), dim=-1)
-        nll = -logprobs.gather(dim=-1, index=target.unsqueeze(1)).squeeze(1)
-        return (self.confidence * nll + self.smoothing * (-logprobs.mean(dim=-1))).mean()
+        return _SoftCE.apply(x, target, None, self.smoothing)
 
 
 class SoftTargetCrossEntropy(torch.nn.Module):
-    """timm 0.4.12 ``timm.loss.SoftTargetCrossEntropy`` (mixup / cutmix targets)."""
+    """timm 0.4.12 ``timm.loss.SoftTargetCrossEntropy`` (mixup / cutmix targets, run_class_finetuning.py:552-553):
+    ``sum_c -t_c log p_c``, batch mean."""
 
     def forward(self, x, target):
-        return torch.sum(-target * F.log_softmax(x.float(), dim=-1), dim=-1).mean()
+        return _SoftCE.apply(x, None, target, 0.0)
 
 
 def accuracy(output, target, topk=(1,)):

@@ -20,6 +20,32 @@ from . import _lib
 from .vit_engine import CHUNK, engine_of
 
 
+def get_num_layer_for_vit(var_name, num_max_layer):
+    """Layer id of a parameter for layer-wise lr decay (mem/optim_factory.py:31-43): embedding 0, block i -> i + 1,
+    everything else (shared rel-pos table, final norm, head) the last id."""
+    if var_name in ("cls_token", "mask_token", "pos_embed") or var_name.startswith("patch_embed"):
+        return 0
+    if var_name.startswith("rel_pos_bias"):
+        return num_max_layer - 1
+    if var_name.startswith("blocks"):
+        return int(var_name.split(".")[1]) + 1
+    return num_max_layer - 1
+
+
+class LayerDecayValueAssigner:
+    """``values[layer_id]`` = lr scale of that layer (mem/optim_factory.py:46-53; built as
+    ``layer_decay ** (num_layers + 1 - i)`` at run_class_finetuning.py:527-529)."""
+
+    def __init__(self, values):
+        self.values = values
+
+    def get_scale(self, layer_id):
+        return self.values[layer_id]
+
+    def get_layer_id(self, var_name):
+        return get_num_layer_for_vit(var_name, len(self.values))
+
+
 def get_parameter_groups(model, weight_decay=1e-5, skip_list=(), get_num_layer=None, get_layer_scale=None):
     names, groups = {}, {}
     for name, param in model.named_parameters():

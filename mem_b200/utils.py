@@ -305,6 +305,138 @@ def auto_load_model(args, model, model_without_ddp, optimizer, loss_scaler, mode
         print("With optim & sched!")
 
 
+# ------------------------------------------------------------------------- pretrain -> finetune seam
+def load_state_dict(model, state_dict, prefix="", ignore_missing="relative_position_index"):
+    """Non-strict load with the reference's report (mem/utils.py:302-348): keys of ``state_dict`` under ``prefix``
+    are copied into ``model``; missing keys containing any ``|``-separated ``ignore_missing`` fragment are reported
+    separately."""
+    own = model.state_dict()
+    missing, unexpected, errors, used = [], [], [], set()
+    with torch.no_grad():
+        for name, dst in own.items():
+            key = prefix + name
+            if key not in state_dict:
+                missing.append(name)
+                continue
+            used.add(key)
+            src = state_dict[key]
+            if tuple(src.shape) != tuple(dst.shape):
+                errors.append("size mismatch for {}: copying a param with shape {} from checkpoint, the shape in current "
+                              "model is {}.".format(name, tuple(src.shape), tuple(dst.shape)))
+                continue
+            dst.copy_(src)            # parameters stay views of the flat buffer
+    unexpected = [k for k in state_dict if k.startswith(prefix) and k not in used]
+    fragments = ignore_missing.split("|")
+    ignored = [k for k in missing if any(f in k for f in fragments)]
+    missing = [k for k in missing if k not in ignored]
+    if missing:
+        print("Weights of {} not initialized from pretrained model: {}".format(model.__class__.__name__, missing))
+    if unexpected:
+        print("Weights from pretrained model not used in {}: {}".format(model.__class__.__name__, unexpected))
+    if ignored:
+        print("Ignored weights of {} not initialized from pretrained model: {}".format(model.__class__.__name__, ignored))
+    if errors:
+        print("\n".join(errors))
+    return missing, unexpected
+
+
+def _interp_rel_pos_table(table, src_size, dst_size, num_extra_tokens):
+    """Resize a ``[(2s-1)^2 + extra, heads]`` relative-position table to ``dst_size`` the way the reference does
+    (mem/utils.py:660-706): source offsets placed on a geometric progression, bicubic spline through them
+    (``scipy.interpolate.interp2d(kind="cubic")``; on a regular grid that is ``RectBivariateSpline(kx=ky=3, s=0)``,
+    the replacement SciPy names for the removed function), evaluated at the integer target offsets."""
+    from scipy import interpolate
+    extra = table[-num_extra_tokens:, :]
+    body = table[:-num_extra_tokens, :]
+
+    def geometric_progression(a, r, n):
+        return a * (1.0 - r ** n) / (1.0 - r)
+    left, right = 1.01, 1.5
+    while right - left > 1e-6:
+        q = (left + right) / 2.0
+        if geometric_progression(1, q, src_size // 2) > dst_size // 2:
+            right = q
+        else:
+            left = q
+    dis, cur = [], 1
+    for i in range(src_size // 2):
+        dis.append(cur)
+        cur += q ** (i + 1)
+    x = [-d for d in reversed(dis)] + [0] + dis
+    t = dst_size // 2.0
+    dx = np.arange(-t, t + 0.1, 1.0)
+    print("Original positions = %s" % str(x))
+    print("Target positions = %s" % str(dx))
+    heads = []
+    for i in range(body.shape[1]):
+        z = body[:, i].view(src_size, src_size).float().cpu().numpy()
+        spline = interpolate.RectBivariateSpline(x, x, z.T, kx=3, ky=3, s=0)      # interp2d(x, y, z): z[j, i] = f(x[i], y[j])
+        heads.append(torch.Tensor(spline(dx, dx).T).contiguous().view(-1, 1).to(table.device))
+    return torch.cat((torch.cat(heads, dim=-1), extra), dim=0)
+
+
+def finetune(args, model):
+    """Start a finetuning model from a pretraining checkpoint (mem/utils.py:613-732): pick the state dict by
+    ``args.model_key``, drop a head of the wrong shape, expand the shared relative-position table to one table per
+    block, resize tables / absolute position embeddings when the patch grid changed, then load non-strictly."""
+    ckpt = torch.load(args.finetune, map_location="cpu", weights_only=False)
+    print("Load ckpt from %s" % args.finetune)
+    checkpoint_model = None
+    for model_key in args.model_key.split("|"):
+        if model_key in ckpt:
+            checkpoint_model = ckpt[model_key]
+            print("Load state_dict by model_key = %s" % model_key)
+            break
+    if checkpoint_model is None:
+        checkpoint_model = ckpt
+    checkpoint_model = remap_pretrain_state_dict(checkpoint_model, model)
+    load_state_dict(model, checkpoint_model, prefix=getattr(args, "model_prefix", ""))
+
+
+def remap_pretrain_state_dict(checkpoint_model, model):
+    """The state-dict surgery of ``finetune`` (mem/utils.py:631-730) as a function of (checkpoint dict, target model)."""
+    checkpoint_model = dict(checkpoint_model)
+    state_dict = model.state_dict()
+    for k in ["head.weight", "head.bias"]:
+        if k in checkpoint_model and checkpoint_model[k].shape != state_dict[k].shape:
+            print(f"Removing key {k} from pretrained checkpoint")
+            del checkpoint_model[k]
+    if model.use_rel_pos_bias and "rel_pos_bias.relative_position_bias_table" in checkpoint_model:
+        print("Expand the shared relative position embedding to each transformer block. ")
+        shared = checkpoint_model.pop("rel_pos_bias.relative_position_bias_table")
+        for i in range(model.get_num_layers()):
+            checkpoint_model["blocks.%d.attn.relative_position_bias_table" % i] = shared.clone()
+    for key in list(checkpoint_model.keys()):
+        if "relative_position_index" in key:
+            checkpoint_model.pop(key)
+        if "relative_position_bias_table" in key:
+            table = checkpoint_model[key]
+            src_num_pos, _ = table.size()
+            dst_num_pos, _ = state_dict[key].size()
+            dst_patch_shape = model.patch_embed.patch_shape
+            num_extra_tokens = dst_num_pos - (dst_patch_shape[0] * 2 - 1) * (dst_patch_shape[1] * 2 - 1)
+            src_size = int((src_num_pos - num_extra_tokens) ** 0.5)
+            dst_size = int((dst_num_pos - num_extra_tokens) ** 0.5)
+            print(dst_patch_shape, src_size, dst_size)
+            if src_size != dst_size:
+                print("Position interpolate for %s from %dx%d to %dx%d" % (key, src_size, src_size, dst_size, dst_size))
+                checkpoint_model[key] = _interp_rel_pos_table(table, src_size, dst_size, num_extra_tokens)
+    if "pos_embed" in checkpoint_model:
+        pos = checkpoint_model["pos_embed"]
+        dim = pos.shape[-1]
+        num_patches = model.patch_embed.num_patches
+        num_extra_tokens = model.pos_embed.shape[-2] - num_patches
+        orig_size = int((pos.shape[-2] - num_extra_tokens) ** 0.5)
+        new_size = int(num_patches ** 0.5)
+        if orig_size != new_size:
+            print("Position interpolate from %dx%d to %dx%d" % (orig_size, orig_size, new_size, new_size))
+            extra = pos[:, :num_extra_tokens]
+            grid = pos[:, num_extra_tokens:].reshape(-1, orig_size, orig_size, dim).permute(0, 3, 1, 2)
+            grid = torch.nn.functional.interpolate(grid, size=(new_size, new_size), mode="bicubic", align_corners=False)
+            checkpoint_model["pos_embed"] = torch.cat((extra, grid.permute(0, 2, 3, 1).flatten(1, 2)), dim=1)
+    return checkpoint_model
+
+
 # -------------------------------------------------------------------------------------- tokenizer
 def create_d_vae(weight_path, d_vae_type, image_size, device):
     if d_vae_type == "event":

@@ -148,6 +148,21 @@ class VitEngine:
         self.model = model
         self.bufs = _Bufs()
         self.saved = None
+        self.generation = 0
+
+    # Activations saved for backward live in engine-owned buffers that the next forward of the same model reuses
+    # (with or without grad: the no-grad path ping-pongs through the same residual buffers): ONE outstanding
+    # autograd graph per model.  The stamp turns a violation (forward, another forward, then backward through the
+    # first) into an error instead of silently wrong gradients.
+    def stamp(self, need_grad):
+        self.generation += 1
+        return self.generation
+
+    def check_stamp(self, generation):
+        if generation != self.generation:
+            raise RuntimeError("mem_b200: backward through a graph whose saved activations were overwritten by a later "
+                               "forward of the same model (one outstanding graph per model: call backward before the "
+                               "next forward of this model)")
 
     # ---- static description of the model ---------------------------------------------------
     def cfg(self):
@@ -317,7 +332,7 @@ class VitEngine:
             out.update(stats=stats, dlogits=dlogits)
         return out
 
-    # ---- classification head (ft_vit): mean pool -> fc_norm -> head --------------------------------
+    # ---- classification head (ft_vit): mean pool -> fc_norm -> head, or norm -> cls token -> head ------
     def classify_head(self, xlast, ctx):
         lib = _lib.load()
         m, c = self.model, ctx["cfg"]
@@ -325,6 +340,21 @@ class VitEngine:
         B, D, N = ctx["B"], c["D"], c["N"]
         C = m.head.out_features
         g, sp = self.bufs.get, _sp(device=dev)
+        if getattr(m, "fc_norm", None) is None:
+            # use_mean_pooling=False (modeling_finetune.py:286-287, :349-352): final LayerNorm, then the cls token.
+            # Only row b*N of every sample reaches the head, so the LayerNorm runs on those B rows (row gather).
+            rows = g("cls_rows", (B,), torch.int32, dev)
+            if getattr(self, "_cls_rows_for", None) != (B, N):
+                rows.copy_(torch.arange(B, dtype=torch.int32, device=dev) * N)
+                self._cls_rows_for = (B, N)
+            cnt = g("cls_count", (1,), torch.int32, dev)
+            cnt.fill_(B)
+            z = g("z_cls", (B, D), torch.bfloat16, dev); mu = g("mu_cls", (B,), torch.float32, dev); rs = g("rs_cls", (B,), torch.float32, dev)
+            _ln_fwd(lib, xlast, m.norm.weight, m.norm.bias, m.norm.eps, z, mu, rs, B, D, rows, cnt)
+            logits = g("cls_logits", (B, C), torch.float32, dev)
+            _lib.check(lib.memb_linear_small_fwd(z.data_ptr(), m.head.weight.data_ptr(), ops._ptr(m.head.bias), B, D, C,
+                                                 logits.data_ptr(), sp))
+            return dict(logits=logits, z=z, mu=mu, rs=rs, rows=rows, count=cnt, cls_token=True)
         pooled = g("pooled", (B, D), torch.float32, dev)
         _lib.check(lib.memb_meanpool_fwd(xlast.data_ptr(), B, N, D, pooled.data_ptr(), sp))
         z = g("z_cls", (B, D), torch.bfloat16, dev); mu = g("mu_cls", (B,), torch.float32, dev); rs = g("rs_cls", (B,), torch.float32, dev)
@@ -347,12 +377,18 @@ class VitEngine:
         _lib.check(lib.memb_linear_small_bwd(dlogits.data_ptr(), head["z"].data_ptr(), m.head.weight.data_ptr(), B, D, C,
                                              flat.g("head.weight").data_ptr(), flat.g("head.bias").data_ptr() if has_bias else None,
                                              dz.data_ptr(), sp))
-        dpool = g("dpool", (B, D), torch.float32, dev)
-        _lib.check(lib.memb_fill_f32(dpool.data_ptr(), dpool.numel(), 0.0, sp))
-        _ln_bwd(lib, dz, head["pooled"], m.fc_norm.weight, head["mu"], head["rs"], B, D, dpool, flat.g("fc_norm.weight"),
-                flat.g("fc_norm.bias"))
         gres = g("gres", (M, D), torch.float32, dev)
-        _lib.check(lib.memb_meanpool_bwd(dpool.data_ptr(), B, N, D, gres.data_ptr(), sp))
+        if head.get("cls_token"):
+            # gradient reaches the residual stream only through the B cls rows of the final LayerNorm
+            _lib.check(lib.memb_fill_f32(gres.data_ptr(), gres.numel(), 0.0, sp))
+            _ln_bwd(lib, dz, ctx["xlast"], m.norm.weight, head["mu"], head["rs"], B, D, gres, flat.g("norm.weight"),
+                    flat.g("norm.bias"), head["rows"], head["count"])
+        else:
+            dpool = g("dpool", (B, D), torch.float32, dev)
+            _lib.check(lib.memb_fill_f32(dpool.data_ptr(), dpool.numel(), 0.0, sp))
+            _ln_bwd(lib, dz, head["pooled"], m.fc_norm.weight, head["mu"], head["rs"], B, D, dpool, flat.g("fc_norm.weight"),
+                    flat.g("fc_norm.bias"))
+            _lib.check(lib.memb_meanpool_bwd(dpool.data_ptr(), B, N, D, gres.data_ptr(), sp))
         if bucket_hook:
             bucket_hook("head")
         self._backward_blocks(ctx, gres, bucket_hook)
@@ -550,11 +586,13 @@ class _MaskedVitFn(torch.autograd.Function):
         head = eng.pretrain_head(xlast, fctx, head_mask_u8, None, need_grad)
         n = int(head["count"].item())  # the output shape is data dependent: one host sync on this path
         ctx.eng, ctx.fctx, ctx.head, ctx.n = eng, fctx, head, n
+        ctx.generation = eng.stamp(need_grad)
         return head["logits"][:n].clone()
 
     @staticmethod
     def backward(ctx, grad_logits):
         eng, head = ctx.eng, ctx.head
+        eng.check_stamp(ctx.generation)
         flat = eng.flat()
         bind_param_grads(flat, flat.params)
         V = grad_logits.shape[1]
@@ -619,11 +657,13 @@ class _ClassifyVitFn(torch.autograd.Function):
         xlast, fctx = eng.forward_features(x, None, need_grad, droppath)
         head = eng.classify_head(xlast, fctx)
         ctx.eng, ctx.fctx, ctx.head = eng, fctx, head
+        ctx.generation = eng.stamp(need_grad)
         return head["logits"].clone()
 
     @staticmethod
     def backward(ctx, grad_logits):
         eng = ctx.eng
+        eng.check_stamp(ctx.generation)
         flat = eng.flat()
         bind_param_grads(flat, flat.params)
         eng.backward_classify(ctx.fctx, ctx.head, grad_logits.contiguous().float())
@@ -631,13 +671,11 @@ class _ClassifyVitFn(torch.autograd.Function):
 
 
 def classify_forward(model, x):
-    """``VisionTransformer.forward`` of ft_vit (mem/modeling_finetune.py:354-357), mean-pooling head."""
+    """``VisionTransformer.forward`` of ft_vit (mem/modeling_finetune.py:354-357): mean-pooling head
+    (``use_mean_pooling=True``, the configs' choice) or final norm + cls token (``False``)."""
     _lib.require_cuda()
     if not x.is_cuda:
         raise RuntimeError("mem_b200 models run on CUDA tensors only (no CPU path)")
-    if getattr(model, "fc_norm", None) is None:
-        raise NotImplementedError("ft_vit without mean pooling (cls-token head) is outside the MEM hot path (configs use "
-                                  "use_mean_pooling=True, run_class_finetuning.py:118)")
     eng = engine_of(model)
     dp = droppath_scales(model, x.shape[0], x.device, model.training)
     flat = eng.flat()

@@ -114,3 +114,18 @@ def run_finetune(vit_sd, batches, heads=2, patch=16, update_freq=FT_UPDATE_FREQ)
             opt.zero_grad()
     mean = lambda v: sum(v) / len(v)  # noqa: E731
     return {"loss": mean(losses), "class_acc": mean(accs), "grad_norm": mean(norms)}, {k: v.detach() for k, v in sd.items()}
+
+
+# ---- timm 0.4.12 criteria the reference's finetuning runner picks (run_class_finetuning.py:551-559); timm is not installed,
+# these are its published formulas (timm/loss/cross_entropy.py)
+def label_smoothing_ce(x, target, smoothing=0.1):
+    import torch.nn.functional as F
+    logprobs = F.log_softmax(x, dim=-1)
+    nll = -logprobs.gather(dim=-1, index=target.unsqueeze(1)).squeeze(1)
+    return ((1.0 - smoothing) * nll + smoothing * (-logprobs.mean(dim=-1))).mean()
+
+
+def soft_target_ce(x, target):
+    import torch
+    import torch.nn.functional as F
+    return torch.sum(-target * F.log_softmax(x, dim=-1), dim=-1).mean()

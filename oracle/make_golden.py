@@ -160,6 +160,128 @@ def golden_vit():
     print("vit_tiny.npz:", len(out), "arrays, pt loss", loss.item(), "ft loss", lossf.item())
 
 
+def _cuda_autocast_policy_on_cpu():
+    """Context: bf16 autocast on the CPU with CUDA autocast's fp32 list restored (layer_norm, softmax, cross_entropy run in
+    fp32 on CUDA; the CPU autocast leaves them in the incoming dtype).  This is how the reference's own mixed-precision
+    step (engine_for_pretraining.py:147, ``torch.cuda.amp.autocast``) can be executed in the build container: the
+    reference files are untouched, only torch functions are wrapped for the duration of the context."""
+    import contextlib
+    import torch
+    import torch.nn.functional as F
+
+    @contextlib.contextmanager
+    def ctx():
+        saved = (F.layer_norm, torch.Tensor.softmax, F.softmax, F.cross_entropy)
+
+        def layer_norm(x, shape, weight=None, bias=None, eps=1e-5):
+            return saved[0](x.float(), shape, None if weight is None else weight.float(), None if bias is None else bias.float(), eps)
+
+        def t_softmax(self, *a, **k):
+            return saved[1](self.float(), *a, **k)
+
+        def f_softmax(x, *a, **k):
+            return saved[2](x.float(), *a, **k)
+
+        def cross_entropy(x, *a, **k):
+            return saved[3](x.float(), *a, **k)
+        F.layer_norm, torch.Tensor.softmax, F.softmax, F.cross_entropy = layer_norm, t_softmax, f_softmax, cross_entropy
+        try:
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                yield
+        finally:
+            F.layer_norm, torch.Tensor.softmax, F.softmax, F.cross_entropy = saved
+    return ctx()
+
+
+def golden_vit_bf16():
+    """Calibration of the ViT parity tolerances (north_star: "within the tolerance of a bf16 run of the reference vs its
+    fp32 run"): the UNMODIFIED reference models are run twice on the exact weights / inputs of the GPU parity tests,
+    once in fp32 and once under bf16 autocast, and the error of the loss, the logits and EVERY parameter gradient is
+    stored per tensor (``<case>/err/<name>`` = L2 norm of the difference, ``<case>/ref/<name>`` = L2 norm of the fp32
+    tensor).  tests/test_vit_model_gpu.py allows a stated multiple of these."""
+    import torch
+    from oracle import vit_ref
+    out = {}
+
+    def run(case, model, fwd_loss):
+        model.train()
+        res = {}
+        for mode in ("fp32", "bf16"):
+            for p in model.parameters():
+                p.grad = None
+            if mode == "fp32":
+                loss, logits = fwd_loss(model)
+            else:
+                with _cuda_autocast_policy_on_cpu():
+                    loss, logits = fwd_loss(model)
+            loss.backward()
+            res[mode] = (loss.item(), logits.detach().float().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters()})
+        l32, lg32, g32 = res["fp32"]
+        l16, lg16, g16 = res["bf16"]
+        out[f"{case}/loss"] = np.array([l32, l16])
+        out[f"{case}/err/logits"] = np.array((lg16 - lg32).double().norm().item())
+        out[f"{case}/ref/logits"] = np.array(lg32.double().norm().item())
+        worst = (None, 0.0)
+        for n in g32:
+            e, r = (g16[n] - g32[n]).double().norm().item(), g32[n].double().norm().item()
+            out[f"{case}/err/{n}"] = np.array(e)
+            out[f"{case}/ref/{n}"] = np.array(r)
+            if r > 0 and e / r > worst[1]:
+                worst = (n, e / r)
+        rels = sorted(out[f"{case}/err/{n}"] / max(out[f"{case}/ref/{n}"], 1e-30) for n in g32)
+        print(f"{case}: loss {l32:.5f} -> {l16:.5f} ({abs(l16 - l32) / l32:.2e}), logits rel "
+              f"{out[f'{case}/err/logits'] / out[f'{case}/ref/logits']:.2e}, grad rel median {rels[len(rels) // 2]:.2e} "
+              f"max {worst[1]:.2e} ({worst[0]})")
+
+    def mem_loss(img, mask, tokens):
+        def f(model):
+            logits = model(img, bool_masked_pos=mask, return_all_tokens=False)
+            return torch.nn.CrossEntropyLoss()(input=logits, target=tokens[mask]), logits
+        return f
+
+    def cls_loss(img, target):
+        def f(model):
+            logits = model(img)
+            return torch.nn.CrossEntropyLoss()(logits, target), logits
+        return f
+
+    def scaled(sd, factor, skip=("relative_position",), gamma=None):
+        for k in sd:
+            if sd[k].is_floating_point() and sd[k].dim() >= 2 and not any(s in k for s in skip):
+                sd[k] = sd[k] * factor
+            if gamma is not None and "gamma_" in k:
+                sd[k] = sd[k] * 0.0 + gamma
+        return sd
+
+    torch.manual_seed(0)
+    # tiny pt_vit / ft_vit: test_tiny_pt_vit_matches_golden_and_oracle, test_tiny_ft_vit_matches_golden_and_oracle
+    m = ref_shims.ref_create_model("pt_vit", **vit_ref.TINY)
+    m.load_state_dict(vit_ref.synth_state_dict(m.state_dict(), seed=11))
+    run("tiny_pt", m, mem_loss(*vit_ref.synth_inputs(3, 2, 112, 112, 49, vit_ref.TINY["vocab_size"], seed=5, n_mask=20)))
+    m = ref_shims.ref_create_model("ft_vit", **vit_ref.TINY_FT)
+    m.load_state_dict(vit_ref.synth_state_dict(m.state_dict(), seed=12))
+    run("tiny_ft", m, cls_loss(vit_ref.synth_inputs(4, 3, 112, 112, 49, 2, seed=6, n_mask=1)[0], torch.tensor([0, 1, 1, 0])))
+    # ViT-B/16 at batch 4: test_vit_base_step_vs_oracle_with_droppath (DropPath off here: it is a per-sample mask)
+    base = dict(img_size=(224, 224), patch_size=(16, 16), in_chans=2, vocab_size=8192, embed_dim=768, depth=12, num_heads=12,
+                mlp_ratio=4, init_values=0.1, use_shared_rel_pos_bias=True, use_abs_pos_emb=False, drop_path_rate=0.0)
+    m = ref_shims.ref_create_model("pt_vit", **base)
+    m.load_state_dict(scaled(vit_ref.synth_state_dict(m.state_dict(), seed=3), 0.4))
+    run("base_pt_b4", m, mem_loss(*vit_ref.synth_inputs(4, 2, 224, 224, 196, 8192, seed=7, n_mask=75)))
+    # ViT-B/16 ft_vit at batch 4: test_ft_vit_base_forward_backward_vs_oracle
+    ftb = dict(img_size=(224, 224), patch_size=(16, 16), in_chans=3, num_classes=2, embed_dim=768, depth=12, num_heads=12,
+               mlp_ratio=4, init_values=0.1, use_rel_pos_bias=True, use_abs_pos_emb=False, use_mean_pooling=True, drop_path_rate=0.0)
+    m = ref_shims.ref_create_model("ft_vit", **ftb)
+    m.load_state_dict(scaled(vit_ref.synth_state_dict(m.state_dict(), seed=4), 0.4, skip=("relative_position", "head")))
+    run("base_ft_b4", m, cls_loss(vit_ref.synth_inputs(4, 3, 224, 224, 196, 2, seed=8, n_mask=1)[0], torch.tensor([0, 1, 1, 0])))
+    # ViT-L/16 at batch 2: test_vit_large_step_vs_oracle
+    large = dict(base, embed_dim=1024, depth=24, num_heads=16, init_values=1e-5)
+    m = ref_shims.ref_create_model("pt_vit", **large)
+    m.load_state_dict(scaled(vit_ref.synth_state_dict(m.state_dict(), seed=5), 0.3, gamma=0.05))
+    run("large_pt_b2", m, mem_loss(*vit_ref.synth_inputs(2, 2, 224, 224, 196, 8192, seed=9, n_mask=75)))
+    np.savez_compressed(os.path.join(GOLD, "vit_bf16_calibration.npz"), **out)
+    print("vit_bf16_calibration.npz:", len(out), "arrays")
+
+
 def golden_dvae():
     """Logits / indices of the UNMODIFIED reference DiscreteVAE (eventvae/vae/vae_model.py) on seeded tiny cases."""
     import torch
@@ -347,8 +469,82 @@ def golden_engine_ft():
     np.savez_compressed(os.path.join(GOLD, "engine_ft_tiny.npz"), **out)
 
 
+def _sd_digest(sd, full=("relative_position_bias_table", "pos_embed", "head.")):
+    out = {}
+    for k, v in sd.items():
+        a = v.detach().cpu().numpy()
+        if any(f in k for f in full) or a.size <= 4096:
+            out["full/" + k] = a
+        else:
+            f = a.reshape(-1).astype(np.float64)
+            out["digest/" + k] = np.concatenate([[f.sum(), np.sqrt((f ** 2).sum())], f[:64]])
+    return out
+
+
+def golden_finetune_remap():
+    """The UNMODIFIED reference ``utils.finetune`` (mem/utils.py:613-732) turning a pretraining checkpoint into a
+    finetuning model, and its layer-decay helper.  Case "same": equal patch grid (shared rel-pos table expanded to one
+    per block, lm_head / mask_token dropped, head kept at init).  Case "interp": 7x7 -> 10x10 patch grid with absolute
+    position embeddings (geometric-progression bicubic spline for every rel-pos table -- through the interp2d
+    replacement of ref_shims, scipy having removed the original -- and F.interpolate for pos_embed).  Also the
+    cls-token head (use_mean_pooling=False) forward / gradients of the reference ft_vit."""
+    import contextlib
+    import io
+    import tempfile
+    import torch
+    from types import SimpleNamespace
+    from oracle import vit_ref
+    rutils = ref_shims.ref_module("utils")
+    optf = ref_shims.ref_module("optim_factory")
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for case, pt_kw, ft_kw in (
+                ("same", dict(vit_ref.TINY, in_chans=3), dict(vit_ref.TINY_FT)),
+                ("interp", dict(vit_ref.TINY, in_chans=3, use_abs_pos_emb=True),
+                 dict(vit_ref.TINY_FT, img_size=(160, 160), use_abs_pos_emb=True))):
+            torch.manual_seed(0)
+            pt = ref_shims.ref_create_model("pt_vit", **pt_kw)
+            pt.load_state_dict(vit_ref.synth_state_dict(pt.state_dict(), seed=51))
+            path = os.path.join(tmp, case + ".pth")
+            torch.save({"model": pt.state_dict(), "epoch": 3}, path)
+            torch.manual_seed(1)
+            ft = ref_shims.ref_create_model("ft_vit", **ft_kw)
+            ft.load_state_dict(vit_ref.synth_state_dict(ft.state_dict(), seed=52))
+            log = io.StringIO()
+            with contextlib.redirect_stdout(log):
+                rutils.finetune(SimpleNamespace(finetune=path, model_key="model|module", model_prefix=""), ft)
+            out.update({f"{case}/{k}": v for k, v in _sd_digest(ft.state_dict()).items()})
+            out[f"{case}/log"] = np.array(log.getvalue())
+            print(case, "->", len(ft.state_dict()), "tensors;", log.getvalue().count("Position interpolate"), "interpolations")
+    # layer-wise lr decay ids / scales (optim_factory.py:31-53, run_class_finetuning.py:527-529)
+    names = ["cls_token", "mask_token", "pos_embed", "patch_embed.proj.weight", "rel_pos_bias.relative_position_bias_table",
+             "blocks.0.norm1.weight", "blocks.7.attn.qkv.weight", "blocks.11.mlp.fc2.bias", "fc_norm.weight", "head.weight", "norm.bias"]
+    num_layers, decay = 12, 0.65
+    assigner = optf.LayerDecayValueAssigner([decay ** (num_layers + 1 - i) for i in range(num_layers + 2)])
+    out["layer_decay/names"] = np.array(names)
+    out["layer_decay/ids"] = np.array([assigner.get_layer_id(n) for n in names])
+    out["layer_decay/scales"] = np.array([assigner.get_scale(assigner.get_layer_id(n)) for n in names])
+    # cls-token head of ft_vit (use_mean_pooling=False, modeling_finetune.py:286-287, :349-352)
+    torch.manual_seed(0)
+    kw = dict(vit_ref.TINY_FT, use_mean_pooling=False)
+    m = ref_shims.ref_create_model("ft_vit", **kw)
+    m.load_state_dict(vit_ref.synth_state_dict(m.state_dict(), seed=53))
+    m.train()
+    img, _, _ = vit_ref.synth_inputs(4, 3, 112, 112, 49, 2, seed=16, n_mask=1)
+    target = torch.tensor([1, 0, 1, 1])
+    logits = m(img)
+    loss = torch.nn.CrossEntropyLoss()(logits, target)
+    loss.backward()
+    out["cls/logits"] = logits.detach().numpy()
+    out["cls/loss"] = np.array(loss.item())
+    out.update({"cls/" + k: v for k, v in _grad_digest({n: p.grad for n, p in m.named_parameters()}).items()})
+    np.savez_compressed(os.path.join(GOLD, "finetune_remap.npz"), **out)
+    print("finetune_remap.npz:", len(out), "arrays; cls loss", loss.item())
+
+
 SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit, "dvae": golden_dvae,
-            "engine": golden_engine, "event_pipeline": golden_event_pipeline, "decode": golden_decode, "engine_ft": golden_engine_ft}
+            "engine": golden_engine, "event_pipeline": golden_event_pipeline, "decode": golden_decode, "engine_ft": golden_engine_ft,
+            "vit_bf16": golden_vit_bf16, "finetune_remap": golden_finetune_remap}
 
 
 def main(argv):

@@ -94,6 +94,23 @@ def install() -> None:
     sys.modules.setdefault("torch._six", six)
     torch._six = sys.modules["torch._six"]
 
+    # scipy.interpolate.interp2d was removed in SciPy 1.14 (utils.py:696 calls it with kind='cubic' on a regular grid);
+    # SciPy's removal notice names the replacement used here: RectBivariateSpline on the same grid, transposed.
+    try:
+        from scipy import interpolate as _si
+
+        def interp2d(x, y, z, kind="linear"):
+            k = {"linear": 1, "cubic": 3, "quintic": 5}[kind]
+            spline = _si.RectBivariateSpline(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64),
+                                             np.asarray(z, dtype=np.float64).T, kx=k, ky=k, s=0)
+            return lambda xn, yn: spline(np.asarray(xn, dtype=np.float64), np.asarray(yn, dtype=np.float64)).T
+        try:
+            _si.interp2d([0, 1, 2, 3], [0, 1, 2, 3], np.zeros((4, 4)), kind="cubic")
+        except NotImplementedError:
+            _si.interp2d = interp2d
+    except ImportError:
+        pass
+
     # Only stub packages that are genuinely missing.
     missing = []
     for root in _STUB_ROOTS:

@@ -101,3 +101,51 @@ def test_evaluate_ema_mixup_and_soft_targets(capsys):
     with pytest.raises(NotImplementedError):
         eft.train_one_epoch(None, model, torch.nn.CrossEntropyLoss(), batches[:1], opt, "cuda", 0, None)
     capsys.readouterr()
+
+
+def test_criteria_kernel_matches_timm_formulas():
+    """memb_soft_ce behind LabelSmoothingCrossEntropy / SoftTargetCrossEntropy: loss and gradient vs the oracle's
+    restatement of timm's formulas (fp32), ragged class counts (C not a multiple of the warp) included."""
+    from oracle import engine_ref
+    g = torch.Generator().manual_seed(3)
+    for B, C in ((7, 5), (128, 2), (33, 101), (4, 1000)):
+        x = torch.randn(B, C, generator=g) * 3
+        t = torch.randint(0, C, (B,), generator=g)
+        soft = torch.softmax(torch.randn(B, C, generator=g), -1) * 0.9      # rows need not sum to one
+        for name, ours, ref in (
+                ("smooth", lambda z: eft.LabelSmoothingCrossEntropy(0.1)(z, t.cuda()), lambda z: engine_ref.label_smoothing_ce(z, t, 0.1)),
+                ("soft", lambda z: eft.SoftTargetCrossEntropy()(z, soft.cuda()), lambda z: engine_ref.soft_target_ce(z, soft))):
+            xc = x.clone().cuda().requires_grad_(True)
+            xr = x.clone().requires_grad_(True)
+            lo, lr = ours(xc), ref(xr)
+            (lo * 1.7).backward()
+            (lr * 1.7).backward()
+            assert abs(lo.item() - lr.item()) < 2e-6 * max(1.0, abs(lr.item())), (name, B, C)
+            assert torch.allclose(xc.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-7), (name, B, C)
+    with torch.no_grad():                                                   # no gradient requested: loss only
+        assert eft.LabelSmoothingCrossEntropy(0.0)(x.cuda(), t.cuda()).item() == pytest.approx(
+            torch.nn.functional.cross_entropy(x, t).item(), rel=1e-6)
+
+
+def test_checkpoint_round_trip_keeps_model_ema(tmp_path):
+    from types import SimpleNamespace
+    from mem_b200 import optim_factory
+    model = registry.create_model("ft_vit", **vit_ref.TINY_FT).cuda()
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        opt = optim_factory.create_optimizer(SimpleNamespace(opt="adamw", weight_decay=0.05, lr=1e-3, opt_eps=1e-8), model)
+    ema = eft.ModelEma(model, decay=0.9)
+    with torch.no_grad():
+        model.head.weight.add_(1.0)
+    ema.update(model)
+    want = {k: v.clone() for k, v in ema.state_dict().items()}
+    args = SimpleNamespace(output_dir=str(tmp_path), resume="", auto_resume=True, model_ema=True, epochs=10, start_epoch=0)
+    utils.save_model(args, "best", model, model, opt, utils.NativeScalerWithGradNormCount(), model_ema=ema)
+    ema2 = eft.ModelEma(model, decay=0.9)                    # starts from the current weights, not the averaged ones
+    assert not torch.equal(ema2.state_dict()["head.weight"], want["head.weight"])
+    args.resume = str(tmp_path / "checkpoint-best.pth")
+    with contextlib.redirect_stdout(io.StringIO()):
+        utils.auto_load_model(args, model, model, opt, utils.NativeScalerWithGradNormCount(), model_ema=ema2)
+    assert args.start_epoch == 11                            # "best" resumes after the last epoch (mem/utils.py:519)
+    for k, v in want.items():
+        assert torch.equal(ema2.state_dict()[k], v), k

