@@ -61,6 +61,10 @@ int64_t memb_launch_count(void);
 #define MEMB_HIST_GLOBAL_REPL 5 /* GLOBAL with 8 copies of the accumulator planes (one stream only): warps RED */
                                 /* into different copies so that a concentrated stream (edges, hot pixels)    */
                                 /* does not serialise on a few L2 sectors; the finalize pass adds the copies  */
+#define MEMB_HIST_HYBRID 6      /* one stream, sensor too large for PRIVATE (up to 1 Mpixel): a sampled pass    */
+                                /* picks the most frequent 64-pixel granules, every SM keeps a private copy of  */
+                                /* those in shared memory and sends the remaining events to L2 REDs; AUTO picks */
+                                /* it for >= 2^20 events (else falls back to GLOBAL)                            */
 
 /* Bytes memb_hist_u8 needs for this problem (n = total rows; same strategy value as the call). */
 size_t memb_hist_workspace_bytes(int B, int64_t n, int H, int W, int timesurface, int strategy);

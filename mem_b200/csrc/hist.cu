@@ -156,8 +156,13 @@ template <bool kAligned, bool kAggregate, bool kTss>
 __global__ void __launch_bounds__(kThreads) hist_scatter_global(
     const double* __restrict__ ev, const long long* __restrict__ offsets, long long n_total, int W,
     long long npix, unsigned int* __restrict__ acc, unsigned long long* __restrict__ last,
-    Header* __restrict__ hdr, const memb_event_aug* __restrict__ aug, int replicas) {
+    Header* __restrict__ hdr, const memb_event_aug* __restrict__ aug, int replicas, const int* __restrict__ skip_if) {
   const int b = blockIdx.y;
+  if (skip_if) {                // HYBRID chain: the prepare kernel decides on the device which rasteriser runs
+    pdl_launch_dependents();
+    pdl_wait();
+    if (*skip_if) return;
+  }
   long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
   memb_event_aug a;
   const bool has_aug = aug != nullptr;
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(kThreads) hist_scatter_global(
   unsigned int* acc_b = acc + ((long long)b * replicas + rep) * 2 * npix;
   unsigned long long* last_b = kTss ? last + (long long)b * npix : nullptr;
   bool bad = false;
-  bool first = true;
+  bool first = skip_if == nullptr;
   pdl_launch_dependents();      // the finalize grid may take the SM slots this grid's tail leaves free
 
   const long long step = (long long)gridDim.x * kThreads * kUnroll;
@@ -766,6 +771,323 @@ __global__ void __launch_bounds__(32 * kFinRows) hist_private_finalize(const uns
   }
 }
 
+// ---------------------------------------------------------------- strategy HYBRID (one long stream, sensor too large for PRIVATE)
+// A 640x480 sensor (1.2 MB of packed counters) does not fit one SM's shared memory, and the GLOBAL strategy collapses on
+// concentrated streams (edges, hot regions): REDs to the same few L2 sectors serialise (10 M edge-like events: 270-430 us
+// against 85 us uniform).  HYBRID privatises only the HOT part of the sensor, chosen per call ON THE DEVICE:
+//   1. hist_hybrid_prepare zero-fills the L2 accumulators; its CTA 0 counts a sample of kHybSamples rows spread over the
+//      stream per 64-pixel granule, picks the most frequent granules (as many as fit a shared-memory tile), writes the
+//      granule -> slot map and decides the mode: privatise (1) when those granules hold at least half of the sample
+//      (or the caller forced HYBRID), else plain L2 REDs (0: a uniform stream gains nothing from a sixth of the sensor);
+//   2. hist_scatter_global runs when mode == 0 and hist_hybrid when mode == 1 (both are launched; the other one's CTAs
+//      return at once): every CTA of hist_hybrid (one per SM) rasterises a strided share of the stream, sends events of
+//      mapped granules to shared-memory atomics (its private copy of the hot pixels) and the rest to L2 REDs, and stores
+//      its copy (mod 256, u16 per pixel) into its own slice of the workspace;
+//   3. hist_hybrid_finalize adds accumulators + slices.
+// The four launches are chained as programmatic dependent launches.
+constexpr int kHybGranule = 64;                 // pixels per granule (a power of two, multiple of 8)
+constexpr int kHybSamples = 4096;               // rows the selector looks at (4 per thread, one batch of loads)
+constexpr int kHybMaxGranules = 16384;          // sensors up to 1 Mpixel (1280x720 = 14400 granules)
+constexpr int kHybHistBins = 1024;
+constexpr int kHybSmemBytes = 222 * 1024;       // dynamic shared memory of hist_hybrid: slot map (u16 per granule) + tile
+
+struct HybState { int nsel; int mode; int pad[2]; };
+
+__host__ __device__ inline int hyb_granules(long long npix) { return (int)((npix + kHybGranule - 1) / kHybGranule); }
+// tile capacity in granules once the slot map has taken its share of the dynamic shared memory
+__host__ __device__ inline int hyb_tile_granules(int granules) {
+  const int map_bytes = ((granules * 2 + 15) / 16) * 16;
+  const int words = (kHybSmemBytes - map_bytes) / 4;
+  return words / kHybGranule < 0xffff ? words / kHybGranule : 0xfffe;
+}
+
+// Block-wide exclusive scan of one int per thread (kTileThreads threads); returns the exclusive prefix, *total = sum.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    warp_sums[lane] = w;           // inclusive over warps
+  }
+  __syncthreads();
+  *total = warp_sums[kTileThreads / 32 - 1];
+  return inc - v + (warp ? warp_sums[warp - 1] : 0);
+}
+
+template <bool kAligned>
+__global__ void __launch_bounds__(kTileThreads) hist_hybrid_prepare(const double* __restrict__ ev, long long n, int W, int H,
+                                                                    long long npix, uint4* __restrict__ zero_from,
+                                                                    long long zero_vecs, int granules, int tile_granules,
+                                                                    int force_mode, unsigned short* __restrict__ slot_map,
+                                                                    unsigned short* __restrict__ sel_list,
+                                                                    HybState* __restrict__ state) {
+  extern __shared__ unsigned int cnt[];           // sample count per granule
+  __shared__ int hist[kHybHistBins];
+  __shared__ int warp_sums[32];
+  __shared__ int s_thr, s_cover[32], s_seen[32];
+  pdl_launch_dependents();
+  if (blockIdx.x != 0) {                          // zero-fill of header + accumulators
+    for (long long i = (blockIdx.x - 1) * (long long)kTileThreads + threadIdx.x; i < zero_vecs; i += (long long)(gridDim.x - 1) * kTileThreads)
+      zero_from[i] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  // ---- CTA 0: sample, select, decide
+  constexpr int kPer = kHybSamples / kTileThreads, kBatch = 4;
+  const long long step = max(1LL, n / kHybSamples);
+  for (int g = threadIdx.x; g < granules; g += kTileThreads) cnt[g] = 0u;
+  for (int i = threadIdx.x; i < kHybHistBins; i += kTileThreads) hist[i] = 0;
+  __syncthreads();
+  int seen = 0;
+  for (int j = 0; j < kPer; j += kBatch) {
+    Event e[kBatch];
+    bool live[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const long long r = ((long long)(j + u) * kTileThreads + threadIdx.x) * step;
+      live[u] = r < n;
+      if (live[u]) e[u] = load_event<kAligned>(ev, r);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      int idx;
+      if (live[u] && (e[u].p == 1.0 || e[u].p == -1.0) && pixel_index_fast(e[u].x, e[u].y, W, H, npix, idx)) {
+        atomicAdd(&cnt[idx / kHybGranule], 1u);
+        ++seen;
+      }
+    }
+  }
+  __syncthreads();
+  {   // histogram of the counts; nearly all of them are 0..3: those are counted in registers, one atomic per warp and bin
+    int small[4] = {0, 0, 0, 0};
+    for (int g = threadIdx.x; g < granules; g += kTileThreads) {
+      const unsigned int c = min(cnt[g], (unsigned int)(kHybHistBins - 1));
+      if (c < 4u) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) small[k] += c == (unsigned int)k;
+      } else {
+        atomicAdd(&hist[c], 1);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int v = __reduce_add_sync(0xffffffffu, small[k]);
+      if ((threadIdx.x & 31) == 0 && v) atomicAdd(&hist[k], v);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // smallest threshold thr >= 1 with #{granules: count >= thr} <= tile_granules
+    const int lane = threadIdx.x;
+    int part = 0;
+    for (int k = 0; k < 32; ++k) part += hist[lane * 32 + k];
+    int suf = part;                               // inclusive suffix sum over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += t;
+    }
+    int run = suf - part, best = kHybHistBins;
+    for (int k = 31; k >= 0; --k) {
+      run += hist[lane * 32 + k];
+      if (run <= tile_granules) best = lane * 32 + k; else break;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) s_thr = max(best, 1);
+  }
+  __syncthreads();
+  const int thr = s_thr;
+  const int per_thread = (granules + kTileThreads - 1) / kTileThreads;
+  const int g0 = threadIdx.x * per_thread, g1 = min(granules, g0 + per_thread);
+  int mine = 0, cover = 0;
+  for (int g = g0; g < g1; ++g)
+    if ((int)min(cnt[g], (unsigned int)(kHybHistBins - 1)) >= thr) { ++mine; cover += (int)cnt[g]; }
+  int nsel = 0;
+  int slot = block_exclusive_scan(mine, warp_sums, &nsel);
+  // how much of the sample the selected granules hold
+  cover = __reduce_add_sync(0xffffffffu, cover);   // counts <= kHybSamples
+  seen = __reduce_add_sync(0xffffffffu, seen);
+  if ((threadIdx.x & 31) == 0) { s_cover[threadIdx.x >> 5] = cover; s_seen[threadIdx.x >> 5] = seen; }
+  __syncthreads();
+  int mode = force_mode;
+  if (force_mode < 0) {
+    int c = 0, t = 0;
+    for (int w = 0; w < kTileThreads / 32; ++w) { c += s_cover[w]; t += s_seen[w]; }
+    mode = (t > 0 && 2 * c >= t) ? 1 : 0;
+  }
+  for (int g = g0; g < g1; ++g) {
+    const bool sel = mode && (int)min(cnt[g], (unsigned int)(kHybHistBins - 1)) >= thr;
+    if (sel) sel_list[slot] = (unsigned short)g;          // slot -> granule, for the finalize pass
+    slot_map[g] = sel ? (unsigned short)slot++ : (unsigned short)0xffffu;
+  }
+  if (threadIdx.x == 0) { state->nsel = mode ? nsel : 0; state->mode = mode; }
+}
+
+template <bool kAligned>
+__global__ void __launch_bounds__(kTileThreads, 1) hist_hybrid(
+    const double* __restrict__ ev, long long n, int W, int H, long long npix, unsigned int* __restrict__ acc,
+    const unsigned short* __restrict__ slot_map_g, int granules, int tile_granules, const HybState* __restrict__ state,
+    unsigned short* __restrict__ slices, Header* __restrict__ hdr) {
+  extern __shared__ __align__(16) unsigned char hyb_smem[];
+  const int map_bytes = ((granules * 2 + 15) / 16) * 16;
+  unsigned short* slot_map = reinterpret_cast<unsigned short*>(hyb_smem);
+  unsigned int* tile = reinterpret_cast<unsigned int*>(hyb_smem + map_bytes);
+  constexpr int kStep = kTileThreads * kFuseUnroll;
+  const long long stride = (long long)gridDim.x * kStep;
+  const long long first = (long long)blockIdx.x * kStep;
+  pdl_launch_dependents();
+  pdl_wait();                                   // map, mode and zeroed accumulators are visible from here on
+  if (state->mode == 0) return;                 // the stream is not concentrated: hist_scatter_global did the work
+  const int nsel = state->nsel;
+
+  if (kAligned && threadIdx.x == 0) {           // the copy engine pulls this CTA's next chunks into L2
+    for (int k = 0; k < kFuseAhead; ++k) {
+      const long long far = first + k * stride;
+      if (far < n) prefetch_l2(ev + 4 * far, (unsigned int)(min((long long)kStep, n - far) * 32));
+    }
+  }
+  Event nxt[kFuseUnroll];
+#pragma unroll
+  for (int u = 0; u < kFuseUnroll; ++u) {
+    const long long r = first + u * kTileThreads + threadIdx.x;
+    if (r < n) nxt[u] = load_event<kAligned>(ev, r);
+  }
+  for (int i = threadIdx.x * 8; i < granules; i += kTileThreads * 8)      // map_bytes is a multiple of 16
+    *reinterpret_cast<uint4*>(slot_map + i) = __ldg(reinterpret_cast<const uint4*>(slot_map_g + i));
+  const int words = nsel * kHybGranule;
+  for (int i = threadIdx.x * 4; i < words; i += kTileThreads * 4) *reinterpret_cast<uint4*>(tile + i) = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+
+  bool bad = false;
+  int it = 0;
+  for (long long base = first; base < n; base += stride, ++it) {
+    Event cur[kFuseUnroll];
+    bool live[kFuseUnroll];
+#pragma unroll
+    for (int u = 0; u < kFuseUnroll; ++u) {
+      cur[u] = nxt[u];
+      live[u] = base + u * kTileThreads + threadIdx.x < n;
+    }
+    if (kAligned && threadIdx.x == 0) {
+      const long long far = base + (long long)kFuseAhead * stride;
+      if (far < n) prefetch_l2(ev + 4 * far, (unsigned int)(min((long long)kStep, n - far) * 32));
+    }
+#pragma unroll
+    for (int u = 0; u < kFuseUnroll; ++u) {
+      const long long r = base + stride + u * kTileThreads + threadIdx.x;
+      if (r < n) nxt[u] = load_event<kAligned>(ev, r);
+    }
+#pragma unroll
+    for (int u = 0; u < kFuseUnroll; ++u) {
+      const bool pos = live[u] && cur[u].p == 1.0, neg = live[u] && cur[u].p == -1.0;
+      if (pos || neg) {
+        int idx;
+        if (!pixel_index_fast(cur[u].x, cur[u].y, W, H, npix, idx)) {
+          bad = true;
+        } else {
+          const unsigned int s = slot_map[idx / kHybGranule];
+          if (s != 0xffffu) atomicAdd(&tile[s * kHybGranule + (idx % kHybGranule)], pos ? 1u : 0x10000u);
+          else atomicAdd(acc + (neg ? npix : 0) + idx, 1u);
+        }
+      }
+    }
+    if ((it + 1) % kFuseFold == 0 && base + stride < n) {     // halves can never carry: fold them mod 256
+      __syncthreads();
+      for (int i = threadIdx.x; i < words; i += kTileThreads) tile[i] &= 0x00ff00ffu;
+      __syncthreads();
+    }
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) hdr->oob = 1;
+  // this CTA's slice: 8 pixels -> 8 x u16 (pos | neg << 8) -> one 16-byte store
+  uint4* slice = reinterpret_cast<uint4*>(slices + (long long)blockIdx.x * tile_granules * kHybGranule);
+  for (int i = threadIdx.x * 8; i < words; i += kTileThreads * 8) {
+    const uint4 a = *reinterpret_cast<const uint4*>(tile + i), b = *reinterpret_cast<const uint4*>(tile + i + 4);
+    auto pack = [](unsigned int lo, unsigned int hi) {
+      return (lo & 0xffu) | ((lo >> 8) & 0xff00u) | ((hi & 0xffu) << 16) | ((hi << 8) & 0xff000000u);
+    };
+    slice[i >> 3] = make_uint4(pack(a.x, a.y), pack(a.z, a.w), pack(b.x, b.y), pack(b.z, b.w));
+  }
+}
+
+// out[px] = (L2 accumulators + sum over the CTA slices of mapped granules) mod 256.  blockDim = (32, kHybFinRows).
+// Blocks [0, hot_blocks): four mapped granules each (slots 4j .. 4j+3 of the slot -> granule list): lane x owns 8 consecutive
+// pixels, row y sums slices y, y + kHybFinRows, ...; the partial sums meet in shared memory (these blocks do the long
+// work, so they are scheduled first).  Blocks beyond: 256 consecutive pixels each, accumulators -> image for the pixels
+// of UNMAPPED granules (every pixel in mode 0).
+constexpr int kHybFinRows = 16;
+__device__ __forceinline__ void hyb_store_px(uint8_t* __restrict__ out, long long px, int C, unsigned int cp, unsigned int cn) {
+  if (C == 2) {
+    out[2 * px] = (uint8_t)cp;
+    out[2 * px + 1] = (uint8_t)cn;
+  } else {
+    out[3 * px] = (uint8_t)cp;
+    out[3 * px + 1] = 0;
+    out[3 * px + 2] = (uint8_t)cn;
+  }
+}
+__global__ void __launch_bounds__(32 * kHybFinRows) hist_hybrid_finalize(
+    const unsigned int* __restrict__ acc, const unsigned short* __restrict__ slot_map, const unsigned short* __restrict__ sel_list,
+    const HybState* __restrict__ state, const unsigned short* __restrict__ slices, int n_slices, int tile_granules, int hot_blocks,
+    long long npix, int C, uint8_t* __restrict__ out) {
+  __shared__ unsigned int part[kHybFinRows][32][8];      // pos | neg << 16 (sums < 65536: at most 160 slices x 255)
+  pdl_wait();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if ((int)blockIdx.x >= hot_blocks) {
+    if (t < 256) {
+      const long long px = (long long)((int)blockIdx.x - hot_blocks) * 256 + t;
+      if (px < npix && (state->mode == 0 || slot_map[px / kHybGranule] == 0xffffu))
+        hyb_store_px(out, px, C, acc[px] & 0xffu, acc[npix + px] & 0xffu);
+    }
+    return;
+  }
+  const int slot = (int)blockIdx.x * 4 + (threadIdx.x >> 3);      // lane x: octet (x & 7) of this slot's granule
+  const int nsel = state->nsel;
+  if ((int)blockIdx.x * 4 >= nsel) return;
+  unsigned int sum[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  if (slot < nsel) {
+    const long long off = ((long long)slot * kHybGranule) / 8 + (threadIdx.x & 7);   // uint4 index inside a slice
+    const long long slice_vecs = (long long)tile_granules * kHybGranule / 8;
+#pragma unroll 5
+    for (int k = threadIdx.y; k < n_slices; k += kHybFinRows) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(slices) + k * slice_vecs + off);
+      const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        sum[2 * q] += (w[q] & 0xffu) | ((w[q] & 0xff00u) << 8);
+        sum[2 * q + 1] += ((w[q] >> 16) & 0xffu) | ((w[q] >> 8) & 0xff0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) part[threadIdx.y][threadIdx.x][q] = sum[q];
+  __syncthreads();
+  if (t < 256) {                                            // 256 threads -> the 4 x 64 pixels of this block's granules
+    const int lane = t >> 3, q = t & 7;                     // (slot in block * 8 + octet, pixel in octet)
+    const int sl = (int)blockIdx.x * 4 + (lane >> 3);
+    if (sl < nsel) {
+      const long long px = (long long)sel_list[sl] * kHybGranule + (lane & 7) * 8 + q;
+      if (px < npix) {
+        unsigned int w = 0;
+#pragma unroll
+        for (int g = 0; g < kHybFinRows; ++g) w += part[g][lane][q];
+        hyb_store_px(out, px, C, (w + acc[px]) & 0xffu, ((w >> 16) + acc[npix + px]) & 0xffu);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- raw record formats
 // The reference turns raw recordings into float64 [N,4] .npy files with byte-by-byte Python loops
 // (process_data/process_dataset.py): N-Caltech101 40-bit big-endian records (:47-60) and N-Cars / Prophesee
@@ -897,7 +1219,12 @@ struct Plan {
   int tiles, tile_pix;
   size_t ws_bytes;
   size_t off_tkeys, off_acc, off_last;
+  // HYBRID: slot map [granules] u16, slot -> granule list [tile_granules] u16, HybState, CTA slices
+  int granules, tile_granules;
+  size_t off_map, off_sel, off_state, off_slices;
 };
+
+constexpr long long kHybMinEvents = 1LL << 20;   // below this the three-launch GLOBAL chain is as fast and needs no sampling
 
 static Plan make_plan(int B, int64_t n, int H, int W, int timesurface, int strategy) {
   Plan p{};
@@ -910,7 +1237,11 @@ static Plan make_plan(int B, int64_t n, int H, int W, int timesurface, int strat
     strategy = (B >= 16 && per_stream <= (1 << 20)) ? MEMB_HIST_TILE : MEMB_HIST_GLOBAL;
     // one long stream on a sensor that fits a shared-memory tile: a privatised copy per SM (immune to hot pixels)
     if (B == 1 && npix <= kTileMaxWords && n >= (1 << 18)) strategy = MEMB_HIST_PRIVATE;
+    // one long stream on a larger sensor: privatise the hot granules, RED the rest
+    if (B == 1 && npix > kTileMaxWords && n >= kHybMinEvents && hyb_granules(npix) <= kHybMaxGranules) strategy = MEMB_HIST_HYBRID;
   }
+  if (strategy == MEMB_HIST_HYBRID && (B != 1 || timesurface || hyb_granules(npix) > kHybMaxGranules || n < kHybSamples))
+    strategy = MEMB_HIST_GLOBAL;
   if (strategy == MEMB_HIST_PRIVATE && (B != 1 || npix > kTileMaxWords)) strategy = MEMB_HIST_GLOBAL;
   p.replicas = 1;
   if (strategy == MEMB_HIST_GLOBAL_REPL) {   // the copies only pay for one long stream
@@ -927,6 +1258,16 @@ static Plan make_plan(int B, int64_t n, int H, int W, int timesurface, int strat
     p.off_last = p.off_acc + (size_t)kPrivMaxCtas * round_up<size_t>((size_t)npix, 8) * 2 + kPrivMaxCtas * 4;
   p.off_last = round_up<size_t>(p.off_last, 16);
   p.ws_bytes = round_up<size_t>(p.off_last + (timesurface ? (size_t)B * npix * 8 : 0), 16);
+  if (strategy == MEMB_HIST_HYBRID) {
+    p.granules = hyb_granules(npix);
+    p.tile_granules = hyb_tile_granules(p.granules);
+    if (const char* e = getenv("MEMB_HYB_TILE_GRANULES")) p.tile_granules = std::max(1, std::min(p.tile_granules, atoi(e)));   // tuning only
+    p.off_map = round_up<size_t>(p.off_acc + (size_t)2 * npix * 4, 16);
+    p.off_sel = round_up<size_t>(p.off_map + (size_t)p.granules * 2, 16);
+    p.off_state = round_up<size_t>(p.off_sel + (size_t)p.tile_granules * 2, 16);
+    p.off_slices = p.off_state + sizeof(HybState);
+    p.ws_bytes = round_up<size_t>(p.off_slices + (size_t)kPrivMaxCtas * p.tile_granules * kHybGranule * 2, 16);
+  }
   return p;
 }
 
@@ -981,6 +1322,65 @@ static int run_private(const void* rows, long long n, int W, int H, int C, unsig
   return MEMB_OK;
 }
 
+// HYBRID strategy: prepare (zero-fill, sample, select, decide) -> GLOBAL scatter | privatised rasteriser -> finalize, chained as
+// programmatic dependent launches.  force_mode: -1 = decided on the device from the sample (AUTO), 1 = always privatise.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_smem(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, memb_stream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+template <bool kAligned>
+static int run_hybrid(const double* ev, long long n, int W, int H, int C, const Plan& p, int force_mode, char* wsb, uint8_t* out,
+                      memb_stream_t stream) {
+  const long long npix = (long long)H * W;
+  Header* hdr = reinterpret_cast<Header*>(wsb);
+  unsigned int* acc = reinterpret_cast<unsigned int*>(wsb + p.off_acc);
+  unsigned short* slot_map = reinterpret_cast<unsigned short*>(wsb + p.off_map);
+  unsigned short* sel_list = reinterpret_cast<unsigned short*>(wsb + p.off_sel);
+  HybState* state = reinterpret_cast<HybState*>(wsb + p.off_state);
+  unsigned short* slices = reinterpret_cast<unsigned short*>(wsb + p.off_slices);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MEMB_CUDA_OK(cudaFuncSetAttribute(hist_hybrid<kAligned>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHybSmemBytes));
+    MEMB_CUDA_OK(cudaFuncSetAttribute(hist_hybrid_prepare<kAligned>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHybMaxGranules * 4));
+    attr_set = true;
+  }
+  const int sms = num_sms();
+  const long long zero_vecs = (long long)((p.off_acc + (size_t)2 * npix * 4 + 15) / 16);
+  const int prep_ctas = 1 + std::max(1, std::min(sms - 1, (int)ceil_div<long long>(zero_vecs, kTileThreads)));
+  hist_hybrid_prepare<kAligned><<<prep_ctas, kTileThreads, (size_t)p.granules * 4, stream>>>(
+      ev, n, W, H, npix, reinterpret_cast<uint4*>(wsb), zero_vecs, p.granules, p.tile_granules, force_mode, slot_map, sel_list, state);
+  MEMB_LAUNCH_OK("hist_hybrid_prepare");
+  if (force_mode < 0) {        // the plain L2-RED rasteriser, for streams the sample finds spread out (skipped when mode == 1)
+    const long long per_cta = (long long)kThreads * kUnroll;
+    const long long gx = std::max<long long>(1, std::min<long long>(ceil_div<long long>(n, per_cta), (long long)sms * 32));   // every CTA costs a skip in mode 1
+    MEMB_CUDA_OK(launch_pdl(hist_scatter_global<kAligned, false, false>, dim3((unsigned)gx), dim3(kThreads), stream, ev,
+                            (const long long*)nullptr, n, W, npix, acc, (unsigned long long*)nullptr, hdr,
+                            (const memb_event_aug*)nullptr, 1, (const int*)&state->mode));
+    MEMB_LAUNCH_OK("hist_scatter_global");
+  }
+  const int ctas = std::min(sms, kPrivMaxCtas);
+  MEMB_CUDA_OK(launch_pdl_smem(hist_hybrid<kAligned>, dim3(ctas), dim3(kTileThreads), (size_t)kHybSmemBytes, stream, ev, n, W, H, npix,
+                               acc, (const unsigned short*)slot_map, p.granules, p.tile_granules, (const HybState*)state, slices, hdr));
+  MEMB_LAUNCH_OK("hist_hybrid");
+  const int cold_blocks = (int)ceil_div<long long>(npix, 256), hot_blocks = ceil_div(p.tile_granules, 4);
+  MEMB_CUDA_OK(launch_pdl_smem(hist_hybrid_finalize, dim3(hot_blocks + cold_blocks), dim3(32, kHybFinRows), (size_t)0, stream,
+                               (const unsigned int*)acc, (const unsigned short*)slot_map, (const unsigned short*)sel_list,
+                               (const HybState*)state, (const unsigned short*)slices, ctas, p.tile_granules, hot_blocks, npix, C, out));
+  MEMB_LAUNCH_OK("hist_hybrid_finalize");
+  return MEMB_OK;
+}
+
 static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, int64_t max_stream_len,
                     const memb_event_aug* aug, int H, int W, int C, int timesurface, int strategy,
                     uint8_t* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
@@ -991,7 +1391,7 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
   MEMB_REQUIRE(offsets != nullptr || B == 1, "hist: a batch needs row offsets");
   MEMB_REQUIRE(out != nullptr && ws != nullptr, "hist: null output / workspace");
   MEMB_REQUIRE((((uintptr_t)ev) & 7u) == 0 && (((uintptr_t)ws) & 15u) == 0, "hist: misaligned pointer");
-  MEMB_REQUIRE(strategy >= MEMB_HIST_AUTO && strategy <= MEMB_HIST_GLOBAL_REPL, "hist: unknown strategy %d", strategy);
+  MEMB_REQUIRE(strategy >= MEMB_HIST_AUTO && strategy <= MEMB_HIST_HYBRID, "hist: unknown strategy %d", strategy);
   const long long npix = (long long)H * W;
   const Plan p = make_plan(B, n, H, W, timesurface, strategy);
   if (ws_bytes < p.ws_bytes)
@@ -1007,6 +1407,10 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
   const long long* offs = reinterpret_cast<const long long*>(offsets);
   const int sms = num_sms();
 
+  if (p.strategy == MEMB_HIST_HYBRID && aug == nullptr && n > 0) {
+    const int force = strategy == MEMB_HIST_HYBRID ? 1 : -1;      // AUTO lets the sample decide
+    return aligned ? run_hybrid<true>(ev, n, W, H, C, p, force, wsb, out, stream) : run_hybrid<false>(ev, n, W, H, C, p, force, wsb, out, stream);
+  }
   const bool use_private = n > 0 && p.strategy == MEMB_HIST_PRIVATE && aug == nullptr && !timesurface;
   if (!use_private) {  // zero the header (+ accumulators) and seed the min/max keys
     const long long n_vec = (long long)((p.strategy == MEMB_HIST_TILE ? (size_t)kHeaderBytes : p.ws_bytes) / 16);
@@ -1047,7 +1451,7 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
     const bool agg = p.strategy == MEMB_HIST_GLOBAL_AGG;
 #define MEMB_SCATTER(A, G, T)                                                                        \
   MEMB_CUDA_OK(launch_pdl(hist_scatter_global<A, G, T>, grid, dim3(kThreads), stream, ev, offs, (long long)n, W, npix, acc, \
-                          last, hdr, aug, p.replicas))
+                          last, hdr, aug, p.replicas, (const int*)nullptr))
     if (timesurface) {
       if (aligned) { if (agg) MEMB_SCATTER(true, true, true); else MEMB_SCATTER(true, false, true); }
       else { if (agg) MEMB_SCATTER(false, true, true); else MEMB_SCATTER(false, false, true); }

@@ -261,6 +261,10 @@ def golden_vit_bf16():
     m = ref_shims.ref_create_model("ft_vit", **vit_ref.TINY_FT)
     m.load_state_dict(vit_ref.synth_state_dict(m.state_dict(), seed=12))
     run("tiny_ft", m, cls_loss(vit_ref.synth_inputs(4, 3, 112, 112, 49, 2, seed=6, n_mask=1)[0], torch.tensor([0, 1, 1, 0])))
+    # cls-token head (use_mean_pooling=False): test_tiny_ft_vit_cls_token_head
+    m = ref_shims.ref_create_model("ft_vit", **dict(vit_ref.TINY_FT, use_mean_pooling=False))
+    m.load_state_dict(vit_ref.synth_state_dict(m.state_dict(), seed=53))
+    run("tiny_ft_cls", m, cls_loss(vit_ref.synth_inputs(4, 3, 112, 112, 49, 2, seed=16, n_mask=1)[0], torch.tensor([1, 0, 1, 1])))
     # ViT-B/16 at batch 4: test_vit_base_step_vs_oracle_with_droppath (DropPath off here: it is a per-sample mask)
     base = dict(img_size=(224, 224), patch_size=(16, 16), in_chans=2, vocab_size=8192, embed_dim=768, depth=12, num_heads=12,
                 mlp_ratio=4, init_values=0.1, use_shared_rel_pos_bias=True, use_abs_pos_emb=False, drop_path_rate=0.0)

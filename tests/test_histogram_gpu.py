@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 from oracle.histogram_ref import event_hist_batched_ref, event_hist_ref
 from oracle.make_golden import synth_events
 
-STRATS = [0, 1, 2, 3, 4, 5]  # auto, global RED, + warp aggregation, smem tile, per-SM private copy, replicated global planes
+STRATS = [0, 1, 2, 3, 4, 5, 6]  # auto, global RED, + warp aggregation, smem tile, per-SM private copy, replicated planes, hybrid
 
 
 def _golden(golden_dir):
@@ -39,7 +39,7 @@ def test_event_arr_to_img_dropin(golden_dir):
 def test_sweep_shapes_vs_oracle(H, W, kind):
     import torch
     from mem_b200.process_data import histogram
-    rng = np.random.default_rng(hash((H, W, kind)) % 2**32)
+    rng = np.random.default_rng(H * 1000 + W + len(kind))      # (hash() of a str is salted per process)
     for n in (1, 31, 10_000, 300_000):
         ev = synth_events(rng, n, H, W, kind, frac=(kind == "edge"))
         want = event_hist_ref(ev, H, W)
@@ -84,6 +84,35 @@ def test_full_size_10M_events_properties():
     assert np.array_equal(full, want)
     agg = histogram(d, H, W, strategy=2).cpu().numpy()
     assert np.array_equal(agg, want)
+
+
+@pytest.mark.parametrize("H,W", [(480, 640), (720, 1280), (333, 517)])
+def test_hybrid_strategy_large_sensors(H, W):
+    """HYBRID (hot granules privatised in shared memory, the rest through L2 REDs) on sensors that do not fit one SM:
+    every distribution, > 65535 hits on one pixel (mod-256 folds of the private copy), negative-wrap rows, and AUTO
+    picking it for a long stream."""
+    import torch
+    from mem_b200.process_data import histogram
+    rng = np.random.default_rng(H * 7 + W)
+    for kind in ("uniform", "edge", "hot"):
+        n = 2_200_000
+        ev = synth_events(rng, n, H, W, kind, frac=(kind == "edge"))
+        if kind == "hot":
+            ev[: 300_000, 0], ev[: 300_000, 1] = 5.0, 3.0            # 300k hits on one pixel
+            ev[: 300_000, 3] = np.where(np.arange(300_000) % 5 == 0, -1.0, 1.0)
+            ev[300_000: 300_400, 0] = -ev[300_000: 300_400, 0] - 1.0   # negative flat index: numpy wraps once
+            ev[300_000: 300_400, 1] = 0.0
+            rng.shuffle(ev)
+        want = event_hist_ref(ev, H, W)
+        d = torch.from_numpy(ev).cuda()
+        for s in (6, 0):
+            for C in (3, 2):
+                got = histogram(d, H, W, channels=C, strategy=s).cpu().numpy()
+                assert np.array_equal(got, want if C == 3 else want[..., 0::2]), (kind, s, C, int((got != (want if C == 3 else want[..., 0::2])).sum()))
+    bad = synth_events(rng, 1_100_000, H, W)
+    bad[777_777, 1] = H
+    with pytest.raises(IndexError):
+        histogram(torch.from_numpy(bad).cuda(), H, W, strategy=6)
 
 
 def test_ragged_batch_training_shape():

@@ -26,7 +26,7 @@ def main():
                 ev = hot_pixel_events(rng, n, H, W) if kind == "hot" else synth_events(rng, n, H, W, kind)
                 d = torch.from_numpy(ev).cuda()
                 ref = histogram(d, H, W, strategy=1, check=False)
-                for s in (1, 5):
+                for s in (1, 5, 6):
                     got = histogram(d, H, W, strategy=s, check=False)
                     assert torch.equal(got, ref), (W, H, kind, n, s)
                     ms = timeit(lambda: histogram(d, H, W, strategy=s, check=False))
