@@ -383,6 +383,48 @@ int memb_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, 
                const float* group_lr_host, const float* group_wd_host, int ngroups, float beta1, float beta2, float eps,
                int step, float grad_scale, float max_norm, const float* sqnorm_dev, memb_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * dVAE training step and decoder.  Replaces DiscreteVAE.forward(return_loss / return_recons) and
+ * DiscreteVAE.decode, eventvae/vae/vae_model.py:160-213, as driven by eventvae/train_vae.py:304-392.  Activations are
+ * NHWC bf16 matrices [B*H*W, C]; the convolutions are im2col / col2im around memb_gemm (bf16 operands, fp32 accumulate):
+ * Conv2d fwd = im2col + GEMM, dgrad = GEMM + col2im, wgrad = GEMM on im2col; ConvTranspose2d swaps the roles.
+ * ---------------------------------------------------------------------- */
+/* fp32 [B,C,H,W] -> bf16 [B,H,W,Cpad] (zero channels beyond C), (x - mean[c]) / std[c] when given (DiscreteVAE.norm, :133-141);
+ * out_f32 (nullable): the normalised image as fp32 [B,H,W,C], the reconstruction target. */
+int memb_vae_nchw_to_nhwc(const float* img, int B, int C, int H, int W, int Cpad, const float* mean, const float* stdv,
+                          void* out_bf16, float* out_f32, memb_stream_t stream);
+/* fp32 [B,H,W,ld] (first C channels) -> fp32 [B,C,H,W] */
+int memb_vae_nhwc_to_nchw(const float* x, int B, int C, int H, int W, int ld, float* out, memb_stream_t stream);
+/* col[(b,oy,ox), (ky,kx,c)] = x[b, oy*stride+ky-pad, ox*stride+kx-pad, c], zero outside; C % 8 == 0. */
+int memb_vae_im2col(const void* x_bf16, int B, int H, int W, int C, int kh, int kw, int stride, int pad, void* col_bf16,
+                    memb_stream_t stream);
+/* The adjoint of im2col as a gather (no atomics): out[b,y,x,c] = sum of the col entries that im2col would have read from that
+ * element, + bias[c], ReLU, then zeroed where gate <= 0 (ReLU backward of the producing layer).  col fp32 [B*OH*OW, ldc]
+ * (OH, OW from H, W, k, stride, pad); out bf16 and / or fp32 [B,H,W,ld_out]. */
+int memb_vae_col2im(const float* col, int64_t ldc, int B, int H, int W, int C, int kh, int kw, int stride, int pad,
+                    const float* bias, int relu, const void* gate_bf16, void* out_bf16, float* out_f32, int ld_out,
+                    memb_stream_t stream);
+/* op 0: out = relu(a); op 1: out = a where b > 0 else 0; op 2: out = a + b (bf16, n elements) */
+int memb_vae_ew_bf16(int op, const void* a, const void* b, void* out, int64_t n, memb_stream_t stream);
+/* out[i, :] = table[idx[i], :] as bf16 [n, ld] (nn.Embedding lookup of decode(), :164); err_flag set on an index outside [0, V). */
+int memb_vae_gather_rows(const float* table, int V, int D, const int64_t* idx, int64_t n, int ld, void* out_bf16, int* err_flag,
+                         memb_stream_t stream);
+/* F.gumbel_softmax(logits, tau, dim=token axis, hard) on rows of logits fp32 [rows, N] with the Gumbel noise given (fp32, same
+ * shape): y = softmax((logits + noise) / tau) (bf16); hard: y_fwd = onehot(argmax) (straight-through forward value).
+ * lse: fp32 [rows, 2] saved for the backward pass.  kl_out[0] += sum_rows sum_n q_n (log q_n + log N), q = softmax(logits)
+ * (the reference's F.kl_div(log_uniform, log_qy, 'batchmean', log_target=True), :204-208). */
+int memb_vae_gumbel_fwd(const float* logits, const float* noise, int64_t rows, int N, float tau, int hard, void* y_bf16,
+                        void* y_fwd_bf16, float* lse, float* kl_out, memb_stream_t stream);
+/* dlogits (bf16) = d/dlogits [ <dy, y> + kl_weight * KL ]; dy fp32 [rows, N]. */
+int memb_vae_gumbel_bwd(const float* logits, const float* noise, const float* lse, const float* dy, int64_t rows, int N, float tau,
+                        const float* grad_scale_dev, float kl_weight, void* dlogits_bf16, memb_stream_t stream);
+/* loss_out[0] += mse_loss (kind 0) or smooth_l1_loss (kind 1) of recon fp32 [pixels, ld_recon] (first C channels) against
+ * target fp32 [pixels, C]; dout (nullable, bf16 [pixels, ld_recon]) = d loss / d recon. */
+int memb_vae_recon_loss(const float* target, const float* recon, int64_t pixels, int C, int ld_recon, int kind, float* loss_out,
+                        void* dout_bf16, memb_stream_t stream);
+/* dst = (accumulate ? dst : 0) + scale_dev[0] * src (fp32; scale_dev NULL = 1) */
+int memb_axpy_f32(const float* src, const float* scale_dev, float* dst, int64_t n, int accumulate, memb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,17 @@ SIGNATURES.update({
     "memb_sqnorm": (_i32, [_vp, _i64, _f32, _vp, _vp]),
     "memb_sqnorm_groups": (_i32, [_vp, _i64, _f32, _vp, _vp, _vp]),
     "memb_soft_ce": (_i32, [_vp, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp]),
+    # dVAE training step / decoder (csrc/vae_train.cu)
+    "memb_vae_nchw_to_nhwc": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "memb_vae_nhwc_to_nchw": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "memb_vae_im2col": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "memb_vae_col2im": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "memb_vae_ew_bf16": (_i32, [_i32, _vp, _vp, _vp, _i64, _vp]),
+    "memb_vae_gather_rows": (_i32, [_vp, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "memb_vae_gumbel_fwd": (_i32, [_vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "memb_vae_gumbel_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _f32, _vp, _vp]),
+    "memb_vae_recon_loss": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "memb_axpy_f32": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "memb_adamw": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _i32, _f32, _f32, _vp, _vp]),
 })
 

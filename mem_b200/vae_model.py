@@ -6,10 +6,12 @@ the pretraining engine uses: ``get_codebook_indices(images)`` (:153-158) and
 (``codebook.weight``, ``encoder.{i}.0.*``, ``encoder.{j}.net.{0,2,4}.*``, ``decoder.*``) so that
 checkpoints written by the reference's ``train_vae.py`` load unchanged.
 
-The encoder runs on libmemb's fp32-faithful convolution kernel (3xTF32 on tcgen05, see
-``csrc/conv.cu``) with the codebook argmax fused into the last convolution's epilogue: logits are never
-written to memory on the token path.  dVAE *training* (gumbel-softmax + decoder, stage 1 of the
-reference pipeline) and ``decode`` are outside the pretraining hot path.
+The tokenizer path runs on libmemb's fp32-faithful convolution kernels (fp16 hi/lo pairs or 3xTF32 on tcgen05,
+``csrc/conv_f16.cu`` / ``csrc/conv.cu``) with the codebook argmax fused into the last convolution's epilogue: logits
+are never written to memory on the token path.  dVAE *training* (``forward(img, return_loss=True, ...)``:
+gumbel-softmax, codebook einsum, ConvTranspose decoder, reconstruction + KL loss, :173-213) and ``decode`` (:160-171,
+what the pretraining engine's visualisation branch calls) run in bf16 on the schedule in ``vae_train.py``
+(SURVEY.md 8f, N4).
 """
 from __future__ import annotations
 
@@ -49,6 +51,7 @@ class DiscreteVAE(nn.Module):
         self.num_resnet_blocks, self.hidden_dim, self.channels = num_resnet_blocks, hidden_dim, channels
         self.temperature, self.straight_through = temperature, straight_through
         self.kl_div_loss_weight, self.normalization = kl_div_loss_weight, normalization
+        self.loss_name = loss
         # Module construction order follows the reference (codebook; encoder/decoder stages interleaved; decoder
         # ResBlock before encoder ResBlock; decoder stem; encoder head; decoder head) so that the same
         # torch.manual_seed gives the same random-init tokenizer.
@@ -70,6 +73,7 @@ class DiscreteVAE(nn.Module):
         self.encoder = nn.Sequential(*enc)
         self.decoder = nn.Sequential(*dec)
         self._tok = None
+        self._trn = None
 
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
@@ -77,16 +81,36 @@ class DiscreteVAE(nn.Module):
         """``logits.argmax(dim=1).flatten(1)`` of the encoder (vae_model.py:153-158): int64 [B, h*w]."""
         return self._tokenizer().run(images, want_logits=False)
 
-    def forward(self, img, return_loss=False, return_recons=False, return_logits=False, temp=None):
-        if not return_logits:
-            raise NotImplementedError(
-                "mem_b200.DiscreteVAE implements the tokenizer path (return_logits=True / get_codebook_indices); "
-                "dVAE training is outside the MEM pretraining hot path")
-        with torch.no_grad():
-            return self._tokenizer().run(img, want_logits=True)
+    def forward(self, img, return_loss=False, return_recons=False, return_logits=False, temp=None, gumbel_noise=None):
+        """``DiscreteVAE.forward`` (vae_model.py:173-213).  ``return_logits``: the fp32-faithful encoder logits (no
+        gradient: the tokenizer path).  Otherwise the training path: reconstruction, or ``loss`` / ``(loss, recons)``;
+        ``loss.backward()`` fills the parameters' ``.grad``.  ``gumbel_noise`` (fp32 ``[B, num_tokens, h, w]``) replaces
+        the internally drawn Gumbel sample (tests); by default it is drawn exactly as ``F.gumbel_softmax`` draws it."""
+        assert img.shape[-1] == self.input_W and img.shape[-2] == self.input_H, \
+            f"input must have the correct image size {self.input_H}x{self.input_W}, but is ({img.shape[-2]},{img.shape[-1]})"
+        if return_logits:
+            with torch.no_grad():
+                return self._tokenizer().run(img, want_logits=True)
+        from .vae_train import train_forward
+        loss, recons = train_forward(self, img, self.temperature if temp is None else temp, gumbel_noise)
+        if not return_loss:
+            return recons
+        return (loss, recons) if return_recons else loss
 
+    @torch.no_grad()
     def decode(self, img_seq):
-        raise NotImplementedError("DiscreteVAE.decode (visualisation branch) is outside the MEM pretraining hot path")
+        """``codebook(img_seq)`` -> ``[B, d, h, w]`` -> decoder (vae_model.py:160-171): fp32 ``[B, channels, H, W]``.
+        (Under ``torch.no_grad()`` as the pretraining engine calls it, engine_for_pretraining.py:181-183.)"""
+        _lib.require_cuda()
+        if not img_seq.is_cuda:
+            raise RuntimeError("mem_b200.DiscreteVAE runs on CUDA tensors only (no CPU path)")
+        return self._trainer().decode(img_seq)
+
+    def _trainer(self):
+        if self._trn is None:
+            from .vae_train import VaeTrainer
+            object.__setattr__(self, "_trn", VaeTrainer(self))
+        return self._trn
 
     def norm(self, images):
         if self.normalization is None:

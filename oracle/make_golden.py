@@ -546,9 +546,75 @@ def golden_finetune_remap():
     print("finetune_remap.npz:", len(out), "arrays; cls loss", loss.item())
 
 
+def golden_dvae_train():
+    """The UNMODIFIED reference ``DiscreteVAE`` on its training path (eventvae/vae/vae_model.py:160-213): loss,
+    reconstruction and every parameter gradient of ``vae(img, return_loss=True, return_recons=True, temp)`` in fp32 with
+    a seeded Gumbel sample, the same under bf16 autocast (the calibration of the GPU test's tolerances, as for the ViT),
+    and ``decode(img_seq)``.  The oracle restatement (oracle/dvae_ref.py ``train_loss`` / ``decode``) is checked against
+    the reference here as well."""
+    import torch
+    from oracle import dvae_ref
+    vm = ref_shims.ref_module("vae.vae_model")
+    out = {}
+    for name, cfg, B, seed, temp in (("a", dvae_ref.TRAIN_A, 3, 61, 0.8), ("b", dvae_ref.TRAIN_B, 2, 62, None),
+                                     ("c", dvae_ref.TRAIN_C, 4, 63, 1.0)):
+        torch.manual_seed(0)
+        vae = vm.DiscreteVAE(**cfg)
+        sd = dvae_ref.synth_train_state_dict(vae.state_dict(), seed)
+        vae.load_state_dict(sd)
+        vae.train()
+        img = dvae_ref.synth_images(B, cfg["channels"], cfg["input_H"], cfg["input_W"], seed + 100)
+        h, w = cfg["input_H"] >> cfg["num_layers"], cfg["input_W"] >> cfg["num_layers"]
+        res = {}
+        for mode in ("fp32", "bf16"):
+            vae.zero_grad()
+            torch.manual_seed(1000 + seed)                   # F.gumbel_softmax draws from the global generator
+            if mode == "fp32":
+                loss, recons = vae(img, return_loss=True, return_recons=True, temp=temp)
+            else:
+                with _cuda_autocast_policy_on_cpu():
+                    loss, recons = vae(img, return_loss=True, return_recons=True, temp=temp)
+            loss.backward()
+            res[mode] = (loss.item(), recons.detach().float().clone(), {n: p.grad.detach().clone() for n, p in vae.named_parameters()})
+        l32, r32, g32 = res["fp32"]
+        l16, r16, g16 = res["bf16"]
+        noise = dvae_ref.gumbel_noise((B, cfg["num_tokens"], h, w), 1000 + seed)
+        # the restatement with the explicit sample reproduces the reference
+        sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        lo, ro = dvae_ref.train_loss(img, sdr, cfg, noise, temp)
+        lo.backward()
+        assert abs(lo.item() - l32) < 1e-6 * max(1.0, abs(l32)) and torch.allclose(ro, r32, atol=1e-5), (name, lo.item(), l32)
+        for n in g32:
+            assert torch.allclose(sdr[n].grad, g32[n], rtol=1e-4, atol=1e-6), (name, n)
+        out[f"{name}/noise"] = noise.numpy()
+        out[f"{name}/loss"] = np.array([l32, l16])
+        out[f"{name}/recons"] = r32.numpy()
+        out[f"{name}/err/recons"] = np.array((r16 - r32).double().norm().item())
+        out[f"{name}/ref/recons"] = np.array(r32.double().norm().item())
+        for n in g32:
+            out[f"{name}/grad/{n}"] = g32[n].numpy()
+            out[f"{name}/err/{n}"] = np.array((g16[n] - g32[n]).double().norm().item())
+            out[f"{name}/ref/{n}"] = np.array(g32[n].double().norm().item())
+        rels = sorted(float(out[f"{name}/err/{n}"]) / max(float(out[f"{name}/ref/{n}"]), 1e-30) for n in g32)
+        # decode (vae_model.py:160-171)
+        seq = torch.randint(0, cfg["num_tokens"], (B, h * w), generator=torch.Generator().manual_seed(seed))
+        with torch.no_grad():
+            dec = vae.decode(seq)
+            with _cuda_autocast_policy_on_cpu():
+                dec16 = vae.decode(seq).float()
+        assert torch.allclose(dvae_ref.decode(seq, sd, cfg), dec, atol=1e-5)
+        out[f"{name}/seq"] = seq.numpy()
+        out[f"{name}/decode"] = dec.numpy()
+        out[f"{name}/err/decode"] = np.array((dec16 - dec).double().norm().item())
+        print(f"{name}: loss {l32:.6f} (bf16 {l16:.6f}), recons rel err {float(out[f'{name}/err/recons']) / float(out[f'{name}/ref/recons']):.2e}, "
+              f"grad rel median {rels[len(rels) // 2]:.2e} max {rels[-1]:.2e}, decode {tuple(dec.shape)}")
+    np.savez_compressed(os.path.join(GOLD, "dvae_train.npz"), **out)
+    print("dvae_train.npz:", len(out), "arrays")
+
+
 SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit, "dvae": golden_dvae,
             "engine": golden_engine, "event_pipeline": golden_event_pipeline, "decode": golden_decode, "engine_ft": golden_engine_ft,
-            "vit_bf16": golden_vit_bf16, "finetune_remap": golden_finetune_remap}
+            "vit_bf16": golden_vit_bf16, "finetune_remap": golden_finetune_remap, "dvae_train": golden_dvae_train}
 
 
 def main(argv):
