@@ -869,6 +869,22 @@ __global__ void __launch_bounds__(kTileThreads) hist_hybrid_prepare(const double
     }
   }
   __syncthreads();
+  if (force_mode < 0) {
+    // cheap early exit for spread-out streams: when the sample touches more than twice as many granules as fit the tile,
+    // the mapped granules cannot hold half of it -- skip the selection, the L2-RED rasteriser runs (mode 0)
+    int touched = 0;
+    for (int g = threadIdx.x; g < granules; g += kTileThreads) touched += cnt[g] != 0u;
+    touched = __reduce_add_sync(0xffffffffu, touched);
+    if ((threadIdx.x & 31) == 0) s_seen[threadIdx.x >> 5] = touched;
+    __syncthreads();
+    int total = 0;
+    for (int w = 0; w < kTileThreads / 32; ++w) total += s_seen[w];
+    __syncthreads();
+    if (total > 2 * tile_granules) {
+      if (threadIdx.x == 0) { state->nsel = 0; state->mode = 0; }
+      return;
+    }
+  }
   {   // histogram of the counts; nearly all of them are 0..3: those are counted in registers, one atomic per warp and bin
     int small[4] = {0, 0, 0, 0};
     for (int g = threadIdx.x; g < granules; g += kTileThreads) {
