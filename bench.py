@@ -189,13 +189,20 @@ class HistogramWorkload:
         hbm, _, _, how = measured_peaks()
         alg_bytes = 32.0 * self.n + self.C * self.H * self.W
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-        private = self.H * self.W <= 51200 and self.n >= (1 << 18)     # what MEMB_HIST_AUTO picks (csrc/hist.cu make_plan)
-        return {"bound": "hbm", "kernel": ("hist_private (+hist_private_finalize: whole step timed)" if private else
-                                           "hist_scatter_global (+init, finalize: whole step timed)"),
+        # what MEMB_HIST_AUTO picks (csrc/hist.cu make_plan)
+        if self.H * self.W <= 51200 and self.n >= (1 << 18):
+            kernel = "hist_private (+hist_private_finalize: whole step timed)"
+        elif self.n >= (1 << 20) and self.H * self.W <= 64 * 16384:
+            kernel = ("adaptive chain, whole step timed: hist_hybrid_prepare (zero-fill + sampled concentration estimate) -> "
+                      "hist_scatter_global (spread-out streams: L2 REDs) | hist_hybrid (concentrated streams: hot granules in "
+                      "shared memory) -> hist_hybrid_finalize")
+        else:
+            kernel = "hist_scatter_global (+init, finalize: whole step timed)"
+        return {"bound": "hbm", "kernel": kernel,
                 "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
                 "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "traffic": ncu_traffic("hist_scatter_global_10M_640x480") if (self.n, self.W, self.H) == (10_000_000, 640, 480) else None}
+                "traffic": ncu_traffic("hist_chain_10M_640x480_" + self.kind) if (self.n, self.W, self.H) == (10_000_000, 640, 480) else None}
 
     # --- reference's CPU path (numpy np.add.at restatement, oracle/histogram_ref.py)
     def cpu_once(self, ev):

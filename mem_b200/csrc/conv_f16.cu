@@ -34,8 +34,14 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 192;  // 384 output channels = 2 tiles
 constexpr int BLOCK_K = 64;   // halves: one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 384;
-constexpr int kEpiCols = BLOCK_N / 2;  // columns per epilogue warp
+// Epilogue warps: 4 lane quarters x (kEpiWarps / 4) column parts.  General tiles keep a 96-column partial sum per thread in
+// registers (two-level accumulation) and run 8 epilogue warps; tiles whose whole K fits one accumulation segment (the
+// first layer: K = 16*C padded to one 64-wide block) need no partial sums, so 12 warps with 64 columns each fit the
+// register file: that layer is bound by the epilogue (1.2 GB of hi/lo output per 64 images), not by the tensor pipe.
+template <int kEpiWarps> struct Cfg {
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
+  static constexpr int kEpiCols = BLOCK_N / (kEpiWarps / 4);  // columns per epilogue warp
+};
 constexpr int A_BYTES = BLOCK_M * 128;
 constexpr int B_BYTES = (BLOCK_N / 2) * 128;  // this CTA's half of the weight tile
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 56 KB
@@ -90,9 +96,11 @@ __device__ __forceinline__ void transpose4x4_quarters(uint4 (&q)[4], int lane) {
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <int kEpiWarps, bool kSingle>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<kEpiWarps>::kThreads, 1)
 conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
            const __grid_constant__ CUtensorMap tmap_w, const Params p) {
+  constexpr int kEpiCols = Cfg<kEpiWarps>::kEpiCols;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -116,7 +124,7 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 16); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 2 * kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair(tmem_slot, TMEM_COLS);
@@ -189,7 +197,7 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
     }
   } else if (warp >= 4) {
     // -------------------------------------------------------------------- epilogue (lane quarter x column half)
-    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int quad = warp & 3, half = (warp - 4) >> 2;      // lane quarter, column part (kEpiCols columns each)
     const uint32_t tmem_empty_leader0 = mapa(smem_u32(&tmem_empty_bar[0]), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -205,29 +213,38 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
       const int py = oy + p.pad, px = ox + p.pad, msk = (1 << p.shift) - 1;
       const long long off = (long long)b * p.sB + (long long)(py >> p.shift) * p.sy_major + (long long)(py & msk) * p.sy_minor +
                             (long long)(px >> p.shift) * p.sx_major + (long long)(px & msk) * p.sx_minor;
-      float sum[kEpiCols];
+      float sum[kSingle ? 32 : kEpiCols];
+      uint32_t taddr_single = 0;
+      if constexpr (!kSingle) {
 #pragma unroll
-      for (int j = 0; j < kEpiCols; ++j) sum[j] = 0.f;
-      // ---- add the K segments with round-to-nearest fp32 adds
-      for (int it0 = 0; it0 < iters; it0 += p.seg) {
+        for (int j = 0; j < kEpiCols; ++j) sum[j] = 0.f;
+        // ---- add the K segments with round-to-nearest fp32 adds
+        for (int it0 = 0; it0 < iters; it0 += p.seg) {
+          mbar_wait(&tmem_full_bar[acc], acc_phase, p.err_flag, 14);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N + half * kEpiCols;
+#pragma unroll
+          for (int c = 0; c < kEpiCols / 32; ++c) {
+            uint32_t raw[32];
+            tmem_ld32(taddr + c * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(raw[j]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tmem_empty_leader0 + acc * 8);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      } else {
+        // one segment per tile: the accumulator is read column group by column group inside the epilogue loop below
         mbar_wait(&tmem_full_bar[acc], acc_phase, p.err_flag, 14);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N + half * kEpiCols;
-#pragma unroll
-        for (int c = 0; c < kEpiCols / 32; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(taddr + c * 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(raw[j]);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader0 + acc * 8);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        taddr_single = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N + half * kEpiCols;
       }
       // ---- fused epilogue from registers
-      unsigned long long best = 0ull;
+      float best_v = -INFINITY;
+      int best_i = -1;
       // hi / lo rows leave through a 4x4 transpose of 16-byte quarters inside each group of four lanes: one store
       // instruction then writes 64 contiguous bytes of each of 8 rows (8 lines, full sectors) instead of 16 bytes of
       // each of 32 rows (32 lines, half sectors).  Row bases / liveness of the group's four rows:
@@ -243,15 +260,29 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < kEpiCols / 32; ++c) {
         const int col0 = n_tile * BLOCK_N + half * kEpiCols + c * 32;
+        if constexpr (kSingle) {
+          uint32_t raw[32];
+          tmem_ld32(taddr_single + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(raw[j]);
+          if (c == kEpiCols / 32 - 1) {          // last read of this accumulator stage: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tmem_empty_leader0 + acc * 8);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
+        }
+        constexpr int kSumBase = kSingle ? 0 : 32;   // sum[] holds one column group (single) or all of them
         if (col0 < p.Cout) {  // warp-uniform (Cout % 32 == 0); rows that are not live compute on zeros and store nothing
           float v[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
-            v[4 * j] = fmaf(sum[c * 32 + 4 * j], p.acc_scale, bq.x);
-            v[4 * j + 1] = fmaf(sum[c * 32 + 4 * j + 1], p.acc_scale, bq.y);
-            v[4 * j + 2] = fmaf(sum[c * 32 + 4 * j + 2], p.acc_scale, bq.z);
-            v[4 * j + 3] = fmaf(sum[c * 32 + 4 * j + 3], p.acc_scale, bq.w);
+            v[4 * j] = fmaf(sum[c * kSumBase + 4 * j], p.acc_scale, bq.x);
+            v[4 * j + 1] = fmaf(sum[c * kSumBase + 4 * j + 1], p.acc_scale, bq.y);
+            v[4 * j + 2] = fmaf(sum[c * kSumBase + 4 * j + 2], p.acc_scale, bq.z);
+            v[4 * j + 3] = fmaf(sum[c * kSumBase + 4 * j + 3], p.acc_scale, bq.w);
           }
           if (p.aux && live) {
             const float4* a4 = reinterpret_cast<const float4*>(p.aux + plain * p.Cout + col0);
@@ -265,7 +296,7 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          if (live) {
+          if (live && p.d_hi) {          // range monitor of the stored fp16 operands (logits are never stored as fp16)
 #pragma unroll
             for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(v[j]));
           }
@@ -274,11 +305,10 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-          if (p.keys && live) {
+          if (p.keys && live) {          // running maximum in float (columns ascend: the first maximum wins), key built once
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const unsigned long long key = argmax_key(v[j], col0 + j);
-              best = key > best ? key : best;
+              if (v[j] > best_v) { best_v = v[j]; best_i = col0 + j; }
             }
           }
           if (p.d_hi) {
@@ -311,7 +341,7 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
           }
         }
       }
-      if (p.keys && live) atomicMax(p.keys + plain, best);
+      if (p.keys && live && best_i >= 0) atomicMax(p.keys + plain, argmax_key(best_v, best_i));
     }
     if (p.absmax) {  // |result| maximum seen by this warp -> one atomic (float bits order like unsigned for x >= 0)
 #pragma unroll
@@ -471,11 +501,14 @@ extern "C" int memb_conv_f16x2(const memb_conv16_desc* dp, memb_stream_t stream)
 
   static bool configured = false;
   if (!configured) {
-    MEMB_CUDA_OK(cudaFuncSetAttribute(conv_f16x2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MEMB_CUDA_OK(cudaFuncSetAttribute(conv_f16x2<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MEMB_CUDA_OK(cudaFuncSetAttribute(conv_f16x2<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   const int clusters = std::max(1, std::min(p.num_tiles, num_sms() / 2));
-  conv_f16x2<<<2 * clusters, kThreads, SMEM_BYTES, stream>>>(ta_hi, ta_lo, tw, p);
+  const int iters = p.ntaps * p.kc_per_tap;
+  if (iters <= p.seg && !d.keys) conv_f16x2<12, true><<<2 * clusters, Cfg<12>::kThreads, SMEM_BYTES, stream>>>(ta_hi, ta_lo, tw, p);
+  else conv_f16x2<8, false><<<2 * clusters, Cfg<8>::kThreads, SMEM_BYTES, stream>>>(ta_hi, ta_lo, tw, p);
   MEMB_LAUNCH_OK("conv_f16x2");
   return MEMB_OK;
 }

@@ -777,8 +777,9 @@ __global__ void __launch_bounds__(32 * kFinRows) hist_private_finalize(const uns
 // against 85 us uniform).  HYBRID privatises only the HOT part of the sensor, chosen per call ON THE DEVICE:
 //   1. hist_hybrid_prepare zero-fills the L2 accumulators; its CTA 0 counts a sample of kHybSamples rows spread over the
 //      stream per 64-pixel granule, picks the most frequent granules (as many as fit a shared-memory tile), writes the
-//      granule -> slot map and decides the mode: privatise (1) when those granules hold at least half of the sample
-//      (or the caller forced HYBRID), else plain L2 REDs (0: a uniform stream gains nothing from a sixth of the sensor);
+//      granule -> slot map and decides the mode: privatise (1) when the sample is concentrated -- its effective number
+//      of granules 1 / sum p_g^2 is below half of the sensor's -- or the caller forced HYBRID, else plain L2 REDs
+//      (0: a uniform stream gains nothing from privatising a sixth of the sensor);
 //   2. hist_scatter_global runs when mode == 0 and hist_hybrid when mode == 1 (both are launched; the other one's CTAs
 //      return at once): every CTA of hist_hybrid (one per SM) rasterises a strided share of the stream, sends events of
 //      mapped granules to shared-memory atomics (its private copy of the hot pixels) and the rest to L2 REDs, and stores
@@ -849,7 +850,6 @@ __global__ void __launch_bounds__(kTileThreads) hist_hybrid_prepare(const double
   for (int g = threadIdx.x; g < granules; g += kTileThreads) cnt[g] = 0u;
   for (int i = threadIdx.x; i < kHybHistBins; i += kTileThreads) hist[i] = 0;
   __syncthreads();
-  int seen = 0;
   for (int j = 0; j < kPer; j += kBatch) {
     Event e[kBatch];
     bool live[kBatch];
@@ -864,23 +864,29 @@ __global__ void __launch_bounds__(kTileThreads) hist_hybrid_prepare(const double
       int idx;
       if (live[u] && (e[u].p == 1.0 || e[u].p == -1.0) && pixel_index_fast(e[u].x, e[u].y, W, H, npix, idx)) {
         atomicAdd(&cnt[idx / kHybGranule], 1u);
-        ++seen;
       }
     }
   }
   __syncthreads();
   if (force_mode < 0) {
-    // cheap early exit for spread-out streams: when the sample touches more than twice as many granules as fit the tile,
-    // the mapped granules cannot hold half of it -- skip the selection, the L2-RED rasteriser runs (mode 0)
-    int touched = 0;
-    for (int g = threadIdx.x; g < granules; g += kTileThreads) touched += cnt[g] != 0u;
-    touched = __reduce_add_sync(0xffffffffu, touched);
-    if ((threadIdx.x & 31) == 0) s_seen[threadIdx.x >> 5] = touched;
+    // Is the stream concentrated?  The effective number of granules N_eff = 1 / sum_g p_g^2, estimated from the sample
+    // counts c_g (S = sum c_g, Poisson sampling: E[sum c_g^2] = S + S^2 sum p_g^2): a uniform stream gives N_eff ~ the
+    // granule count, 8 line segments ~ 500, 50 segments ~ 1500.  The L2-RED rasteriser starts to serialise on hot sectors
+    // once the events sit on fewer than about half of the sensor's granules; above that it is the faster one: mode 0.
+    long long sum_c = 0, sum_c2 = 0;
+    for (int g = threadIdx.x; g < granules; g += kTileThreads) {
+      const long long c = cnt[g];
+      sum_c += c;
+      sum_c2 += c * c;
+    }
+    const int s1 = __reduce_add_sync(0xffffffffu, (int)sum_c), s2 = __reduce_add_sync(0xffffffffu, (int)min(sum_c2, 0x3ffffffLL));
+    if ((threadIdx.x & 31) == 0) { s_seen[threadIdx.x >> 5] = s1; s_cover[threadIdx.x >> 5] = s2; }
     __syncthreads();
-    int total = 0;
-    for (int w = 0; w < kTileThreads / 32; ++w) total += s_seen[w];
+    long long S = 0, Q = 0;
+    for (int w = 0; w < kTileThreads / 32; ++w) { S += s_seen[w]; Q += s_cover[w]; }
     __syncthreads();
-    if (total > 2 * tile_granules) {
+    // N_eff >= granules / 2   <=>   S^2 >= (Q - S) * granules / 2
+    if (S == 0 || 2 * S * S >= (Q - S) * (long long)granules) {
       if (threadIdx.x == 0) { state->nsel = 0; state->mode = 0; }
       return;
     }
@@ -927,28 +933,16 @@ __global__ void __launch_bounds__(kTileThreads) hist_hybrid_prepare(const double
   const int thr = s_thr;
   const int per_thread = (granules + kTileThreads - 1) / kTileThreads;
   const int g0 = threadIdx.x * per_thread, g1 = min(granules, g0 + per_thread);
-  int mine = 0, cover = 0;
-  for (int g = g0; g < g1; ++g)
-    if ((int)min(cnt[g], (unsigned int)(kHybHistBins - 1)) >= thr) { ++mine; cover += (int)cnt[g]; }
+  int mine = 0;
+  for (int g = g0; g < g1; ++g) mine += (int)min(cnt[g], (unsigned int)(kHybHistBins - 1)) >= thr;
   int nsel = 0;
   int slot = block_exclusive_scan(mine, warp_sums, &nsel);
-  // how much of the sample the selected granules hold
-  cover = __reduce_add_sync(0xffffffffu, cover);   // counts <= kHybSamples
-  seen = __reduce_add_sync(0xffffffffu, seen);
-  if ((threadIdx.x & 31) == 0) { s_cover[threadIdx.x >> 5] = cover; s_seen[threadIdx.x >> 5] = seen; }
-  __syncthreads();
-  int mode = force_mode;
-  if (force_mode < 0) {
-    int c = 0, t = 0;
-    for (int w = 0; w < kTileThreads / 32; ++w) { c += s_cover[w]; t += s_seen[w]; }
-    mode = (t > 0 && 2 * c >= t) ? 1 : 0;
-  }
   for (int g = g0; g < g1; ++g) {
-    const bool sel = mode && (int)min(cnt[g], (unsigned int)(kHybHistBins - 1)) >= thr;
+    const bool sel = (int)min(cnt[g], (unsigned int)(kHybHistBins - 1)) >= thr;
     if (sel) sel_list[slot] = (unsigned short)g;          // slot -> granule, for the finalize pass
     slot_map[g] = sel ? (unsigned short)slot++ : (unsigned short)0xffffu;
   }
-  if (threadIdx.x == 0) { state->nsel = mode ? nsel : 0; state->mode = mode; }
+  if (threadIdx.x == 0) { state->nsel = nsel; state->mode = 1; }      // forced, or the sample is concentrated (see above)
 }
 
 template <bool kAligned>
