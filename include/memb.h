@@ -138,6 +138,18 @@ int memb_event_pipeline_f32(const double* ev, int64_t n, const int64_t* offsets,
                             float hot_num_stds, int normalize, float* out, void* ws, size_t ws_bytes,
                             memb_stream_t stream);
 
+/* The same chain for recordings WITHOUT a fixed sensor size (the N-Caltech101 / N-Cars branch of build_transformNPY,
+ * H = W = None): flip width, cull window and raster size are inferred per stream from the rows (int(max) + 1 at the
+ * stage where the reference infers them, datasets.py:513-515, :538-541, :571-575), the (H3 x W3) raster is resized to
+ * (outH, outW) with torchvision's Resize(BILINEAR, antialias=True) (ATen upsample_bilinear2d_aa), then RemoveTimesurface,
+ * RemoveHotPixels (float32 statistics of the resized planes) and NormalizeEvent.  aug[b]: start / count / time_flip /
+ * flip_x / cull / shift_x / shift_y are used (scale_*, flip_w, cull_w, cull_h ignored).  canvas_H x canvas_W bounds the
+ * recordings' extent (<= 51200 pixels: one shared-memory tile).  One CTA per stream; memb_hist_status afterwards returns
+ * MEMB_EINVAL for an empty stream (the reference raises ValueError) or a recording larger than the canvas. */
+int memb_event_pipeline_var_f32(const double* ev, int64_t n, const int64_t* offsets, int B, const memb_event_aug* aug,
+                                int canvas_H, int canvas_W, int outH, int outW, int C, float hot_num_stds, int normalize,
+                                float* out, void* ws, size_t ws_bytes, memb_stream_t stream);
+
 size_t memb_raster_post_workspace_bytes(int B);
 int memb_raster_post_f32(const uint8_t* hist, int B, int H, int W, int C, const int32_t* crop_tl, int pad_t,
                          int pad_l, int outH, int outW, int remove_ts, float hot_num_stds, int normalize,

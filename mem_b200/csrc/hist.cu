@@ -591,6 +591,189 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
   }
 }
 
+// ---------------------------------------------------------------- fused event pipeline, VARIABLE sensor size
+// The N-Caltech101 / N-Cars branch of build_transformNPY (datasets.py:611-660 with H = W = None): recordings differ in
+// extent, every stage infers its size from the rows it sees, and the raster is resized to the model input:
+//   SliceRandomMaxEvs (:488-498) -> RandomTimeFlip (:598-608) -> Aug_FlipEvsAlongX (W = int(max x) + 1, :513-519) ->
+//   Aug_RandomShiftEvs (H, W = int(max) + 1 BEFORE the shift; shift; drop rows outside, :538-547) ->
+//   EventArrToImg(None, None) (H, W = int(max) + 1 over the surviving rows, :571-575) -> ToTensor ->
+//   Resize((outH, outW), BILINEAR, antialias=True) -> RemoveTimesurface -> RemoveHotPixels -> NormalizeEvent.
+// One CTA per stream: pass 1 over the window finds min x / max x / max y, pass 2 rasterises the augmented rows into a
+// shared-memory tile of the cull window (H2 x W2 <= canvas) and tracks the survivors' extent (H3 x W3, a top-left
+// sub-rectangle of the tile), the resize then evaluates ATen's separable anti-aliased triangle filter
+// (UpSampleKernel.cpp: support = max(scale, 1), taps normalised per output index, horizontal then vertical) straight
+// from the tile, and the float32 statistics / filter / normalisation run over this stream's own output.
+// status codes left in the header: 1 = index error (never here: rows are culled), 2 = a stage saw an empty stream
+// (the reference raises ValueError from max() of an empty array), 3 = the recording does not fit the canvas.
+constexpr int kVarMaxTaps = 16;      // ceil(max(scale, 1)) * 2 + 1 taps per axis: input extent <= 7 x output extent
+
+struct AaTaps { int lo, n; float w[kVarMaxTaps]; };
+__device__ __forceinline__ AaTaps aa_taps(int o, int in_size, int out_size) {
+  // at::native upsample_bilinear2d_aa index / weight computation, align_corners = false
+  AaTaps t;
+  const float scale = (float)in_size / (float)out_size;
+  const float support = scale >= 1.0f ? scale : 1.0f;
+  const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+  const float center = scale * ((float)o + 0.5f);
+  t.lo = max((int)(center - support + 0.5f), 0);
+  t.n = min(min((int)(center + support + 0.5f), in_size) - t.lo, kVarMaxTaps);
+  float total = 0.f;
+  for (int j = 0; j < t.n; ++j) {
+    const float x = fabsf(((float)(j + t.lo) - center + 0.5f) * invscale);
+    const float w = x < 1.0f ? 1.0f - x : 0.0f;
+    t.w[j] = w;
+    total += w;
+  }
+  if (total != 0.f)
+    for (int j = 0; j < t.n; ++j) t.w[j] /= total;
+  return t;
+}
+
+template <bool kAligned>
+__global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_var_fused(
+    const double* __restrict__ ev, const long long* __restrict__ offsets, long long n_total,
+    const memb_event_aug* __restrict__ aug, int Hc, int Wc, int outH, int outW, int C, float hot_num_stds, int normalize,
+    float* __restrict__ out, Header* __restrict__ hdr) {
+  extern __shared__ unsigned int tile[];
+  __shared__ double redd[3][kTileThreads / 32];
+  __shared__ float redf[kTileThreads / 32];
+  __shared__ float lut[256];
+  __shared__ int ext[2];
+  __shared__ float s_thr, s_factor;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
+  const memb_event_aug a = aug[b];
+  aug_window(a, begin, end);
+  if (begin >= end) { if (threadIdx.x == 0) hdr->oob = 2; return; }
+  if (threadIdx.x < 256) lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+  if (threadIdx.x < 2) ext[threadIdx.x] = -1;
+
+  // ---- pass 1: extent of the window (numpy max / min over every row, whatever its polarity)
+  double mnx = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (long long r = begin + threadIdx.x; r < end; r += kTileThreads) {
+    const Event e = load_event<kAligned>(ev, r);
+    mnx = fmin(mnx, e.x); mxx = fmax(mxx, e.x); mxy = fmax(mxy, e.y);
+  }
+  for (int o = 16; o; o >>= 1) {
+    mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+    mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  if (lane == 0) { redd[0][warp] = mnx; redd[1][warp] = mxx; redd[2][warp] = mxy; }
+  __syncthreads();
+  for (int w = 0; w < kTileThreads / 32; ++w) { mnx = fmin(mnx, redd[0][w]); mxx = fmax(mxx, redd[1][w]); mxy = fmax(mxy, redd[2][w]); }
+  // sizes as the reference derives them: W1 for the flip, (H2, W2) for the cull window (both from the data BEFORE the shift)
+  const long long W1 = __double2ll_rz(mxx) + 1;
+  const double mxx_flipped = a.flip_x ? __dsub_rn((double)(W1 - 1), mnx) : mxx;
+  const long long W2 = __double2ll_rz(mxx_flipped) + 1, H2 = __double2ll_rz(mxy) + 1;
+  if (!(W2 >= 1 && H2 >= 1 && W2 <= Wc && H2 <= Hc) || !(mnx >= 0.0)) {      // (negative coordinates: outside the format)
+    if (threadIdx.x == 0) hdr->oob = 3;
+    return;
+  }
+  const int tw = (int)W2, th = (int)H2, words = (tw * th + 3) & ~3;
+  for (int i = threadIdx.x * 4; i < words; i += kTileThreads * 4) *reinterpret_cast<uint4*>(tile + i) = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+
+  // ---- pass 2: augment, cull, rasterise into the (H2 x W2) tile; extent of the surviving rows
+  int sx = -1, sy = -1, it = 0;
+  for (long long base = begin; base < end; base += kTileThreads, ++it) {
+    const long long r = base + threadIdx.x;
+    if (r < end) {
+      Event e = load_event<kAligned>(ev, r);
+      if (a.time_flip) e.p = -e.p;
+      if (a.flip_x) e.x = __dsub_rn((double)(W1 - 1), e.x);
+      bool keep = true;
+      if (a.cull) {
+        e.x = __dadd_rn(e.x, (double)a.shift_x);
+        e.y = __dadd_rn(e.y, (double)a.shift_y);
+        keep = e.x >= 0.0 && e.x < (double)W2 && e.y >= 0.0 && e.y < (double)H2;
+      }
+      if (keep) {
+        const int x = __double2int_rz(e.x), y = __double2int_rz(e.y);
+        sx = max(sx, x); sy = max(sy, y);
+        if (e.p == 1.0) atomicAdd(&tile[y * tw + x], 1u);
+        else if (e.p == -1.0) atomicAdd(&tile[y * tw + x], 0x10000u);
+      }
+    }
+    if ((it + 1) % (kTileChunk / kTileThreads) == 0 && base + kTileThreads < end) {     // halves can never carry
+      __syncthreads();
+      for (int i = threadIdx.x; i < words; i += kTileThreads) tile[i] &= 0x00ff00ffu;
+      __syncthreads();
+    }
+  }
+  sx = __reduce_max_sync(0xffffffffu, sx);
+  sy = __reduce_max_sync(0xffffffffu, sy);
+  if (lane == 0) { atomicMax(&ext[0], sx); atomicMax(&ext[1], sy); }
+  __syncthreads();
+  const int W3 = ext[0] + 1, H3 = ext[1] + 1;
+  if (W3 < 1 || H3 < 1) { if (threadIdx.x == 0) hdr->oob = 2; return; }     // every row was culled
+
+  // ---- resize (H3 x W3) -> (outH x outW), anti-aliased bilinear, horizontal then vertical; raw planes + statistics
+  const int npx = outH * outW;
+  float* o_pos = out + (long long)b * C * npx;
+  float* o_neg = o_pos + (long long)(C - 1) * npx;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < npx; i += kTileThreads) {
+    const int oy = i / outW, ox = i - oy * outW;
+    const AaTaps tx = aa_taps(ox, W3, outW), ty = aa_taps(oy, H3, outH);
+    float vp = 0.f, vn = 0.f;
+    for (int jy = 0; jy < ty.n; ++jy) {
+      const unsigned int* row = tile + (ty.lo + jy) * tw + tx.lo;
+      float rp = 0.f, rn = 0.f;
+      for (int jx = 0; jx < tx.n; ++jx) {
+        const unsigned int w = row[jx];
+        rp = fmaf(lut[w & 0xffu], tx.w[jx], rp);
+        rn = fmaf(lut[(w >> 16) & 0xffu], tx.w[jx], rn);
+      }
+      vp = fmaf(rp, ty.w[jy], vp);
+      vn = fmaf(rn, ty.w[jy], vn);
+    }
+    o_pos[i] = vp;
+    o_neg[i] = vn;
+    if (C == 3) o_pos[npx + i] = 0.0f;
+    s1 += (double)vp + (double)vn;
+    s2 += (double)vp * vp + (double)vn * vn;
+  }
+  // ---- RemoveHotPixels threshold: mean + k * std (unbiased) over both polarity planes
+  const bool filter = hot_num_stds >= 0.0f;
+  for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if (lane == 0) { redd[0][warp] = s1; redd[1][warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int w = 0; w < kTileThreads / 32; ++w) { t1 += redd[0][w]; t2 += redd[1][w]; }
+    const double n = 2.0 * (double)npx, mean = t1 / n;
+    double var = (t2 - t1 * t1 / n) / (n - 1.0);
+    var = var > 0.0 ? var : 0.0;
+    s_thr = filter ? (float)(mean + (double)hot_num_stds * sqrt(var)) : INFINITY;
+  }
+  __syncthreads();
+  const float thr = s_thr;
+  if (!filter && !normalize) return;
+  // ---- maximum of what survives the filter (this CTA re-reads its own stores: plain loads after the barrier)
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < npx; i += kTileThreads) {
+    const float vp = __ldcg(o_pos + i), vn = __ldcg(o_neg + i);
+    if (!(vp > thr || vn > thr)) mx = fmaxf(mx, fmaxf(vp, vn));
+  }
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) redf[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int w = 0; w < kTileThreads / 32; ++w) m = fmaxf(m, redf[w]);
+    s_factor = (normalize && m != 0.f) ? __fdiv_rn(1.0f, m) : 1.0f;      // factor = 1.0 / x.max()  (transforms.py:234-236)
+  }
+  __syncthreads();
+  const float factor = s_factor;
+  for (int i = threadIdx.x; i < npx; i += kTileThreads) {
+    float vp = __ldcg(o_pos + i), vn = __ldcg(o_neg + i);
+    if (vp > thr || vn > thr) { vp = 0.f; vn = 0.f; }
+    o_pos[i] = __fmul_rn(vp, factor);
+    o_neg[i] = __fmul_rn(vn, factor);
+  }
+}
+
 // ---------------------------------------------------------------- row sources for the PRIVATE strategy
 // kSrc: 0 = float64 rows, 32-byte aligned; -1 = float64 rows, 8-byte aligned; MEMB_RAW_NCALTECH101 / MEMB_RAW_NCARS =
 // raw records decoded on the fly (bit fields as in decode_record below, process_dataset.py:52-60, :88-99).
@@ -1531,6 +1714,36 @@ extern "C" int memb_event_pipeline_f32(const double* ev, int64_t n, const int64_
   return MEMB_OK;
 }
 
+extern "C" int memb_event_pipeline_var_f32(const double* ev, int64_t n, const int64_t* offsets, int B, const memb_event_aug* aug,
+                                           int canvas_H, int canvas_W, int outH, int outW, int C, float hot_num_stds,
+                                           int normalize, float* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
+  MEMB_REQUIRE(B >= 1 && canvas_H >= 1 && canvas_W >= 1 && outH >= 1 && outW >= 1, "event_pipeline_var: bad shape");
+  MEMB_REQUIRE(C == 2 || C == 3, "event_pipeline_var: C must be 2 or 3, got %d", C);
+  MEMB_REQUIRE((long long)canvas_H * canvas_W <= kTileMaxWords,
+               "event_pipeline_var: the %dx%d canvas does not fit one shared-memory tile (%d pixels)", canvas_H, canvas_W, kTileMaxWords);
+  MEMB_REQUIRE(canvas_H <= 7 * outH && canvas_W <= 7 * outW, "event_pipeline_var: down-scaling by more than 7x is not supported");
+  MEMB_REQUIRE(n >= 0 && (n == 0 || ev != nullptr), "event_pipeline_var: null event pointer");
+  MEMB_REQUIRE(offsets != nullptr || B == 1, "event_pipeline_var: a batch needs row offsets");
+  MEMB_REQUIRE(aug != nullptr && (((uintptr_t)aug) & 7u) == 0, "event_pipeline_var: null / misaligned augmentation array");
+  MEMB_REQUIRE(out != nullptr && (((uintptr_t)out) & 15u) == 0, "event_pipeline_var: null / misaligned output");
+  MEMB_REQUIRE(ws != nullptr && (((uintptr_t)ws) & 15u) == 0 && ws_bytes >= (size_t)kHeaderBytes,
+               "event_pipeline_var: workspace must hold the %d-byte status header", kHeaderBytes);
+  MEMB_REQUIRE((((uintptr_t)ev) & 7u) == 0, "event_pipeline_var: misaligned event pointer");
+  MEMB_CUDA_OK(cudaMemsetAsync(ws, 0, kHeaderBytes, stream));
+  const bool aligned = (((uintptr_t)ev) & 31u) == 0;
+  auto kern = aligned ? event_pipeline_var_fused<true> : event_pipeline_var_fused<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[aligned]) {
+    MEMB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxWords * 4));
+    attr_set[aligned] = true;
+  }
+  const size_t smem = (size_t)round_up<long long>((long long)canvas_H * canvas_W, 4) * 4;
+  kern<<<B, kTileThreads, smem, stream>>>(ev, reinterpret_cast<const long long*>(offsets), n, aug, canvas_H, canvas_W, outH, outW,
+                                          C, hot_num_stds, normalize, out, reinterpret_cast<Header*>(ws));
+  MEMB_LAUNCH_OK("event_pipeline_var_fused");
+  return MEMB_OK;
+}
+
 extern "C" int memb_decode_events_f64(const uint8_t* raw, int64_t n_records, int format, double* out,
                                       memb_stream_t stream) {
   MEMB_REQUIRE(format == MEMB_RAW_NCALTECH101 || format == MEMB_RAW_NCARS, "decode: unknown record format %d", format);
@@ -1596,6 +1809,10 @@ extern "C" int memb_hist_status(const void* ws, memb_stream_t stream) {
   int flag = 0;
   MEMB_CUDA_OK(cudaMemcpyAsync(&flag, ws, sizeof(int), cudaMemcpyDeviceToHost, stream));
   MEMB_CUDA_OK(cudaStreamSynchronize(stream));
+  if (flag == 2)
+    return fail(MEMB_EINVAL, "zero-size array to reduction operation maximum which has no identity (a stream was empty, or "
+                             "every row was dropped by the shift augmentation: the reference raises here)");
+  if (flag == 3) return fail(MEMB_EINVAL, "event pipeline: a recording's extent does not fit the canvas (or has negative coordinates)");
   if (flag) return fail(MEMB_EOOB, "hist: event index out of bounds for the sensor (reference: IndexError)");
   return MEMB_OK;
 }

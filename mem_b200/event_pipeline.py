@@ -11,9 +11,12 @@ Division of labour: the random draws stay on the host and consume Python's ``ran
 ``MaskingGenerator``); the arithmetic runs on the device for the whole batch: ``memb_hist_aug_u8`` (one pass over the
 raw float64 rows, bit-exact counts) and ``memb_raster_post_f32`` (uint8 counts -> float32 [B,C,h,w]).
 
-Not covered (raise / documented in DESIGN.md): variable sensor size (``H = W = None``, N-Caltech101 / N-Cars paths and
-their bilinear ``Resize``), the time surface together with augmentations, ``LogTransform`` / ``GammaTransform``,
-``ColorJitter`` and ``EventRandAugment``.
+The branch WITHOUT a fixed sensor (``H = W = None``: N-Caltech101 / N-Cars, sizes inferred per sample, bilinear
+anti-aliased ``Resize`` to the input size) is ``VarPipelineConfig`` / ``draw_params_var`` / ``pipeline_var_fused`` /
+``EventBatchPipelineVar`` below (one kernel, ``memb_event_pipeline_var_f32``).
+
+Not covered (raise / documented in DESIGN.md): the time surface together with augmentations, ``LogTransform`` /
+``GammaTransform``, ``ColorJitter`` and ``EventRandAugment``.
 """
 from __future__ import annotations
 
@@ -26,7 +29,8 @@ import numpy as np
 from . import _lib
 
 __all__ = ["PipelineConfig", "EventAug", "draw_params", "pack_params", "rasterise_augmented", "post_raster",
-           "pipeline_fused", "EventBatchPipeline"]
+           "pipeline_fused", "EventBatchPipeline", "VarPipelineConfig", "draw_params_var", "pipeline_var_fused",
+           "EventBatchPipelineVar"]
 
 FUSED_MAX_PIXELS = 50 * 1024      # one shared-memory tile (csrc/hist.cu kTileMaxWords)
 
@@ -298,3 +302,103 @@ class EventBatchPipeline:
         return post_raster(hist, crop if cfg.is_train else None, (cfg.input_H, cfg.input_W) if cfg.is_train else None,
                            remove_timesurface=not cfg.timesurface,
                            hot_num_stds=cfg.hotpix_num_stds if cfg.hotpixfilter else None, normalize=cfg.normalize_events)
+
+
+# ------------------------------------------------------------------------- variable sensor size (N-Caltech101 / N-Cars)
+@dataclass
+class VarPipelineConfig:
+    """The ``args`` fields ``build_transformNPY`` reads on its branch without a fixed sensor (datasets.py:614, :623-642);
+    ``canvas_H`` / ``canvas_W`` bound the recordings' extent (the sensor: 180 x 240 for N-Caltech101, 100 x 120 for N-Cars)."""
+    is_train: bool = True
+    canvas_H: int = 180
+    canvas_W: int = 240
+    input_H: int = 224
+    input_W: int = 224
+    slice_max_evs: int = 30000
+    max_random_shift_evs: int = 15
+    timesurface: bool = False
+    hotpixfilter: bool = True
+    hotpix_num_stds: float = 10
+    normalize_events: bool = False
+
+    def __post_init__(self):
+        assert 5000 <= self.slice_max_evs < 200000 and 0 <= self.max_random_shift_evs <= 200     # datasets.py:491, :530
+        assert self.canvas_H * self.canvas_W <= FUSED_MAX_PIXELS, "the canvas must fit one shared-memory tile"
+
+
+def draw_params_var(n_events: int, cfg: VarPipelineConfig) -> dict:
+    """One sample's draws in the reference's order: ``random.choice`` (window start, long streams only, datasets.py:495),
+    ``np.random.random`` (time flip, :603), ``np.random.random`` (x flip, :518), ``np.random.randint(size=(2,))`` (shift,
+    :541).  ``RandomCrop`` draws nothing on this branch: ``Resize`` already produced the crop size."""
+    p = dict(scale_x=1.0, scale_y=1.0, start=0, count=n_events, time_flip=False, flip_x=False, flip_w=0, cull=False,
+             shift_x=0, shift_y=0, cull_w=0, cull_h=0, top=0, left=0)
+    if n_events > cfg.slice_max_evs:
+        p["start"] = random.choice(range(n_events - cfg.slice_max_evs + 1))
+        p["count"] = cfg.slice_max_evs
+    if cfg.is_train:
+        p["time_flip"] = bool(np.random.random() < 0.5)
+        p["flip_x"] = bool(np.random.random() < 0.5)
+        xs, ys = np.random.randint(-cfg.max_random_shift_evs, cfg.max_random_shift_evs + 1, size=(2,))
+        p["shift_x"], p["shift_y"], p["cull"] = int(xs), int(ys), True
+    return p
+
+
+def pipeline_var_fused(events, offsets, aug, canvas_hw, out_hw, channels=3, *, hot_num_stds=10.0, normalize=False, check=True,
+                       out=None):
+    """Ragged batch of raw streams -> ``float32 (B,C,outH,outW)`` through ``memb_event_pipeline_var_f32`` (sizes inferred
+    per stream, anti-aliased bilinear resize).  ``check`` synchronises and raises ``ValueError`` where the reference
+    raises (a stream that is empty after the window / shift) or when a recording exceeds the canvas."""
+    torch = _lib.require_cuda()
+    from .process_data import _as_device_events
+    device = torch.device(events.device if (isinstance(events, torch.Tensor) and events.is_cuda) else "cuda")
+    with torch.cuda.device(device):
+        ev, _ = _as_device_events(torch, events, device)
+        off = offsets if isinstance(offsets, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64))
+        off = off.to(device=device, dtype=torch.int64).contiguous()
+        B = int(off.numel()) - 1
+        if B < 1:
+            raise ValueError("offsets must have B+1 >= 2 entries")
+        aug_dev = _aug_to_device(torch, aug, B, device)
+        outH, outW = int(out_hw[0]), int(out_hw[1])
+        if out is None:
+            out = torch.empty((B, channels, outH, outW), dtype=torch.float32, device=device)
+        lib = _lib.load()
+        ws = _lib.workspace.get(torch, 256, device, "hist")
+        stream = _lib.stream_ptr(torch, device)
+        n = int(ev.shape[0])
+        _lib.check(lib.memb_event_pipeline_var_f32(ev.data_ptr() if n else None, n, off.data_ptr(), B, aug_dev.data_ptr(),
+                                                   int(canvas_hw[0]), int(canvas_hw[1]), outH, outW, channels,
+                                                   float(hot_num_stds) if hot_num_stds is not None else -1.0, int(bool(normalize)),
+                                                   out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        if check:
+            _lib.check(lib.memb_hist_status(ws.data_ptr(), stream))
+    return out
+
+
+class EventBatchPipelineVar:
+    """Batched GPU replacement of ``build_transformNPY(is_train, args)`` for data without a fixed sensor size
+    (N-Caltech101, N-Cars): ``pipe(streams)`` -> ``float32 (B, C, input_H, input_W)`` on the device, equal (to float32
+    rounding of the resize filter) to stacking the reference transform's outputs under the same generator state."""
+
+    def __init__(self, cfg: VarPipelineConfig, channels: int = 3):
+        if cfg.timesurface:
+            raise NotImplementedError("the fused augmentation path rasterises polarity counts only (no time surface)")
+        self.cfg, self.channels = cfg, channels
+
+    def __call__(self, streams, offsets=None, params=None, check=True):
+        torch = _lib.require_cuda()
+        if offsets is None:
+            lens = [len(s) for s in streams]
+            offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            events = np.concatenate([np.asarray(s).reshape(-1, 4) for s in streams], axis=0) if sum(lens) else np.zeros((0, 4))
+        else:
+            events = streams
+            off_host = offsets.cpu().numpy() if isinstance(offsets, torch.Tensor) else np.asarray(offsets)
+            lens = np.diff(off_host).tolist()
+        cfg = self.cfg
+        if params is None:
+            params = [draw_params_var(int(n), cfg) for n in lens]
+        aug, _ = pack_params(params)
+        return pipeline_var_fused(events, offsets, aug, (cfg.canvas_H, cfg.canvas_W), (cfg.input_H, cfg.input_W), self.channels,
+                                  hot_num_stds=cfg.hotpix_num_stds if cfg.hotpixfilter else None,
+                                  normalize=cfg.normalize_events, check=check)

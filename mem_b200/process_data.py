@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["histogram", "histogram_batch", "decode_events", "histogram_raw", "read_ncaltech101_bin", "read_ncars_dat",
-           "RAW_NCALTECH101", "RAW_NCARS"]
+           "read_nimagenet_npz", "convert_nimagenet", "RAW_NCALTECH101", "RAW_NCARS"]
 
 RAW_NCALTECH101, RAW_NCARS = _lib.RAW_NCALTECH101, _lib.RAW_NCARS
 _RECORD_BYTES = {RAW_NCALTECH101: 5, RAW_NCARS: 8}
@@ -29,15 +29,23 @@ def _as_device_events(torch, events, device):
         ev = events
         host = not ev.is_cuda
     else:
-        ev = torch.from_numpy(np.ascontiguousarray(np.asarray(events), dtype=np.float64))
+        arr = np.ascontiguousarray(np.asarray(events))
+        if arr.dtype == np.bool_ or arr.dtype.kind not in "iuf":
+            arr = arr.astype(np.float64)
+        try:
+            ev = torch.from_numpy(arr)
+        except TypeError:                      # a dtype torch has no tensor type for
+            ev = torch.from_numpy(arr.astype(np.float64))
         host = True
     if ev.ndim != 2 or ev.shape[1] != 4:
         raise ValueError(f"events must be (N, 4) rows [x, y, t, p], got {tuple(ev.shape)}")
-    if ev.dtype != torch.float64:
-        ev = ev.to(torch.float64)
     ev = ev.contiguous()
     if host:
+        # recordings stored in a narrower dtype (N-ImageNet .npz arrays, int16 / float32 exports) cross PCIe as they
+        # are and are widened on the device: the rasteriser reads float64 rows (the reference's arithmetic type)
         ev = ev.to(device, non_blocking=False)
+    if ev.dtype != torch.float64:
+        ev = ev.to(torch.float64)
     return ev, host
 
 
@@ -151,6 +159,30 @@ def read_ncars_dat(path) -> np.ndarray:
     if raw.size % 8:
         raise ValueError(f"{path}: {raw.size} payload bytes is not a whole number of 8-byte records")
     return raw
+
+
+def read_nimagenet_npz(path) -> np.ndarray:
+    """The ``(N, 4)`` event array of an N-ImageNet recording, ``np.load(path)["event_data"]`` in its stored dtype
+    (reference ``process_data/process_dataset.py:115``: the conversion is a container change, no arithmetic).  Feed it
+    to ``histogram`` / ``histogram_batch`` / the event pipeline as is: it is uploaded in its own dtype and widened to
+    float64 on the device."""
+    with np.load(path) as z:
+        if "event_data" not in z.files:
+            raise KeyError(f"{path}: no 'event_data' array (N-ImageNet recordings store their events under that key)")
+        data = z["event_data"]
+    if data.ndim != 2 or data.shape[1] != 4:
+        raise ValueError(f"{path}: event_data must be (N, 4), got {data.shape}")
+    return data
+
+
+def convert_nimagenet(src_npz, dst_npy=None) -> str:
+    """One file of the reference's ``nimagenet()`` conversion (process_dataset.py:108-117): ``event_data`` of
+    ``src_npz`` saved as ``<name>.npy`` (next to the source unless ``dst_npy`` is given).  Returns the path written."""
+    import os
+    if dst_npy is None:
+        dst_npy = os.path.join(os.path.dirname(src_npz), os.path.basename(src_npz).split(".")[0] + ".npy")
+    np.save(dst_npy, read_nimagenet_npz(src_npz))
+    return dst_npy
 
 
 def _raw_on_device(torch, raw, fmt, device):

@@ -129,3 +129,77 @@ def pipeline_ref(events: np.ndarray, cfg: PipelineCfg, params: dict | None = Non
     ev = apply_event_aug(events, p)
     hist = event_hist_ref(ev, H, W, cfg.timesurface) if len(ev) else np.zeros((H, W, 3), np.uint8)
     return apply_post_raster(hist, p, cfg)
+
+
+# ---------------------------------------------------------------------------------------------
+# Variable sensor size: the N-Caltech101 / N-Cars branch of build_transformNPY (H = W = None, datasets.py:611-660)
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class VarPipelineCfg:
+    """The ``args`` fields build_transformNPY reads on the branch without a fixed sensor."""
+    is_train: bool = True
+    input_H: int = 224
+    input_W: int = 224
+    slice_max_evs: int = 30000
+    max_random_shift_evs: int = 15
+    hotpixfilter: bool = True
+    hotpix_num_stds: float = 10
+    normalize_events: bool = False
+
+
+def draw_params_var(n_events: int, cfg: VarPipelineCfg) -> dict:
+    """Generator consumption of one sample: ``random.choice`` (window, only for long streams), two ``np.random.random``
+    (time flip, x flip), ``np.random.randint(size=(2,))`` (shift).  ``RandomCrop`` draws nothing: after ``Resize`` the
+    image already has the crop size (torchvision ``get_params`` returns early)."""
+    p = dict(start=0, count=n_events, time_flip=False, flip_x=False, cull=False, shift_x=0, shift_y=0)
+    if n_events > cfg.slice_max_evs:
+        p["start"] = random.choice(range(n_events - cfg.slice_max_evs + 1))
+        p["count"] = cfg.slice_max_evs
+    if cfg.is_train:
+        p["time_flip"] = bool(np.random.random() < 0.5)
+        p["flip_x"] = bool(np.random.random() < 0.5)
+        xs, ys = np.random.randint(-cfg.max_random_shift_evs, cfg.max_random_shift_evs + 1, size=(2,))
+        p["shift_x"], p["shift_y"], p["cull"] = int(xs), int(ys), True
+    return p
+
+
+def apply_event_aug_var(events: np.ndarray, p: dict) -> np.ndarray:
+    """Sizes are inferred where the reference infers them: the flip width from the window (datasets.py:513-515), the cull
+    window from the flipped rows before the shift (:538-541)."""
+    x = np.array(events, dtype=np.float64, copy=True)
+    x = x[p["start"]:p["start"] + p["count"], :]
+    if p["time_flip"]:
+        x = np.flip(x, axis=0)
+        x[:, 2] = x[0, 2] - x[:, 2]
+        x[:, 3] = -x[:, 3]
+    if p["flip_x"]:
+        W = x[:, 0].max().astype(np.int64) + 1
+        x[:, 0] = W - 1 - x[:, 0]
+    if p["cull"]:
+        W = x[:, 0].max().astype(np.int64) + 1
+        H = x[:, 1].max().astype(np.int64) + 1
+        x[:, 0] += np.int64(p["shift_x"])
+        x[:, 1] += np.int64(p["shift_y"])
+        x = x[(x[:, 0] >= 0) & (x[:, 0] < W) & (x[:, 1] >= 0) & (x[:, 1] < H)]
+    return x
+
+
+def pipeline_var_ref(events: np.ndarray, cfg: VarPipelineCfg, params: dict | None = None) -> torch.Tensor:
+    p = params if params is not None else draw_params_var(len(events), cfg)
+    ev = apply_event_aug_var(events, p)
+    hist = event_hist_ref(ev, None, None)                       # raises ValueError on an empty stream, like the reference
+    x = torch.from_numpy(np.ascontiguousarray(hist)).permute(2, 0, 1).contiguous().to(torch.float32).div(255)
+    # transforms.Resize((H, W), BILINEAR, antialias=True) on a tensor image
+    x = torch.nn.functional.interpolate(x[None], size=(cfg.input_H, cfg.input_W), mode="bilinear", align_corners=False,
+                                        antialias=True)[0]
+    x[1, :, :] = 0.0
+    if cfg.hotpixfilter:
+        pol = x[0::2, :, :]
+        thr = torch.mean(pol) + cfg.hotpix_num_stds * torch.std(pol)
+        hot = torch.atleast_1d(torch.squeeze(torch.argwhere(pol.flatten() > thr)))
+        idx = np.asarray(np.unravel_index(hot, x.shape)).T
+        x[0::2, idx[:, 1], idx[:, 2]] = 0
+    if cfg.normalize_events:
+        if x[0::2, :, :].max() != 0:
+            x[0::2, :, :] = x[0::2, :, :] * (1.0 / x[0::2, :, :].max())
+    return x.float()

@@ -612,9 +612,42 @@ def golden_dvae_train():
     print("dvae_train.npz:", len(out), "arrays")
 
 
+def golden_event_pipeline_var():
+    """Reference build_transformNPY on its VARIABLE-sensor branch (data_path containing "Caltech" / "ncars": H = W = None,
+    per-sample inferred sizes, bilinear antialiased Resize to the input size; mem/datasets.py:611-660) on seeded synthetic
+    N-Caltech101-shaped (240x180, p = +-1) and N-Cars-shaped (120x100, p in {0,1}) streams."""
+    import torch
+    from types import SimpleNamespace
+    ds = ref_shims.ref_module("datasets")
+    out = {}
+    cases = [  # name, data_path, (H, W), polarity, is_train, n_events, kind, normalize, seed
+        ("cal_train_a", "/data/N-Caltech101", (180, 240), (-1.0, 1.0), True, 45000, "edge", 1, 21),
+        ("cal_train_b", "/data/N-Caltech101", (180, 240), (-1.0, 1.0), True, 20000, "hot", 0, 22),
+        ("cal_train_c", "/data/N-Caltech101", (172, 233), (-1.0, 1.0), True, 38000, "uniform", 1, 23),
+        ("cal_eval_a", "/data/N-Caltech101", (180, 240), (-1.0, 1.0), False, 45000, "edge", 1, 24),
+        ("cars_train_a", "/data/ncars", (100, 120), (0.0, 1.0), True, 9000, "edge", 1, 25),
+        ("cars_eval_a", "/data/ncars", (100, 120), (0.0, 1.0), False, 6000, "uniform", 0, 26),
+    ]
+    for name, path, (H, W), pol, is_train, n, kind, norm, seed in cases:
+        args = SimpleNamespace(data_path=path, input_H=224, input_W=224, slice_max_evs=30000, max_random_shift_evs=15,
+                               timesurface=0, hotpixfilter=1, hotpix_num_stds=10, logtrafo=0, gammatrafo=0, gamma=0.5,
+                               normalize_events=norm, rand_aug=0)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            tf = ds.build_transformNPY(is_train, args)
+        ev = np.floor(synth_events(np.random.default_rng(seed), n, H, W, kind, polarity=pol))     # recordings hold integer pixels
+        random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+        res = tf(ev.copy())
+        out[name + "_out"] = res.numpy()
+        out[name + "_meta"] = np.array([int(is_train), n, norm, seed, H, W, int(pol[0] == 0.0)], dtype=np.int64)
+        out[name + "_kind"] = np.array(kind)
+        print(f"event_pipeline_var {name}: out {tuple(res.shape)} nnz {int((res != 0).sum())} max {float(res.max()):.4f}")
+    np.savez_compressed(os.path.join(GOLD, "event_pipeline_var.npz"), **out)
+
+
 SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit, "dvae": golden_dvae,
             "engine": golden_engine, "event_pipeline": golden_event_pipeline, "decode": golden_decode, "engine_ft": golden_engine_ft,
-            "vit_bf16": golden_vit_bf16, "finetune_remap": golden_finetune_remap, "dvae_train": golden_dvae_train}
+            "vit_bf16": golden_vit_bf16, "finetune_remap": golden_finetune_remap, "dvae_train": golden_dvae_train, "event_pipeline_var": golden_event_pipeline_var}
 
 
 def main(argv):

@@ -181,6 +181,19 @@ def test_unaligned_event_pointer():
         assert np.array_equal(histogram(view, 120, 160, strategy=s).cpu().numpy(), want)
 
 
+def test_recordings_in_narrow_dtypes_are_widened_on_the_device():
+    """N-ImageNet event_data arrays / integer exports: uploaded in their own dtype, widened to float64 rows on the GPU."""
+    from mem_b200.process_data import histogram
+    rng = np.random.default_rng(11)
+    ev = np.floor(synth_events(rng, 50_000, 480, 640, "edge"))
+    want = event_hist_ref(ev, 480, 640)
+    for dt in (np.int16, np.int32, np.int64, np.float32):
+        assert np.array_equal(histogram(ev.astype(dt), 480, 640), want), dt
+    pol01 = ev.copy()
+    pol01[:, 3] = (pol01[:, 3] > 0)
+    assert np.array_equal(histogram(pol01.astype(np.int16), 480, 640), event_hist_ref(pol01, 480, 640))
+
+
 def test_hypothesis_small_streams():
     from hypothesis import given, settings, strategies as st
     from mem_b200.process_data import histogram

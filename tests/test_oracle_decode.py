@@ -3,6 +3,7 @@ process_data/process_dataset.py produced from synthetic recordings (tests/golden
 import os
 
 import numpy as np
+import pytest
 
 from oracle import decode_ref
 
@@ -51,3 +52,49 @@ def test_file_readers_skip_header(tmp_path):
     q = tmp_path / "b.bin"
     q.write_bytes(decode_ref.synth_ncaltech101(rng, 7))
     assert read_ncaltech101_bin(q).size == 35
+
+
+def test_nimagenet_npz_reader(tmp_path):
+    """N-ImageNet recordings are .npz files whose ``event_data`` array the reference stores unchanged as .npy
+    (process_dataset.py:108-117)."""
+    from mem_b200.process_data import convert_nimagenet, read_nimagenet_npz
+    rng = np.random.default_rng(0)
+    ev = np.stack([rng.integers(0, 640, 500), rng.integers(0, 480, 500), np.sort(rng.integers(0, 10**6, 500)),
+                   rng.integers(0, 2, 500)], axis=1).astype(np.int32)
+    src = tmp_path / "n01440764_10026.npz"
+    np.savez_compressed(src, event_data=ev)
+    got = read_nimagenet_npz(str(src))
+    assert got.dtype == np.int32 and np.array_equal(got, ev)
+    dst = convert_nimagenet(str(src))
+    assert dst.endswith("n01440764_10026.npy") and np.array_equal(np.load(dst), ev)
+    np.savez(tmp_path / "bad.npz", other=ev)
+    with pytest.raises(KeyError):
+        read_nimagenet_npz(str(tmp_path / "bad.npz"))
+
+
+@pytest.mark.reference
+def test_nimagenet_conversion_matches_reference(tmp_path):
+    """The unmodified reference ``nimagenet()`` on a temporary dataset tree writes the same .npy as convert_nimagenet."""
+    from types import SimpleNamespace
+    from mem_b200.process_data import convert_nimagenet
+    from oracle import ref_shims
+    ref_shims.install()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_process_dataset", "/root/reference/process_data/process_dataset.py")
+    mod = importlib.util.module_from_spec(spec)
+    import sys
+    sys.path.insert(0, "/root/reference/process_data")
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove("/root/reference/process_data")
+    rng = np.random.default_rng(1)
+    ev = np.stack([rng.integers(0, 640, 300), rng.integers(0, 480, 300), np.sort(rng.uniform(0, 1e5, 300)),
+                   rng.integers(0, 2, 300)], axis=1).astype(np.float64)
+    for split in ("extracted_train", "extracted_val"):
+        (tmp_path / "in" / split / "n0").mkdir(parents=True)
+        np.savez_compressed(tmp_path / "in" / split / "n0" / "rec_1.npz", event_data=ev)
+    mod.nimagenet("n0", SimpleNamespace(input=str(tmp_path / "in"), output=str(tmp_path / "out")))
+    want = np.load(tmp_path / "out" / "train" / "n0" / "rec_1.npy")
+    got = np.load(convert_nimagenet(str(tmp_path / "in" / "extracted_train" / "n0" / "rec_1.npz"), str(tmp_path / "ours.npy")))
+    assert got.dtype == want.dtype and np.array_equal(got, want)

@@ -107,3 +107,30 @@ def test_product_draws_and_record_layout_match_the_oracle_and_the_header():
     assert names == [f[0] for f in ep.EventAug._fields_]
     with pytest.raises(AssertionError):
         ep.PipelineConfig(slice_max_evs=100)          # the reference's own range check (datasets.py:491)
+
+
+def var_golden_cases(golden_dir):
+    from oracle.event_pipeline_ref import VarPipelineCfg
+    z = np.load(os.path.join(golden_dir, "event_pipeline_var.npz"))
+    for name in sorted(k[:-4] for k in z.files if k.endswith("_out")):
+        is_train, n, norm, seed, H, W, pol01 = (int(v) for v in z[name + "_meta"])
+        kind = str(z[name + "_kind"])
+        ev = np.floor(synth_events(np.random.default_rng(seed), n, H, W, kind, polarity=(0.0, 1.0) if pol01 else (-1.0, 1.0)))
+        yield name, ev, VarPipelineCfg(is_train=bool(is_train), normalize_events=bool(norm)), seed, (H, W), z[name + "_out"]
+
+
+def test_variable_sensor_oracle_matches_reference_golden(golden_dir):
+    """The N-Caltech101 / N-Cars branch of build_transformNPY (H = W = None, per-sample sizes, antialiased bilinear
+    Resize): tests/golden/event_pipeline_var.npz holds the reference chain's own outputs."""
+    from oracle.event_pipeline_ref import pipeline_var_ref
+    seen = 0
+    for name, ev, cfg, seed, _, want in var_golden_cases(golden_dir):
+        seed_all(seed)
+        got = pipeline_var_ref(ev, cfg).numpy()
+        assert got.shape == want.shape and got.dtype == np.float32, name
+        assert np.array_equal(got, want), f"{name}: {np.abs(got - want).max()}"
+        seen += 1
+    assert seen == 6
+    with pytest.raises(ValueError):                       # every row shifted out: the reference raises from max() of nothing
+        pipeline_var_ref(np.array([[0.0, 0.0, 1.0, 1.0]]), cfg, dict(start=0, count=1, time_flip=False, flip_x=False, cull=True,
+                                                                    shift_x=-5, shift_y=0))
