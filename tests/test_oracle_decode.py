@@ -83,11 +83,20 @@ def test_nimagenet_conversion_matches_reference(tmp_path):
     spec = importlib.util.spec_from_file_location("ref_process_dataset", "/root/reference/process_data/process_dataset.py")
     mod = importlib.util.module_from_spec(spec)
     import sys
+    # process_dataset.py does ``import utils`` (its own sibling); mem/ has a different ``utils`` that the other
+    # live-reference tests import under the same name, so keep this one out of sys.modules afterwards
+    saved = {k: sys.modules.get(k) for k in ("utils",)}
+    for k in saved:
+        sys.modules.pop(k, None)
     sys.path.insert(0, "/root/reference/process_data")
     try:
         spec.loader.exec_module(mod)
     finally:
         sys.path.remove("/root/reference/process_data")
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
     rng = np.random.default_rng(1)
     ev = np.stack([rng.integers(0, 640, 300), rng.integers(0, 480, 300), np.sort(rng.uniform(0, 1e5, 300)),
                    rng.integers(0, 2, 300)], axis=1).astype(np.float64)
