@@ -65,6 +65,13 @@ int64_t memb_launch_count(void);
                                 /* picks the most frequent 64-pixel granules, every SM keeps a private copy of  */
                                 /* those in shared memory and sends the remaining events to L2 REDs; AUTO picks */
                                 /* it for >= 2^20 events (else falls back to GLOBAL)                            */
+#define MEMB_HIST_SORT 7        /* one stream, sensor up to 4 Mpixel: no global atomics.  Pass 1 turns every    */
+                                /* event into a 16-bit key inside one of 296 interleaved pixel classes and      */
+                                /* counting-sorts each 8192-event chunk by class in shared memory (2 B written  */
+                                /* per event); pass 2 runs one CTA per class over its segments with shared-     */
+                                /* memory counters and writes the image directly.  Bit-exact, but measured      */
+                                /* slower than HYBRID (10 M events at 640x480: 118-126 us vs 94), so AUTO does  */
+                                /* not pick it                                                                  */
 
 /* Bytes memb_hist_u8 needs for this problem (n = total rows; same strategy value as the call). */
 size_t memb_hist_workspace_bytes(int B, int64_t n, int H, int W, int timesurface, int strategy);

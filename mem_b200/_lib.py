@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("MEMB_LIB_PATH") or os.path.join(_HERE, "libmemb.so") 
 
 MEMB_OK, MEMB_EINVAL, MEMB_EOOB, MEMB_ECUDA, MEMB_EWORKSPACE = 0, -1, -2, -3, -4
 
-HIST_AUTO, HIST_GLOBAL, HIST_GLOBAL_AGG, HIST_TILE, HIST_PRIVATE, HIST_GLOBAL_REPL, HIST_HYBRID = 0, 1, 2, 3, 4, 5, 6
+HIST_AUTO, HIST_GLOBAL, HIST_GLOBAL_AGG, HIST_TILE, HIST_PRIVATE, HIST_GLOBAL_REPL, HIST_HYBRID, HIST_SORT = 0, 1, 2, 3, 4, 5, 6, 7
 RAW_NCALTECH101, RAW_NCARS = 1, 2
 
 _c = ctypes

@@ -1281,6 +1281,270 @@ __global__ void __launch_bounds__(32 * kHybFinRows) hist_hybrid_finalize(
   }
 }
 
+// ---------------------------------------------------------------- strategy SORT (one long stream, large sensor)
+// GLOBAL pays one L2 RED per event (reads alone 53 us, REDs alone 52 us, together 84 us per 10 M events at 640x480,
+// 2-4x more on edge-like streams where REDs to one sector serialise); HYBRID moves the hot granules into shared memory
+// but keeps the cold REDs.  SORT has no global atomics at all:
+//   1. hist_sort_partition (two CTAs per SM, equal chunks of <= 4096 events): every event becomes a 16-bit key -- its
+//      place inside one of kSortBins interleaved pixel classes (class idx % kSortBins, key = (idx / kSortBins) << 1 |
+//      polarity) -- and the chunk's keys are counting-sorted by class in shared memory (one shared-memory atomic per
+//      event returns its rank) and stored as one contiguous block, with the class boundaries of the chunk in a
+//      transposed table off[class][chunk].  HBM traffic: 32 B read + 2 B written per event.
+//   2. hist_sort_accumulate (one CTA per class, two resident per SM): gathers the class's segment of every chunk with
+//      16-byte loads (the vectors of all segments are dealt round-robin to the threads, so long and short segments cost
+//      the same), counts into its private shared-memory image of the class's pixels and writes their uint8 values
+//      straight into the image: no zero-fill, no finalize pass.
+// Classes interleave the sensor pixel by pixel, so edges and blobs spread evenly; a class far above its share (a hot
+// pixel) switches its CTA to warp-aggregated atomics.  Out-of-range rows are reported through one flag per chunk, so
+// nothing needs zeroing before the chain starts.
+constexpr int kSortThreads = 512;
+constexpr int kSortCap = 4096;                                       // key slots per chunk
+constexpr int kSortBatch = 4;                                        // rows per thread in flight (reloaded as soon as consumed)
+constexpr int kSortStep = kSortThreads * kSortBatch;                 // rows per batch (64 KB)
+constexpr int kSortBatches = kSortCap / kSortStep;                   // batches per chunk
+constexpr int kSortBins = 296;                                       // pixel classes
+constexpr unsigned int kSortMagic = (unsigned int)((0x100000000ULL + kSortBins - 1) / kSortBins);   // idx / kSortBins, exact for idx < 2^23
+constexpr long long kSortMaxPixels = 1LL << 22;                      // key = (idx / kSortBins) << 1 | polarity < 2^16
+constexpr int kSortPerLane = (kSortBins + 31) / 32;                  // classes per lane in the one-warp scan
+constexpr int kSortSlices = 4;                                       // accumulate CTAs per class (each takes a quarter of the chunks)
+constexpr int kSortAccThreads = 512;
+constexpr int kSortSmemBytes = kSortCap * 4 + kSortCap * 2 + kSortCap * 2;   // unsorted words, ranks, sorted keys
+
+__host__ __device__ inline int sort_local_words(long long npix) {    // counters per class: pixels per class x 2, in whole uint4
+  return (int)(((((npix - 1) / kSortBins + 1) * 2 + 3) / 4) * 4);
+}
+
+// float64 row through the read-only path, no L1 allocation, first in line for L2 eviction: the 320 MB stream must not
+// push the sorted keys (re-read by the accumulate pass) out of the L2
+template <bool kAligned>
+__device__ __forceinline__ Event load_event_stream(const double* __restrict__ ev, long long row, unsigned long long policy) {
+  Event e;
+  const double* p = ev + 4 * row;
+  if constexpr (kAligned) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=d"(e.x), "=d"(e.y), "=d"(e.t), "=d"(e.p) : "l"(p), "l"(policy));
+  } else {
+    e.x = __ldg(p); e.y = __ldg(p + 1); e.t = __ldg(p + 2); e.p = __ldg(p + 3);
+  }
+  return e;
+}
+
+template <bool kAligned>
+__global__ void __launch_bounds__(kSortThreads, 2) hist_sort_partition(
+    const double* __restrict__ ev, long long n, int W, int H, long long npix, int nchunks, int chunk_len,
+    unsigned short* __restrict__ keys, unsigned short* __restrict__ offs, unsigned char* __restrict__ bad_chunk,
+    unsigned int* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  unsigned int* unsorted = reinterpret_cast<unsigned int*>(sort_smem);                               // key | class << 16
+  unsigned short* rank = reinterpret_cast<unsigned short*>(sort_smem + kSortCap * 4);
+  unsigned short* sorted = reinterpret_cast<unsigned short*>(sort_smem + kSortCap * 6);
+  __shared__ unsigned int cnt[kSortPerLane * 32];
+  __shared__ unsigned int start[kSortPerLane * 32 + 1];
+  const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  unsigned long long stream_policy, keep_policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream_policy));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
+  for (int i = tid; i < kSortPerLane * 32; i += kSortThreads) cnt[i] = 0u;
+  if (blockIdx.x == 0) {                          // hand-off flags of the accumulate pass (it starts after this grid has completed)
+    for (int i = tid; i < kSortBins * (kSortSlices - 1); i += kSortThreads) flags[i] = 0u;
+  }
+  // this CTA's it-th batch: chunk blockIdx.x + (it / kSortBatches) * gridDim.x, rows [chunk * chunk_len + batch * kSortStep, ...)
+  auto batch_rows = [&](int it, long long& first, long long& end) {
+    const long long chunk = (long long)blockIdx.x + (long long)(it / kSortBatches) * gridDim.x;
+    end = min(n, (chunk + 1) * (long long)chunk_len);
+    first = chunk * (long long)chunk_len + (long long)(it % kSortBatches) * kSortStep;
+  };
+  Event nxt[kSortBatch];
+  {
+    long long f, e;
+    batch_rows(0, f, e);
+#pragma unroll
+    for (int u = 0; u < kSortBatch; ++u) {
+      const long long r = f + u * kSortThreads + tid;
+      if (r < e) nxt[u] = load_event_stream<kAligned>(ev, r, stream_policy);
+    }
+  }
+  __syncthreads();
+  int it = 0;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    bool bad = false;
+#pragma unroll 1
+    for (int j = 0; j < kSortBatches; ++j, ++it) {
+      long long first, end, nfirst, nend;
+      batch_rows(it, first, end);
+      batch_rows(it + 1, nfirst, nend);
+#pragma unroll
+      for (int u = 0; u < kSortBatch; ++u) {
+        const int slot = (j * kSortBatch + u) * kSortThreads + tid;
+        const Event cur = nxt[u];
+        {                                         // the register is free again: request the row of the next batch
+          const long long r = nfirst + u * kSortThreads + tid;
+          if (r < nend) nxt[u] = load_event_stream<kAligned>(ev, r, stream_policy);
+        }
+        unsigned int w = 0xffffffffu;
+        if (first + u * kSortThreads + tid < end) {
+          const bool pos = cur.p == 1.0, neg = cur.p == -1.0;
+          if (pos || neg) {
+            int idx;
+            if (!pixel_index_fast(cur.x, cur.y, W, H, npix, idx)) {
+              bad = true;
+            } else {
+              const unsigned int q = __umulhi((unsigned int)idx, kSortMagic);
+              const unsigned int cls = (unsigned int)idx - q * kSortBins;
+              rank[slot] = (unsigned short)atomicAdd(&cnt[cls], 1u);
+              w = (q << 1) | (neg ? 1u : 0u) | (cls << 16);
+            }
+          }
+        }
+        unsorted[slot] = w;
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {                               // exclusive scan of the class counts by one warp; counts reset for the next chunk
+      unsigned int c[kSortPerLane], sum = 0;
+#pragma unroll
+      for (int k = 0; k < kSortPerLane; ++k) {
+        c[k] = cnt[tid * kSortPerLane + k];
+        cnt[tid * kSortPerLane + k] = 0u;
+        sum += c[k];
+      }
+      unsigned int inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (tid >= o) inc += t;
+      }
+      unsigned int run = inc - sum;
+#pragma unroll
+      for (int k = 0; k < kSortPerLane; ++k) {
+        const int cls = tid * kSortPerLane + k;
+        if (cls <= kSortBins) {                   // cls == kSortBins: the chunk's key count (classes beyond hold zero)
+          start[cls] = run;
+          offs[(size_t)cls * nchunks + chunk] = (unsigned short)run;
+        }
+        run += c[k];
+      }
+    }
+    const int any_bad = __syncthreads_or(bad);
+    if (tid == 0) bad_chunk[chunk] = any_bad ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < kSortCap / kSortThreads; ++k) {
+      const int slot = k * kSortThreads + tid;
+      const unsigned int w = unsorted[slot];
+      if (w != 0xffffffffu) sorted[start[w >> 16] + rank[slot]] = (unsigned short)w;
+    }
+    __syncthreads();
+    static_assert(kSortCap * 2 / 16 == kSortThreads, "one 16-byte vector of sorted keys per thread");
+    const uint4 v = reinterpret_cast<const uint4*>(sorted)[tid];
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(reinterpret_cast<uint4*>(keys + (size_t)chunk * kSortCap) + tid), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+                   "l"(keep_policy) : "memory");
+  }
+}
+
+// CTA (class, slice): blockIdx.x = (kSortSlices - 1 - slice) * kSortBins + class, so the CTAs that only produce a partial
+// image (slices 1 ..) are dispatched before the CTAs that wait for them (slice 0).
+__global__ void __launch_bounds__(kSortAccThreads, 2) hist_sort_accumulate(
+    const unsigned short* __restrict__ keys, const unsigned short* __restrict__ offs, const unsigned char* __restrict__ bad_chunk,
+    int nchunks, int local_words, long long npix, int C, long long n, unsigned int* __restrict__ partial,
+    unsigned int* __restrict__ flags, uint8_t* __restrict__ out, Header* __restrict__ hdr) {
+  extern __shared__ __align__(16) unsigned int sort_acc[];
+  __shared__ unsigned int s_total;
+  const int cls = blockIdx.x % kSortBins, slice = kSortSlices - 1 - blockIdx.x / kSortBins, tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < local_words; i += kSortAccThreads) sort_acc[i] = 0u;
+  if (tid == 0) s_total = 0u;
+  pdl_wait();                                    // keys, boundaries and flags of the partition pass are visible from here on
+  __syncthreads();
+  const unsigned short* o0 = offs + (size_t)cls * nchunks;
+  const unsigned short* o1 = o0 + nchunks;
+  const int c_begin = (int)((long long)nchunks * slice / kSortSlices), c_end = (int)((long long)nchunks * (slice + 1) / kSortSlices);
+  const int rounds = (c_end - c_begin + kSortAccThreads - 1) / kSortAccThreads;
+  // a class far above its share (a hot pixel): merge equal keys inside the warp before the shared-memory atomic
+  // (same-address shared-memory atomics serialise at ~8 clocks each); decided from this slice's key count
+  unsigned int mine = 0;
+  for (int c = c_begin + tid; c < c_end; c += kSortAccThreads) mine += (unsigned int)o1[c] - (unsigned int)o0[c];
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if (lane == 0 && mine) atomicAdd(&s_total, mine);
+  __syncthreads();
+  const bool aggregate = (unsigned long long)s_total * (kSortBins * kSortSlices) > 2ull * (unsigned long long)n;
+  for (int r = 0; r < rounds; ++r) {             // every lane of a warp runs the same trip counts (full-mask match below)
+    const int c = c_begin + r * kSortAccThreads + tid;
+    unsigned int s = 0, e = 0;
+    if (c < c_end) { s = o0[c]; e = o1[c]; }
+    const unsigned short* kb = keys + (size_t)c * kSortCap;
+    const unsigned int k0 = s & ~7u;
+    const unsigned int nv = e > s ? ((e + 7u) >> 3) - (s >> 3) : 0u;
+    const unsigned int maxv = __reduce_max_sync(0xffffffffu, nv);
+    constexpr int kU = 2;
+    for (unsigned int j0 = 0; j0 < maxv; j0 += kU) {
+      uint4 vec[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        vec[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (j0 + u < nv) vec[u] = __ldcg(reinterpret_cast<const uint4*>(kb + k0 + (j0 + u) * 8u));
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const unsigned int k = k0 + (j0 + u) * 8u;
+        const unsigned int w[4] = {vec[u].x, vec[u].y, vec[u].z, vec[u].w};
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const bool live = j0 + u < nv && k + m >= s && k + m < e;
+          const unsigned int key = (m & 1) ? (w[m >> 1] >> 16) : (w[m >> 1] & 0xffffu);
+          if (aggregate) {                         // CTA-uniform branch, the warp is converged here
+            const unsigned int peers = __match_any_sync(0xffffffffu, live ? key : 0x10000u + (unsigned int)lane);
+            if (live && (int)(__ffs(peers) - 1) == lane) atomicAdd(&sort_acc[key], (unsigned int)__popc(peers));
+          } else if (live) {
+            atomicAdd(&sort_acc[key], 1u);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int vecs = local_words >> 2;
+  if (slice > 0) {
+    // partial image of this slice, one byte per counter (the image is a count mod 256), then the hand-off flag
+    unsigned int* dst = partial + ((size_t)(slice - 1) * kSortBins + cls) * vecs;
+    for (int i = tid; i < vecs; i += kSortAccThreads) {
+      const uint4 a = reinterpret_cast<const uint4*>(sort_acc)[i];
+      __stcg(dst + i, (a.x & 0xffu) | ((a.y & 0xffu) << 8) | ((a.z & 0xffu) << 16) | (a.w << 24));
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(&flags[(slice - 1) * kSortBins + cls], 1u);
+    return;
+  }
+  if (tid < kSortSlices - 1) {
+    volatile unsigned int* f = flags + tid * kSortBins + cls;
+    while (*f == 0u) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+  for (int i = tid; i < vecs; i += kSortAccThreads) {
+    unsigned int add = 0;                         // byte-wise sums mod 256 of the other slices' partial images
+#pragma unroll
+    for (int sl = 0; sl < kSortSlices - 1; ++sl) {
+      const unsigned int b = __ldcg(partial + ((size_t)sl * kSortBins + cls) * vecs + i);
+      add = ((add & 0x00ff00ffu) + (b & 0x00ff00ffu)) & 0x00ff00ffu | ((add & 0xff00ff00u) + (b & 0xff00ff00u)) & 0xff00ff00u;
+    }
+    const uint4 a = reinterpret_cast<const uint4*>(sort_acc)[i];
+    const unsigned int v[4] = {a.x + (add & 0xffu), a.y + ((add >> 8) & 0xffu), a.z + ((add >> 16) & 0xffu), a.w + (add >> 24)};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                 // counters 4i + 2h, 4i + 2h + 1: pixel 2i + h of this class (pos, neg)
+      const long long px = (long long)(2 * i + h) * kSortBins + cls;
+      if (px < npix) hyb_store_px(out, px, C, v[2 * h] & 0xffu, v[2 * h + 1] & 0xffu);
+    }
+  }
+  if (cls == 0) {
+    int any = 0;
+    for (int c = tid; c < nchunks; c += kSortAccThreads) any |= bad_chunk[c];
+    any = __syncthreads_or(any);
+    if (tid == 0) hdr->oob = any ? 1 : 0;
+  }
+}
+
 // ---------------------------------------------------------------- raw record formats
 // The reference turns raw recordings into float64 [N,4] .npy files with byte-by-byte Python loops
 // (process_data/process_dataset.py): N-Caltech101 40-bit big-endian records (:47-60) and N-Cars / Prophesee
@@ -1406,6 +1670,16 @@ static int repl_count() {
   return k;
 }
 
+static bool auto_large_is_sort() {
+  static const bool v = [] {
+    const char* e = getenv("MEMB_HIST_AUTO_LARGE");
+    return e != nullptr && e[0] == 's';
+  }();
+  return v;
+}
+
+constexpr int kSortGridSms = 148;   // the SORT chunking is laid out for a B200 (the workspace size must not depend on a device query)
+
 struct Plan {
   int strategy;
   int replicas;
@@ -1415,6 +1689,9 @@ struct Plan {
   // HYBRID: slot map [granules] u16, slot -> granule list [tile_granules] u16, HybState, CTA slices
   int granules, tile_granules;
   size_t off_map, off_sel, off_state, off_slices;
+  // SORT: class boundaries [kSortBins + 1][nchunks] u16, one out-of-range flag per chunk, sorted keys [nchunks][kSortChunk] u16
+  int nchunks, chunk_len, local_words;
+  size_t off_offs, off_bad, off_flags, off_partial, off_keys;
 };
 
 constexpr long long kHybMinEvents = 1LL << 20;   // below this the three-launch GLOBAL chain is as fast and needs no sampling
@@ -1432,7 +1709,11 @@ static Plan make_plan(int B, int64_t n, int H, int W, int timesurface, int strat
     if (B == 1 && npix <= kTileMaxWords && n >= (1 << 18)) strategy = MEMB_HIST_PRIVATE;
     // one long stream on a larger sensor: privatise the hot granules, RED the rest
     if (B == 1 && npix > kTileMaxWords && n >= kHybMinEvents && hyb_granules(npix) <= kHybMaxGranules) strategy = MEMB_HIST_HYBRID;
+    // (SORT -- events binned by pixel class first, no global atomics -- is correct but measured slower than HYBRID on every
+    // distribution, profiles/r02_hist_sort_attempt.txt; MEMB_HIST_AUTO_LARGE=sort selects it here: tuning only)
+    if (B == 1 && npix > kTileMaxWords && n >= kHybMinEvents && npix <= kSortMaxPixels && auto_large_is_sort()) strategy = MEMB_HIST_SORT;
   }
+  if (strategy == MEMB_HIST_SORT && (B != 1 || timesurface || npix > kSortMaxPixels || n < 1)) strategy = MEMB_HIST_GLOBAL;
   if (strategy == MEMB_HIST_HYBRID && (B != 1 || timesurface || hyb_granules(npix) > kHybMaxGranules || n < kHybSamples))
     strategy = MEMB_HIST_GLOBAL;
   if (strategy == MEMB_HIST_PRIVATE && (B != 1 || npix > kTileMaxWords)) strategy = MEMB_HIST_GLOBAL;
@@ -1460,6 +1741,20 @@ static Plan make_plan(int B, int64_t n, int H, int W, int timesurface, int strat
     p.off_state = round_up<size_t>(p.off_sel + (size_t)p.tile_granules * 2, 16);
     p.off_slices = p.off_state + sizeof(HybState);
     p.ws_bytes = round_up<size_t>(p.off_slices + (size_t)kPrivMaxCtas * p.tile_granules * kHybGranule * 2, 16);
+  }
+  if (strategy == MEMB_HIST_SORT) {
+    // equal chunks: every CTA of the partition grid (two per SM) gets the same number of chunks of the same length
+    const long long grid = 2LL * kSortGridSms;
+    const long long rounds = std::max<long long>(1, ceil_div<long long>(n, grid * kSortCap));
+    p.chunk_len = (int)std::min<long long>(kSortCap, round_up<long long>(ceil_div<long long>(std::max<long long>(n, 1), grid * rounds), 16));
+    p.nchunks = (int)ceil_div<long long>(std::max<long long>(n, 1), p.chunk_len);
+    p.local_words = sort_local_words(npix);
+    p.off_offs = kHeaderBytes;
+    p.off_bad = round_up<size_t>(p.off_offs + (size_t)(kSortBins + 1) * p.nchunks * 2, 16);
+    p.off_flags = round_up<size_t>(p.off_bad + (size_t)p.nchunks, 16);
+    p.off_partial = round_up<size_t>(p.off_flags + (size_t)kSortBins * (kSortSlices - 1) * 4, 16);
+    p.off_keys = round_up<size_t>(p.off_partial + (size_t)(kSortSlices - 1) * kSortBins * p.local_words, 16);
+    p.ws_bytes = round_up<size_t>(p.off_keys + (size_t)p.nchunks * kSortCap * 2, 16);
   }
   return p;
 }
@@ -1574,6 +1869,33 @@ static int run_hybrid(const double* ev, long long n, int W, int H, int C, const 
   return MEMB_OK;
 }
 
+// SORT strategy: partition (counting sort of 16-bit keys per 8192-event chunk) -> accumulate (one CTA per pixel class), chained
+// as a programmatic dependent launch; nothing in the workspace needs initialising.
+template <bool kAligned>
+static int run_sort(const double* ev, long long n, int W, int H, int C, const Plan& p, char* wsb, uint8_t* out, memb_stream_t stream) {
+  const long long npix = (long long)H * W;
+  Header* hdr = reinterpret_cast<Header*>(wsb);
+  unsigned short* offs = reinterpret_cast<unsigned short*>(wsb + p.off_offs);
+  unsigned char* bad = reinterpret_cast<unsigned char*>(wsb + p.off_bad);
+  unsigned short* keys = reinterpret_cast<unsigned short*>(wsb + p.off_keys);
+  unsigned int* flags = reinterpret_cast<unsigned int*>(wsb + p.off_flags);
+  unsigned int* partial = reinterpret_cast<unsigned int*>(wsb + p.off_partial);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MEMB_CUDA_OK(cudaFuncSetAttribute(hist_sort_partition<kAligned>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemBytes));
+    MEMB_CUDA_OK(cudaFuncSetAttribute(hist_sort_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    attr_set = true;
+  }
+  const int ctas = std::max(1, std::min(2 * kSortGridSms, p.nchunks));
+  hist_sort_partition<kAligned><<<ctas, kSortThreads, kSortSmemBytes, stream>>>(ev, n, W, H, npix, p.nchunks, p.chunk_len, keys, offs, bad, flags);
+  MEMB_LAUNCH_OK("hist_sort_partition");
+  MEMB_CUDA_OK(launch_pdl_smem(hist_sort_accumulate, dim3(kSortBins * kSortSlices), dim3(kSortAccThreads), (size_t)p.local_words * 4, stream,
+                               (const unsigned short*)keys, (const unsigned short*)offs, (const unsigned char*)bad, p.nchunks,
+                               p.local_words, npix, C, (long long)n, partial, flags, out, hdr));
+  MEMB_LAUNCH_OK("hist_sort_accumulate");
+  return MEMB_OK;
+}
+
 static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, int64_t max_stream_len,
                     const memb_event_aug* aug, int H, int W, int C, int timesurface, int strategy,
                     uint8_t* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
@@ -1584,7 +1906,7 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
   MEMB_REQUIRE(offsets != nullptr || B == 1, "hist: a batch needs row offsets");
   MEMB_REQUIRE(out != nullptr && ws != nullptr, "hist: null output / workspace");
   MEMB_REQUIRE((((uintptr_t)ev) & 7u) == 0 && (((uintptr_t)ws) & 15u) == 0, "hist: misaligned pointer");
-  MEMB_REQUIRE(strategy >= MEMB_HIST_AUTO && strategy <= MEMB_HIST_HYBRID, "hist: unknown strategy %d", strategy);
+  MEMB_REQUIRE(strategy >= MEMB_HIST_AUTO && strategy <= MEMB_HIST_SORT, "hist: unknown strategy %d", strategy);
   const long long npix = (long long)H * W;
   const Plan p = make_plan(B, n, H, W, timesurface, strategy);
   if (ws_bytes < p.ws_bytes)
@@ -1604,6 +1926,8 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
     const int force = strategy == MEMB_HIST_HYBRID ? 1 : -1;      // AUTO lets the sample decide
     return aligned ? run_hybrid<true>(ev, n, W, H, C, p, force, wsb, out, stream) : run_hybrid<false>(ev, n, W, H, C, p, force, wsb, out, stream);
   }
+  if (p.strategy == MEMB_HIST_SORT && aug == nullptr && n > 0)
+    return aligned ? run_sort<true>(ev, n, W, H, C, p, wsb, out, stream) : run_sort<false>(ev, n, W, H, C, p, wsb, out, stream);
   const bool use_private = n > 0 && p.strategy == MEMB_HIST_PRIVATE && aug == nullptr && !timesurface;
   if (!use_private) {  // zero the header (+ accumulators) and seed the min/max keys
     const long long n_vec = (long long)((p.strategy == MEMB_HIST_TILE ? (size_t)kHeaderBytes : p.ws_bytes) / 16);

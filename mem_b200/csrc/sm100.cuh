@@ -154,8 +154,13 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster WITHOUT release semantics: `.release.cluster` compiles to
+// MEMBAR.ALL.GPU + ERRBAR, which parks the warp until every global store it has in flight is acknowledged (measured:
+// 12-14 % of the warp samples of the conv / GEMM epilogues, profiles/r02_ncu_conv_l1_src_top.txt).  The callers hand
+// TMEM accumulator stages back to the MMA warp: the reads are complete (tcgen05.wait::ld) and ordered before the arrive by
+// tcgen05.fence::before_thread_sync; no memory written by this thread is consumed by the waiter.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -141,14 +141,17 @@ class DiscreteVAE(nn.Module):
 
 
 def _out_layout(kind, C, OH, OW):
-    """(sB, sy_major, sy_minor, sx_major, sx_minor, pad, shift, slots shape) of a conv output written for its consumer."""
+    """(sB, sy_major, sy_minor, sx_major, sx_minor, pad, shift, slots shape per image, closing rows) of a conv output
+    written for its consumer."""
     if kind == "s2d":      # next: 4x4/s2/p1 conv -> space-to-depth(2) of the zero-padded map, slot inner = (dy, dx, c)
         h2, w2 = OH // 2 + 1, OW // 2 + 1
         return dict(sB=h2 * w2 * 4 * C, sy_major=w2 * 4 * C, sy_minor=2 * C, sx_major=4 * C, sx_minor=C, pad=1, shift=1,
-                    slots=(h2, w2, 4 * C))
+                    slots=(h2, w2, 4 * C), tail_rows=0)
     if kind == "pad":      # next: 3x3/p1 conv (or a 1x1 conv reading at tap offset (1,1))
-        return dict(sB=(OH + 2) * (OW + 2) * C, sy_major=(OW + 2) * C, sy_minor=0, sx_major=C, sx_minor=0, pad=1, shift=0,
-                    slots=(OH + 2, OW + 2, C))
+        # consecutive images share a zero row: the row under image b is the row above image b+1 (OH+1 rows per image
+        # and one closing row), so a 14-row map costs 15 virtual output rows per image instead of 16
+        return dict(sB=(OH + 1) * (OW + 2) * C, sy_major=(OW + 2) * C, sy_minor=0, sx_major=C, sx_minor=0, pad=1, shift=0,
+                    slots=(OH + 1, OW + 2, C), tail_rows=1)
     raise ValueError(kind)
 
 
@@ -327,7 +330,8 @@ class _Tokenizer:
     # ---- one convolution ------------------------------------------------------------------------
     def _conv(self, lib, a, geom, w, bias, B, OH, OW, relu, out_kind, out_name, device, aux=None, full=None, keys=None,
               layer=None, calibrating=False, alg_k=None):
-        """a = (hi, lo, exp) tensors [B*rows_per_img, x_slots, inner]; geom = (taps_y, taps_x, tap_y0, tap_x0).
+        """a = (hi, lo, exp, rows_per_img) tensors [B*rows_per_img (+ closing row), x_slots, inner]; geom = (taps_y, taps_x,
+        tap_y0, tap_x0).
         out_kind: slot layout of the hi/lo result for its consumer, or None (only ``full`` / ``keys`` outputs)."""
         w, w_exp = w
         Cout = w.shape[0]
@@ -337,14 +341,14 @@ class _Tokenizer:
             lay = _out_layout(out_kind, Cout, OH, OW)
             sh = lay["slots"]
             dt = torch.float16 if self.f16 else torch.float32
-            hi = self._buf(out_name + "_hi", (B * sh[0], sh[1], sh[2]), device, dt)
-            lo = self._buf(out_name + "_lo", (B * sh[0], sh[1], sh[2]), device, dt)
-            d.d_hi, d.d_lo, out = hi.data_ptr(), lo.data_ptr(), (hi, lo)
+            hi = self._buf(out_name + "_hi", (B * sh[0] + lay["tail_rows"], sh[1], sh[2]), device, dt)
+            lo = self._buf(out_name + "_lo", (B * sh[0] + lay["tail_rows"], sh[1], sh[2]), device, dt)
+            d.d_hi, d.d_lo, out, out_rpi = hi.data_ptr(), lo.data_ptr(), (hi, lo), sh[0]
             d.sB, d.sy_major, d.sy_minor, d.sx_major, d.sx_minor = lay["sB"], lay["sy_major"], lay["sy_minor"], lay["sx_major"], lay["sx_minor"]
             d.pad, d.shift = lay["pad"], lay["shift"]
         d.a_hi, d.a_lo = a[0].data_ptr(), a[1].data_ptr()
         d.r_slots, d.x_slots, d.inner = a[0].shape
-        d.rows_per_img = a[0].shape[0] // B
+        d.rows_per_img = a[3]
         d.taps_y, d.taps_x, d.tap_y0, d.tap_x0 = geom
         d.w, d.bias = w.data_ptr(), bias.data_ptr()
         assert w.shape[1] == 2 * geom[0] * geom[1] * d.inner, "weight K does not match the activation layout"
@@ -355,7 +359,7 @@ class _Tokenizer:
         sp = _lib.stream_ptr(torch, device)
         if not self.f16:
             _lib.check(lib.memb_conv_tf32x3(ctypes.byref(d), sp))
-            return None if out is None else out + (0,)
+            return None if out is None else out + (0, out_rpi)
         d.a_exp, d.w_exp = a[2], w_exp
         d.absmax = self._absmax_ptr(layer)
 
@@ -380,7 +384,7 @@ class _Tokenizer:
             launch(0)
             return None
         e = self._layer(layer, launch, calibrating)
-        return out + (e,)
+        return out + (e, out_rpi)
 
     def run(self, images, want_logits):
         _lib.require_cuda()
@@ -445,7 +449,7 @@ class _Tokenizer:
             return "s2d" if stage + 1 < L else "pad"
 
         x_full = self._buf(tag + "x_full", (B * (H >> L) * (W >> L), Hd), device) if R > 0 else None
-        cur = self._conv(lib, (a_hi, a_lo, e_in), (1, 1, 0, 0), self.w[0], self.b[0], B, OH, OW, True, consumer(0), tag + "act0",
+        cur = self._conv(lib, (a_hi, a_lo, e_in, OH), (1, 1, 0, 0), self.w[0], self.b[0], B, OH, OW, True, consumer(0), tag + "act0",
                          device, full=x_full if (L == 1 and R > 0) else None, layer="act0", alg_k=16 * C, **cal)
         for i in range(1, L):
             OH, OW = OH // 2, OW // 2

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 from oracle.histogram_ref import event_hist_batched_ref, event_hist_ref
 from oracle.make_golden import synth_events
 
-STRATS = [0, 1, 2, 3, 4, 5, 6]  # auto, global RED, + warp aggregation, smem tile, per-SM private copy, replicated planes, hybrid
+STRATS = [0, 1, 2, 3, 4, 5, 6, 7]  # auto, global RED, + warp aggregation, smem tile, per-SM private copy, replicated planes, hybrid, sort
 
 
 def _golden(golden_dir):
@@ -87,10 +87,11 @@ def test_full_size_10M_events_properties():
 
 
 @pytest.mark.parametrize("H,W", [(480, 640), (720, 1280), (333, 517)])
-def test_hybrid_strategy_large_sensors(H, W):
-    """HYBRID (hot granules privatised in shared memory, the rest through L2 REDs) on sensors that do not fit one SM:
-    every distribution, > 65535 hits on one pixel (mod-256 folds of the private copy), negative-wrap rows, and AUTO
-    picking it for a long stream."""
+def test_hybrid_and_sort_strategies_large_sensors(H, W):
+    """HYBRID (hot granules privatised in shared memory, the rest through L2 REDs) and SORT (events binned by pixel class,
+    shared-memory counters only) on sensors that do not fit one SM: every distribution, > 65535 hits on one pixel (mod-256
+    folds of the private copy / a class far above its share), negative-wrap rows, and AUTO picking one of them for a
+    long stream."""
     import torch
     from mem_b200.process_data import histogram
     rng = np.random.default_rng(H * 7 + W)
@@ -105,14 +106,36 @@ def test_hybrid_strategy_large_sensors(H, W):
             rng.shuffle(ev)
         want = event_hist_ref(ev, H, W)
         d = torch.from_numpy(ev).cuda()
-        for s in (6, 0):
+        for s in (6, 7, 0):
             for C in (3, 2):
                 got = histogram(d, H, W, channels=C, strategy=s).cpu().numpy()
                 assert np.array_equal(got, want if C == 3 else want[..., 0::2]), (kind, s, C, int((got != (want if C == 3 else want[..., 0::2])).sum()))
     bad = synth_events(rng, 1_100_000, H, W)
     bad[777_777, 1] = H
-    with pytest.raises(IndexError):
-        histogram(torch.from_numpy(bad).cuda(), H, W, strategy=6)
+    for s in (6, 7):
+        with pytest.raises(IndexError):
+            histogram(torch.from_numpy(bad).cuda(), H, W, strategy=s)
+
+
+def test_sort_strategy_edges_of_its_layout():
+    """SORT: a stream that ends inside a chunk / exactly on a chunk boundary, rows whose polarity is neither +1 nor -1
+    (skipped, N-Cars 0/1 convention), an 8-byte-aligned (not 32-byte-aligned) view, a sensor whose pixel count is not a
+    multiple of the 8-pixel granule, every event on one pixel (one class holds the whole stream)."""
+    import torch
+    from mem_b200.process_data import histogram
+    rng = np.random.default_rng(11)
+    H, W = 301, 533                                   # 160433 pixels: last granule partial
+    for n in (8192, 8193, 3 * 8192, 100_001):
+        ev = synth_events(rng, n + 1, H, W, "edge", frac=True)
+        ev[::7, 3] = 0.0
+        want = event_hist_ref(ev[1:], H, W)
+        d = torch.from_numpy(ev).cuda()[1:]           # rows start 32 bytes into the allocation: still aligned
+        assert np.array_equal(histogram(d, H, W, strategy=7).cpu().numpy(), want), n
+        flat = torch.from_numpy(np.concatenate([[0.0], ev[1:].ravel()])).cuda()[1:].view(-1, 4)   # 8-byte aligned only
+        assert np.array_equal(histogram(flat, H, W, strategy=7).cpu().numpy(), want), n
+    one = np.zeros((700_000, 4))
+    one[:, 0], one[:, 1], one[:, 3] = 532.0, 300.0, np.where(np.arange(700_000) % 3 == 0, -1.0, 1.0)
+    assert np.array_equal(histogram(torch.from_numpy(one).cuda(), H, W, strategy=7).cpu().numpy(), event_hist_ref(one, H, W))
 
 
 def test_ragged_batch_training_shape():

@@ -1,4 +1,6 @@
-"""Run the tokenizer on 64 images a few times (for ncu: per-layer conv launch list / --set full of one launch)."""
+"""Run the tokenizer on N images a few times (for ncu: per-layer conv launch list / --set full of one launch).
+The last pass sits between cudaProfilerStart/Stop: with `ncu --profile-from-start off`, launch k of that pass is
+im2col (0), act0..act3 (1-4), res blocks (5-13), head (14), argmax_decode (15)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,6 +10,10 @@ cfg = dict(input_H=224, input_W=224, num_tokens=8192, codebook_dim=32, num_layer
 torch.manual_seed(0)
 vae = DiscreteVAE(**cfg).cuda()
 img = dvae_ref.synth_images(int(sys.argv[1]) if len(sys.argv) > 1 else 64, 2, 224, 224, seed=6).cuda()
-for _ in range(3):
+for _ in range(2):
     vae.get_codebook_indices(img)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()
+vae.get_codebook_indices(img)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
