@@ -33,6 +33,15 @@ def _unwrap(model):
     return model.module if hasattr(model, "module") else model
 
 
+def _bucket_policy(flat):
+    """MEMB_DP_BUCKET: minimum elements per overlapped bucket; "all" = one all-reduce after backward (tuning)."""
+    import os
+    v = os.environ.get("MEMB_DP_BUCKET")
+    if not v:
+        return {}
+    return {"min_bucket_elems": flat.numel if v == "all" else int(float(v))}
+
+
 def _reducer_for(core):
     """One GradReducer per model (rebuilt if the process group or the flat buffer changes).
 
@@ -44,7 +53,7 @@ def _reducer_for(core):
     flat = engine_of(core).flat()
     red = getattr(core, "_memb_reducer", None)
     if red is None or red.grad is not flat.grad:
-        red = GradReducer(flat.grad, bucket_ranges(flat, len(core.blocks)))
+        red = GradReducer(flat.grad, bucket_ranges(flat, len(core.blocks), **_bucket_policy(flat)))
         red.sync_parameters(flat)
         object.__setattr__(core, "_memb_reducer", red)
     return red

@@ -43,6 +43,11 @@ def test_bucket_ranges_cover_flat_buffer_in_backward_order():
         assert a <= o < b, n
     merged = bucket_ranges(flat, 4, min_bucket_elems=10 ** 9)
     assert len(merged) == 1 and merged[0] == ("embed", 0, flat.numel)
+    # merging stops before the end of backward: the last two blocks fire alone and "embed" carries only the embedding
+    blk = by_tag[3][1] - by_tag[3][0]
+    tail = bucket_ranges(flat, 4, min_bucket_elems=3 * blk)
+    assert [t for t, _, _ in tail] == [2, 1, 0, "embed"]
+    assert tail[0][1] == 0 and tail[-1][1:] == by_tag["embed"] and tail[1][1:] == by_tag[1] and tail[2][1:] == by_tag[0]
 
 
 def test_shard_indices_matches_distributed_sampler():
@@ -68,12 +73,21 @@ def _worker(rank, world, port, out):
         g = torch.Generator().manual_seed(100 + rank)
         flat.grad.copy_(torch.randn(flat.numel, generator=g))
         mine = flat.grad.clone()
-        red = GradReducer(flat.grad, bucket_ranges(flat, 2, min_bucket_elems=1))
+        red = GradReducer(flat.grad, bucket_ranges(flat, 2, min_bucket_elems=1), wire_dtype=torch.float32)
         for tag in ("head", 1, 0, "embed"):       # the order VitEngine.backward_pretrain fires them
             red.hook(tag)
         red.finish()
         other = torch.randn(flat.numel, generator=torch.Generator().manual_seed(100 + (1 - rank)))
         ok = torch.allclose(flat.grad, mine + other, atol=1e-6) and red.launched == 4
+        # bf16 wire (the default): each rank's slice is rounded to bf16, summed in bf16, written back as fp32
+        flat.grad.copy_(mine)
+        red16 = GradReducer(flat.grad, bucket_ranges(flat, 2, min_bucket_elems=1))
+        assert red16.wire_dtype == torch.bfloat16
+        for tag in ("head", 1, 0, "embed"):
+            red16.hook(tag)
+        red16.finish()
+        want16 = (mine.bfloat16() + other.bfloat16()).float()
+        ok = ok and torch.equal(flat.grad, want16) and red16.launched == 4
         # fused meter all-reduce
         ml = utils.MetricLogger()
         ml.update(loss=1.0 + rank, mlm_acc=0.5 * rank)

@@ -56,14 +56,23 @@ utils.get_world_size = lambda: 1
 with contextlib.redirect_stdout(io.StringIO()):
     s_1 = engine_for_pretraining.train_one_epoch(m_1, vae1, [((img, img, mask), None)], o_1, dev, 0, scaler, 1.0)
 utils.get_world_size = real
-worst = 0.0
+worst, off, total = 0.0, 0, 0
 for (n, a), (_, b) in zip(m_dp.state_dict().items(), m_1.state_dict().items()):
     if a.is_floating_point():
-        worst = max(worst, (a - b).abs().max().item())
+        d = (a - b).abs()
+        worst = max(worst, d.max().item())
+        off += int((d > 2e-4).sum())
+        total += d.numel()
 red = m_dp._memb_reducer
-ok = worst < 2e-4 and abs(s_dp["grad_norm"] - s_1["grad_norm"]) < 2e-2 * s_1["grad_norm"] and abs(s_dp["loss"] - s_1["loss"]) < 1e-3
-print(f"[rank {rank}] dp loss {s_dp['loss']:.5f} vs single {s_1['loss']:.5f}; grad_norm {s_dp['grad_norm']:.4f} vs {s_1['grad_norm']:.4f}; "
-      f"max weight diff after 1 step {worst:.2e}; buckets launched {red.launched}; {'OK' if ok else 'MISMATCH'}", flush=True)
+wire = str(red.wire_dtype).replace("torch.", "")
+# fp32 wire: every weight agrees.  bf16 wire: each rank's gradient is rounded before the sum, so an element whose per-rank
+# gradients nearly cancel can change sign, and the first AdamW step moves it by lr the other way (2 * lr apart): such elements
+# must stay a small fraction, the global statistics must agree.
+weights_ok = worst < 2e-4 if red.wire_dtype == torch.float32 else (off <= 2e-3 * total and worst <= 2.5e-3)
+ok = weights_ok and abs(s_dp["grad_norm"] - s_1["grad_norm"]) < 2e-2 * s_1["grad_norm"] and abs(s_dp["loss"] - s_1["loss"]) < 1e-3
+print(f"[rank {rank}] wire {wire}; dp loss {s_dp['loss']:.5f} vs single {s_1['loss']:.5f}; grad_norm {s_dp['grad_norm']:.4f} vs {s_1['grad_norm']:.4f}; "
+      f"max weight diff after 1 step {worst:.2e}, {off} of {total} elements beyond 2e-4; buckets launched {red.launched}; "
+      f"{'OK' if ok else 'MISMATCH'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
