@@ -322,6 +322,14 @@ int memb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const fl
 int memb_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
                        const float* mean, const float* rstd, int rows, int D, float* dx, int64_t lddx, float* dgamma,
                        float* dbeta, const int32_t* row_index, const int32_t* count, memb_stream_t stream);
+/* memb_layernorm_bwd (without row_index / count) followed, on the updated dx row while it is still in registers, by
+ * memb_branch_bwd of the NEXT sub-block of the backward pass with gout = dx (see below): one launch and one read of the
+ * fp32 residual gradient less per sub-block.  4 * 8 * D floats of shared memory per block: D <= 896. */
+int memb_layernorm_bwd_branch(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
+                              const float* mean, const float* rstd, int rows, int D, float* dx, int64_t lddx,
+                              float* dgamma, float* dbeta, const void* branch, int64_t ldb, const float* colscale,
+                              const float* rowscale, int rows_per_group, void* dz, int64_t lddz, float* dcolscale,
+                              float* dbias, memb_stream_t stream);
 /* Backward of x_out = x_in + rowscale[row/g]*colscale[n]*branch (modeling_finetune.py:187-188):
  * dz(bf16) = rowscale*colscale*gout; dcolscale += sum rowscale*gout*branch; dbias += sum dz. */
 int memb_branch_bwd(const float* gout, int64_t ldg, const void* branch, int64_t ldb, const float* colscale,

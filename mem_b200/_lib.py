@@ -66,6 +66,8 @@ SIGNATURES["memb_gemm"] = (_i32, [_c.POINTER(GemmDesc), _vp])
 SIGNATURES.update({
     "memb_layernorm_fwd": (_i32, [_vp, _i64, _vp, _vp, _f32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "memb_layernorm_bwd": (_i32, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "memb_layernorm_bwd_branch": (_i32, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp,
+                                         _vp, _i64, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp]),
     "memb_branch_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "memb_colsum_bf16": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "memb_patchify": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -118,7 +118,17 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd(const float* __rest
 // The column sums live in per-warp shared-memory rows (plain read-modify-write, a lane owns its columns), not in
 // registers: 48 fewer registers per thread lets two blocks share an SM, which is what this HBM-bound kernel needs
 // (16 warps x ~4.5 KB of loads in flight instead of 8).
-template <typename DyT, int CH>
+// kBranch: the branch backward of the NEXT sub-block (see branch_bwd below) runs on the freshly updated residual gradient
+// row while it is still in registers -- dz = rowscale*colscale*dx (bf16), dcolscale += sum rowscale*dx*branch, dbias += sum dz
+// -- which saves that kernel's read of the fp32 gradient (77 MB per sub-block at ViT-B/16, batch 128) and its launch.
+struct BranchArgs {
+  const bf16* branch; long long ldb;
+  const float* colscale; const float* rowscale; int rows_per_group;
+  bf16* dz; long long lddz;
+  float* dcolscale; float* dbias;
+};
+
+template <typename DyT, int CH, bool kBranch>
 __global__ void __launch_bounds__(kRowThreads, 2) layernorm_bwd(const DyT* __restrict__ dy, long long lddy,
                                                                 const float* __restrict__ x, long long ldx,
                                                                 const float* __restrict__ gamma,
@@ -127,17 +137,23 @@ __global__ void __launch_bounds__(kRowThreads, 2) layernorm_bwd(const DyT* __res
                                                                 float* __restrict__ dx, long long lddx,
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                 const int* __restrict__ row_index,
-                                                                const int* __restrict__ count) {
-  extern __shared__ float smem[];                 // [2][kRowWarps][D]: dgamma partials, dbeta partials
+                                                                const int* __restrict__ count, const BranchArgs br) {
+  extern __shared__ float smem[];                 // [2 (+2)][kRowWarps][D]: dgamma, dbeta (, dcolscale, dbias) partials
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int live = count ? min(rows, *count) : rows;
   float* sg = smem + (size_t)warp * D;
   float* sb = smem + (size_t)(kRowWarps + warp) * D;
+  float* sc = smem + (size_t)(2 * kRowWarps + warp) * D;
+  float* sz = smem + (size_t)(3 * kRowWarps + warp) * D;
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     const int col = (c * 32 + lane) * 4;
     st4(sg + col, make_float4(0.f, 0.f, 0.f, 0.f));
     st4(sb + col, make_float4(0.f, 0.f, 0.f, 0.f));
+    if constexpr (kBranch) {
+      st4(sc + col, make_float4(0.f, 0.f, 0.f, 0.f));
+      st4(sz + col, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
   }
 
   for (int r = blockIdx.x * kRowWarps + warp; r < live; r += gridDim.x * kRowWarps) {
@@ -177,17 +193,44 @@ __global__ void __launch_bounds__(kRowThreads, 2) layernorm_bwd(const DyT* __res
       o[c].w += rs * (dg[c].w - s1 - xh[c].w * s2);
       st4(dxr + col, o[c]);
     }
+    if constexpr (kBranch) {
+      const float brs = br.rowscale ? br.rowscale[r / br.rows_per_group] : 1.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int col = (c * 32 + lane) * 4;
+        const float4 cs = br.colscale ? ld4(br.colscale + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 z = make_float4(brs * cs.x * o[c].x, brs * cs.y * o[c].y, brs * cs.z * o[c].z, brs * cs.w * o[c].w);
+        st4_bf16(br.dz + (long long)r * br.lddz + col, z);
+        if (br.dcolscale) {
+          const float4 b = ld4_bf16(br.branch + (long long)r * br.ldb + col);
+          float4 a = ld4(sc + col);
+          a.x += brs * o[c].x * b.x; a.y += brs * o[c].y * b.y; a.z += brs * o[c].z * b.z; a.w += brs * o[c].w * b.w;
+          st4(sc + col, a);
+        }
+        float4 zb = ld4(sz + col);
+        zb.x += z.x; zb.y += z.y; zb.z += z.z; zb.w += z.w;
+        st4(sz + col, zb);
+      }
+    }
   }
   __syncthreads();
   for (int col = threadIdx.x; col < D; col += kRowThreads) {
-    float g = 0.f, b = 0.f;
+    float g = 0.f, b = 0.f, cs = 0.f, z = 0.f;
 #pragma unroll
     for (int w = 0; w < kRowWarps; ++w) {
       g += smem[(size_t)w * D + col];
       b += smem[(size_t)(kRowWarps + w) * D + col];
+      if constexpr (kBranch) {
+        cs += smem[(size_t)(2 * kRowWarps + w) * D + col];
+        z += smem[(size_t)(3 * kRowWarps + w) * D + col];
+      }
     }
     if (dgamma) atomicAdd(dgamma + col, g);
     if (dbeta) atomicAdd(dbeta + col, b);
+    if constexpr (kBranch) {
+      if (br.dcolscale) atomicAdd(br.dcolscale + col, cs);
+      if (br.dbias) atomicAdd(br.dbias + col, z);
+    }
   }
 }
 
@@ -768,21 +811,48 @@ extern "C" int memb_layernorm_fwd(const float* x, int64_t ldx, const float* gamm
   return MEMB_OK;
 }
 
+static int layernorm_bwd_launch(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx,
+                                const float* gamma, const float* mean, const float* rstd, int rows, int D, float* dx,
+                                int64_t lddx, float* dgamma, float* dbeta, const int32_t* row_index,
+                                const int32_t* count, const BranchArgs* br, memb_stream_t s) {
+  MEMB_REQ_D(D);
+  MEMB_REQUIRE(dy && x && gamma && mean && rstd && dx && rows > 0, "layernorm_bwd: bad arguments");
+  const size_t smem = (size_t)(br ? 4 : 2) * kRowWarps * D * sizeof(float);
+  MEMB_REQUIRE(smem <= 113 * 1024, "layernorm_bwd: D = %d needs %zu B of shared memory per block", D, smem);
+  const int grid = std::max(1, std::min(ceil_div(rows, kRowWarps), num_sms() * 2));   // persistent: 2 blocks per SM
+  const BranchArgs none{};
+#define MEMB_LN_BWD(T, BR)                                                                                              \
+  MEMB_CH_DISPATCH(D, (cudaFuncSetAttribute(layernorm_bwd<T, CH, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
+                       layernorm_bwd<T, CH, BR><<<grid, kRowThreads, smem, s>>>((const T*)dy, lddy, x, ldx, gamma, mean, rstd, rows, D, dx, \
+                                                                                lddx, dgamma, dbeta, row_index, count, br ? *br : none)))
+  if (dy_dtype == MEMB_DT_BF16) {
+    if (br) { MEMB_LN_BWD(bf16, true); } else { MEMB_LN_BWD(bf16, false); }
+  } else {
+    if (br) { MEMB_LN_BWD(float, true); } else { MEMB_LN_BWD(float, false); }
+  }
+#undef MEMB_LN_BWD
+  MEMB_LAUNCH_OK("layernorm_bwd");
+  return MEMB_OK;
+}
+
 extern "C" int memb_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx,
                                   const float* gamma, const float* mean, const float* rstd, int rows, int D, float* dx,
                                   int64_t lddx, float* dgamma, float* dbeta, const int32_t* row_index,
                                   const int32_t* count, memb_stream_t s) {
-  MEMB_REQ_D(D);
-  MEMB_REQUIRE(dy && x && gamma && mean && rstd && dx && rows > 0, "layernorm_bwd: bad arguments");
-  const size_t smem = (size_t)2 * kRowWarps * D * sizeof(float);
-  const int grid = std::max(1, std::min(ceil_div(rows, kRowWarps), num_sms() * 2));   // persistent: 2 blocks per SM
-  if (dy_dtype == MEMB_DT_BF16) {
-    MEMB_CH_DISPATCH(D, (cudaFuncSetAttribute(layernorm_bwd<bf16, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), layernorm_bwd<bf16, CH><<<grid, kRowThreads, smem, s>>>((const bf16*)dy, lddy, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dgamma, dbeta, row_index, count)));
-  } else {
-    MEMB_CH_DISPATCH(D, (cudaFuncSetAttribute(layernorm_bwd<float, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), layernorm_bwd<float, CH><<<grid, kRowThreads, smem, s>>>((const float*)dy, lddy, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dgamma, dbeta, row_index, count)));
-  }
-  MEMB_LAUNCH_OK("layernorm_bwd");
-  return MEMB_OK;
+  return layernorm_bwd_launch(dy, dy_dtype, lddy, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dgamma, dbeta, row_index, count,
+                              nullptr, s);
+}
+
+extern "C" int memb_layernorm_bwd_branch(const void* dy, int dy_dtype, int64_t lddy, const float* x, int64_t ldx,
+                                         const float* gamma, const float* mean, const float* rstd, int rows, int D, float* dx,
+                                         int64_t lddx, float* dgamma, float* dbeta, const void* branch, int64_t ldb,
+                                         const float* colscale, const float* rowscale, int rows_per_group, void* dz,
+                                         int64_t lddz, float* dcolscale, float* dbias, memb_stream_t s) {
+  MEMB_REQUIRE(dz && (!dcolscale || branch), "layernorm_bwd_branch: bad arguments");
+  MEMB_REQUIRE(!rowscale || rows_per_group > 0, "layernorm_bwd_branch: rows_per_group must be positive");
+  const BranchArgs br{(const bf16*)branch, ldb, colscale, rowscale, rows_per_group, (bf16*)dz, lddz, dcolscale, dbias};
+  return layernorm_bwd_launch(dy, dy_dtype, lddy, x, ldx, gamma, mean, rstd, rows, D, dx, lddx, dgamma, dbeta, nullptr, nullptr,
+                              &br, s);
 }
 
 extern "C" int memb_branch_bwd(const float* gout, int64_t ldg, const void* branch, int64_t ldb, const float* colscale,

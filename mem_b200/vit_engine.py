@@ -449,24 +449,47 @@ class VitEngine:
         if shared:
             _lib.check(lib.memb_fill_f32(dbias_acc.data_ptr(), dbias_acc.numel(), 0.0, sp))
         scale = m.blocks[0].attn.scale
+        # The branch backward (LayerScale x DropPath, bias gradient) of a sub-block runs inside the LayerNorm backward that
+        # precedes it in the backward pass (memb_layernorm_bwd_branch) whenever four column accumulators fit the block's
+        # shared memory; only the first one of the pass (last block, MLP branch) is a launch of its own.
+        fuse = 4 * 8 * D * 4 <= 113 * 1024
+
+        def branch_args(j, which):
+            """(branch, colscale, rowscale, dcolscale, dbias) of block j's MLP (2) / attention (1) branch."""
+            b, sj, pj = m.blocks[j], ctx["blocks"][j], f"blocks.{j}."
+            gamma = b.gamma_2 if which == 2 else b.gamma_1
+            bias = flat.g(pj + ("mlp.fc2.bias" if which == 2 else "attn.proj.bias"))
+            return (sj[f"br{which}"], gamma, sj[f"s{which}"], flat.g(pj + f"gamma_{which}") if gamma is not None else None, bias)
+
+        def branch_bwd(j, which):
+            br, cs, rs, dcs, db = branch_args(j, which)
+            _lib.check(lib.memb_branch_bwd(gres.data_ptr(), D, ops._ptr(br), D, ops._ptr(cs), ops._ptr(rs), N, M, D, dz.data_ptr(), D,
+                                           ops._ptr(dcs), db.data_ptr(), sp))
+
+        def ln_bwd_then_branch(dy, x, norm, mean, rstd, dw, db_, j, which):
+            if not fuse or j < 0:
+                _ln_bwd(lib, dy, x, norm.weight, mean, rstd, M, D, gres, dw, db_)
+                if j >= 0:
+                    branch_bwd(j, which)
+                return
+            br, cs, rs, dcs, db = branch_args(j, which)
+            _lib.check(lib.memb_layernorm_bwd_branch(dy.data_ptr(), DT_BF16 if dy.dtype == torch.bfloat16 else DT_F32, dy.stride(0),
+                                                     x.data_ptr(), x.stride(0), norm.weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                     M, D, gres.data_ptr(), gres.stride(0), ops._ptr(dw), ops._ptr(db_), ops._ptr(br), D,
+                                                     ops._ptr(cs), ops._ptr(rs), N, dz.data_ptr(), D, ops._ptr(dcs), db.data_ptr(), sp))
+
+        branch_bwd(len(m.blocks) - 1, 2)
         for i in reversed(range(len(m.blocks))):
             blk, s, pre = m.blocks[i], ctx["blocks"][i], f"blocks.{i}."
             G = lambda n: flat.g(pre + n)  # noqa: E731
-            has_ls = blk.gamma_1 is not None
-            # ---- MLP branch
-            _lib.check(lib.memb_branch_bwd(gres.data_ptr(), D, ops._ptr(s["br2"]), D, ops._ptr(blk.gamma_2), ops._ptr(s["s2"]), N,
-                                           M, D, dz.data_ptr(), D, G("gamma_2").data_ptr() if has_ls else None,
-                                           G("mlp.fc2.bias").data_ptr(), sp))
+            # ---- MLP branch (dz = its branch backward, produced by the previous LayerNorm backward)
             ops.gemm(dz, s["act"], out=G("mlp.fc2.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD)
             ops.gemm(dz, flat.w16(pre + "mlp.fc2.weight"), out=dh, b_layout=1, epilogue=EPI_DGELU, aux=s["fpre"])
             _lib.check(lib.memb_colsum_bf16(dh.data_ptr(), hidden, M, hidden, G("mlp.fc1.bias").data_ptr(), sp))
             ops.gemm(dh, s["ln2"], out=G("mlp.fc1.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD)
             ops.gemm(dh, flat.w16(pre + "mlp.fc1.weight"), out=dln, b_layout=1)
-            _ln_bwd(lib, dln, s["xmid"], blk.norm2.weight, s["mu2"], s["rs2"], M, D, gres, G("norm2.weight"), G("norm2.bias"))
-            # ---- attention branch
-            _lib.check(lib.memb_branch_bwd(gres.data_ptr(), D, ops._ptr(s["br1"]), D, ops._ptr(blk.gamma_1), ops._ptr(s["s1"]), N,
-                                           M, D, dz.data_ptr(), D, G("gamma_1").data_ptr() if has_ls else None,
-                                           G("attn.proj.bias").data_ptr(), sp))
+            # ---- attention branch (its branch backward rides on the LayerNorm backward of norm2)
+            ln_bwd_then_branch(dln, s["xmid"], blk.norm2, s["mu2"], s["rs2"], G("norm2.weight"), G("norm2.bias"), i, 1)
             ops.gemm(dz, s["ao"], out=G("attn.proj.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD)
             ops.gemm(dz, flat.w16(pre + "attn.proj.weight"), out=dao, b_layout=1)
             bias_pair = s["bias"]
@@ -487,7 +510,8 @@ class VitEngine:
                 _lib.check(lib.memb_colsum_bf16(dqkv.data_ptr() + 2 * D * 2, 3 * D, M, D, G("attn.v_bias").data_ptr(), sp))
             ops.gemm(dqkv, s["ln1"], out=G("attn.qkv.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD)
             ops.gemm(dqkv, flat.w16(pre + "attn.qkv.weight"), out=dln, b_layout=1)
-            _ln_bwd(lib, dln, s["xin"], blk.norm1.weight, s["mu1"], s["rs1"], M, D, gres, G("norm1.weight"), G("norm1.bias"))
+            # block i - 1's MLP branch backward rides on the LayerNorm backward of norm1 (its gradients belong to the next bucket)
+            ln_bwd_then_branch(dln, s["xin"], blk.norm1, s["mu1"], s["rs1"], G("norm1.weight"), G("norm1.bias"), i - 1, 2)
             if bucket_hook:
                 bucket_hook(i)
         if shared:

@@ -183,6 +183,47 @@ def test_relpos_gather_scatter(L):
     torch.testing.assert_close(dtable, tr.grad, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("D,with_ls,with_dp", [(768, True, True), (128, True, False), (384, False, True)])
+def test_layernorm_bwd_branch_equals_the_two_launches(L, D, with_ls, with_dp):
+    """memb_layernorm_bwd_branch == memb_layernorm_bwd followed by memb_branch_bwd on the updated residual gradient
+    (same dx bit for bit; dz from the same fp32 row; column sums up to summation order)."""
+    torch.manual_seed(9)
+    B, N = 5, 197
+    rows = B * N
+    x = torch.randn(rows, D, device="cuda") * 1.5
+    w = torch.randn(D, device="cuda") * 0.2 + 1
+    mean = x.mean(1).contiguous(); rstd = (x.var(1, unbiased=False) + 1e-6).rsqrt().contiguous()
+    dy = torch.randn(rows, D, device="cuda").bfloat16()
+    g0 = torch.randn(rows, D, device="cuda")
+    branch = torch.randn(rows, D, device="cuda").bfloat16()
+    gamma = (torch.randn(D, device="cuda") * 0.1) if with_ls else None
+    rs = torch.tensor([0.0, 1.25, 1.25, 0.0, 1.25], device="cuda") if with_dp else None
+    p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+
+    def run(fused):
+        dx = g0.clone()
+        dw = torch.zeros(D, device="cuda"); db = torch.zeros(D, device="cuda")
+        dz = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+        dgam = torch.zeros(D, device="cuda") if with_ls else None
+        dbias = torch.zeros(D, device="cuda")
+        if fused:
+            ck(L.memb_layernorm_bwd_branch(dy.data_ptr(), 0, D, x.data_ptr(), D, w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, D,
+                                           dx.data_ptr(), D, dw.data_ptr(), db.data_ptr(), branch.data_ptr(), D, p(gamma), p(rs), N,
+                                           dz.data_ptr(), D, p(dgam), dbias.data_ptr(), sp()))
+        else:
+            ck(L.memb_layernorm_bwd(dy.data_ptr(), 0, D, x.data_ptr(), D, w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, D,
+                                    dx.data_ptr(), D, dw.data_ptr(), db.data_ptr(), None, None, sp()))
+            ck(L.memb_branch_bwd(dx.data_ptr(), D, branch.data_ptr(), D, p(gamma), p(rs), N, rows, D, dz.data_ptr(), D, p(dgam),
+                                 dbias.data_ptr(), sp()))
+        return dx, dw, db, dz, dgam, dbias
+
+    a, b = run(True), run(False)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3])
+    for u, v in zip(a[1:3] + a[4:], b[1:3] + b[4:]):
+        if u is not None:
+            assert rel_err(u, v) < 1e-5
+
+
 def test_branch_bwd_colsum_patchify_embed(L):
     torch.manual_seed(4)
     B, N, D = 3, 50, 128
