@@ -18,7 +18,7 @@ rng = np.random.default_rng(3)
 for kind in ("uniform", "edge"):
     ev = synth_events(rng, 1_100_000, 480, 640, kind)
     want = event_hist_ref(ev, 480, 640)
-    for s in (0, 5, 6):
+    for s in (0, 5, 6, 7):
         assert np.array_equal(histogram(torch.from_numpy(ev).cuda(), 480, 640, strategy=s).cpu().numpy(), want), (kind, s)
 print("hybrid / replicated strategies ok")
 PY
