@@ -157,6 +157,34 @@ int memb_event_pipeline_var_f32(const double* ev, int64_t n, const int64_t* offs
                                 int canvas_H, int canvas_W, int outH, int outW, int C, float hot_num_stds, int normalize,
                                 float* out, void* ws, size_t ws_bytes, memb_stream_t stream);
 
+/* EventRandAugment on uint8 [pos, 0, neg] images (mem/transforms.py:351-471, applied between ToUnit8 and ToFloat32 at the
+ * end of build_transformNPY when args.rand_aug is set, mem/datasets.py:655-658).  The HOST draws each sample's operations
+ * in the reference's generator order (three torch.randint calls per operation) and describes them with one record per
+ * (sample, operation); the kernel applies them in order, one CTA per sample with the image in shared memory
+ * (3 * H * W <= 200 KB).  Arithmetic follows torchvision's tensor code path operation by operation: the photometric
+ * operations are bit-exact with the reference, the bilinear resampling of the geometric ones up to the summation order
+ * of its affine-grid GEMM (a few pixels per image can differ by one count). */
+#define MEMB_RA_IDENTITY 0
+#define MEMB_RA_AFFINE 1        /* ShearX, ShearY, TranslateX, TranslateY, Rotate: theta = torchvision's inverse matrix      */
+#define MEMB_RA_BRIGHTNESS 2    /* f0 = float32(ratio), f1 = float32(1 - ratio), ratio = 1 + magnitude (also 3, 4, 5)      */
+#define MEMB_RA_COLOR 3
+#define MEMB_RA_CONTRAST 4
+#define MEMB_RA_SHARPNESS 5
+#define MEMB_RA_POSTERIZE 6     /* ival = bits                                                                             */
+#define MEMB_RA_SOLARIZE 7      /* f0 = threshold                                                                          */
+#define MEMB_RA_AUTOCONTRAST 8
+#define MEMB_RA_EQUALIZE 9
+typedef struct memb_randaug_op {  /* 40 bytes, device memory, [B][num_ops] */
+  int32_t op;
+  int32_t ival;
+  float f0, f1;
+  float theta[6];
+} memb_randaug_op;
+/* in  : uint8 [B,3,H,W], or float32 [B,3,H,W] converted like ToUnit8 ((255 * x).to(uint8)) when in_f32 != 0.
+ * out : uint8 [B,3,H,W], or float32 converted like ToFloat32 (x / 255) when out_f32 != 0; may alias `in`. */
+int memb_event_randaug(const void* in, int in_f32, int B, int C, int H, int W, const memb_randaug_op* ops, int num_ops,
+                       void* out, int out_f32, memb_stream_t stream);
+
 size_t memb_raster_post_workspace_bytes(int B);
 int memb_raster_post_f32(const uint8_t* hist, int B, int H, int W, int C, const int32_t* crop_tl, int pad_t,
                          int pad_l, int outH, int outW, int remove_ts, float hot_num_stds, int normalize,

@@ -15,8 +15,11 @@ The branch WITHOUT a fixed sensor (``H = W = None``: N-Caltech101 / N-Cars, size
 anti-aliased ``Resize`` to the input size) is ``VarPipelineConfig`` / ``draw_params_var`` / ``pipeline_var_fused`` /
 ``EventBatchPipelineVar`` below (one kernel, ``memb_event_pipeline_var_f32``).
 
+``rand_aug`` (the reference scripts' default) appends ``ToUnit8 -> EventRandAugment(magnitude=20) -> ToFloat32`` as one more
+launch over the batch (``mem_b200/transforms.py``, ``csrc/randaug.cu``), with each sample's operations drawn right after its
+other draws so the torch generator is consumed in the reference's order.
 Not covered (raise / documented in DESIGN.md): the time surface together with augmentations, ``LogTransform`` /
-``GammaTransform``, ``ColorJitter`` and ``EventRandAugment``.
+``GammaTransform`` (off by default in the reference's scripts).
 """
 from __future__ import annotations
 
@@ -63,6 +66,7 @@ class PipelineConfig:
     hotpixfilter: bool = True
     hotpix_num_stds: float = 10
     normalize_events: bool = False
+    rand_aug: bool = False          # args.rand_aug (the reference's scripts default to 1): EventRandAugment(magnitude=20) when training
 
     def __post_init__(self):
         # the reference's own range checks (datasets.py:466-469, 491, 530)
@@ -88,6 +92,37 @@ class PipelineConfig:
         return self._raster
 
 
+_RANDAUG = None
+
+
+def _draw_randaug(cfg) -> list:
+    """The sample's EventRandAugment operations (mem/datasets.py:655-658: ``EventRandAugment(small=False, magnitude=20)``),
+    drawn from the global torch generator right after the sample's other draws -- the order the reference's per-sample
+    transform chain consumes it in."""
+    global _RANDAUG
+    if _RANDAUG is None:
+        import contextlib
+        import io
+        from .transforms import EventRandAugment
+        with contextlib.redirect_stdout(io.StringIO()):
+            _RANDAUG = EventRandAugment(small=False, magnitude=20)
+    return _RANDAUG.draw(cfg.input_H, cfg.input_W)
+
+
+def _apply_randaug(out, params, cfg, channels):
+    """ToUnit8 -> EventRandAugment -> ToFloat32 on the pipeline's float32 batch, one launch (mem/datasets.py:655-658)."""
+    if not (cfg.is_train and cfg.rand_aug):
+        return out
+    if channels != 3:
+        raise ValueError("EventRandAugment needs the 3-channel [pos, 0, neg] image (torchvision's colour operations)")
+    from .transforms import OP_DTYPE, apply_ops, encode_op
+    ops = np.zeros((len(params), max(len(p["randaug"]) for p in params)), dtype=OP_DTYPE)
+    for b, p in enumerate(params):
+        for k, (name, mag) in enumerate(p["randaug"]):
+            ops[b, k] = encode_op(name, mag)
+    return apply_ops(out, ops, out_float=True)
+
+
 def draw_params(n_events: int, cfg: PipelineConfig) -> dict:
     """One sample's random draws, consuming the global generators in the reference's order:
     ``random.choice`` (slice start, only when the stream is longer than ``slice_max_evs``, datasets.py:495-496),
@@ -111,6 +146,8 @@ def draw_params(n_events: int, cfg: PipelineConfig) -> dict:
         if not (ph == cfg.input_H and pw == cfg.input_W):
             p["top"] = int(torch.randint(0, ph - cfg.input_H + 1, size=(1,)).item())
             p["left"] = int(torch.randint(0, pw - cfg.input_W + 1, size=(1,)).item())
+        if cfg.rand_aug:
+            p["randaug"] = _draw_randaug(cfg)
     return p
 
 
@@ -293,15 +330,17 @@ class EventBatchPipeline:
         H, W = cfg.raster_hw()
         hot = cfg.hotpix_num_stds if cfg.hotpixfilter else None
         if self.fused:
-            return pipeline_fused(events, offsets, aug, crop if cfg.is_train else None, H, W,
-                                  (cfg.input_H, cfg.input_W) if cfg.is_train else (H, W), self.channels,
-                                  hot_num_stds=hot, normalize=cfg.normalize_events, check=not cfg.is_train)
+            out = pipeline_fused(events, offsets, aug, crop if cfg.is_train else None, H, W,
+                                 (cfg.input_H, cfg.input_W) if cfg.is_train else (H, W), self.channels,
+                                 hot_num_stds=hot, normalize=cfg.normalize_events, check=not cfg.is_train)
+            return _apply_randaug(out, params, cfg, self.channels)
         hist = rasterise_augmented(events, offsets, aug, H, W, self.channels,
                                    max_stream_len=int(max(p["count"] for p in params)) if params else 0,
                                    check=not cfg.is_train)   # after the cull every row is inside the sensor
-        return post_raster(hist, crop if cfg.is_train else None, (cfg.input_H, cfg.input_W) if cfg.is_train else None,
-                           remove_timesurface=not cfg.timesurface,
-                           hot_num_stds=cfg.hotpix_num_stds if cfg.hotpixfilter else None, normalize=cfg.normalize_events)
+        out = post_raster(hist, crop if cfg.is_train else None, (cfg.input_H, cfg.input_W) if cfg.is_train else None,
+                          remove_timesurface=not cfg.timesurface,
+                          hot_num_stds=cfg.hotpix_num_stds if cfg.hotpixfilter else None, normalize=cfg.normalize_events)
+        return _apply_randaug(out, params, cfg, self.channels)
 
 
 # ------------------------------------------------------------------------- variable sensor size (N-Caltech101 / N-Cars)
@@ -320,6 +359,7 @@ class VarPipelineConfig:
     hotpixfilter: bool = True
     hotpix_num_stds: float = 10
     normalize_events: bool = False
+    rand_aug: bool = False
 
     def __post_init__(self):
         assert 5000 <= self.slice_max_evs < 200000 and 0 <= self.max_random_shift_evs <= 200     # datasets.py:491, :530
@@ -340,6 +380,8 @@ def draw_params_var(n_events: int, cfg: VarPipelineConfig) -> dict:
         p["flip_x"] = bool(np.random.random() < 0.5)
         xs, ys = np.random.randint(-cfg.max_random_shift_evs, cfg.max_random_shift_evs + 1, size=(2,))
         p["shift_x"], p["shift_y"], p["cull"] = int(xs), int(ys), True
+        if cfg.rand_aug:
+            p["randaug"] = _draw_randaug(cfg)
     return p
 
 
@@ -399,6 +441,7 @@ class EventBatchPipelineVar:
         if params is None:
             params = [draw_params_var(int(n), cfg) for n in lens]
         aug, _ = pack_params(params)
-        return pipeline_var_fused(events, offsets, aug, (cfg.canvas_H, cfg.canvas_W), (cfg.input_H, cfg.input_W), self.channels,
-                                  hot_num_stds=cfg.hotpix_num_stds if cfg.hotpixfilter else None,
-                                  normalize=cfg.normalize_events, check=check)
+        out = pipeline_var_fused(events, offsets, aug, (cfg.canvas_H, cfg.canvas_W), (cfg.input_H, cfg.input_W), self.channels,
+                                 hot_num_stds=cfg.hotpix_num_stds if cfg.hotpixfilter else None,
+                                 normalize=cfg.normalize_events, check=check)
+        return _apply_randaug(out, params, cfg, self.channels)

@@ -43,6 +43,7 @@ class PipelineCfg:
     hotpixfilter: bool = True
     hotpix_num_stds: float = 10
     normalize_events: bool = False
+    rand_aug: bool = False                                     # args.rand_aug: datasets.py:655-658
 
     def scales(self):
         if self.is_train:                                      # datasets.py:472-478
@@ -77,7 +78,22 @@ def draw_params(n_events: int, cfg: PipelineCfg) -> dict:
         if not (ph == cfg.input_H and pw == cfg.input_W):
             p["top"] = int(torch.randint(0, ph - cfg.input_H + 1, size=(1,)).item())
             p["left"] = int(torch.randint(0, pw - cfg.input_W + 1, size=(1,)).item())
+        if cfg.rand_aug:
+            p["randaug"] = _draw_randaug(cfg)
     return p
+
+
+def _draw_randaug(cfg):
+    """EventRandAugment(small=False, magnitude=20)'s draws (datasets.py:657), after the sample's other draws."""
+    from . import randaug_ref
+    return randaug_ref.draw_ops(lambda n: int(torch.randint(n, (1,)).item()), randaug_ref.OPS, 2, 20, 31, cfg.input_H, cfg.input_W)
+
+
+def _apply_randaug(x: torch.Tensor, p: dict) -> torch.Tensor:
+    """ToUnit8 -> EventRandAugment -> ToFloat32 (datasets.py:655-658) on the chain's float32 [3, h, w] output."""
+    from . import randaug_ref
+    u8 = randaug_ref.rand_augment(randaug_ref.to_uint8(x.numpy()), p["randaug"])
+    return torch.from_numpy(randaug_ref.to_float32(u8))
 
 
 def apply_event_aug(events: np.ndarray, p: dict) -> np.ndarray:
@@ -128,7 +144,8 @@ def pipeline_ref(events: np.ndarray, cfg: PipelineCfg, params: dict | None = Non
     H, W = cfg.raster_hw()
     ev = apply_event_aug(events, p)
     hist = event_hist_ref(ev, H, W, cfg.timesurface) if len(ev) else np.zeros((H, W, 3), np.uint8)
-    return apply_post_raster(hist, p, cfg)
+    out = apply_post_raster(hist, p, cfg)
+    return _apply_randaug(out, p) if (cfg.is_train and cfg.rand_aug) else out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -145,6 +162,7 @@ class VarPipelineCfg:
     hotpixfilter: bool = True
     hotpix_num_stds: float = 10
     normalize_events: bool = False
+    rand_aug: bool = False
 
 
 def draw_params_var(n_events: int, cfg: VarPipelineCfg) -> dict:
@@ -160,6 +178,8 @@ def draw_params_var(n_events: int, cfg: VarPipelineCfg) -> dict:
         p["flip_x"] = bool(np.random.random() < 0.5)
         xs, ys = np.random.randint(-cfg.max_random_shift_evs, cfg.max_random_shift_evs + 1, size=(2,))
         p["shift_x"], p["shift_y"], p["cull"] = int(xs), int(ys), True
+        if cfg.rand_aug:
+            p["randaug"] = _draw_randaug(cfg)
     return p
 
 
@@ -202,4 +222,5 @@ def pipeline_var_ref(events: np.ndarray, cfg: VarPipelineCfg, params: dict | Non
     if cfg.normalize_events:
         if x[0::2, :, :].max() != 0:
             x[0::2, :, :] = x[0::2, :, :] * (1.0 / x[0::2, :, :].max())
-    return x.float()
+    x = x.float()
+    return _apply_randaug(x, p) if (cfg.is_train and cfg.rand_aug) else x

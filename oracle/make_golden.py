@@ -645,9 +645,114 @@ def golden_event_pipeline_var():
     np.savez_compressed(os.path.join(GOLD, "event_pipeline_var.npz"), **out)
 
 
+def synth_event_image(rng, H, W):
+    """uint8 [3, H, W] image shaped like the pipeline's output after ToUnit8: sparse polarity counts on a few edges plus
+    noise, an empty middle channel, a few saturated pixels."""
+    img = np.zeros((3, H, W), dtype=np.uint8)
+    for c in (0, 2):
+        n = H * W // 6
+        y, x = rng.integers(0, H, n), rng.integers(0, W, n)
+        np.add.at(img[c], (y, x), rng.integers(1, 40, n).astype(np.uint8))
+        for _ in range(5):
+            y0, x0 = rng.integers(0, H), rng.integers(0, W)
+            t = np.arange(0, min(H, W) // 2)
+            yy = np.clip(y0 + (t * rng.uniform(-1, 1)).astype(int), 0, H - 1)
+            xx = np.clip(x0 + (t * rng.uniform(-1, 1)).astype(int), 0, W - 1)
+            img[c, yy, xx] = rng.integers(80, 256, len(t)).astype(np.uint8)
+    return img
+
+
+def golden_randaug():
+    """The reference's EventRandAugment (mem/transforms.py:351-471) on torchvision (not vendored; the image's 0.26.0):
+    every operation of its augmentation space at several magnitude bins and both signs through ``_apply_op``, and the whole
+    module under fixed torch seeds (pins the order of its three draws per operation)."""
+    import contextlib, io
+    import torch
+    from torchvision.transforms import InterpolationMode
+    tr = ref_shims.ref_module("transforms")
+    from oracle import randaug_ref as R
+    out = {}
+    rng = np.random.default_rng(77)
+    imgs = {"a": synth_event_image(rng, 48, 64), "b": synth_event_image(rng, 224, 224)}
+    bins_of = {"a": (0, 3, 11, 20), "b": (7, 20)}
+    for k, v in imgs.items():
+        out[f"img_{k}"] = v
+    with contextlib.redirect_stdout(io.StringIO()):
+        aug = tr.EventRandAugment(small=False, magnitude=20)
+    cases = []
+    for key, img in imgs.items():
+        H, W = img.shape[1:]
+        space = aug._augmentation_space(aug.num_magnitude_bins, (H, W))
+        for name, (mags, signed) in space.items():
+            bins = bins_of[key] if mags.ndim > 0 else (0,)
+            for i0 in bins:
+                for neg in ((0, 1) if signed else (0,)):
+                    mag = float(mags[i0].item()) if mags.ndim > 0 else 0.0
+                    if signed and neg:
+                        mag *= -1.0
+                    res = tr._apply_op(torch.from_numpy(img.copy()), name, mag, interpolation=InterpolationMode.BILINEAR, fill=None)
+                    tag = f"op_{key}_{name}_{i0}_{neg}"
+                    out[tag] = res.numpy()
+                    out[tag + "_mag"] = np.array(mag, dtype=np.float64)
+                    cases.append(tag)
+    out["cases"] = np.array(cases)
+    for seed in range(12):
+        for key, img in imgs.items():
+            if key == "b" and seed >= 6:
+                continue
+            torch.manual_seed(1000 + seed)
+            out[f"full_{key}_{seed}"] = aug(torch.from_numpy(img.copy())).numpy()
+    # ToUnit8 / ToFloat32 around it (transforms.py:333-349) on a float image of counts / 255 and of counts / max
+    x = torch.from_numpy(imgs["a"].astype(np.float32) / np.float32(255))
+    out["tou8_in"], out["tou8_out"] = x.numpy(), tr.ToUnit8()(x.clone()).numpy()
+    out["tof32_out"] = tr.ToFloat32()(torch.from_numpy(imgs["a"].copy())).numpy()
+    y = x / x.max()
+    out["tou8n_in"], out["tou8n_out"] = y.numpy(), tr.ToUnit8()(y.clone()).numpy()
+    np.savez_compressed(os.path.join(GOLD, "randaug.npz"), **out)
+    print(f"randaug: {len(cases)} single-operation cases, 24 seeded runs of the module")
+
+
+def golden_event_pipeline_randaug():
+    """Reference build_transformNPY WITH its default ``rand_aug=1`` tail (ToUnit8 -> EventRandAugment(magnitude=20) ->
+    ToFloat32, mem/datasets.py:655-658) on the fixed-sensor and the variable-sensor branch: pins the order in which one
+    sample's crop and RandAugment draws consume the torch generator."""
+    import contextlib, io
+    import torch
+    from types import SimpleNamespace
+    ds = ref_shims.ref_module("datasets")
+    out = {}
+    cases = [  # name, data_path, (H, W), polarity, n_events, kind, normalize, seed
+        ("im_a", "/data/N_imagenet", (480, 640), (-1.0, 1.0), 45000, "edge", 1, 31),
+        ("im_b", "/data/N_imagenet", (480, 640), (-1.0, 1.0), 45000, "hot", 0, 32),
+        ("im_c", "/data/N_imagenet", (480, 640), (-1.0, 1.0), 20000, "uniform", 1, 33),
+        ("im_d", "/data/N_imagenet", (480, 640), (-1.0, 1.0), 45000, "edge", 0, 34),
+        ("cal_a", "/data/N-Caltech101", (180, 240), (-1.0, 1.0), 45000, "edge", 1, 35),
+        ("cars_a", "/data/ncars", (100, 120), (0.0, 1.0), 9000, "edge", 1, 36),
+    ]
+    for name, path, (H, W), pol, n, kind, norm, seed in cases:
+        args = SimpleNamespace(data_path=path, input_H=224, input_W=224, slice_max_evs=30000, max_random_shift_evs=15,
+                               timesurface=0, hotpixfilter=1, hotpix_num_stds=10, logtrafo=0, gammatrafo=0, gamma=0.5,
+                               normalize_events=norm, rand_aug=1)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tf = ds.build_transformNPY(True, args)
+        fixed = "imagenet" in path
+        ev = synth_events(np.random.default_rng(seed), n, H, W, kind, polarity=pol, frac=(fixed and kind == "edge"))
+        if not fixed:
+            ev = np.floor(ev)
+        random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+        res = tf(ev.copy())
+        out[name + "_out"] = (res.numpy() * 255).round().astype(np.uint8)        # ToFloat32 output is exactly k / 255
+        assert np.array_equal(out[name + "_out"].astype(np.float32) / np.float32(255), res.numpy())
+        out[name + "_meta"] = np.array([n, norm, seed, H, W, int(pol[0] == 0.0), int(fixed)], dtype=np.int64)
+        out[name + "_kind"] = np.array(kind)
+        print(f"event_pipeline_randaug {name}: nnz {int((res != 0).sum())} max {float(res.max()):.4f}")
+    np.savez_compressed(os.path.join(GOLD, "event_pipeline_randaug.npz"), **out)
+
+
 SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit, "dvae": golden_dvae,
             "engine": golden_engine, "event_pipeline": golden_event_pipeline, "decode": golden_decode, "engine_ft": golden_engine_ft,
-            "vit_bf16": golden_vit_bf16, "finetune_remap": golden_finetune_remap, "dvae_train": golden_dvae_train, "event_pipeline_var": golden_event_pipeline_var}
+            "vit_bf16": golden_vit_bf16, "finetune_remap": golden_finetune_remap, "dvae_train": golden_dvae_train, "event_pipeline_var": golden_event_pipeline_var, "randaug": golden_randaug,
+            "event_pipeline_randaug": golden_event_pipeline_randaug}
 
 
 def main(argv):
