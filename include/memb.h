@@ -365,6 +365,10 @@ int memb_branch_bwd(const float* gout, int64_t ldg, const void* branch, int64_t 
                     float* dbias, memb_stream_t stream);
 /* out[n] += sum over rows of x(bf16)[row, n]  (bias gradients). */
 int memb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float* out, memb_stream_t stream);
+/* v_bias gradient from the proj bias gradient of the same backward pass (softmax rows sum to one: colsum(dV) = colsum(dAO) =
+ * colsum(dZ) W_proj; Attention.forward, modeling_finetune.py:128-157): dv_bias[j] += sum_i t[i] * w_proj[i, j],
+ * dproj_bias[i] += t[i].  t: fp32 [D] (this pass's column sum of the proj output gradient), w_proj: fp32 [D, D] as stored. */
+int memb_vbias_chain(const float* t, const float* w_proj, int D, float* dproj_bias, float* dv_bias, memb_stream_t stream);
 /* img fp32 [B,C,H,W] -> bf16 [B*(H/P)*(W/P), C*P*P] in Conv2d weight order (PatchEmbed.proj, modeling_finetune.py:203,209). */
 int memb_patchify(const float* img, int B, int C, int H, int W, int P, void* out, memb_stream_t stream);
 /* x[b,0,:] = cls (+pos[0]); x[b,n,:] += pos[n] if pos (modeling_pretrain.py:101-112). */

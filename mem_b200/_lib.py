@@ -71,6 +71,7 @@ SIGNATURES.update({
                                          _vp, _i64, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp]),
     "memb_branch_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "memb_colsum_bf16": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "memb_vbias_chain": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "memb_patchify": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "memb_cls_pos": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "memb_embed_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -272,6 +272,25 @@ __global__ void __launch_bounds__(kRowThreads) branch_bwd(const float* __restric
   block_column_atomic<2, CH>(acc, D, dst, smem);
 }
 
+// v_bias gradient without a pass over dV.  The rows of a softmax sum to one, so  sum_keys dV[key, :] = sum_queries dAO[query, :]
+// (dV = P^T dAO), and dAO = dZ W_proj, so  colsum(dV) = colsum(dZ) W_proj  where colsum(dZ) is the proj bias gradient of
+// THIS backward pass (t, accumulated by the branch backward into a scratch vector): dv_bias[j] += sum_i t[i] W[i, j]  (W the
+// fp32 master weight [D, D], row i = output feature i), dproj_bias[i] += t[i].  Block (x, y): 256 columns j, rows i of slice y.
+constexpr int kChainSlices = 16;
+__global__ void __launch_bounds__(256) vbias_chain(const float* __restrict__ t, const float* __restrict__ W, int D,
+                                                   float* __restrict__ dproj_bias, float* __restrict__ dv_bias) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int per = (D + kChainSlices - 1) / kChainSlices;
+  const int i0 = blockIdx.y * per, i1 = min(D, i0 + per);
+  if (j < D) {
+    float acc = 0.f;
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) acc = fmaf(__ldg(t + i), __ldg(W + (long long)i * D + j), acc);
+    atomicAdd(dv_bias + j, acc);
+    if (blockIdx.y == 0) atomicAdd(dproj_bias + j, __ldg(t + j));
+  }
+}
+
 // out[n] += sum_rows x[row, n]   (bias gradients of fc1 / qkv); N % 8 == 0, rows 16-byte aligned.
 // Block = 32 column lanes (8 columns = one 16-byte load each) x 8 row phases; every thread keeps 8 independent loads
 // in flight, the 8 phases meet in shared memory and one atomic per column leaves the block.
@@ -876,6 +895,13 @@ extern "C" int memb_colsum_bf16(const void* x, int64_t ld, int rows, int N, floa
   const int rpb = ceil_div(rows, gy);
   colsum_bf16<<<dim3(gx, ceil_div(rows, rpb)), dim3(32, kColsumRows), 0, s>>>((const bf16*)x, ld, rows, N, rpb, out);
   MEMB_LAUNCH_OK("colsum_bf16");
+  return MEMB_OK;
+}
+
+extern "C" int memb_vbias_chain(const float* t, const float* w_proj, int D, float* dproj_bias, float* dv_bias, memb_stream_t s) {
+  MEMB_REQUIRE(t && w_proj && dproj_bias && dv_bias && D > 0, "vbias_chain: bad arguments");
+  vbias_chain<<<dim3(ceil_div(D, 256), kChainSlices), 256, 0, s>>>(t, w_proj, D, dproj_bias, dv_bias);
+  MEMB_LAUNCH_OK("vbias_chain");
   return MEMB_OK;
 }
 

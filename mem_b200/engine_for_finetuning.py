@@ -151,7 +151,16 @@ def _all_reduce_grads(core, optimizer):
     if utils.get_world_size() > 1:
         if not hasattr(optimizer, "grad_divisor"):
             raise RuntimeError("multi-GPU finetuning needs optim_factory.FlatAdamW (gradients are sum-reduced)")
-        torch.distributed.all_reduce(engine_of(core).flat().grad)
+        # one bucket after the last micro-batch's backward (accumulated gradients are only final then); same wire format
+        # as the pretraining loop (bf16 unless MEMB_DP_WIRE=fp32, parallel.default_wire_dtype)
+        flat = engine_of(core).flat()
+        red = getattr(core, "_memb_ft_reducer", None)
+        if red is None or red.grad is not flat.grad:
+            from .parallel import GradReducer
+            red = GradReducer(flat.grad, [("all", 0, flat.numel)])
+            object.__setattr__(core, "_memb_ft_reducer", red)
+        red.hook("all")
+        red.finish()
         optimizer.grad_divisor = float(utils.get_world_size())
 
 

@@ -454,11 +454,20 @@ class VitEngine:
         # shared memory; only the first one of the pass (last block, MLP branch) is a launch of its own.
         fuse = 4 * 8 * D * 4 <= 113 * 1024
 
+        # attention branch: the proj bias gradient of THIS pass goes to a scratch row first; memb_vbias_chain adds it to the
+        # parameter's gradient and turns it into the v_bias gradient (colsum(dV) = colsum(dZ) W_proj: no pass over dV)
+        pw = m.blocks[0].attn.proj.weight
+        chain = (m.blocks[0].attn.q_bias is not None and m.blocks[0].attn.proj.bias is not None and tuple(pw.shape) == (D, D)
+                 and pw.dtype == torch.float32)
+        pb_tmp = g("proj_bias_pass", (len(m.blocks), D), torch.float32, dev) if chain else None
+        if chain:
+            _lib.check(lib.memb_fill_f32(pb_tmp.data_ptr(), pb_tmp.numel(), 0.0, sp))
+
         def branch_args(j, which):
             """(branch, colscale, rowscale, dcolscale, dbias) of block j's MLP (2) / attention (1) branch."""
             b, sj, pj = m.blocks[j], ctx["blocks"][j], f"blocks.{j}."
             gamma = b.gamma_2 if which == 2 else b.gamma_1
-            bias = flat.g(pj + ("mlp.fc2.bias" if which == 2 else "attn.proj.bias"))
+            bias = flat.g(pj + "mlp.fc2.bias") if which == 2 else (pb_tmp[j] if chain else flat.g(pj + "attn.proj.bias"))
             return (sj[f"br{which}"], gamma, sj[f"s{which}"], flat.g(pj + f"gamma_{which}") if gamma is not None else None, bias)
 
         def branch_bwd(j, which):
@@ -507,7 +516,11 @@ class VitEngine:
                                                        N, H, G("attn.relative_position_bias_table").data_ptr(), sp))
             if blk.attn.q_bias is not None:
                 _lib.check(lib.memb_colsum_bf16(dqkv.data_ptr(), 3 * D, M, D, G("attn.q_bias").data_ptr(), sp))
-                _lib.check(lib.memb_colsum_bf16(dqkv.data_ptr() + 2 * D * 2, 3 * D, M, D, G("attn.v_bias").data_ptr(), sp))
+                if chain:
+                    _lib.check(lib.memb_vbias_chain(pb_tmp[i].data_ptr(), blk.attn.proj.weight.data_ptr(), D,
+                                                    G("attn.proj.bias").data_ptr(), G("attn.v_bias").data_ptr(), sp))
+                else:
+                    _lib.check(lib.memb_colsum_bf16(dqkv.data_ptr() + 2 * D * 2, 3 * D, M, D, G("attn.v_bias").data_ptr(), sp))
             ops.gemm(dqkv, s["ln1"], out=G("attn.qkv.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD)
             ops.gemm(dqkv, flat.w16(pre + "attn.qkv.weight"), out=dln, b_layout=1)
             # block i - 1's MLP branch backward rides on the LayerNorm backward of norm1 (its gradients belong to the next bucket)

@@ -130,7 +130,7 @@ def test_bad_arguments_fail_loudly():
     ops = np.zeros((1, 1), dtype=T.OP_DTYPE)
     with pytest.raises(AssertionError):
         T.apply_ops(torch.zeros(1, 2, 32, 32, dtype=torch.uint8, device="cuda"), ops)
-    with pytest.raises(RuntimeError):
+    with pytest.raises(ValueError):
         T.apply_ops(torch.zeros(1, 3, 300, 300, dtype=torch.uint8, device="cuda"), ops)       # 270 KB: no shared-memory tile
     with pytest.raises(ValueError):
         T.encode_op("Hue", 0.1)

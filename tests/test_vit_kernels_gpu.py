@@ -224,6 +224,24 @@ def test_layernorm_bwd_branch_equals_the_two_launches(L, D, with_ls, with_dp):
             assert rel_err(u, v) < 1e-5
 
 
+def test_vbias_chain_is_the_column_sum_of_dv(L):
+    """dv_bias = colsum(dZ) W_proj equals the column sum of dV = P^T dAO when the rows of P sum to one (what the engine
+    relies on instead of a pass over dV), and the kernel is that matrix-vector product."""
+    torch.manual_seed(12)
+    D = 768
+    t = torch.randn(D, device="cuda")
+    W = torch.randn(D, D, device="cuda") * 0.05
+    pb = torch.full((D,), 0.5, device="cuda"); vb = torch.full((D,), -0.25, device="cuda")
+    ck(L.memb_vbias_chain(t.data_ptr(), W.data_ptr(), D, pb.data_ptr(), vb.data_ptr(), sp()))
+    assert rel_err(pb - 0.5, t) < 1e-6
+    assert rel_err(vb + 0.25, (t.double() @ W.double()).float()) < 1e-5
+    # the identity itself, in float64: one head, softmax rows
+    N, d = 50, 64
+    P = torch.softmax(torch.randn(N, N, dtype=torch.float64), -1)
+    dAO = torch.randn(N, d, dtype=torch.float64)
+    assert torch.allclose((P.T @ dAO).sum(0), dAO.sum(0), atol=1e-10)
+
+
 def test_branch_bwd_colsum_patchify_embed(L):
     torch.manual_seed(4)
     B, N, D = 3, 50, 128
