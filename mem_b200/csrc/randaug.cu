@@ -67,13 +67,26 @@ __global__ void __launch_bounds__(kThreads, 1) event_randaug(const void* __restr
   Scratch* sc = reinterpret_cast<Scratch*>(ra_smem + ((CHW + 15) / 16) * 16);
   uint8_t* stash = static_cast<uint8_t*>(out) + (size_t)b * CHW * (out_f32 ? 4 : 1);   // this sample's slab of the output
 
-  // ---- load (ToUnit8: (255 * x).to(uint8))
+  // ---- load (ToUnit8: (255 * x).to(uint8)); four pixels per thread when the slab allows 16-byte / 4-byte accesses
+  const bool vec = (CHW & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
   if (in_f32) {
     const float* src = static_cast<const float*>(in) + (size_t)b * CHW;
-    for (int i = tid; i < CHW; i += kThreads) img[i] = to_u8_trunc(__fmul_rn(255.f, src[i]));
+    if (vec) {
+      for (int i = tid; i < CHW / 4; i += kThreads) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + i);
+        reinterpret_cast<uchar4*>(img)[i] = make_uchar4(to_u8_trunc(__fmul_rn(255.f, v.x)), to_u8_trunc(__fmul_rn(255.f, v.y)),
+                                                        to_u8_trunc(__fmul_rn(255.f, v.z)), to_u8_trunc(__fmul_rn(255.f, v.w)));
+      }
+    } else {
+      for (int i = tid; i < CHW; i += kThreads) img[i] = to_u8_trunc(__fmul_rn(255.f, src[i]));
+    }
   } else {
     const uint8_t* src = static_cast<const uint8_t*>(in) + (size_t)b * CHW;
-    for (int i = tid; i < CHW; i += kThreads) img[i] = src[i];
+    if (vec) {
+      for (int i = tid; i < CHW / 4; i += kThreads) reinterpret_cast<uchar4*>(img)[i] = reinterpret_cast<const uchar4*>(src)[i];
+    } else {
+      for (int i = tid; i < CHW; i += kThreads) img[i] = src[i];
+    }
   }
   __syncthreads();
 
@@ -216,17 +229,33 @@ __global__ void __launch_bounds__(kThreads, 1) event_randaug(const void* __restr
     }
     __syncthreads();
     if (gathered) {                                   // read the gathered image back from this sample's slab
-      for (int i = tid; i < CHW; i += kThreads) img[i] = stash[i];
+      if (vec) {
+        for (int i = tid; i < CHW / 4; i += kThreads) reinterpret_cast<uchar4*>(img)[i] = reinterpret_cast<const uchar4*>(stash)[i];
+      } else {
+        for (int i = tid; i < CHW; i += kThreads) img[i] = stash[i];
+      }
       __syncthreads();
     }
   }
   // ---- store (ToFloat32: x.to(float32) / 255)
   if (out_f32) {
     float* dst = static_cast<float*>(out) + (size_t)b * CHW;
-    for (int i = tid; i < CHW; i += kThreads) dst[i] = __fdiv_rn((float)img[i], 255.f);
+    if (vec) {
+      for (int i = tid; i < CHW / 4; i += kThreads) {
+        const uchar4 v = reinterpret_cast<const uchar4*>(img)[i];
+        __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(__fdiv_rn((float)v.x, 255.f), __fdiv_rn((float)v.y, 255.f),
+                                                               __fdiv_rn((float)v.z, 255.f), __fdiv_rn((float)v.w, 255.f)));
+      }
+    } else {
+      for (int i = tid; i < CHW; i += kThreads) dst[i] = __fdiv_rn((float)img[i], 255.f);
+    }
   } else {
     uint8_t* dst = static_cast<uint8_t*>(out) + (size_t)b * CHW;
-    for (int i = tid; i < CHW; i += kThreads) dst[i] = img[i];
+    if (vec) {
+      for (int i = tid; i < CHW / 4; i += kThreads) reinterpret_cast<uchar4*>(dst)[i] = reinterpret_cast<const uchar4*>(img)[i];
+    } else {
+      for (int i = tid; i < CHW; i += kThreads) dst[i] = img[i];
+    }
   }
 }
 
