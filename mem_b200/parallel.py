@@ -21,11 +21,13 @@ import torch
 import torch.distributed as dist
 
 
-def bucket_ranges(flat, depth, min_bucket_elems=8 << 20, tail_blocks=2):
+def bucket_ranges(flat, depth, min_bucket_elems=32 << 20, tail_blocks=2):
     """[(tag, start, end)] slices of the flat buffer that become final at each backward hook.
 
     Tags: "head", block index (depth-1 .. 0), "embed".  Adjacent slices are merged until a bucket holds at
-    least ``min_bucket_elems`` elements (launch latency, not link count, is what matters on NVSwitch) -- except at the
+    least ``min_bucket_elems`` elements (32 M by default: every NCCL kernel that runs under backward takes SMs from
+    one-CTA-per-SM persistent GEMMs, so few large collectives beat many small ones -- 8 GPUs, ViT segment: 8 M buckets
+    22.87 ms, 32 M 22.69 ms, one all-reduce after backward 22.49 ms, 21.2 ms on one GPU; profiles/r02_scale_n8_sweep.txt) -- except at the
     end of backward: the slices of the last ``tail_blocks`` blocks and of the embedding are never merged into their
     neighbours, because nothing is left to hide a late all-reduce behind: block 1 and block 0 each fire alone and the
     bucket that fires at "embed" is only the embedding's own parameters (0.4 M elements for ViT-B/16; a forward merge
