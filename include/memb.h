@@ -145,6 +145,16 @@ int memb_event_pipeline_f32(const double* ev, int64_t n, const int64_t* offsets,
                             float hot_num_stds, int normalize, float* out, void* ws, size_t ws_bytes,
                             memb_stream_t stream);
 
+/* memb_event_pipeline_f32 with a value table: count c of a surviving pixel is written as value_lut[c] instead of c / 255
+ * (device float32 [256], value_lut[0] must be 0).  This is how LogTransform / GammaTransform (mem/transforms.py:200-222,
+ * applied between RemoveHotPixels and NormalizeEvent, mem/datasets.py:647-652) ride on the fused kernel bit-exactly: the image
+ * holds 256 distinct values, so the host evaluates torch.log(x + 1) / x ** gamma on them once with the reference's own CPU
+ * routines; the hot-pixel statistics keep using c / 255, NormalizeEvent divides by the table value of the largest count. */
+int memb_event_pipeline_lut_f32(const double* ev, int64_t n, const int64_t* offsets, int B, const memb_event_aug* aug,
+                                const int32_t* crop_tl, int H, int W, int pad_t, int pad_l, int outH, int outW, int C,
+                                float hot_num_stds, int normalize, const float* value_lut, float* out, void* ws,
+                                size_t ws_bytes, memb_stream_t stream);
+
 /* The same chain for recordings WITHOUT a fixed sensor size (the N-Caltech101 / N-Cars branch of build_transformNPY,
  * H = W = None): flip width, cull window and raster size are inferred per stream from the rows (int(max) + 1 at the
  * stage where the reference infers them, datasets.py:513-515, :538-541, :571-575), the (H3 x W3) raster is resized to

@@ -398,11 +398,13 @@ template <bool kAligned>
 __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
     const double* __restrict__ ev, const long long* __restrict__ offsets, long long n_total,
     const memb_event_aug* __restrict__ aug, const int* __restrict__ crop_tl, int H, int W, int pad_t, int pad_l,
-    int outH, int outW, int C, float hot_num_stds, int normalize, float* __restrict__ out, Header* __restrict__ hdr) {
+    int outH, int outW, int C, float hot_num_stds, int normalize, const float* __restrict__ value_lut,
+    float* __restrict__ out, Header* __restrict__ hdr) {
   extern __shared__ unsigned int tile[];
   __shared__ unsigned long long red[2][kTileThreads / 32];   // per-warp partial sums (no 64-bit smem atomics)
   __shared__ unsigned int present[8];
-  __shared__ float lut[256];
+  __shared__ float lut[256];      // ToTensor value of count c (what the hot-pixel statistics see)
+  __shared__ float vlut[256];     // value written for count c: lut, or the caller's table (LogTransform / GammaTransform of lut)
   __shared__ int params[3];
   const int b = blockIdx.x;
   long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
@@ -428,7 +430,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
     if (r < end) nxt[u] = load_event<kAligned>(ev, r);
   }
   if (threadIdx.x < 8) present[threadIdx.x] = 0u;
-  if (threadIdx.x < 256) lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);   // ToTensor value of count c
+  if (threadIdx.x < 256) {
+    lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);   // ToTensor value of count c
+    vlut[threadIdx.x] = value_lut ? __ldg(value_lut + threadIdx.x) : lut[threadIdx.x];
+  }
   for (int i = threadIdx.x * 4; i < npx4; i += kTileThreads * 4) *reinterpret_cast<uint4*>(tile + i) = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
 
@@ -547,8 +552,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
         if (present[c >> 5] >> (c & 31) & 1u) m = c;
       params[0] = c_keep;
       params[1] = (normalize && m != 0) ? 1 : 0;
-      // factor = 1.0 / x.max(), x.max() = fl32(cmax / 255)   (transforms.py:234-236)
-      params[2] = __float_as_int((normalize && m != 0) ? __fdiv_rn(1.0f, lut[m]) : 1.0f);
+      // factor = 1.0 / x.max(), x.max() = fl32(cmax / 255) (transforms.py:234-236), or its transformed value (the
+      // transforms are monotone, and a zero maximum leaves the image alone like `if x.max() != 0`)
+      const bool on = normalize && m != 0 && vlut[m] != 0.0f;
+      params[1] = on ? 1 : 0;
+      params[2] = __float_as_int(on ? __fdiv_rn(1.0f, vlut[m]) : 1.0f);
     }
   }
   __syncthreads();
@@ -568,8 +576,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_fused(
       for (int k = 0; k < 4; ++k) {
         const int cp = (int)(w[k] & 0xffu), cn = (int)(w[k] >> 16);
         if (w[k] != 0u && cp <= c_keep && cn <= c_keep) {
-          vp[k] = lut[cp];
-          vn[k] = lut[cn];
+          vp[k] = vlut[cp];
+          vn[k] = vlut[cn];
           if (scale) {
             vp[k] = __fmul_rn(vp[k], factor);
             vn[k] = __fmul_rn(vn[k], factor);
@@ -2010,6 +2018,15 @@ extern "C" int memb_event_pipeline_f32(const double* ev, int64_t n, const int64_
                                        const memb_event_aug* aug, const int32_t* crop_tl, int H, int W, int pad_t,
                                        int pad_l, int outH, int outW, int C, float hot_num_stds, int normalize,
                                        float* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
+  return memb_event_pipeline_lut_f32(ev, n, offsets, B, aug, crop_tl, H, W, pad_t, pad_l, outH, outW, C, hot_num_stds, normalize,
+                                     nullptr, out, ws, ws_bytes, stream);
+}
+
+extern "C" int memb_event_pipeline_lut_f32(const double* ev, int64_t n, const int64_t* offsets, int B,
+                                           const memb_event_aug* aug, const int32_t* crop_tl, int H, int W, int pad_t,
+                                           int pad_l, int outH, int outW, int C, float hot_num_stds, int normalize,
+                                           const float* value_lut, float* out, void* ws, size_t ws_bytes,
+                                           memb_stream_t stream) {
   MEMB_REQUIRE(B >= 1 && H >= 1 && W >= 1 && outH >= 1 && outW >= 1, "event_pipeline: bad shape");
   MEMB_REQUIRE(C == 2 || C == 3, "event_pipeline: C must be 2 or 3, got %d", C);
   MEMB_REQUIRE((long long)outH * outW <= kTileMaxWords,
@@ -2032,7 +2049,7 @@ extern "C" int memb_event_pipeline_f32(const double* ev, int64_t n, const int64_
   }
   const size_t smem = (size_t)round_up<long long>((long long)outH * outW, 4) * 4;
   kern<<<B, kTileThreads, smem, stream>>>(ev, reinterpret_cast<const long long*>(offsets), n, aug, crop_tl, H, W, pad_t,
-                                          pad_l, outH, outW, C, hot_num_stds, normalize, out,
+                                          pad_l, outH, outW, C, hot_num_stds, normalize, value_lut, out,
                                           reinterpret_cast<Header*>(ws));
   MEMB_LAUNCH_OK("event_pipeline_fused");
   return MEMB_OK;

@@ -18,8 +18,10 @@ anti-aliased ``Resize`` to the input size) is ``VarPipelineConfig`` / ``draw_par
 ``rand_aug`` (the reference scripts' default) appends ``ToUnit8 -> EventRandAugment(magnitude=20) -> ToFloat32`` as one more
 launch over the batch (``mem_b200/transforms.py``, ``csrc/randaug.cu``), with each sample's operations drawn right after its
 other draws so the torch generator is consumed in the reference's order.
-Not covered (raise / documented in DESIGN.md): the time surface together with augmentations, ``LogTransform`` /
-``GammaTransform`` (off by default in the reference's scripts).
+``logtrafo`` / ``gammatrafo`` (``LogTransform`` / ``GammaTransform``, off in the reference's scripts) are a 256-entry value
+table evaluated on the host with the reference's own CPU routines (``value_table``) and applied inside the fused kernel.
+Not covered (raise / documented in DESIGN.md): the time surface together with augmentations; log / gamma on the
+variable-sensor branch (its resized image is not a function of 256 counts).
 """
 from __future__ import annotations
 
@@ -67,6 +69,9 @@ class PipelineConfig:
     hotpix_num_stds: float = 10
     normalize_events: bool = False
     rand_aug: bool = False          # args.rand_aug (the reference's scripts default to 1): EventRandAugment(magnitude=20) when training
+    logtrafo: bool = False          # LogTransform / GammaTransform (off in the reference's scripts); fused path only
+    gammatrafo: bool = False
+    gamma: float = 0.5
 
     def __post_init__(self):
         # the reference's own range checks (datasets.py:466-469, 491, 530)
@@ -205,8 +210,24 @@ def _aug_to_device(torch, aug, B, device):
     return aug_dev
 
 
+def value_table(logtrafo=False, gammatrafo=False, gamma=0.5):
+    """The 256 values an image can hold after ``LogTransform`` / ``GammaTransform`` (mem/transforms.py:200-222; applied in
+    this order between RemoveHotPixels and NormalizeEvent, mem/datasets.py:647-652), evaluated on ``c / 255`` with the
+    reference's own CPU routines (``torch.log``, ``Tensor.__pow__``) so that the device path reproduces them bit for bit.
+    None when neither transform is on."""
+    if not (logtrafo or gammatrafo):
+        return None
+    import torch
+    x = torch.arange(256, dtype=torch.uint8).to(torch.float32).div(255)        # ToTensor
+    if logtrafo:
+        x = torch.log(x + torch.ones(x.shape))
+    if gammatrafo:
+        x = x ** gamma
+    return x.float().contiguous()
+
+
 def pipeline_fused(events, offsets, aug, crop_tl, H, W, out_hw, channels=3, *, hot_num_stds=10.0, normalize=False,
-                   check=True, out=None):
+                   check=True, out=None, value_lut=None):
     """The whole chain in one kernel (``memb_event_pipeline_f32``): raw ragged batch -> ``float32 (B,C,outH,outW)``.
     Needs ``outH * outW <= FUSED_MAX_PIXELS``; arguments as ``rasterise_augmented`` + ``post_raster``.
     Inputs that already are contiguous CUDA tensors of the right dtype are used as they are (no copies)."""
@@ -219,7 +240,7 @@ def pipeline_fused(events, offsets, aug, crop_tl, H, W, out_hw, channels=3, *, h
     if device.index is not None and device.index != torch.cuda.current_device():
         with torch.cuda.device(device):
             return pipeline_fused(events, offsets, aug, crop_tl, H, W, out_hw, channels, hot_num_stds=hot_num_stds,
-                                  normalize=normalize, check=check, out=out)
+                                  normalize=normalize, check=check, out=out, value_lut=value_lut)
     if ready:
         ev = events
     else:
@@ -254,11 +275,16 @@ def pipeline_fused(events, offsets, aug, crop_tl, H, W, out_hw, channels=3, *, h
     ws = _lib.workspace.get(torch, 256, device, "hist")
     stream = _lib.stream_ptr(torch, device)
     n = ev.shape[0]
-    _lib.check(lib.memb_event_pipeline_f32(
+    lut = None
+    if value_lut is not None:      # LogTransform / GammaTransform: float32 [256] table of the values written per count
+        lut = value_lut.to(device=device, dtype=torch.float32).contiguous()
+        if lut.numel() != 256:
+            raise ValueError("value_lut must hold 256 float32 values")
+    _lib.check(lib.memb_event_pipeline_lut_f32(
         ev.data_ptr() if n else None, n, off.data_ptr(), B, aug_dev.data_ptr(),
         crop.data_ptr() if crop is not None else None, H, W, max(outH - H, 0), max(outW - W, 0), outH, outW, channels,
-        float(hot_num_stds) if hot_num_stds is not None else -1.0, int(bool(normalize)), out.data_ptr(),
-        ws.data_ptr(), ws.numel(), stream))
+        float(hot_num_stds) if hot_num_stds is not None else -1.0, int(bool(normalize)),
+        lut.data_ptr() if lut is not None else None, out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
     if check:
         _lib.check(lib.memb_hist_status(ws.data_ptr(), stream))
     return out
@@ -329,11 +355,14 @@ class EventBatchPipeline:
         aug, crop = pack_params(params)
         H, W = cfg.raster_hw()
         hot = cfg.hotpix_num_stds if cfg.hotpixfilter else None
+        lut = value_table(cfg.logtrafo, cfg.gammatrafo, cfg.gamma)
         if self.fused:
             out = pipeline_fused(events, offsets, aug, crop if cfg.is_train else None, H, W,
                                  (cfg.input_H, cfg.input_W) if cfg.is_train else (H, W), self.channels,
-                                 hot_num_stds=hot, normalize=cfg.normalize_events, check=not cfg.is_train)
+                                 hot_num_stds=hot, normalize=cfg.normalize_events, check=not cfg.is_train, value_lut=lut)
             return _apply_randaug(out, params, cfg, self.channels)
+        if lut is not None:
+            raise NotImplementedError("LogTransform / GammaTransform ride on the fused kernel only (output raster <= one tile)")
         hist = rasterise_augmented(events, offsets, aug, H, W, self.channels,
                                    max_stream_len=int(max(p["count"] for p in params)) if params else 0,
                                    check=not cfg.is_train)   # after the cull every row is inside the sensor

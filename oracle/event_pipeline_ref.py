@@ -44,6 +44,9 @@ class PipelineCfg:
     hotpix_num_stds: float = 10
     normalize_events: bool = False
     rand_aug: bool = False                                     # args.rand_aug: datasets.py:655-658
+    logtrafo: bool = False                                     # datasets.py:647-650
+    gammatrafo: bool = False
+    gamma: float = 0.5
 
     def scales(self):
         if self.is_train:                                      # datasets.py:472-478
@@ -133,6 +136,15 @@ def apply_post_raster(hist: np.ndarray, p: dict, cfg: PipelineCfg) -> torch.Tens
         hot = torch.atleast_1d(torch.squeeze(torch.argwhere(pol.flatten() > thr)))
         idx = np.asarray(np.unravel_index(hot, x.shape)).T        # the reference unravels against x.shape (transforms.py:272)
         x[0::2, idx[:, 1], idx[:, 2]] = 0
+    if cfg.logtrafo:                                            # LogTransform (transforms.py:200-210)
+        ones = torch.ones(x[0:1, :, :].shape)
+        x[0:1, :, :] = torch.log(x[0:1, :, :] + ones)
+        x[2:3, :, :] = torch.log(x[2:3, :, :] + ones)
+        x = x.float()
+    if cfg.gammatrafo:                                          # GammaTransform (transforms.py:212-222)
+        x[0:1, :, :] = x[0:1, :, :] ** cfg.gamma
+        x[2:3, :, :] = x[2:3, :, :] ** cfg.gamma
+        x = x.float()
     if cfg.normalize_events:
         if x[0::2, :, :].max() != 0:
             x[0::2, :, :] = x[0::2, :, :] * (1.0 / x[0::2, :, :].max())

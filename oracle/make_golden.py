@@ -749,10 +749,39 @@ def golden_event_pipeline_randaug():
     np.savez_compressed(os.path.join(GOLD, "event_pipeline_randaug.npz"), **out)
 
 
+def golden_event_pipeline_loggamma():
+    """Reference build_transformNPY with LogTransform / GammaTransform switched on (args.logtrafo / args.gammatrafo,
+    mem/datasets.py:647-650), fixed-sensor branch, with and without NormalizeEvent."""
+    import contextlib, io
+    import torch
+    from types import SimpleNamespace
+    ds = ref_shims.ref_module("datasets")
+    out = {}
+    cases = [  # name, is_train, n_events, kind, normalize, log, gamma on, gamma, seed
+        ("log_a", True, 45000, "edge", 1, 1, 0, 0.5, 41), ("gam_a", True, 45000, "hot", 0, 0, 1, 0.5, 42),
+        ("both_a", True, 20000, "uniform", 1, 1, 1, 0.7, 43), ("both_eval", False, 45000, "edge", 0, 1, 1, 0.5, 44),
+    ]
+    for name, is_train, n, kind, norm, lg, gm, gamma, seed in cases:
+        args = SimpleNamespace(data_path="/data/N_imagenet", input_H=224, input_W=224, slice_max_evs=30000,
+                               max_random_shift_evs=15, timesurface=0, hotpixfilter=1, hotpix_num_stds=10, logtrafo=lg,
+                               gammatrafo=gm, gamma=gamma, normalize_events=norm, rand_aug=0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tf = ds.build_transformNPY(is_train, args)
+        ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
+        random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+        res = tf(ev.copy())
+        out[name + "_out"] = res.numpy()
+        out[name + "_meta"] = np.array([int(is_train), n, norm, lg, gm, seed], dtype=np.int64)
+        out[name + "_gamma"] = np.array(gamma, dtype=np.float64)
+        out[name + "_kind"] = np.array(kind)
+        print(f"event_pipeline_loggamma {name}: nnz {int((res != 0).sum())} max {float(res.max()):.4f}")
+    np.savez_compressed(os.path.join(GOLD, "event_pipeline_loggamma.npz"), **out)
+
+
 SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit, "dvae": golden_dvae,
             "engine": golden_engine, "event_pipeline": golden_event_pipeline, "decode": golden_decode, "engine_ft": golden_engine_ft,
             "vit_bf16": golden_vit_bf16, "finetune_remap": golden_finetune_remap, "dvae_train": golden_dvae_train, "event_pipeline_var": golden_event_pipeline_var, "randaug": golden_randaug,
-            "event_pipeline_randaug": golden_event_pipeline_randaug}
+            "event_pipeline_randaug": golden_event_pipeline_randaug, "event_pipeline_loggamma": golden_event_pipeline_loggamma}
 
 
 def main(argv):

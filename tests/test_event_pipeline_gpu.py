@@ -301,3 +301,25 @@ def test_variable_sensor_batch_vs_oracle():
     with pytest.raises(ValueError):
         EventBatchPipelineVar(pc)([np.array([[0.0, 0.0, 1.0, 1.0]])],
                                   params=[dict(draw_params_var(1, pc), shift_x=-5, cull=True)])
+
+
+def test_log_and_gamma_transforms_reference_golden(golden_dir):
+    """args.logtrafo / args.gammatrafo: the fused kernel with the host-evaluated value table reproduces the reference's
+    build_transformNPY outputs bit for bit (tests/golden/event_pipeline_loggamma.npz)."""
+    from mem_b200.event_pipeline import EventBatchPipeline, PipelineConfig
+    z = np.load(os.path.join(golden_dir, "event_pipeline_loggamma.npz"))
+    names = sorted(k[:-4] for k in z.files if k.endswith("_out"))
+    assert len(names) == 4
+    for name in names:
+        is_train, n, norm, lg, gm, seed = (int(v) for v in z[name + "_meta"])
+        kind = str(z[name + "_kind"])
+        ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
+        cfg = PipelineConfig(is_train=bool(is_train), normalize_events=bool(norm), logtrafo=bool(lg), gammatrafo=bool(gm),
+                             gamma=float(z[name + "_gamma"]))
+        seed_all(seed)
+        got = EventBatchPipeline(cfg)([ev])
+        want = z[name + "_out"]
+        assert tuple(got.shape) == (1,) + want.shape
+        assert np.array_equal(got[0].cpu().numpy(), want), (name, float(np.abs(got[0].cpu().numpy() - want).max()))
+    with pytest.raises(NotImplementedError):
+        EventBatchPipeline(PipelineConfig(is_train=True, logtrafo=True), fused=False)([ev])

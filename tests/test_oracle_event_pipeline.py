@@ -134,3 +134,39 @@ def test_variable_sensor_oracle_matches_reference_golden(golden_dir):
     with pytest.raises(ValueError):                       # every row shifted out: the reference raises from max() of nothing
         pipeline_var_ref(np.array([[0.0, 0.0, 1.0, 1.0]]), cfg, dict(start=0, count=1, time_flip=False, flip_x=False, cull=True,
                                                                     shift_x=-5, shift_y=0))
+
+
+def _loggamma_cases(golden_dir):
+    z = np.load(os.path.join(golden_dir, "event_pipeline_loggamma.npz"))
+    for name in sorted(k[:-4] for k in z.files if k.endswith("_out")):
+        is_train, n, norm, lg, gm, seed = (int(v) for v in z[name + "_meta"])
+        kind = str(z[name + "_kind"])
+        ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
+        cfg = PipelineCfg(is_train=bool(is_train), normalize_events=bool(norm), logtrafo=bool(lg), gammatrafo=bool(gm),
+                          gamma=float(z[name + "_gamma"]))
+        yield name, ev, cfg, seed, z[name + "_out"]
+
+
+def test_log_and_gamma_transforms_match_the_reference(golden_dir):
+    """LogTransform / GammaTransform (transforms.py:200-222): the oracle chain against the reference's own outputs, and
+    the product's route -- a 256-entry table of the transformed ``c / 255`` values evaluated with torch's CPU routines --
+    against the oracle: identical float32 images, which is what lets the device path be bit-exact."""
+    from mem_b200.event_pipeline import value_table
+    seen = 0
+    for name, ev, cfg, seed, want in _loggamma_cases(golden_dir):
+        seed_all(seed)
+        got = pipeline_ref(ev, cfg).numpy()
+        assert np.array_equal(got, want), (name, float(np.abs(got - want).max()))
+        # table route: the plain chain's image holds only c / 255 values (times the normalisation factor afterwards)
+        plain = PipelineCfg(**{**cfg.__dict__, "logtrafo": False, "gammatrafo": False, "normalize_events": False})
+        seed_all(seed)
+        base = pipeline_ref(ev, plain)
+        counts = torch.round(base * 255).long()
+        assert torch.equal(counts.float() / 255, base)
+        lut = value_table(cfg.logtrafo, cfg.gammatrafo, cfg.gamma)
+        x = lut[counts]
+        if cfg.normalize_events and x[0::2].max() != 0:
+            x[0::2] = x[0::2] * (1.0 / x[0::2].max())
+        assert np.array_equal(x.numpy(), want), name
+        seen += 1
+    assert seen == 4 and value_table(False, False) is None
