@@ -125,6 +125,15 @@ int memb_hist_aug_u8(const double* ev, int64_t n, const int64_t* offsets, int B,
                      const memb_event_aug* aug, int H, int W, int C, int strategy, uint8_t* out,
                      void* ws, size_t ws_bytes, memb_stream_t stream);
 
+/* The same with the time surface in the middle channel (C == 3, strategy GLOBAL; workspace:
+ * memb_hist_workspace_bytes(B, n, H, W, 1, MEMB_HIST_GLOBAL)): EventArrToImg(timeSurface=True) after the event-space
+ * augmentations (mem/datasets.py:583-590) -- the timestamps are normalised over the rows that survive the window and the
+ * shift stage's cull; after RandomTimeFlip (t' = t[last row of the window] - t, array reversed, :603-606) the row that
+ * writes a pixel last is the one with the smallest index. */
+int memb_hist_aug_tss_u8(const double* ev, int64_t n, const int64_t* offsets, int B, int64_t max_stream_len,
+                         const memb_event_aug* aug, int H, int W, int timesurface, uint8_t* out, void* ws,
+                         size_t ws_bytes, memb_stream_t stream);
+
 /* hist    : uint8 [B,H,W,C] counts, C == 3 [pos, ts, neg] or C == 2 [pos, neg].
  * crop_tl : device int32 [B,2] (top, left) of the outH x outW window in the (virtually) padded image, or NULL
  *           for (0,0); pad_t / pad_l: rows / columns of zero padding torchvision's RandomCrop(pad_if_needed)

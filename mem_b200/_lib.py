@@ -34,6 +34,7 @@ SIGNATURES = {
     "memb_decode_events_f64": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "memb_hist_raw_u8": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "memb_hist_aug_u8": (_i32, [_vp, _i64, _vp, _i32, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "memb_hist_aug_tss_u8": (_i32, [_vp, _i64, _vp, _i32, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "memb_event_pipeline_f32": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32,
                                        _vp, _vp, _sz, _vp]),
     "memb_event_pipeline_lut_f32": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32,

@@ -128,13 +128,25 @@ template <bool kAligned>
 __global__ void __launch_bounds__(kThreads) hist_time_range(const double* __restrict__ ev,
                                                             const long long* __restrict__ offsets,
                                                             long long n_total,
-                                                            unsigned long long* __restrict__ tkeys) {
+                                                            unsigned long long* __restrict__ tkeys,
+                                                            const memb_event_aug* __restrict__ aug) {
+  // min / max of t over the rows the rasteriser will see: the stream's window, minus the rows the shift stage culls
+  // (EventArrToImg normalises the time surface over the array it is handed, datasets.py:587-589)
   const int b = blockIdx.y;
-  const long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
+  long long begin = offsets ? offsets[b] : 0, end = offsets ? offsets[b + 1] : n_total;
+  memb_event_aug a;
+  const bool has_aug = aug != nullptr;
+  if (has_aug) {
+    a = aug[b];
+    aug_window(a, begin, end);
+  }
   unsigned long long lo = ~0ull, hi = 0ull;
   for (long long r = begin + blockIdx.x * (long long)kThreads + threadIdx.x; r < end;
        r += (long long)gridDim.x * kThreads) {
-    unsigned long long k = order_key(load_event<kAligned>(ev, r).t);
+    Event e = load_event<kAligned>(ev, r);
+    const double t = e.t;
+    if (has_aug && !apply_aug(e, a)) continue;
+    unsigned long long k = order_key(t);
     lo = k < lo ? k : lo;
     hi = k > hi ? k : hi;
   }
@@ -214,7 +226,10 @@ __global__ void __launch_bounds__(kThreads) hist_scatter_global(
         if (count) atomicAdd(acc_b + slot, 1u);
       }
       if constexpr (kTss) {
-        if (ok) atomicMax(last_b + idx, (unsigned long long)(base + u * kThreads + threadIdx.x - begin + 1));
+        // the LAST row (in array order) that hits a pixel writes its time surface value (numpy fancy assignment); after
+        // RandomTimeFlip the array runs backwards, so the winner is the row with the smallest index: key = end - row
+        const long long r = base + u * kThreads + threadIdx.x;
+        if (ok) atomicMax(last_b + idx, (unsigned long long)((has_aug && a.time_flip) ? end - r : r - begin + 1));
       }
     }
   }
@@ -229,18 +244,34 @@ __global__ void __launch_bounds__(256) hist_finalize(const unsigned int* __restr
                                                      const unsigned long long* __restrict__ tkeys,
                                                      const double* __restrict__ ev,
                                                      const long long* __restrict__ offsets,
-                                                     long long npix, int C, uint8_t* __restrict__ out, int replicas) {
+                                                     long long npix, int C, uint8_t* __restrict__ out, int replicas,
+                                                     const memb_event_aug* __restrict__ aug, long long n_total) {
   const int b = blockIdx.y;
   const unsigned int* pos = acc + (long long)b * replicas * 2 * npix;
   const unsigned int* neg = pos + npix;
   uint8_t* o = out + (long long)b * npix * C;
   pdl_wait();
-  double tmin = 0.0, span = 0.0;
-  const double* ev_b = nullptr;
+  double tmin = 0.0, span = 0.0, t_last = 0.0;
+  long long begin = 0, end = 0;
+  bool flip = false;
   if constexpr (kTss) {
-    tmin = key_value(tkeys[2 * b]);
-    span = key_value(tkeys[2 * b + 1]) - tmin;
-    ev_b = ev + 4 * (offsets ? offsets[b] : 0);
+    begin = offsets ? offsets[b] : 0;
+    end = offsets ? offsets[b + 1] : n_total;
+    if (aug) {
+      const memb_event_aug a = aug[b];
+      aug_window(a, begin, end);
+      flip = a.time_flip != 0;
+    }
+    const double t_lo = key_value(tkeys[2 * b]), t_hi = key_value(tkeys[2 * b + 1]);
+    if (flip && end > begin) {
+      // RandomTimeFlip (datasets.py:603-606): t' = t[last row of the window] - t, one float64 subtraction per row
+      t_last = ev[4 * (end - 1) + 2];
+      tmin = t_last - t_hi;
+      span = (t_last - t_lo) - tmin;
+    } else {
+      tmin = t_lo;
+      span = t_hi - tmin;
+    }
   }
   for (long long px = blockIdx.x * (long long)blockDim.x + threadIdx.x; px < npix;
        px += (long long)gridDim.x * blockDim.x) {
@@ -259,7 +290,9 @@ __global__ void __launch_bounds__(256) hist_finalize(const unsigned int* __restr
         const unsigned long long w = last[(long long)b * npix + px];
         if (w) {
           // (t - tmin) / (tmax - tmin) * 255, float64, same operation order as datasets.py:588-589.
-          const double v = (ev_b[4 * (w - 1) + 2] - tmin) / span * 255.0;
+          const long long r = flip ? end - (long long)w : begin + (long long)w - 1;
+          const double t = flip ? t_last - ev[4 * r + 2] : ev[4 * r + 2];
+          const double v = (t - tmin) / span * 255.0;
           ts = (v == v) ? (uint8_t)(long long)v : (uint8_t)0;
         }
       }
@@ -1966,8 +1999,8 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
   const dim3 grid((unsigned)gx, (unsigned)B);
 
   if (timesurface && n > 0) {
-    if (aligned) hist_time_range<true><<<grid, kThreads, 0, stream>>>(ev, offs, n, tkeys);
-    else hist_time_range<false><<<grid, kThreads, 0, stream>>>(ev, offs, n, tkeys);
+    if (aligned) hist_time_range<true><<<grid, kThreads, 0, stream>>>(ev, offs, n, tkeys, aug);
+    else hist_time_range<false><<<grid, kThreads, 0, stream>>>(ev, offs, n, tkeys, aug);
     MEMB_LAUNCH_OK("hist_time_range");
   }
   if (use_private) {
@@ -1991,9 +2024,11 @@ static int run_hist(const double* ev, int64_t n, const int64_t* offsets, int B, 
     long long fx = std::min<long long>(ceil_div<long long>(npix, 256), std::max<long long>(1, (long long)sms * 8 / B));
     const dim3 fgrid((unsigned)std::max<long long>(1, fx), (unsigned)B);
     if (timesurface)
-      MEMB_CUDA_OK(launch_pdl(hist_finalize<true>, fgrid, dim3(256), stream, acc, last, tkeys, ev, offs, npix, C, out, p.replicas));
+      MEMB_CUDA_OK(launch_pdl(hist_finalize<true>, fgrid, dim3(256), stream, acc, last, tkeys, ev, offs, npix, C, out, p.replicas,
+                              aug, (long long)n));
     else
-      MEMB_CUDA_OK(launch_pdl(hist_finalize<false>, fgrid, dim3(256), stream, acc, nullptr, nullptr, ev, offs, npix, C, out, p.replicas));
+      MEMB_CUDA_OK(launch_pdl(hist_finalize<false>, fgrid, dim3(256), stream, acc, nullptr, nullptr, ev, offs, npix, C, out, p.replicas,
+                              (const memb_event_aug*)nullptr, (long long)n));
     MEMB_LAUNCH_OK("hist_finalize");
   }
   return MEMB_OK;
@@ -2012,6 +2047,14 @@ extern "C" int memb_hist_aug_u8(const double* ev, int64_t n, const int64_t* offs
   MEMB_REQUIRE(aug != nullptr, "hist_aug: null augmentation array");
   MEMB_REQUIRE((((uintptr_t)aug) & 7u) == 0, "hist_aug: misaligned augmentation array");
   return run_hist(ev, n, offsets, B, max_stream_len, aug, H, W, C, 0, strategy, out, ws, ws_bytes, stream);
+}
+
+extern "C" int memb_hist_aug_tss_u8(const double* ev, int64_t n, const int64_t* offsets, int B,
+                                    int64_t max_stream_len, const memb_event_aug* aug, int H, int W, int timesurface,
+                                    uint8_t* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
+  MEMB_REQUIRE(aug != nullptr, "hist_aug_tss: null augmentation array");
+  MEMB_REQUIRE((((uintptr_t)aug) & 7u) == 0, "hist_aug_tss: misaligned augmentation array");
+  return run_hist(ev, n, offsets, B, max_stream_len, aug, H, W, 3, timesurface, MEMB_HIST_GLOBAL, out, ws, ws_bytes, stream);
 }
 
 extern "C" int memb_event_pipeline_f32(const double* ev, int64_t n, const int64_t* offsets, int B,
@@ -2139,7 +2182,7 @@ extern "C" int memb_hist_raw_u8(const uint8_t* raw, int64_t n_records, int forma
   {
     const long long fx = std::min<long long>(ceil_div<long long>(npix, 256), (long long)sms * 8);
     hist_finalize<false><<<(unsigned)std::max<long long>(1, fx), 256, 0, stream>>>(acc, nullptr, nullptr, nullptr, nullptr,
-                                                                                  npix, C, out, 1);
+                                                                                  npix, C, out, 1, nullptr, 0LL);
     MEMB_LAUNCH_OK("hist_finalize");
   }
   return MEMB_OK;

@@ -20,8 +20,10 @@ launch over the batch (``mem_b200/transforms.py``, ``csrc/randaug.cu``), with ea
 other draws so the torch generator is consumed in the reference's order.
 ``logtrafo`` / ``gammatrafo`` (``LogTransform`` / ``GammaTransform``, off in the reference's scripts) are a 256-entry value
 table evaluated on the host with the reference's own CPU routines (``value_table``) and applied inside the fused kernel.
-Not covered (raise / documented in DESIGN.md): the time surface together with augmentations; log / gamma on the
-variable-sensor branch (its resized image is not a function of 256 counts).
+``timesurface`` (off in the reference's scripts) takes the two-kernel path: ``memb_hist_aug_tss_u8`` normalises the
+timestamps over the rows that survive the augmentations and honours RandomTimeFlip's reversed order, then ``post_raster``.
+Not covered (raise / documented in DESIGN.md): log / gamma on the variable-sensor branch (its resized image is not a
+function of 256 counts) or together with the time surface; the time surface on the variable-sensor branch.
 """
 from __future__ import annotations
 
@@ -168,7 +170,7 @@ def pack_params(params) -> tuple[np.ndarray, np.ndarray]:
 
 
 def rasterise_augmented(events, offsets, aug, H, W, channels=3, *, max_stream_len=None, strategy=_lib.HIST_AUTO,
-                        check=True, out=None):
+                        check=True, out=None, timesurface=False):
     """Ragged batch of raw streams + per-stream ``memb_event_aug`` records -> ``uint8 (B,H,W,channels)`` on the device.
 
     events ``float64 (sum N_b, 4)`` CUDA tensor (or numpy / CPU tensor: copied), offsets ``int64 (B+1,)``,
@@ -188,12 +190,19 @@ def rasterise_augmented(events, offsets, aug, H, W, channels=3, *, max_stream_le
             out = torch.empty((B, H, W, channels), dtype=torch.uint8, device=device)
         n = int(ev.shape[0])
         lib = _lib.load()
-        need = lib.memb_hist_workspace_bytes(B, n, H, W, 0, strategy)
+        if timesurface and channels != 3:
+            raise ValueError("the time surface is the middle one of three channels")
+        need = lib.memb_hist_workspace_bytes(B, n, H, W, int(bool(timesurface)), _lib.HIST_GLOBAL if timesurface else strategy)
         ws = _lib.workspace.get(torch, need, device, "hist")
         stream = _lib.stream_ptr(torch, device)
-        _lib.check(lib.memb_hist_aug_u8(ev.data_ptr() if n else None, n, off.data_ptr(), B,
-                                        int(max_stream_len if max_stream_len is not None else n), aug_dev.data_ptr(),
-                                        H, W, channels, strategy, out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        if timesurface:     # EventArrToImg(timeSurface=True) after the augmentations: L2-RED strategy + last-writer pass
+            _lib.check(lib.memb_hist_aug_tss_u8(ev.data_ptr() if n else None, n, off.data_ptr(), B,
+                                                int(max_stream_len if max_stream_len is not None else n), aug_dev.data_ptr(),
+                                                H, W, 1, out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        else:
+            _lib.check(lib.memb_hist_aug_u8(ev.data_ptr() if n else None, n, off.data_ptr(), B,
+                                            int(max_stream_len if max_stream_len is not None else n), aug_dev.data_ptr(),
+                                            H, W, channels, strategy, out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
         if check:
             _lib.check(lib.memb_hist_status(ws.data_ptr(), stream))
     return out
@@ -330,12 +339,18 @@ class EventBatchPipeline:
     transform's outputs when the generators start from the same state and samples are drawn in order."""
 
     def __init__(self, cfg: PipelineConfig, channels: int = 3, device="cuda", fused=None):
-        if cfg.timesurface:
-            raise NotImplementedError("the fused augmentation path rasterises polarity counts only (no time surface)")
         self.cfg, self.channels, self.device = cfg, channels, device
         fits = cfg.input_H * cfg.input_W <= FUSED_MAX_PIXELS
         if fused and not fits:
             raise ValueError("the output raster does not fit one shared-memory tile; use fused=False")
+        if cfg.timesurface:
+            # args.timesurface: the one-kernel path rasterises polarity counts only; the time surface takes the
+            # rasterise (L2 REDs + last-writer pass) + post-raster pair
+            if fused:
+                raise NotImplementedError("the fused kernel has no time surface; use fused=False (the default with timesurface)")
+            if channels != 3 or cfg.logtrafo or cfg.gammatrafo:
+                raise NotImplementedError("the time surface needs 3 channels and is not combined with logtrafo / gammatrafo")
+            fused = False
         self.fused = fits if fused is None else bool(fused)   # one kernel when the crop fits a shared-memory tile
 
     def __call__(self, streams, offsets=None, params=None):
@@ -365,7 +380,8 @@ class EventBatchPipeline:
             raise NotImplementedError("LogTransform / GammaTransform ride on the fused kernel only (output raster <= one tile)")
         hist = rasterise_augmented(events, offsets, aug, H, W, self.channels,
                                    max_stream_len=int(max(p["count"] for p in params)) if params else 0,
-                                   check=not cfg.is_train)   # after the cull every row is inside the sensor
+                                   check=not cfg.is_train,   # after the cull every row is inside the sensor
+                                   timesurface=cfg.timesurface)
         out = post_raster(hist, crop if cfg.is_train else None, (cfg.input_H, cfg.input_W) if cfg.is_train else None,
                           remove_timesurface=not cfg.timesurface,
                           hot_num_stds=cfg.hotpix_num_stds if cfg.hotpixfilter else None, normalize=cfg.normalize_events)

@@ -778,10 +778,43 @@ def golden_event_pipeline_loggamma():
     np.savez_compressed(os.path.join(GOLD, "event_pipeline_loggamma.npz"), **out)
 
 
+def golden_event_pipeline_tss():
+    """Reference build_transformNPY with args.timesurface=1 (EventArrToImg(timeSurface=True) after the event-space
+    augmentations, the middle channel kept), fixed-sensor branch: seeds chosen so that both time-flip outcomes occur."""
+    import contextlib, io
+    import torch
+    from types import SimpleNamespace
+    ds = ref_shims.ref_module("datasets")
+    out = {}
+    cases = [  # name, is_train, n_events, kind, normalize, seed
+        ("tss_a", True, 45000, "edge", 1, 51), ("tss_b", True, 45000, "hot", 0, 52), ("tss_c", True, 20000, "uniform", 1, 53),
+        ("tss_d", True, 45000, "edge", 0, 54), ("tss_e", True, 33000, "uniform", 0, 55), ("tss_eval", False, 45000, "edge", 1, 56),
+    ]
+    flips = []
+    for name, is_train, n, kind, norm, seed in cases:
+        args = SimpleNamespace(data_path="/data/N_imagenet", input_H=224, input_W=224, slice_max_evs=30000,
+                               max_random_shift_evs=15, timesurface=1, hotpixfilter=1, hotpix_num_stds=10, logtrafo=0,
+                               gammatrafo=0, gamma=0.5, normalize_events=norm, rand_aug=0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tf = ds.build_transformNPY(is_train, args)
+        ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
+        random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+        res = tf(ev.copy())
+        np.random.seed(seed)
+        flips.append(bool(is_train and np.random.random() < 0.5))
+        out[name + "_out"] = res.numpy()
+        out[name + "_meta"] = np.array([int(is_train), n, norm, seed], dtype=np.int64)
+        out[name + "_kind"] = np.array(kind)
+        print(f"event_pipeline_tss {name}: nnz {int((res != 0).sum())} tss nnz {int((res[1] != 0).sum())} time flip {flips[-1]}")
+    assert any(flips) and not all(flips[:5])
+    np.savez_compressed(os.path.join(GOLD, "event_pipeline_tss.npz"), **out)
+
+
 SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit, "dvae": golden_dvae,
             "engine": golden_engine, "event_pipeline": golden_event_pipeline, "decode": golden_decode, "engine_ft": golden_engine_ft,
             "vit_bf16": golden_vit_bf16, "finetune_remap": golden_finetune_remap, "dvae_train": golden_dvae_train, "event_pipeline_var": golden_event_pipeline_var, "randaug": golden_randaug,
-            "event_pipeline_randaug": golden_event_pipeline_randaug, "event_pipeline_loggamma": golden_event_pipeline_loggamma}
+            "event_pipeline_randaug": golden_event_pipeline_randaug, "event_pipeline_loggamma": golden_event_pipeline_loggamma,
+            "event_pipeline_tss": golden_event_pipeline_tss}
 
 
 def main(argv):

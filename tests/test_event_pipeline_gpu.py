@@ -181,7 +181,9 @@ def test_bad_arguments_fail_loudly():
     from mem_b200 import _lib
     from mem_b200.event_pipeline import AUG_DTYPE, EventBatchPipeline, PipelineConfig, post_raster, rasterise_augmented
     with pytest.raises(NotImplementedError):
-        EventBatchPipeline(PipelineConfig(timesurface=True))
+        EventBatchPipeline(PipelineConfig(timesurface=True), channels=2)        # the time surface is the middle of 3 channels
+    with pytest.raises(NotImplementedError):
+        EventBatchPipeline(PipelineConfig(timesurface=True, logtrafo=True))
     ev = np.zeros((4, 4))
     with pytest.raises(ValueError):
         rasterise_augmented(ev, np.array([0, 4]), np.zeros(2, dtype=AUG_DTYPE), 100, 100)
@@ -323,3 +325,35 @@ def test_log_and_gamma_transforms_reference_golden(golden_dir):
         assert np.array_equal(got[0].cpu().numpy(), want), (name, float(np.abs(got[0].cpu().numpy() - want).max()))
     with pytest.raises(NotImplementedError):
         EventBatchPipeline(PipelineConfig(is_train=True, logtrafo=True), fused=False)([ev])
+
+
+def test_time_surface_with_augmentations_reference_golden(golden_dir):
+    """args.timesurface=1 through the rasterise (memb_hist_aug_tss_u8) + post-raster pair: timestamps normalised over the
+    rows that survive window / shift / cull, RandomTimeFlip's reversed order and t' = t_last - t, middle channel kept;
+    bit-exact with the reference's build_transformNPY outputs.  Also a ragged batch against the oracle with shared draws."""
+    from mem_b200.event_pipeline import EventBatchPipeline, PipelineConfig, draw_params
+    z = np.load(os.path.join(golden_dir, "event_pipeline_tss.npz"))
+    names = sorted(k[:-4] for k in z.files if k.endswith("_out"))
+    assert len(names) == 6
+    streams = []
+    for name in names:
+        is_train, n, norm, seed = (int(v) for v in z[name + "_meta"])
+        kind = str(z[name + "_kind"])
+        ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
+        streams.append(ev)
+        cfg = PipelineConfig(is_train=bool(is_train), normalize_events=bool(norm), timesurface=True)
+        seed_all(seed)
+        got = EventBatchPipeline(cfg)([ev])
+        want = z[name + "_out"]
+        assert tuple(got.shape) == (1,) + want.shape
+        assert np.array_equal(got[0].cpu().numpy(), want), (name, int((got[0].cpu().numpy() != want).sum()))
+    cfg = PipelineConfig(is_train=True, normalize_events=True, timesurface=True)
+    seed_all(77)
+    params = [draw_params(len(s), cfg) for s in streams]
+    assert any(p["time_flip"] for p in params) and not all(p["time_flip"] for p in params)
+    got = EventBatchPipeline(cfg)(streams, params=params).cpu().numpy()
+    for b, (s, p) in enumerate(zip(streams, params)):
+        want = pipeline_ref(s, PipelineCfg(is_train=True, normalize_events=True, timesurface=True), p).numpy()
+        assert np.array_equal(got[b], want), b
+    with pytest.raises(NotImplementedError):
+        EventBatchPipeline(cfg, fused=True)

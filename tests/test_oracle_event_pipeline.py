@@ -170,3 +170,19 @@ def test_log_and_gamma_transforms_match_the_reference(golden_dir):
         assert np.array_equal(x.numpy(), want), name
         seen += 1
     assert seen == 4 and value_table(False, False) is None
+
+
+def test_time_surface_chain_matches_the_reference(golden_dir):
+    """args.timesurface=1: EventArrToImg(timeSurface=True) after the augmentations, middle channel kept
+    (tests/golden/event_pipeline_tss.npz; two of the training cases draw RandomTimeFlip)."""
+    z = np.load(os.path.join(golden_dir, "event_pipeline_tss.npz"))
+    names = sorted(k[:-4] for k in z.files if k.endswith("_out"))
+    assert len(names) == 6
+    for name in names:
+        is_train, n, norm, seed = (int(v) for v in z[name + "_meta"])
+        kind = str(z[name + "_kind"])
+        ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
+        seed_all(seed)
+        got = pipeline_ref(ev, PipelineCfg(is_train=bool(is_train), normalize_events=bool(norm), timesurface=True)).numpy()
+        assert np.array_equal(got, z[name + "_out"]), (name, float(np.abs(got - z[name + "_out"]).max()))
+        assert (got[1] != 0).any()
