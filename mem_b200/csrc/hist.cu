@@ -1558,8 +1558,14 @@ __global__ void __launch_bounds__(kSortAccThreads, 2) hist_sort_accumulate(
     return;
   }
   if (tid < kSortSlices - 1) {
+    // the producers of this class have lower block indices, so they were dispatched before this CTA; the wait is bounded
+    // all the same (a stuck hand-off reports an error through the status header instead of hanging the device)
     volatile unsigned int* f = flags + tid * kSortBins + cls;
-    while (*f == 0u) __nanosleep(64);
+    const long long t0 = clock64();
+    while (*f == 0u) {
+      __nanosleep(64);
+      if (clock64() - t0 > 4000000000LL) { hdr->oob = 1; break; }
+    }
     __threadfence();
   }
   __syncthreads();
