@@ -137,36 +137,35 @@ class EventRandAugment(torch.nn.Module):
         print(f"Created RandAug with {self.names}")
 
     def set_names(self, x):
+        """A list of operation names, or "all" / "small" (same behaviour as the reference's method)."""
+        presets = {"all": ALL, "small": SMALL}
         if isinstance(x, list):
             self.names = copy.copy(x)
-        elif isinstance(x, str):
-            if x == "all":
-                self.names = list(ALL)
-            elif x == "small":
-                self.names = list(SMALL)
-            else:
-                raise RuntimeError(f"Not implemented for {x}")
+        elif isinstance(x, str) and x in presets:
+            self.names = list(presets[x])
         else:
             raise RuntimeError(f"Not implemented for {x}")
 
     def _augmentation_space(self, num_bins, image_size):
-        d = {
-            "Identity": (torch.tensor(0.0), False),
-            "ShearX": (torch.linspace(0.0, 0.3, num_bins), True),
-            "ShearY": (torch.linspace(0.0, 0.3, num_bins), True),
-            "TranslateX": (torch.linspace(0.0, 150.0 / 331.0 * image_size[1], num_bins), True),
-            "TranslateY": (torch.linspace(0.0, 150.0 / 331.0 * image_size[0], num_bins), True),
-            "Rotate": (torch.linspace(0.0, 30.0, num_bins), True),
-            "Brightness": (torch.linspace(0.0, 0.9, num_bins), True),
-            "Color": (torch.linspace(0.0, 0.9, num_bins), True),
-            "Contrast": (torch.linspace(0.0, 0.9, num_bins), True),
-            "Sharpness": (torch.linspace(0.0, 0.9, num_bins), True),
-            "Posterize": (8 - (torch.arange(num_bins) / ((num_bins - 1) / 4)).round().int(), False),
-            "Solarize": (torch.linspace(255.0, 0.0, num_bins), False),
-            "AutoContrast": (torch.tensor(0.0), False),
-            "Equalize": (torch.tensor(0.0), False),
-        }
-        return {k: v for k, v in d.items() if k in self.names}
+        """name -> (magnitude table, signed), in the reference's key order (the operation index is drawn against it).
+        Ranges as in transforms.py:411-430; the tables are ``torch.linspace`` values like the reference's."""
+        height, width = image_size
+        ranged = {"ShearX": (0.0, 0.3), "ShearY": (0.0, 0.3), "TranslateX": (0.0, 150.0 / 331.0 * width),
+                  "TranslateY": (0.0, 150.0 / 331.0 * height), "Rotate": (0.0, 30.0), "Brightness": (0.0, 0.9),
+                  "Color": (0.0, 0.9), "Contrast": (0.0, 0.9), "Sharpness": (0.0, 0.9)}
+        space = {}
+        for name in ALL:
+            if name not in self.names:
+                continue
+            if name in ranged:
+                space[name] = (torch.linspace(ranged[name][0], ranged[name][1], num_bins), True)
+            elif name == "Posterize":
+                space[name] = (8 - (torch.arange(num_bins) / ((num_bins - 1) / 4)).round().int(), False)
+            elif name == "Solarize":
+                space[name] = (torch.linspace(255.0, 0.0, num_bins), False)
+            else:                                   # Identity, AutoContrast, Equalize: no magnitude
+                space[name] = (torch.tensor(0.0), False)
+        return space
 
     def draw(self, height: int, width: int):
         """One sample's ``[(name, magnitude)]``: the reference's draws in its order (transforms.py:447-462)."""
