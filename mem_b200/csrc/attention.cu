@@ -213,6 +213,7 @@ __device__ __forceinline__ void fwd_out_tile(const FwdParams& p, uint8_t* smem, 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attention_fwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const FwdParams p) {
   using namespace fwd;
+  grid_dependency_trigger();   // the proj GEMM (a programmatic dependent) sets itself up under this kernel's tail
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);

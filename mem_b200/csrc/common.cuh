@@ -56,6 +56,31 @@ inline int num_sms() {
   return sms;
 }
 
+// Programmatic dependent launch.  A kernel launched through launch_dependent() may become resident while its predecessor in
+// the stream is still running (as SMs free up); it must call grid_dependency_wait() before it touches global memory the
+// predecessor writes or reads -- the call returns once the predecessor has completed and its writes are visible.  A kernel
+// that calls grid_dependency_trigger() early lets such a successor start its prologue (barrier init, TMEM allocation,
+// tensor-map prefetch) under this kernel's tail instead of after the launch gap; for a normally launched successor the
+// trigger is a no-op, and so is the wait in a normally launched kernel.
+#ifdef __CUDACC__
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 template <typename T>
 inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 template <typename T>

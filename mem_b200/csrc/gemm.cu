@@ -289,6 +289,7 @@ gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  grid_dependency_trigger();      // the next kernel of the stream may set itself up under this kernel's tail
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
@@ -309,6 +310,7 @@ gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dependency_wait();         // everything above ran while the previous kernel drained; operands / outputs from here on
 
   const int kb_mult = p.split_precision ? 3 : 1;
 
@@ -502,7 +504,7 @@ static int launch(const memb_gemm_desc& g, const Params& p, const CUtensorMap& t
     MEMB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  MEMB_CUDA_OK(launch_dependent(kern, dim3(grid), dim3(kThreads), (size_t)C::SMEM_BYTES, stream, ta, tb, p));
   MEMB_LAUNCH_OK("gemm_tcgen05");
   return MEMB_OK;
 }

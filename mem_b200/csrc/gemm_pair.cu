@@ -107,6 +107,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (threadIdx.x == 0 && p.err_flag) atomicExch(p.err_flag, 90);
     return;
   }
+  grid_dependency_trigger();      // the next kernel of the stream may set itself up under this kernel's tail
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
@@ -131,6 +132,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dependency_wait();         // everything above ran while the previous kernel drained; operands / outputs from here on
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (both CTAs)
@@ -464,7 +466,8 @@ static int launch(const Params& p, const CUtensorMap* t, cudaStream_t stream) {
     configured = true;
   }
   const int clusters = std::max(1, std::min(p.num_tiles, num_sms() / 2));
-  kern<<<2 * clusters, kThreads, C::SMEM_BYTES, stream>>>(t[0], t[1], t[2], t[3], t[4], p);
+  MEMB_CUDA_OK(launch_dependent(kern, dim3(2 * clusters), dim3(kThreads), (size_t)C::SMEM_BYTES, stream, t[0], t[1], t[2], t[3],
+                                t[4], p));
   MEMB_LAUNCH_OK("gemm_pair_kernel");
   return MEMB_OK;
 }

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd(const float* __rest
                                                              bf16* __restrict__ y, long long ldy, float* __restrict__ mean,
                                                              float* __restrict__ rstd, const int* __restrict__ row_index,
                                                              const int* __restrict__ count) {
+  grid_dependency_trigger();   // a GEMM launched as a programmatic dependent sets itself up under this kernel's tail
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int live = count ? min(rows, *count) : rows;
   for (int r = blockIdx.x * kRowWarps + warp; r < rows; r += gridDim.x * kRowWarps) {
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) layernorm_bwd(const DyT* __res
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                 const int* __restrict__ row_index,
                                                                 const int* __restrict__ count, const BranchArgs br) {
+  grid_dependency_trigger();
   extern __shared__ float smem[];                 // [2 (+2)][kRowWarps][D]: dgamma, dbeta (, dcolscale, dbias) partials
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int live = count ? min(rows, *count) : rows;
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(kRowThreads) branch_bwd(const float* __restric
 constexpr int kChainSlices = 16;
 __global__ void __launch_bounds__(256) vbias_chain(const float* __restrict__ t, const float* __restrict__ W, int D,
                                                    float* __restrict__ dproj_bias, float* __restrict__ dv_bias) {
+  grid_dependency_trigger();
   const int j = blockIdx.x * 256 + threadIdx.x;
   const int per = (D + kChainSlices - 1) / kChainSlices;
   const int i0 = blockIdx.y * per, i1 = min(D, i0 + per);
@@ -297,6 +300,7 @@ __global__ void __launch_bounds__(256) vbias_chain(const float* __restrict__ t, 
 constexpr int kColsumRows = 8;
 __global__ void __launch_bounds__(32 * kColsumRows) colsum_bf16(const bf16* __restrict__ x, long long ld, int rows, int N,
                                                                 int rows_per_block, float* __restrict__ out) {
+  grid_dependency_trigger();
   __shared__ float part[kColsumRows][32][8];
   const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
