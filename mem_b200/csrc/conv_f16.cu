@@ -117,6 +117,7 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
     if (threadIdx.x == 0 && p.err_flag) atomicExch(p.err_flag, 91);
     return;
   }
+  grid_dependency_trigger();      // the next layer's launch sets itself up under this one's tail
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a_hi);
     prefetch_tmap(&tmap_a_lo);
@@ -132,6 +133,7 @@ conv_f16x2(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dependency_wait();         // launched as a programmatic dependent: the previous layer's output is complete from here on
   const int iters = p.ntaps * p.kc_per_tap;
 
   if (warp == 0) {
@@ -507,8 +509,10 @@ extern "C" int memb_conv_f16x2(const memb_conv16_desc* dp, memb_stream_t stream)
   }
   const int clusters = std::max(1, std::min(p.num_tiles, num_sms() / 2));
   const int iters = p.ntaps * p.kc_per_tap;
-  if (iters <= p.seg && !d.keys) conv_f16x2<12, true><<<2 * clusters, Cfg<12>::kThreads, SMEM_BYTES, stream>>>(ta_hi, ta_lo, tw, p);
-  else conv_f16x2<8, false><<<2 * clusters, Cfg<8>::kThreads, SMEM_BYTES, stream>>>(ta_hi, ta_lo, tw, p);
+  if (iters <= p.seg && !d.keys)
+    MEMB_CUDA_OK(launch_dependent(conv_f16x2<12, true>, dim3(2 * clusters), dim3(Cfg<12>::kThreads), (size_t)SMEM_BYTES, stream, ta_hi, ta_lo, tw, p));
+  else
+    MEMB_CUDA_OK(launch_dependent(conv_f16x2<8, false>, dim3(2 * clusters), dim3(Cfg<8>::kThreads), (size_t)SMEM_BYTES, stream, ta_hi, ta_lo, tw, p));
   MEMB_LAUNCH_OK("conv_f16x2");
   return MEMB_OK;
 }
