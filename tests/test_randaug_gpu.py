@@ -98,6 +98,36 @@ def test_mixed_batch_two_operations_float_in_float_out():
         assert np.array_equal(again[i], R.rand_augment(imgs[i], chosen[i]))
 
 
+def test_random_shapes_and_operation_counts_vs_oracle():
+    """Odd image sizes (the scalar load / store path: 3 * H * W not a multiple of 4), zero to three operations per sample,
+    tiny images (Sharpness leaves images with a side <= 2 alone), a constant image (AutoContrast's non-finite scale, Equalize's
+    zero step): the kernel equals the oracle bit for bit."""
+    from mem_b200 import transforms as T
+    rng = np.random.default_rng(8)
+    for H, W, num_ops in ((37, 53, 3), (2, 41, 2), (64, 64, 0), (101, 7, 1), (224, 224, 3)):
+        B = 6
+        imgs = np.stack([synth_event_image(rng, H, W) for _ in range(B)])
+        imgs[1] = 77                                               # constant image
+        space = R.augmentation_space(R.OPS, 31, H, W)
+        ops = np.zeros((B, num_ops), dtype=T.OP_DTYPE)
+        chosen = []
+        for b in range(B):
+            row = []
+            for k in range(num_ops):
+                name = R.OPS[int(rng.integers(0, len(R.OPS)))]
+                mags, signed = space[name]
+                mag = float(mags[int(rng.integers(0, 31))]) if mags is not None else 0.0
+                if signed and rng.integers(0, 2):
+                    mag = -mag
+                ops[b, k] = T.encode_op(name, mag)
+                row.append((name, mag))
+            chosen.append(row)
+        got = T.apply_ops(torch.from_numpy(imgs).cuda(), ops).cpu().numpy()
+        for b in range(B):
+            want = R.rand_augment(imgs[b], chosen[b])
+            assert np.array_equal(got[b], want), (H, W, chosen[b], int((got[b] != want).sum()))
+
+
 def test_whole_chain_with_rand_aug_vs_reference(golden_dir):
     """The reference's build_transformNPY(is_train=True, rand_aug=1) outputs under fixed seeds, fixed-sensor and
     variable-sensor branch, against EventBatchPipeline / EventBatchPipelineVar with ``rand_aug=True``."""
