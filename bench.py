@@ -524,7 +524,8 @@ def _time_steps(torch, fn, steps, warm):
 
 def histogram_record(args):
     """`Gevents/s histogram rasterise` (BASELINE.json's second metric) at the top size of config 2 -- 10 M events on the
-    640x480 N-ImageNet sensor -- for every spatial distribution of SURVEY.md 8(d), each checked against the oracle."""
+    640x480 N-ImageNet sensor (`streams`) and on the 240x180 N-Caltech101 sensor (`streams_240x180`) -- for the spatial
+    distributions of SURVEY.md 8(d), each checked against the oracle."""
     import torch
     rec = {"metric": HistogramWorkload.metric, "unit": HistogramWorkload.unit, "dtype": HistogramWorkload.dtype,
            "config": {"workload": "event->histogram rasterise, 10000000 events, 640x480 sensor, float64[N,4] rows -> uint8[H,W,3]",
@@ -551,6 +552,17 @@ def histogram_record(args):
     rec["value"] = rec["streams"]["uniform"]["value"]
     rec["worst_stream_value"] = min(vals)
     rec["roofline"] = rec["streams"]["uniform"]["roofline"]
+    # the other sensor of config 2 (N-Caltech101, 240x180): the whole sensor fits one SM's shared memory (strategy PRIVATE)
+    rec["streams_240x180"] = {}
+    for kind in ("uniform", "edge8", "hot"):
+        wl = HistogramWorkload(argparse.Namespace(sensor="240x180", events=10_000_000, dist=kind))
+        wl.setup(torch, 0)
+        ok = wl.verify()
+        ms = _time_steps(torch, wl.step_device, 20, 3)
+        rec["streams_240x180"][kind] = {"value": round(wl.n / (ms * 1e-3) / 1e9, 2), "us_per_step": round(ms * 1e3, 2),
+                                        "parity_vs_oracle": ok, "roofline": wl.roofline(ms)}
+        del wl
+        torch.cuda.empty_cache()
     return rec
 
 

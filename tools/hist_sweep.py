@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 from mem_b200.process_data import histogram, histogram_batch  # noqa: E402
 from oracle.make_golden import synth_events  # noqa: E402
 
-NAMES = {1: "global", 2: "global_agg", 3: "tile", 4: "private"}
+NAMES = {0: "auto", 1: "global", 2: "global_agg", 3: "tile", 4: "private", 6: "hybrid", 7: "sort"}
 
 
 def timeit(fn, iters=20, warm=3):
@@ -52,10 +52,12 @@ def main():
             for n in [10_000, 30_000, 100_000, 1_000_000, 10_000_000]:
                 ev = hot_pixel_events(rng, n, H, W) if kind == "hot" else synth_events(rng, n, H, W, kind)
                 d = torch.from_numpy(ev).cuda()
-                for s in (1, 2, 3, 4):
+                for s in (0, 1, 2, 3, 4, 6, 7):
                     if s == 3 and n > 1_000_000 and W == 640:
                         continue
                     if s == 4 and W == 640:            # sensor does not fit a tile: PRIVATE is GLOBAL there
+                        continue
+                    if s in (6, 7) and (W != 640 or n < 1_000_000):   # large-sensor, long-stream strategies
                         continue
                     if ONLY and s not in ONLY:
                         continue
