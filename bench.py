@@ -393,6 +393,29 @@ class EventPipelineWorkload:
         self.torch.cuda.current_stream().synchronize()
         return self.out_host
 
+    def with_rand_aug(self, steps=50, warm=10):
+        """Sub-record: the same batch with the reference scripts' default tail (ToUnit8 -> EventRandAugment(magnitude=20) ->
+        ToFloat32, mem/datasets.py:655-658) as one more launch; operations drawn once per resident batch like the other
+        per-sample records of the device-resident arm."""
+        import contextlib
+        import io
+        from mem_b200 import transforms as T
+        torch = self.torch
+        with contextlib.redirect_stdout(io.StringIO()):
+            aug = T.EventRandAugment(small=False, magnitude=20)
+        torch.manual_seed(11)
+        ops = [T.ops_to_device(aug.draw_batch(self.B, 224, 224), "cuda") for _ in range(4)]
+        out2 = torch.empty(self.B, self.C, 224, 224, dtype=torch.float32, device="cuda")
+
+        def step():
+            self.step_device()
+            T.apply_ops(self.out, ops[self.k % 4], out_float=True, out=out2)
+
+        ms = _time_steps(torch, step, steps, warm)
+        return {"value": round(self.units_per_step / (ms * 1e-3) / 1e9, 3), "unit": self.unit, "us_per_step": round(ms * 1e3, 2),
+                "gpu_launches_per_step": 2,
+                "what": "event_pipeline_fused + event_randaug (two drawn operations per sample), device-resident"}
+
     def verify(self):
         import random
         import numpy as np
@@ -677,6 +700,8 @@ def main():
                     "d2h_bytes_per_step": wl.d2h, "ms_per_step": round(ms_e2e / e2e_steps, 3)},
             "gpu_launches": int(launches), "parity_vs_oracle": ok, "clocks": clocks,
             "roofline": wl.roofline(ms_step)}
+    if hasattr(wl, "with_rand_aug") and world == 1:
+        line["with_rand_aug"] = wl.with_rand_aug()
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = wl.cpu_baseline()
     print(json.dumps(line))

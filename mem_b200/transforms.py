@@ -98,22 +98,35 @@ def encode_op(name: str, magnitude: float) -> np.void:
     return rec
 
 
-def apply_ops(x: torch.Tensor, ops: np.ndarray, out_float: Optional[bool] = None) -> torch.Tensor:
+def ops_to_device(ops: np.ndarray, device) -> torch.Tensor:
+    """``OP_DTYPE`` records ``[B, num_ops]`` -> the uint8 CUDA tensor ``[B, num_ops, 40]`` ``apply_ops`` also accepts."""
+    ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+    return torch.from_numpy(ops.view(np.uint8).reshape(ops.shape + (OP_DTYPE.itemsize,)).copy()).to(device, non_blocking=True)
+
+
+def apply_ops(x: torch.Tensor, ops, out_float: Optional[bool] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x: CUDA uint8 or float32 ``[B, 3, H, W]`` (float32 is converted like ``ToUnit8``); ops: ``OP_DTYPE`` array
-    ``[B, num_ops]``.  Returns uint8, or float32 converted like ``ToFloat32`` (default: the dtype class of ``x``)."""
+    ``[B, num_ops]`` (or its device copy from ``ops_to_device``).  Returns uint8, or float32 converted like ``ToFloat32``
+    (default: the dtype class of ``x``)."""
     _lib.require_cuda()
     if not x.is_cuda:
         raise RuntimeError("mem_b200.transforms runs on CUDA tensors only (no CPU path)")
     assert x.ndim == 4 and x.shape[1] == 3 and x.dtype in (torch.uint8, torch.float32), "expected uint8 / float32 [B, 3, H, W]"
     B, C, H, W = x.shape
-    ops = np.ascontiguousarray(ops, dtype=OP_DTYPE).reshape(B, -1)
+    if isinstance(ops, torch.Tensor):
+        assert ops.is_cuda and ops.dtype == torch.uint8 and ops.is_contiguous() and ops.shape[0] == B and ops.shape[-1] == OP_DTYPE.itemsize
+        dev_ops, num_ops = ops, (ops.shape[1] if ops.ndim == 3 else 1)
+    else:
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE).reshape(B, -1)
+        num_ops = ops.shape[1]
+        dev_ops = ops_to_device(ops, x.device) if ops.size else None
     x = x.contiguous()
     out_float = (x.dtype == torch.float32) if out_float is None else out_float
-    out = torch.empty(B, C, H, W, dtype=torch.float32 if out_float else torch.uint8, device=x.device)
-    dev_ops = torch.from_numpy(ops.view(np.uint8).reshape(-1).copy()).to(x.device, non_blocking=True) if ops.size else None
+    if out is None:
+        out = torch.empty(B, C, H, W, dtype=torch.float32 if out_float else torch.uint8, device=x.device)
     lib = _lib.load()
     _lib.check(lib.memb_event_randaug(x.data_ptr(), int(x.dtype == torch.float32), B, C, H, W,
-                                      dev_ops.data_ptr() if dev_ops is not None else None, ops.shape[1] if ops.size else 0,
+                                      dev_ops.data_ptr() if dev_ops is not None and num_ops else None, num_ops,
                                       out.data_ptr(), int(out_float), _lib.stream_ptr(torch, x.device)))
     return out
 
