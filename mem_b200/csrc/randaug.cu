@@ -22,6 +22,7 @@ constexpr int kThreads = 1024;
 constexpr int kMaxImageBytes = 200 * 1024;
 
 struct Scratch {
+  float unit[256];            // ToFloat32 value of every count: c / 255 (one correctly rounded division each)
   unsigned int hist[3][256];
   unsigned int lut[3][256];
   unsigned int sum;
@@ -39,6 +40,20 @@ __device__ __forceinline__ uint8_t gray_u8(uint8_t r, uint8_t g, uint8_t b) {
 __device__ __forceinline__ uint8_t blend_u8(float r0, float r1, uint8_t a, float other) {
   // (ratio * img1 + (1 - ratio) * img2).clamp(0, 255).to(uint8)
   return clamp_u8(__fadd_rn(__fmul_rn(r0, (float)a), __fmul_rn(r1, other)));
+}
+
+// In-place point-wise operation over the image bytes, four per thread when possible: f(value, byte index) -> value
+template <typename F>
+__device__ __forceinline__ void map_bytes(uint8_t* img, int n, bool vec, int tid, F f) {
+  if (vec) {
+    for (int i = tid; i < n / 4; i += 1024) {
+      uchar4 v = reinterpret_cast<uchar4*>(img)[i];
+      v.x = f(v.x, 4 * i); v.y = f(v.y, 4 * i + 1); v.z = f(v.z, 4 * i + 2); v.w = f(v.w, 4 * i + 3);
+      reinterpret_cast<uchar4*>(img)[i] = v;
+    }
+  } else {
+    for (int i = tid; i < n; i += 1024) img[i] = f(img[i], i);
+  }
 }
 
 // grid_sample(bilinear, zeros, align_corners=False) of one output pixel for the three channels
@@ -66,16 +81,27 @@ __global__ void __launch_bounds__(kThreads, 1) event_randaug(const void* __restr
   uint8_t* img = ra_smem;
   Scratch* sc = reinterpret_cast<Scratch*>(ra_smem + ((CHW + 15) / 16) * 16);
   uint8_t* stash = static_cast<uint8_t*>(out) + (size_t)b * CHW * (out_f32 ? 4 : 1);   // this sample's slab of the output
+  if (tid < 256) sc->unit[tid] = __fdiv_rn((float)tid, 255.f);
 
   // ---- load (ToUnit8: (255 * x).to(uint8)); four pixels per thread when the slab allows 16-byte / 4-byte accesses
   const bool vec = (CHW & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  // (eight independent loads per thread in flight: a load -> convert -> st.shared loop issues one load per round trip)
+  constexpr int kLd = 8;
   if (in_f32) {
     const float* src = static_cast<const float*>(in) + (size_t)b * CHW;
     if (vec) {
-      for (int i = tid; i < CHW / 4; i += kThreads) {
-        const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + i);
-        reinterpret_cast<uchar4*>(img)[i] = make_uchar4(to_u8_trunc(__fmul_rn(255.f, v.x)), to_u8_trunc(__fmul_rn(255.f, v.y)),
-                                                        to_u8_trunc(__fmul_rn(255.f, v.z)), to_u8_trunc(__fmul_rn(255.f, v.w)));
+      const int n4 = CHW / 4;
+      for (int i0 = tid; i0 < n4; i0 += kThreads * kLd) {
+        float4 v[kLd];
+#pragma unroll
+        for (int u = 0; u < kLd; ++u)
+          if (i0 + u * kThreads < n4) v[u] = __ldcs(reinterpret_cast<const float4*>(src) + i0 + u * kThreads);
+#pragma unroll
+        for (int u = 0; u < kLd; ++u)
+          if (i0 + u * kThreads < n4)
+            reinterpret_cast<uchar4*>(img)[i0 + u * kThreads] =
+                make_uchar4(to_u8_trunc(__fmul_rn(255.f, v[u].x)), to_u8_trunc(__fmul_rn(255.f, v[u].y)),
+                            to_u8_trunc(__fmul_rn(255.f, v[u].z)), to_u8_trunc(__fmul_rn(255.f, v[u].w)));
       }
     } else {
       for (int i = tid; i < CHW; i += kThreads) img[i] = to_u8_trunc(__fmul_rn(255.f, src[i]));
@@ -83,7 +109,16 @@ __global__ void __launch_bounds__(kThreads, 1) event_randaug(const void* __restr
   } else {
     const uint8_t* src = static_cast<const uint8_t*>(in) + (size_t)b * CHW;
     if (vec) {
-      for (int i = tid; i < CHW / 4; i += kThreads) reinterpret_cast<uchar4*>(img)[i] = reinterpret_cast<const uchar4*>(src)[i];
+      const int n4 = CHW / 4;
+      for (int i0 = tid; i0 < n4; i0 += kThreads * kLd) {
+        uchar4 v[kLd];
+#pragma unroll
+        for (int u = 0; u < kLd; ++u)
+          if (i0 + u * kThreads < n4) v[u] = reinterpret_cast<const uchar4*>(src)[i0 + u * kThreads];
+#pragma unroll
+        for (int u = 0; u < kLd; ++u)
+          if (i0 + u * kThreads < n4) reinterpret_cast<uchar4*>(img)[i0 + u * kThreads] = v[u];
+      }
     } else {
       for (int i = tid; i < CHW; i += kThreads) img[i] = src[i];
     }
@@ -102,23 +137,42 @@ __global__ void __launch_bounds__(kThreads, 1) event_randaug(const void* __restr
         const float r00 = __fdiv_rn(op.theta[0], hw), r10 = __fdiv_rn(op.theta[1], hw), r20 = __fdiv_rn(op.theta[2], hw);
         const float r01 = __fdiv_rn(op.theta[3], hh), r11 = __fdiv_rn(op.theta[4], hh), r21 = __fdiv_rn(op.theta[5], hh);
         const float xo = -hw + 0.5f, yo = -hh + 0.5f;
-        for (int i = tid; i < HW; i += kThreads) {
+        auto pixel = [&](int i, float (&v)[3]) {
           const int y = i / W, x = i - y * W;
           const float xb = (float)x + xo, yb = (float)y + yo;
           const float gx = __fadd_rn(__fadd_rn(__fmul_rn(xb, r00), __fmul_rn(yb, r10)), r20);
           const float gy = __fadd_rn(__fadd_rn(__fmul_rn(xb, r01), __fmul_rn(yb, r11)), r21);
           const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), 1.f), 2.f);
           const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), 1.f), 2.f);
-          float v[3];
           sample3(img, H, W, ix, iy, v);
+        };
+        if (vec && (HW & 3) == 0) {                  // four pixels per thread: one 4-byte store per channel
+          for (int i = tid; i < HW / 4; i += kThreads) {
+            uint8_t r[3][4];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) stash[c * HW + i] = (uint8_t)(int)rintf(v[c]);       // torch.round, then .to(uint8)
+            for (int k = 0; k < 4; ++k) {
+              float v[3];
+              pixel(4 * i + k, v);
+#pragma unroll
+              for (int c = 0; c < 3; ++c) r[c][k] = (uint8_t)(int)rintf(v[c]);       // torch.round, then .to(uint8)
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              reinterpret_cast<uchar4*>(stash + c * HW)[i] = make_uchar4(r[c][0], r[c][1], r[c][2], r[c][3]);
+          }
+        } else {
+          for (int i = tid; i < HW; i += kThreads) {
+            float v[3];
+            pixel(i, v);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) stash[c * HW + i] = (uint8_t)(int)rintf(v[c]);
+          }
         }
         gathered = true;
         break;
       }
       case MEMB_RA_BRIGHTNESS:
-        for (int i = tid; i < CHW; i += kThreads) img[i] = blend_u8(op.f0, op.f1, img[i], 0.f);
+        map_bytes(img, CHW, vec, tid, [&](uint8_t v, int) { return blend_u8(op.f0, op.f1, v, 0.f); });
         break;
       case MEMB_RA_COLOR:
         for (int i = tid; i < HW; i += kThreads) {
@@ -138,13 +192,13 @@ __global__ void __launch_bounds__(kThreads, 1) event_randaug(const void* __restr
         if ((tid & 31) == 0) atomicAdd(&sc->sum, part);
         __syncthreads();
         const float mean = __fdiv_rn((float)sc->sum, (float)HW);       // integer sum < 2^24: exact in float32 in any order
-        for (int i = tid; i < CHW; i += kThreads) img[i] = blend_u8(op.f0, op.f1, img[i], mean);
+        map_bytes(img, CHW, vec, tid, [&](uint8_t v, int) { return blend_u8(op.f0, op.f1, v, mean); });
         break;
       }
       case MEMB_RA_SHARPNESS: {
         if (H <= 2 || W <= 2) break;
         const float k1 = __fdiv_rn(1.f, 13.f), k5 = __fdiv_rn(5.f, 13.f);
-        for (int i = tid; i < CHW; i += kThreads) {
+        auto sharpen = [&](int i) -> uint8_t {
           const int c = i / HW, r = i - c * HW, y = r / W, x = r - y * W;
           float other = (float)img[i];
           if (y > 0 && y < H - 1 && x > 0 && x < W - 1) {
@@ -156,21 +210,24 @@ __global__ void __launch_bounds__(kThreads, 1) event_randaug(const void* __restr
                 acc = __fadd_rn(acc, __fmul_rn((float)img[i + dy * W + dx], (dy == 0 && dx == 0) ? k5 : k1));
             other = (float)(uint8_t)(int)rintf(acc);
           }
-          stash[i] = blend_u8(op.f0, op.f1, img[i], other);
+          return blend_u8(op.f0, op.f1, img[i], other);
+        };
+        if (vec) {
+          for (int i = tid; i < CHW / 4; i += kThreads)
+            reinterpret_cast<uchar4*>(stash)[i] = make_uchar4(sharpen(4 * i), sharpen(4 * i + 1), sharpen(4 * i + 2), sharpen(4 * i + 3));
+        } else {
+          for (int i = tid; i < CHW; i += kThreads) stash[i] = sharpen(i);
         }
         gathered = true;
         break;
       }
       case MEMB_RA_POSTERIZE: {
         const uint8_t mask = (uint8_t)((-(1 << (8 - op.ival))) & 0xff);
-        for (int i = tid; i < CHW; i += kThreads) img[i] &= mask;
+        map_bytes(img, CHW, vec, tid, [&](uint8_t v, int) { return (uint8_t)(v & mask); });
         break;
       }
       case MEMB_RA_SOLARIZE:
-        for (int i = tid; i < CHW; i += kThreads) {
-          const uint8_t v = img[i];
-          img[i] = ((float)v >= op.f0) ? (uint8_t)(255 - v) : v;
-        }
+        map_bytes(img, CHW, vec, tid, [&](uint8_t v, int) { return ((float)v >= op.f0) ? (uint8_t)(255 - v) : v; });
         break;
       case MEMB_RA_AUTOCONTRAST: {
         if (tid < 3) { sc->lo[tid] = 255u; sc->hi[tid] = 0u; }
@@ -187,13 +244,18 @@ __global__ void __launch_bounds__(kThreads, 1) event_randaug(const void* __restr
           if ((tid & 31) == 0) { atomicMin(&sc->lo[c], lo); atomicMax(&sc->hi[c], hi); }
         }
         __syncthreads();
-        for (int i = tid; i < CHW; i += kThreads) {
-          const int c = i / HW;
-          float lo = (float)sc->lo[c];
-          float scale = __fdiv_rn(255.f, __fsub_rn((float)sc->hi[c], lo));
-          if (!isfinite(scale)) { lo = 0.f; scale = 1.f; }
-          img[i] = clamp_u8(__fmul_rn(__fsub_rn((float)img[i], lo), scale));
+        float lo3[3], sc3[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          lo3[c] = (float)sc->lo[c];
+          sc3[c] = __fdiv_rn(255.f, __fsub_rn((float)sc->hi[c], lo3[c]));
+          if (!isfinite(sc3[c])) { lo3[c] = 0.f; sc3[c] = 1.f; }
         }
+        map_bytes(img, CHW, vec, tid, [&](uint8_t v, int i) {
+          const int c = i >= 2 * HW ? 2 : (i >= HW ? 1 : 0);
+          return clamp_u8(__fmul_rn(__fsub_rn((float)v, c == 0 ? lo3[0] : (c == 1 ? lo3[1] : lo3[2])),
+                                    c == 0 ? sc3[0] : (c == 1 ? sc3[1] : sc3[2])));
+        });
         break;
       }
       case MEMB_RA_EQUALIZE: {
@@ -218,10 +280,10 @@ __global__ void __launch_bounds__(kThreads, 1) event_randaug(const void* __restr
           }
         }
         __syncthreads();
-        for (int i = tid; i < CHW; i += kThreads) {
-          const int c = i / HW;
-          if (sc->lut_on[c]) img[i] = (uint8_t)sc->lut[c][img[i]];
-        }
+        map_bytes(img, CHW, vec, tid, [&](uint8_t v, int i) {
+          const int c = i >= 2 * HW ? 2 : (i >= HW ? 1 : 0);
+          return sc->lut_on[c] ? (uint8_t)sc->lut[c][v] : v;
+        });
         break;
       }
       default:
@@ -230,7 +292,16 @@ __global__ void __launch_bounds__(kThreads, 1) event_randaug(const void* __restr
     __syncthreads();
     if (gathered) {                                   // read the gathered image back from this sample's slab
       if (vec) {
-        for (int i = tid; i < CHW / 4; i += kThreads) reinterpret_cast<uchar4*>(img)[i] = reinterpret_cast<const uchar4*>(stash)[i];
+        const int n4 = CHW / 4;
+        for (int i0 = tid; i0 < n4; i0 += kThreads * kLd) {
+          uchar4 v[kLd];
+#pragma unroll
+          for (int u = 0; u < kLd; ++u)
+            if (i0 + u * kThreads < n4) v[u] = __ldcg(reinterpret_cast<const uchar4*>(stash) + i0 + u * kThreads);
+#pragma unroll
+          for (int u = 0; u < kLd; ++u)
+            if (i0 + u * kThreads < n4) reinterpret_cast<uchar4*>(img)[i0 + u * kThreads] = v[u];
+        }
       } else {
         for (int i = tid; i < CHW; i += kThreads) img[i] = stash[i];
       }
@@ -243,11 +314,10 @@ __global__ void __launch_bounds__(kThreads, 1) event_randaug(const void* __restr
     if (vec) {
       for (int i = tid; i < CHW / 4; i += kThreads) {
         const uchar4 v = reinterpret_cast<const uchar4*>(img)[i];
-        __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(__fdiv_rn((float)v.x, 255.f), __fdiv_rn((float)v.y, 255.f),
-                                                               __fdiv_rn((float)v.z, 255.f), __fdiv_rn((float)v.w, 255.f)));
+        __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(sc->unit[v.x], sc->unit[v.y], sc->unit[v.z], sc->unit[v.w]));
       }
     } else {
-      for (int i = tid; i < CHW; i += kThreads) dst[i] = __fdiv_rn((float)img[i], 255.f);
+      for (int i = tid; i < CHW; i += kThreads) dst[i] = sc->unit[img[i]];
     }
   } else {
     uint8_t* dst = static_cast<uint8_t*>(out) + (size_t)b * CHW;
