@@ -674,7 +674,7 @@ template <bool kAligned>
 __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_var_fused(
     const double* __restrict__ ev, const long long* __restrict__ offsets, long long n_total,
     const memb_event_aug* __restrict__ aug, int Hc, int Wc, int outH, int outW, int C, float hot_num_stds, int normalize,
-    float* __restrict__ out, Header* __restrict__ hdr) {
+    int logtrafo, int gammatrafo, float gamma, float* __restrict__ out, Header* __restrict__ hdr) {
   extern __shared__ unsigned int tile[];
   __shared__ double redd[3][kTileThreads / 32];
   __shared__ float redf[kTileThreads / 32];
@@ -790,13 +790,23 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_var_fused(
   }
   __syncthreads();
   const float thr = s_thr;
-  if (!filter && !normalize) return;
+  const bool transform = logtrafo || gammatrafo;
+  if (!filter && !normalize && !transform) return;
+  // LogTransform / GammaTransform act on the resized float32 planes here (transforms.py:200-222): log(x + 1) and x ** gamma,
+  // evaluated in double and rounded once (torch's float32 kernels are within 1 ulp of that); gamma = 0.5 is a square root in
+  // torch (pow_tensor_scalar's special case), correctly rounded on both sides.
+  auto value_transform = [&](float v) {
+    if (logtrafo) v = (float)log((double)__fadd_rn(v, 1.0f));
+    if (gammatrafo) v = gamma == 0.5f ? __fsqrt_rn(v) : (float)pow((double)v, (double)gamma);
+    return v;
+  };
   // ---- maximum of what survives the filter (this CTA re-reads its own stores: plain loads after the barrier)
   float mx = 0.f;
   for (int i = threadIdx.x; i < npx; i += kTileThreads) {
     const float vp = __ldcg(o_pos + i), vn = __ldcg(o_neg + i);
     if (!(vp > thr || vn > thr)) mx = fmaxf(mx, fmaxf(vp, vn));
   }
+  if (transform) mx = value_transform(mx);        // both maps are non-decreasing: the maximum commutes with them
   for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) redf[warp] = mx;
   __syncthreads();
@@ -810,6 +820,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_var_fused(
   for (int i = threadIdx.x; i < npx; i += kTileThreads) {
     float vp = __ldcg(o_pos + i), vn = __ldcg(o_neg + i);
     if (vp > thr || vn > thr) { vp = 0.f; vn = 0.f; }
+    if (transform) { vp = value_transform(vp); vn = value_transform(vn); }
     o_pos[i] = __fmul_rn(vp, factor);
     o_neg[i] = __fmul_rn(vn, factor);
   }
@@ -2107,6 +2118,15 @@ extern "C" int memb_event_pipeline_lut_f32(const double* ev, int64_t n, const in
 extern "C" int memb_event_pipeline_var_f32(const double* ev, int64_t n, const int64_t* offsets, int B, const memb_event_aug* aug,
                                            int canvas_H, int canvas_W, int outH, int outW, int C, float hot_num_stds,
                                            int normalize, float* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
+  return memb_event_pipeline_var_tf_f32(ev, n, offsets, B, aug, canvas_H, canvas_W, outH, outW, C, hot_num_stds, normalize, 0, 0,
+                                        0.5f, out, ws, ws_bytes, stream);
+}
+
+extern "C" int memb_event_pipeline_var_tf_f32(const double* ev, int64_t n, const int64_t* offsets, int B,
+                                              const memb_event_aug* aug, int canvas_H, int canvas_W, int outH, int outW, int C,
+                                              float hot_num_stds, int normalize, int logtrafo, int gammatrafo, float gamma,
+                                              float* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
+  MEMB_REQUIRE(!gammatrafo || gamma > 0.0f, "event_pipeline_var: gamma must be positive, got %g", (double)gamma);
   MEMB_REQUIRE(B >= 1 && canvas_H >= 1 && canvas_W >= 1 && outH >= 1 && outW >= 1, "event_pipeline_var: bad shape");
   MEMB_REQUIRE(C == 2 || C == 3, "event_pipeline_var: C must be 2 or 3, got %d", C);
   MEMB_REQUIRE((long long)canvas_H * canvas_W <= kTileMaxWords,
@@ -2129,7 +2149,8 @@ extern "C" int memb_event_pipeline_var_f32(const double* ev, int64_t n, const in
   }
   const size_t smem = (size_t)round_up<long long>((long long)canvas_H * canvas_W, 4) * 4;
   kern<<<B, kTileThreads, smem, stream>>>(ev, reinterpret_cast<const long long*>(offsets), n, aug, canvas_H, canvas_W, outH, outW,
-                                          C, hot_num_stds, normalize, out, reinterpret_cast<Header*>(ws));
+                                          C, hot_num_stds, normalize, logtrafo, gammatrafo, gamma, out,
+                                          reinterpret_cast<Header*>(ws));
   MEMB_LAUNCH_OK("event_pipeline_var_fused");
   return MEMB_OK;
 }

@@ -405,6 +405,9 @@ class VarPipelineConfig:
     hotpix_num_stds: float = 10
     normalize_events: bool = False
     rand_aug: bool = False
+    logtrafo: bool = False
+    gammatrafo: bool = False
+    gamma: float = 0.5
 
     def __post_init__(self):
         assert 5000 <= self.slice_max_evs < 200000 and 0 <= self.max_random_shift_evs <= 200     # datasets.py:491, :530
@@ -431,10 +434,11 @@ def draw_params_var(n_events: int, cfg: VarPipelineConfig) -> dict:
 
 
 def pipeline_var_fused(events, offsets, aug, canvas_hw, out_hw, channels=3, *, hot_num_stds=10.0, normalize=False, check=True,
-                       out=None):
-    """Ragged batch of raw streams -> ``float32 (B,C,outH,outW)`` through ``memb_event_pipeline_var_f32`` (sizes inferred
-    per stream, anti-aliased bilinear resize).  ``check`` synchronises and raises ``ValueError`` where the reference
-    raises (a stream that is empty after the window / shift) or when a recording exceeds the canvas."""
+                       out=None, logtrafo=False, gammatrafo=False, gamma=0.5):
+    """Ragged batch of raw streams -> ``float32 (B,C,outH,outW)`` through ``memb_event_pipeline_var_tf_f32`` (sizes inferred
+    per stream, anti-aliased bilinear resize, optional log / gamma maps of the resized planes).  ``check`` synchronises and
+    raises ``ValueError`` where the reference raises (a stream that is empty after the window / shift) or when a recording
+    exceeds the canvas."""
     torch = _lib.require_cuda()
     from .process_data import _as_device_events
     device = torch.device(events.device if (isinstance(events, torch.Tensor) and events.is_cuda) else "cuda")
@@ -453,10 +457,11 @@ def pipeline_var_fused(events, offsets, aug, canvas_hw, out_hw, channels=3, *, h
         ws = _lib.workspace.get(torch, 256, device, "hist")
         stream = _lib.stream_ptr(torch, device)
         n = int(ev.shape[0])
-        _lib.check(lib.memb_event_pipeline_var_f32(ev.data_ptr() if n else None, n, off.data_ptr(), B, aug_dev.data_ptr(),
-                                                   int(canvas_hw[0]), int(canvas_hw[1]), outH, outW, channels,
-                                                   float(hot_num_stds) if hot_num_stds is not None else -1.0, int(bool(normalize)),
-                                                   out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        _lib.check(lib.memb_event_pipeline_var_tf_f32(ev.data_ptr() if n else None, n, off.data_ptr(), B, aug_dev.data_ptr(),
+                                                      int(canvas_hw[0]), int(canvas_hw[1]), outH, outW, channels,
+                                                      float(hot_num_stds) if hot_num_stds is not None else -1.0,
+                                                      int(bool(normalize)), int(bool(logtrafo)), int(bool(gammatrafo)), float(gamma),
+                                                      out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
         if check:
             _lib.check(lib.memb_hist_status(ws.data_ptr(), stream))
     return out
@@ -488,5 +493,6 @@ class EventBatchPipelineVar:
         aug, _ = pack_params(params)
         out = pipeline_var_fused(events, offsets, aug, (cfg.canvas_H, cfg.canvas_W), (cfg.input_H, cfg.input_W), self.channels,
                                  hot_num_stds=cfg.hotpix_num_stds if cfg.hotpixfilter else None,
-                                 normalize=cfg.normalize_events, check=check)
+                                 normalize=cfg.normalize_events, check=check, logtrafo=cfg.logtrafo, gammatrafo=cfg.gammatrafo,
+                                 gamma=cfg.gamma)
         return _apply_randaug(out, params, cfg, self.channels)

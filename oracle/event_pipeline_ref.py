@@ -175,6 +175,9 @@ class VarPipelineCfg:
     hotpix_num_stds: float = 10
     normalize_events: bool = False
     rand_aug: bool = False
+    logtrafo: bool = False
+    gammatrafo: bool = False
+    gamma: float = 0.5
 
 
 def draw_params_var(n_events: int, cfg: VarPipelineCfg) -> dict:
@@ -231,6 +234,10 @@ def pipeline_var_ref(events: np.ndarray, cfg: VarPipelineCfg, params: dict | Non
         hot = torch.atleast_1d(torch.squeeze(torch.argwhere(pol.flatten() > thr)))
         idx = np.asarray(np.unravel_index(hot, x.shape)).T
         x[0::2, idx[:, 1], idx[:, 2]] = 0
+    if cfg.logtrafo:                                            # LogTransform, transforms.py:200-210 (float32 here: after Resize)
+        x[0::2, :, :] = torch.log(x[0::2, :, :] + 1.0)
+    if cfg.gammatrafo:                                          # GammaTransform, transforms.py:212-222
+        x[0::2, :, :] = x[0::2, :, :] ** cfg.gamma
     if cfg.normalize_events:
         if x[0::2, :, :].max() != 0:
             x[0::2, :, :] = x[0::2, :, :] * (1.0 / x[0::2, :, :].max())

@@ -810,11 +810,43 @@ def golden_event_pipeline_tss():
     np.savez_compressed(os.path.join(GOLD, "event_pipeline_tss.npz"), **out)
 
 
+def golden_event_pipeline_var_loggamma():
+    """Reference build_transformNPY on its variable-sensor branch with LogTransform / GammaTransform on: there they act on
+    the float32 image after Resize (mem/datasets.py:639, :648-651), not on integer counts."""
+    import contextlib, io
+    import torch
+    from types import SimpleNamespace
+    ds = ref_shims.ref_module("datasets")
+    out = {}
+    cases = [  # name, data_path, (H, W), polarity, is_train, n_events, kind, normalize, log, gamma on, gamma, seed
+        ("cal_log", "/data/N-Caltech101", (180, 240), (-1.0, 1.0), True, 45000, "edge", 1, 1, 0, 0.5, 61),
+        ("cal_sqrt", "/data/N-Caltech101", (180, 240), (-1.0, 1.0), True, 20000, "hot", 0, 0, 1, 0.5, 62),
+        ("cal_both", "/data/N-Caltech101", (172, 233), (-1.0, 1.0), True, 38000, "uniform", 1, 1, 1, 0.7, 63),
+        ("cars_both_eval", "/data/ncars", (100, 120), (0.0, 1.0), False, 6000, "edge", 0, 1, 1, 0.5, 64),
+        ("cars_pow", "/data/ncars", (100, 120), (0.0, 1.0), True, 9000, "uniform", 1, 0, 1, 1.6, 65),
+    ]
+    for name, path, (H, W), pol, is_train, n, kind, norm, lg, gm, gamma, seed in cases:
+        args = SimpleNamespace(data_path=path, input_H=224, input_W=224, slice_max_evs=30000, max_random_shift_evs=15,
+                               timesurface=0, hotpixfilter=1, hotpix_num_stds=10, logtrafo=lg, gammatrafo=gm, gamma=gamma,
+                               normalize_events=norm, rand_aug=0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tf = ds.build_transformNPY(is_train, args)
+        ev = np.floor(synth_events(np.random.default_rng(seed), n, H, W, kind, polarity=pol))
+        random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+        res = tf(ev.copy())
+        out[name + "_out"] = res.numpy()
+        out[name + "_meta"] = np.array([int(is_train), n, norm, lg, gm, seed, H, W, int(pol[0] == 0.0)], dtype=np.int64)
+        out[name + "_gamma"] = np.array(gamma, dtype=np.float64)
+        out[name + "_kind"] = np.array(kind)
+        print(f"event_pipeline_var_loggamma {name}: nnz {int((res != 0).sum())} max {float(res.max()):.4f}")
+    np.savez_compressed(os.path.join(GOLD, "event_pipeline_var_loggamma.npz"), **out)
+
+
 SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit, "dvae": golden_dvae,
             "engine": golden_engine, "event_pipeline": golden_event_pipeline, "decode": golden_decode, "engine_ft": golden_engine_ft,
             "vit_bf16": golden_vit_bf16, "finetune_remap": golden_finetune_remap, "dvae_train": golden_dvae_train, "event_pipeline_var": golden_event_pipeline_var, "randaug": golden_randaug,
             "event_pipeline_randaug": golden_event_pipeline_randaug, "event_pipeline_loggamma": golden_event_pipeline_loggamma,
-            "event_pipeline_tss": golden_event_pipeline_tss}
+            "event_pipeline_tss": golden_event_pipeline_tss, "event_pipeline_var_loggamma": golden_event_pipeline_var_loggamma}
 
 
 def main(argv):

@@ -276,6 +276,43 @@ def test_variable_sensor_reference_golden(golden_dir):
     assert seen == 6
 
 
+# log(x + 1) / x ** gamma of the resized planes: this side rounds the double-precision value once, torch's float32 kernels
+# are within 1 ulp of that per map (gamma = 0.5 is a square root on both sides).  Everything after the resize is
+# multiplicative, so the bound is relative: the resize's summation-order differences (a few ulp of all-positive sums),
+# stretched by gamma when gamma > 1, plus the maps' own ulp and the normalising multiply.
+VAR_TF_RTOL = 2e-6
+
+
+def _var_loggamma_cases(golden_dir):
+    z = np.load(os.path.join(golden_dir, "event_pipeline_var_loggamma.npz"))
+    for name in sorted(k[:-4] for k in z.files if k.endswith("_out")):
+        is_train, n, norm, lg, gm, seed, H, W, pol01 = (int(v) for v in z[name + "_meta"])
+        ev = np.floor(synth_events(np.random.default_rng(seed), n, H, W, str(z[name + "_kind"]),
+                                   polarity=(0.0, 1.0) if pol01 else (-1.0, 1.0)))
+        yield name, ev, dict(is_train=bool(is_train), normalize_events=bool(norm), logtrafo=bool(lg), gammatrafo=bool(gm),
+                             gamma=float(z[name + "_gamma"])), seed, z[name + "_out"]
+
+
+def test_variable_sensor_log_gamma_reference_golden(golden_dir):
+    """args.logtrafo / args.gammatrafo on the variable-sensor branch (tests/golden/event_pipeline_var_loggamma.npz: outputs
+    of the reference's own build_transformNPY), gamma in {0.5, 0.7, 1.6}."""
+    from mem_b200.event_pipeline import EventBatchPipelineVar, VarPipelineConfig
+    seen, worst = 0, {}
+    for name, ev, kw, seed, want in _var_loggamma_cases(golden_dir):
+        seed_all(seed)
+        got = EventBatchPipelineVar(VarPipelineConfig(canvas_H=180, canvas_W=240, **kw))([ev])[0].cpu().numpy()
+        assert got.shape == want.shape, name
+        flipped = (got == 0) != (want == 0)
+        assert int(flipped.sum()) <= 2, (name, int(flipped.sum()))
+        rel = (np.abs(got - want) / np.maximum(np.abs(want), 1e-30))[~flipped & (want != 0)]
+        worst[name] = float(rel.max())
+        seen += 1
+    print("var log/gamma worst relative error:", worst)
+    assert seen == 5 and max(worst.values()) <= VAR_TF_RTOL, worst
+    with pytest.raises(ValueError):
+        EventBatchPipelineVar(VarPipelineConfig(gammatrafo=True, gamma=-1.0))([ev])
+
+
 def test_variable_sensor_batch_vs_oracle():
     """A ragged batch (different extents, polarities, lengths; int16 rows uploaded as stored) against the oracle chain
     with shared draws; C = 2; errors where the reference raises."""

@@ -136,6 +136,31 @@ def test_variable_sensor_oracle_matches_reference_golden(golden_dir):
                                                                     shift_x=-5, shift_y=0))
 
 
+def var_loggamma_cases(golden_dir):
+    from oracle.event_pipeline_ref import VarPipelineCfg
+    z = np.load(os.path.join(golden_dir, "event_pipeline_var_loggamma.npz"))
+    for name in sorted(k[:-4] for k in z.files if k.endswith("_out")):
+        is_train, n, norm, lg, gm, seed, H, W, pol01 = (int(v) for v in z[name + "_meta"])
+        kind = str(z[name + "_kind"])
+        ev = np.floor(synth_events(np.random.default_rng(seed), n, H, W, kind, polarity=(0.0, 1.0) if pol01 else (-1.0, 1.0)))
+        cfg = VarPipelineCfg(is_train=bool(is_train), normalize_events=bool(norm), logtrafo=bool(lg), gammatrafo=bool(gm),
+                             gamma=float(z[name + "_gamma"]))
+        yield name, ev, cfg, seed, (H, W), z[name + "_out"]
+
+
+def test_variable_sensor_log_gamma_oracle_matches_reference_golden(golden_dir):
+    """LogTransform / GammaTransform on the variable-sensor branch act on the resized float32 image
+    (tests/golden/event_pipeline_var_loggamma.npz: the reference chain's own outputs)."""
+    from oracle.event_pipeline_ref import pipeline_var_ref
+    seen = 0
+    for name, ev, cfg, seed, _, want in var_loggamma_cases(golden_dir):
+        seed_all(seed)
+        got = pipeline_var_ref(ev, cfg).numpy()
+        assert np.array_equal(got, want), f"{name}: {np.abs(got - want).max()}"
+        seen += 1
+    assert seen == 5
+
+
 def _loggamma_cases(golden_dir):
     z = np.load(os.path.join(golden_dir, "event_pipeline_loggamma.npz"))
     for name in sorted(k[:-4] for k in z.files if k.endswith("_out")):
