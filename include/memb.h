@@ -179,11 +179,14 @@ int memb_event_pipeline_var_f32(const double* ev, int64_t n, const int64_t* offs
 /* ... with LogTransform (logtrafo != 0: log(x + 1)) and / or GammaTransform (gammatrafo != 0: x ** gamma, gamma > 0) between
  * RemoveHotPixels and NormalizeEvent (mem/datasets.py:648-651, mem/transforms.py:200-222).  On this branch they act on the
  * resized float32 planes: evaluated per pixel in double and rounded once, within 1 ulp of torch's float32 log / pow per
- * map; gamma == 0.5 is torch's square-root special case (bit-exact). */
+ * map; gamma == 0.5 is torch's square-root special case (bit-exact).  timesurface != 0 (C = 3 only): the middle plane is
+ * EventArrToImg's time surface of the augmented rows (mem/datasets.py:585-589: last writer per pixel, every polarity,
+ * normalised over the surviving rows; RandomTimeFlip reverses order and time), resized like the polarity planes and kept
+ * (no RemoveTimesurface, mem/datasets.py:644); the filter, the maps and the normalisation do not touch it. */
 int memb_event_pipeline_var_tf_f32(const double* ev, int64_t n, const int64_t* offsets, int B, const memb_event_aug* aug,
                                    int canvas_H, int canvas_W, int outH, int outW, int C, float hot_num_stds, int normalize,
-                                   int logtrafo, int gammatrafo, float gamma, float* out, void* ws, size_t ws_bytes,
-                                   memb_stream_t stream);
+                                   int logtrafo, int gammatrafo, float gamma, int timesurface, float* out, void* ws,
+                                   size_t ws_bytes, memb_stream_t stream);
 
 /* EventRandAugment on uint8 [pos, 0, neg] images (mem/transforms.py:351-471, applied between ToUnit8 and ToFloat32 at the
  * end of build_transformNPY when args.rand_aug is set, mem/datasets.py:655-658).  The HOST draws each sample's operations

@@ -41,7 +41,7 @@ SIGNATURES = {
                                            _vp, _vp, _vp, _sz, _vp]),
     "memb_event_pipeline_var_f32": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _sz, _vp]),
     "memb_event_pipeline_var_tf_f32": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _f32,
-                                              _vp, _vp, _sz, _vp]),
+                                              _i32, _vp, _vp, _sz, _vp]),
     "memb_event_randaug": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp]),
     "memb_raster_post_workspace_bytes": (_sz, [_i32]),
     "memb_raster_post_f32": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp,

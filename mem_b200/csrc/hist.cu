@@ -674,9 +674,10 @@ template <bool kAligned>
 __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_var_fused(
     const double* __restrict__ ev, const long long* __restrict__ offsets, long long n_total,
     const memb_event_aug* __restrict__ aug, int Hc, int Wc, int outH, int outW, int C, float hot_num_stds, int normalize,
-    int logtrafo, int gammatrafo, float gamma, float* __restrict__ out, Header* __restrict__ hdr) {
+    int logtrafo, int gammatrafo, float gamma, int timesurface, float* __restrict__ out, Header* __restrict__ hdr) {
   extern __shared__ unsigned int tile[];
   __shared__ double redd[3][kTileThreads / 32];
+  __shared__ unsigned long long redk[2][kTileThreads / 32];
   __shared__ float redf[kTileThreads / 32];
   __shared__ float lut[256];
   __shared__ int ext[2];
@@ -771,9 +772,68 @@ __global__ void __launch_bounds__(kTileThreads, 1) event_pipeline_var_fused(
     }
     o_pos[i] = vp;
     o_neg[i] = vn;
-    if (C == 3) o_pos[npx + i] = 0.0f;
+    if (C == 3 && !timesurface) o_pos[npx + i] = 0.0f;       // RemoveTimesurface
     s1 += (double)vp + (double)vn;
     s2 += (double)vp * vp + (double)vn * vn;
+  }
+  if (C == 3 && timesurface) {
+    // ---- time surface (EventArrToImg(timeSurface=True), datasets.py:585-589): the tile is reused for the row that writes
+    // each pixel last -- every surviving row whatever its polarity; after RandomTimeFlip the array runs backwards, so the
+    // winner is the smallest row index -- then holds that row's (t - t.min()) / (t - t.min()).max() * 255 as uint8 and is
+    // resized like the polarity planes.  The filter / log / gamma / normalisation below leave this plane alone.
+    __syncthreads();
+    for (int i = threadIdx.x * 4; i < words; i += kTileThreads * 4) *reinterpret_cast<uint4*>(tile + i) = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (long long r = begin + threadIdx.x; r < end; r += kTileThreads) {
+      Event e = load_event<kAligned>(ev, r);
+      if (a.flip_x) e.x = __dsub_rn((double)(W1 - 1), e.x);
+      if (a.cull) {
+        e.x = __dadd_rn(e.x, (double)a.shift_x);
+        e.y = __dadd_rn(e.y, (double)a.shift_y);
+        if (!(e.x >= 0.0 && e.x < (double)W2 && e.y >= 0.0 && e.y < (double)H2)) continue;
+      }
+      const unsigned long long k = order_key(e.t);
+      lo = k < lo ? k : lo;
+      hi = k > hi ? k : hi;
+      atomicMax(&tile[__double2int_rz(e.y) * tw + __double2int_rz(e.x)], (unsigned int)(a.time_flip ? end - r : r - begin + 1));
+    }
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+      lo = l2 < lo ? l2 : lo;
+      hi = h2 > hi ? h2 : hi;
+    }
+    if (lane == 0) { redk[0][warp] = lo; redk[1][warp] = hi; }
+    __syncthreads();
+    for (int w = 0; w < kTileThreads / 32; ++w) { lo = redk[0][w] < lo ? redk[0][w] : lo; hi = redk[1][w] > hi ? redk[1][w] : hi; }
+    const double t_lo = key_value(lo), t_hi = key_value(hi);
+    const bool flip = a.time_flip != 0;
+    const double t_last = ev[4 * (end - 1) + 2];          // RandomTimeFlip: t' = t[last row of the window] - t (datasets.py:603-606)
+    const double tmin = flip ? t_last - t_hi : t_lo;
+    const double span = flip ? (t_last - t_lo) - tmin : t_hi - tmin;
+    for (int i = threadIdx.x; i < tw * th; i += kTileThreads) {
+      const unsigned int w = tile[i];
+      if (w) {
+        const long long r = flip ? end - (long long)w : begin + (long long)w - 1;
+        const double t = flip ? t_last - ev[4 * r + 2] : ev[4 * r + 2];
+        const double v = (t - tmin) / span * 255.0;     // float64, the reference's operation order; numpy's cast truncates
+        tile[i] = (v == v) ? (unsigned int)(uint8_t)(long long)v : 0u;
+      }
+    }
+    __syncthreads();
+    float* o_tss = o_pos + npx;
+    for (int i = threadIdx.x; i < npx; i += kTileThreads) {
+      const int oy = i / outW, ox = i - oy * outW;
+      const AaTaps tx = aa_taps(ox, W3, outW), ty = aa_taps(oy, H3, outH);
+      float v = 0.f;
+      for (int jy = 0; jy < ty.n; ++jy) {
+        const unsigned int* row = tile + (ty.lo + jy) * tw + tx.lo;
+        float rv = 0.f;
+        for (int jx = 0; jx < tx.n; ++jx) rv = fmaf(lut[row[jx] & 0xffu], tx.w[jx], rv);
+        v = fmaf(rv, ty.w[jy], v);
+      }
+      o_tss[i] = v;
+    }
   }
   // ---- RemoveHotPixels threshold: mean + k * std (unbiased) over both polarity planes
   const bool filter = hot_num_stds >= 0.0f;
@@ -2119,14 +2179,16 @@ extern "C" int memb_event_pipeline_var_f32(const double* ev, int64_t n, const in
                                            int canvas_H, int canvas_W, int outH, int outW, int C, float hot_num_stds,
                                            int normalize, float* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
   return memb_event_pipeline_var_tf_f32(ev, n, offsets, B, aug, canvas_H, canvas_W, outH, outW, C, hot_num_stds, normalize, 0, 0,
-                                        0.5f, out, ws, ws_bytes, stream);
+                                        0.5f, 0, out, ws, ws_bytes, stream);
 }
 
 extern "C" int memb_event_pipeline_var_tf_f32(const double* ev, int64_t n, const int64_t* offsets, int B,
                                               const memb_event_aug* aug, int canvas_H, int canvas_W, int outH, int outW, int C,
                                               float hot_num_stds, int normalize, int logtrafo, int gammatrafo, float gamma,
-                                              float* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
+                                              int timesurface, float* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
   MEMB_REQUIRE(!gammatrafo || gamma > 0.0f, "event_pipeline_var: gamma must be positive, got %g", (double)gamma);
+  MEMB_REQUIRE(!timesurface || C == 3, "event_pipeline_var: the time surface needs C = 3, got %d", C);
+  MEMB_REQUIRE(!timesurface || n < 0xffffffffLL, "event_pipeline_var: too many rows for the time surface's row keys");
   MEMB_REQUIRE(B >= 1 && canvas_H >= 1 && canvas_W >= 1 && outH >= 1 && outW >= 1, "event_pipeline_var: bad shape");
   MEMB_REQUIRE(C == 2 || C == 3, "event_pipeline_var: C must be 2 or 3, got %d", C);
   MEMB_REQUIRE((long long)canvas_H * canvas_W <= kTileMaxWords,
@@ -2149,7 +2211,7 @@ extern "C" int memb_event_pipeline_var_tf_f32(const double* ev, int64_t n, const
   }
   const size_t smem = (size_t)round_up<long long>((long long)canvas_H * canvas_W, 4) * 4;
   kern<<<B, kTileThreads, smem, stream>>>(ev, reinterpret_cast<const long long*>(offsets), n, aug, canvas_H, canvas_W, outH, outW,
-                                          C, hot_num_stds, normalize, logtrafo, gammatrafo, gamma, out,
+                                          C, hot_num_stds, normalize, logtrafo, gammatrafo, gamma, timesurface, out,
                                           reinterpret_cast<Header*>(ws));
   MEMB_LAUNCH_OK("event_pipeline_var_fused");
   return MEMB_OK;

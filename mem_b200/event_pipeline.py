@@ -434,9 +434,10 @@ def draw_params_var(n_events: int, cfg: VarPipelineConfig) -> dict:
 
 
 def pipeline_var_fused(events, offsets, aug, canvas_hw, out_hw, channels=3, *, hot_num_stds=10.0, normalize=False, check=True,
-                       out=None, logtrafo=False, gammatrafo=False, gamma=0.5):
+                       out=None, logtrafo=False, gammatrafo=False, gamma=0.5, timesurface=False):
     """Ragged batch of raw streams -> ``float32 (B,C,outH,outW)`` through ``memb_event_pipeline_var_tf_f32`` (sizes inferred
-    per stream, anti-aliased bilinear resize, optional log / gamma maps of the resized planes).  ``check`` synchronises and
+    per stream, anti-aliased bilinear resize, optional log / gamma maps of the resized planes, optional time surface in the
+    middle plane).  ``check`` synchronises and
     raises ``ValueError`` where the reference raises (a stream that is empty after the window / shift) or when a recording
     exceeds the canvas."""
     torch = _lib.require_cuda()
@@ -461,7 +462,7 @@ def pipeline_var_fused(events, offsets, aug, canvas_hw, out_hw, channels=3, *, h
                                                       int(canvas_hw[0]), int(canvas_hw[1]), outH, outW, channels,
                                                       float(hot_num_stds) if hot_num_stds is not None else -1.0,
                                                       int(bool(normalize)), int(bool(logtrafo)), int(bool(gammatrafo)), float(gamma),
-                                                      out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                                                      int(bool(timesurface)), out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
         if check:
             _lib.check(lib.memb_hist_status(ws.data_ptr(), stream))
     return out
@@ -473,8 +474,8 @@ class EventBatchPipelineVar:
     rounding of the resize filter) to stacking the reference transform's outputs under the same generator state."""
 
     def __init__(self, cfg: VarPipelineConfig, channels: int = 3):
-        if cfg.timesurface:
-            raise NotImplementedError("the fused augmentation path rasterises polarity counts only (no time surface)")
+        if cfg.timesurface and channels != 3:
+            raise ValueError("the time surface lives in the middle plane of the 3-channel image")
         self.cfg, self.channels = cfg, channels
 
     def __call__(self, streams, offsets=None, params=None, check=True):
@@ -494,5 +495,5 @@ class EventBatchPipelineVar:
         out = pipeline_var_fused(events, offsets, aug, (cfg.canvas_H, cfg.canvas_W), (cfg.input_H, cfg.input_W), self.channels,
                                  hot_num_stds=cfg.hotpix_num_stds if cfg.hotpixfilter else None,
                                  normalize=cfg.normalize_events, check=check, logtrafo=cfg.logtrafo, gammatrafo=cfg.gammatrafo,
-                                 gamma=cfg.gamma)
+                                 gamma=cfg.gamma, timesurface=cfg.timesurface)
         return _apply_randaug(out, params, cfg, self.channels)

@@ -178,6 +178,7 @@ class VarPipelineCfg:
     logtrafo: bool = False
     gammatrafo: bool = False
     gamma: float = 0.5
+    timesurface: bool = False
 
 
 def draw_params_var(n_events: int, cfg: VarPipelineCfg) -> dict:
@@ -222,12 +223,13 @@ def apply_event_aug_var(events: np.ndarray, p: dict) -> np.ndarray:
 def pipeline_var_ref(events: np.ndarray, cfg: VarPipelineCfg, params: dict | None = None) -> torch.Tensor:
     p = params if params is not None else draw_params_var(len(events), cfg)
     ev = apply_event_aug_var(events, p)
-    hist = event_hist_ref(ev, None, None)                       # raises ValueError on an empty stream, like the reference
+    hist = event_hist_ref(ev, None, None, cfg.timesurface)      # raises ValueError on an empty stream, like the reference
     x = torch.from_numpy(np.ascontiguousarray(hist)).permute(2, 0, 1).contiguous().to(torch.float32).div(255)
     # transforms.Resize((H, W), BILINEAR, antialias=True) on a tensor image
     x = torch.nn.functional.interpolate(x[None], size=(cfg.input_H, cfg.input_W), mode="bilinear", align_corners=False,
                                         antialias=True)[0]
-    x[1, :, :] = 0.0
+    if not cfg.timesurface:                                     # RemoveTimesurface, datasets.py:644-645
+        x[1, :, :] = 0.0
     if cfg.hotpixfilter:
         pol = x[0::2, :, :]
         thr = torch.mean(pol) + cfg.hotpix_num_stds * torch.std(pol)

@@ -842,11 +842,50 @@ def golden_event_pipeline_var_loggamma():
     np.savez_compressed(os.path.join(GOLD, "event_pipeline_var_loggamma.npz"), **out)
 
 
+def golden_event_pipeline_var_tss():
+    """Reference build_transformNPY on its variable-sensor branch with args.timesurface=1: EventArrToImg(None, None, True)
+    after the event-space augmentations, the time-surface plane resized with the polarity planes and kept."""
+    import contextlib, io
+    import torch
+    from types import SimpleNamespace
+    ds = ref_shims.ref_module("datasets")
+    out = {}
+    cases = [  # name, data_path, (H, W), polarity, is_train, n_events, kind, normalize, log, seed
+        ("cal_tss_a", "/data/N-Caltech101", (180, 240), (-1.0, 1.0), True, 45000, "edge", 1, 0, 71),
+        ("cal_tss_b", "/data/N-Caltech101", (180, 240), (-1.0, 1.0), True, 20000, "hot", 0, 0, 72),
+        ("cal_tss_c", "/data/N-Caltech101", (172, 233), (-1.0, 1.0), True, 38000, "uniform", 1, 1, 73),
+        ("cal_tss_d", "/data/N-Caltech101", (180, 240), (-1.0, 1.0), True, 26000, "edge", 0, 0, 74),
+        ("cars_tss_eval", "/data/ncars", (100, 120), (0.0, 1.0), False, 6000, "edge", 0, 0, 75),
+        ("cars_tss_a", "/data/ncars", (100, 120), (0.0, 1.0), True, 9000, "uniform", 1, 0, 76),
+    ]
+    flips = []
+    for name, path, (H, W), pol, is_train, n, kind, norm, lg, seed in cases:
+        args = SimpleNamespace(data_path=path, input_H=224, input_W=224, slice_max_evs=30000, max_random_shift_evs=15,
+                               timesurface=1, hotpixfilter=1, hotpix_num_stds=10, logtrafo=lg, gammatrafo=0, gamma=0.5,
+                               normalize_events=norm, rand_aug=0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tf = ds.build_transformNPY(is_train, args)
+        ev = np.floor(synth_events(np.random.default_rng(seed), n, H, W, kind, polarity=pol))
+        random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+        res = tf(ev.copy())
+        random.seed(seed); np.random.seed(seed)
+        if n > 30000:
+            random.choice(range(n - 30000 + 1))
+        flips.append(bool(is_train and np.random.random() < 0.5))
+        out[name + "_out"] = res.numpy()
+        out[name + "_meta"] = np.array([int(is_train), n, norm, lg, seed, H, W, int(pol[0] == 0.0)], dtype=np.int64)
+        out[name + "_kind"] = np.array(kind)
+        print(f"event_pipeline_var_tss {name}: nnz {int((res != 0).sum())} tss nnz {int((res[1] != 0).sum())} time flip {flips[-1]}")
+    assert any(flips) and not all(flips[:4])
+    np.savez_compressed(os.path.join(GOLD, "event_pipeline_var_tss.npz"), **out)
+
+
 SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_vit, "dvae": golden_dvae,
             "engine": golden_engine, "event_pipeline": golden_event_pipeline, "decode": golden_decode, "engine_ft": golden_engine_ft,
             "vit_bf16": golden_vit_bf16, "finetune_remap": golden_finetune_remap, "dvae_train": golden_dvae_train, "event_pipeline_var": golden_event_pipeline_var, "randaug": golden_randaug,
             "event_pipeline_randaug": golden_event_pipeline_randaug, "event_pipeline_loggamma": golden_event_pipeline_loggamma,
-            "event_pipeline_tss": golden_event_pipeline_tss, "event_pipeline_var_loggamma": golden_event_pipeline_var_loggamma}
+            "event_pipeline_tss": golden_event_pipeline_tss, "event_pipeline_var_loggamma": golden_event_pipeline_var_loggamma,
+            "event_pipeline_var_tss": golden_event_pipeline_var_tss}
 
 
 def main(argv):

@@ -161,6 +161,30 @@ def test_variable_sensor_log_gamma_oracle_matches_reference_golden(golden_dir):
     assert seen == 5
 
 
+def var_tss_cases(golden_dir):
+    from oracle.event_pipeline_ref import VarPipelineCfg
+    z = np.load(os.path.join(golden_dir, "event_pipeline_var_tss.npz"))
+    for name in sorted(k[:-4] for k in z.files if k.endswith("_out")):
+        is_train, n, norm, lg, seed, H, W, pol01 = (int(v) for v in z[name + "_meta"])
+        ev = np.floor(synth_events(np.random.default_rng(seed), n, H, W, str(z[name + "_kind"]),
+                                   polarity=(0.0, 1.0) if pol01 else (-1.0, 1.0)))
+        cfg = VarPipelineCfg(is_train=bool(is_train), normalize_events=bool(norm), logtrafo=bool(lg), timesurface=True)
+        yield name, ev, cfg, seed, z[name + "_out"]
+
+
+def test_variable_sensor_time_surface_oracle_matches_reference_golden(golden_dir):
+    """args.timesurface on the variable-sensor branch: the time-surface plane is resized with the polarity planes and kept
+    (tests/golden/event_pipeline_var_tss.npz: the reference chain's own outputs, both time-flip outcomes)."""
+    from oracle.event_pipeline_ref import pipeline_var_ref
+    seen = 0
+    for name, ev, cfg, seed, want in var_tss_cases(golden_dir):
+        seed_all(seed)
+        got = pipeline_var_ref(ev, cfg).numpy()
+        assert np.array_equal(got, want) and (got[1] != 0).any(), f"{name}: {np.abs(got - want).max()}"
+        seen += 1
+    assert seen == 6
+
+
 def _loggamma_cases(golden_dir):
     z = np.load(os.path.join(golden_dir, "event_pipeline_loggamma.npz"))
     for name in sorted(k[:-4] for k in z.files if k.endswith("_out")):
