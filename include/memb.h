@@ -220,7 +220,12 @@ size_t memb_raster_post_workspace_bytes(int B);
 int memb_raster_post_f32(const uint8_t* hist, int B, int H, int W, int C, const int32_t* crop_tl, int pad_t,
                          int pad_l, int outH, int outW, int remove_ts, float hot_num_stds, int normalize,
                          float* out, void* ws, size_t ws_bytes, memb_stream_t stream);
-
+/* ... with LogTransform / GammaTransform (mem/transforms.py:200-222) as the 256-entry value table of
+ * memb_event_pipeline_lut_f32 (NULL: c / 255): applied to the polarity channels after the filter, the middle channel (time
+ * surface, when kept) is left at c / 255 as in the reference. */
+int memb_raster_post_lut_f32(const uint8_t* hist, int B, int H, int W, int C, const int32_t* crop_tl, int pad_t,
+                             int pad_l, int outH, int outW, int remove_ts, float hot_num_stds, int normalize,
+                             const float* value_lut, float* out, void* ws, size_t ws_bytes, memb_stream_t stream);
 
 
 /* ------------------------------------------------------------------------

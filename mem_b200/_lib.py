@@ -46,6 +46,8 @@ SIGNATURES = {
     "memb_raster_post_workspace_bytes": (_sz, [_i32]),
     "memb_raster_post_f32": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp,
                                     _sz, _vp]),
+    "memb_raster_post_lut_f32": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp,
+                                        _sz, _vp]),
 }
 
 DT_BF16, DT_F32 = 0, 1

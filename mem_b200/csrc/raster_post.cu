@@ -109,7 +109,13 @@ __global__ void __launch_bounds__(kThreads) max_kernel(const uint8_t* __restrict
 // One thread per output pixel: all channels of the pixel, planar float32 stores (coalesced per plane).
 __global__ void __launch_bounds__(kThreads) write_kernel(const uint8_t* __restrict__ hist, const int32_t* __restrict__ crop_tl,
                                                          Geom g, int remove_ts, float hot_num_stds, int normalize,
-                                                         const ImgStats* __restrict__ stats, float* __restrict__ out) {
+                                                         const ImgStats* __restrict__ stats,
+                                                         const float* __restrict__ value_lut, float* __restrict__ out) {
+  // value_lut: LogTransform / GammaTransform of the 256 possible c / 255 (evaluated on the host, see memb.h); the filter
+  // compares c / 255, the maps act on what survives, NormalizeEvent divides by the mapped maximum (both maps are monotone)
+  __shared__ float vlut[256];
+  if (threadIdx.x < 256) vlut[threadIdx.x] = value_lut ? value_lut[threadIdx.x] : __fdiv_rn((float)threadIdx.x, 255.0f);
+  __syncthreads();
   const int b = blockIdx.y;
   int y0, x0;
   crop_origin(crop_tl, b, g, y0, x0);
@@ -121,9 +127,9 @@ __global__ void __launch_bounds__(kThreads) write_kernel(const uint8_t* __restri
   if (filter || normalize) {
     const ImgStats st = stats[b];
     if (filter) thr = hot_threshold(st, 2LL * npx, hot_num_stds);
-    if (normalize && st.cmax != 0u) {
-      // factor = 1.0 / x.max() with x.max() = fl32(cmax / 255)   (transforms.py:234-236)
-      factor = __fdiv_rn(1.0f, __fdiv_rn((float)st.cmax, 255.0f));
+    if (normalize && st.cmax != 0u && vlut[st.cmax & 0xffu] != 0.0f) {
+      // factor = 1.0 / x.max() with x.max() = fl32(cmax / 255) or its mapped value   (transforms.py:234-236)
+      factor = __fdiv_rn(1.0f, vlut[st.cmax & 0xffu]);
       scale = true;
     }
   }
@@ -132,7 +138,9 @@ __global__ void __launch_bounds__(kThreads) write_kernel(const uint8_t* __restri
     unsigned int cp, cn, cm;
     load_pol(img, g, y0, x0, i / g.outW, i % g.outW, cp, cn, cm);
     float vp = __fdiv_rn((float)cp, 255.0f), vn = __fdiv_rn((float)cn, 255.0f);
-    if (filter && (vp > thr || vn > thr)) vp = vn = 0.0f;
+    if (filter && (vp > thr || vn > thr)) { cp = 0u; cn = 0u; }
+    vp = vlut[cp];
+    vn = vlut[cn];
     if (scale) {
       vp = __fmul_rn(vp, factor);
       vn = __fmul_rn(vn, factor);
@@ -160,6 +168,13 @@ extern "C" size_t memb_raster_post_workspace_bytes(int B) {
 extern "C" int memb_raster_post_f32(const uint8_t* hist, int B, int H, int W, int C, const int32_t* crop_tl, int pad_t,
                                     int pad_l, int outH, int outW, int remove_ts, float hot_num_stds, int normalize,
                                     float* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
+  return memb_raster_post_lut_f32(hist, B, H, W, C, crop_tl, pad_t, pad_l, outH, outW, remove_ts, hot_num_stds, normalize, nullptr,
+                                  out, ws, ws_bytes, stream);
+}
+
+extern "C" int memb_raster_post_lut_f32(const uint8_t* hist, int B, int H, int W, int C, const int32_t* crop_tl, int pad_t,
+                                        int pad_l, int outH, int outW, int remove_ts, float hot_num_stds, int normalize,
+                                        const float* value_lut, float* out, void* ws, size_t ws_bytes, memb_stream_t stream) {
   MEMB_REQUIRE(B >= 1 && H >= 1 && W >= 1 && outH >= 1 && outW >= 1, "raster_post: bad shape");
   MEMB_REQUIRE(C == 2 || C == 3, "raster_post: C must be 2 or 3, got %d", C);
   MEMB_REQUIRE(hist != nullptr && out != nullptr, "raster_post: null pointer");
@@ -190,7 +205,7 @@ extern "C" int memb_raster_post_f32(const uint8_t* hist, int B, int H, int W, in
       MEMB_LAUNCH_OK("raster_post max");
     }
   }
-  write_kernel<<<grid, kThreads, 0, stream>>>(hist, crop_tl, g, remove_ts, hot_num_stds, normalize, stats, out);
+  write_kernel<<<grid, kThreads, 0, stream>>>(hist, crop_tl, g, remove_ts, hot_num_stds, normalize, stats, value_lut, out);
   MEMB_LAUNCH_OK("raster_post write");
   return MEMB_OK;
 }

@@ -19,11 +19,11 @@ anti-aliased ``Resize`` to the input size) is ``VarPipelineConfig`` / ``draw_par
 launch over the batch (``mem_b200/transforms.py``, ``csrc/randaug.cu``), with each sample's operations drawn right after its
 other draws so the torch generator is consumed in the reference's order.
 ``logtrafo`` / ``gammatrafo`` (``LogTransform`` / ``GammaTransform``, off in the reference's scripts) are a 256-entry value
-table evaluated on the host with the reference's own CPU routines (``value_table``) and applied inside the fused kernel.
-``timesurface`` (off in the reference's scripts) takes the two-kernel path: ``memb_hist_aug_tss_u8`` normalises the
-timestamps over the rows that survive the augmentations and honours RandomTimeFlip's reversed order, then ``post_raster``.
-Not covered (raise / documented in DESIGN.md): log / gamma on the variable-sensor branch (its resized image is not a
-function of 256 counts) or together with the time surface; the time surface on the variable-sensor branch.
+table evaluated on the host with the reference's own CPU routines (``value_table``) and applied inside the fused kernel
+or the post-raster pass; on the variable-sensor branch they act on the resized float32 planes (evaluated on the device).
+``timesurface`` (off in the reference's scripts) takes the two-kernel path on the fixed-sensor branch:
+``memb_hist_aug_tss_u8`` normalises the timestamps over the rows that survive the augmentations and honours
+RandomTimeFlip's reversed order, then ``post_raster``; the variable-sensor kernel makes a second pass over its window.
 """
 from __future__ import annotations
 
@@ -71,7 +71,7 @@ class PipelineConfig:
     hotpix_num_stds: float = 10
     normalize_events: bool = False
     rand_aug: bool = False          # args.rand_aug (the reference's scripts default to 1): EventRandAugment(magnitude=20) when training
-    logtrafo: bool = False          # LogTransform / GammaTransform (off in the reference's scripts); fused path only
+    logtrafo: bool = False          # LogTransform / GammaTransform (off in the reference's scripts)
     gammatrafo: bool = False
     gamma: float = 0.5
 
@@ -300,9 +300,10 @@ def pipeline_fused(events, offsets, aug, crop_tl, H, W, out_hw, channels=3, *, h
 
 
 def post_raster(hist, crop_tl=None, out_hw=None, *, remove_timesurface=True, hot_num_stds=10.0, normalize=False,
-                out=None):
+                out=None, value_lut=None):
     """``uint8 (B,H,W,C)`` counts -> ``float32 (B,C,outH,outW)``: /255, crop (zero padding like
-    ``RandomCrop(pad_if_needed=True)``), RemoveTimesurface, RemoveHotPixels (``hot_num_stds=None`` = off), NormalizeEvent.
+    ``RandomCrop(pad_if_needed=True)``), RemoveTimesurface, RemoveHotPixels (``hot_num_stds=None`` = off), LogTransform /
+    GammaTransform as ``value_lut`` (``value_table(...)``, None = off), NormalizeEvent.
 
     crop_tl: ``int32 (B,2)`` (top, left) in the padded image (numpy or tensor) or None for (0,0)."""
     torch = _lib.require_cuda()
@@ -324,10 +325,16 @@ def post_raster(hist, crop_tl=None, out_hw=None, *, remove_timesurface=True, hot
             out = torch.empty((B, C, outH, outW), dtype=torch.float32, device=device)
         lib = _lib.load()
         ws = _lib.workspace.get(torch, max(lib.memb_raster_post_workspace_bytes(B), 16), device, "raster_post")
-        _lib.check(lib.memb_raster_post_f32(hist.data_ptr(), B, H, W, C, crop.data_ptr() if crop is not None else None,
-                                            pad_t, pad_l, outH, outW, int(bool(remove_timesurface)),
-                                            float(hot_num_stds) if hot_num_stds is not None else -1.0, int(bool(normalize)),
-                                            out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch, device)))
+        lut = None
+        if value_lut is not None:
+            lut = torch.as_tensor(value_lut, dtype=torch.float32).to(device).contiguous()
+            if lut.numel() != 256:
+                raise ValueError("value_lut must hold 256 float32 values")
+        _lib.check(lib.memb_raster_post_lut_f32(hist.data_ptr(), B, H, W, C, crop.data_ptr() if crop is not None else None,
+                                                pad_t, pad_l, outH, outW, int(bool(remove_timesurface)),
+                                                float(hot_num_stds) if hot_num_stds is not None else -1.0, int(bool(normalize)),
+                                                lut.data_ptr() if lut is not None else None,
+                                                out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch, device)))
     return out
 
 
@@ -348,8 +355,8 @@ class EventBatchPipeline:
             # rasterise (L2 REDs + last-writer pass) + post-raster pair
             if fused:
                 raise NotImplementedError("the fused kernel has no time surface; use fused=False (the default with timesurface)")
-            if channels != 3 or cfg.logtrafo or cfg.gammatrafo:
-                raise NotImplementedError("the time surface needs 3 channels and is not combined with logtrafo / gammatrafo")
+            if channels != 3:
+                raise NotImplementedError("the time surface is the middle plane of the 3-channel image")
             fused = False
         self.fused = fits if fused is None else bool(fused)   # one kernel when the crop fits a shared-memory tile
 
@@ -376,15 +383,14 @@ class EventBatchPipeline:
                                  (cfg.input_H, cfg.input_W) if cfg.is_train else (H, W), self.channels,
                                  hot_num_stds=hot, normalize=cfg.normalize_events, check=not cfg.is_train, value_lut=lut)
             return _apply_randaug(out, params, cfg, self.channels)
-        if lut is not None:
-            raise NotImplementedError("LogTransform / GammaTransform ride on the fused kernel only (output raster <= one tile)")
         hist = rasterise_augmented(events, offsets, aug, H, W, self.channels,
                                    max_stream_len=int(max(p["count"] for p in params)) if params else 0,
                                    check=not cfg.is_train,   # after the cull every row is inside the sensor
                                    timesurface=cfg.timesurface)
         out = post_raster(hist, crop if cfg.is_train else None, (cfg.input_H, cfg.input_W) if cfg.is_train else None,
                           remove_timesurface=not cfg.timesurface,
-                          hot_num_stds=cfg.hotpix_num_stds if cfg.hotpixfilter else None, normalize=cfg.normalize_events)
+                          hot_num_stds=cfg.hotpix_num_stds if cfg.hotpixfilter else None, normalize=cfg.normalize_events,
+                          value_lut=lut)
         return _apply_randaug(out, params, cfg, self.channels)
 
 

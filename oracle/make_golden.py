@@ -810,6 +810,35 @@ def golden_event_pipeline_tss():
     np.savez_compressed(os.path.join(GOLD, "event_pipeline_tss.npz"), **out)
 
 
+def golden_event_pipeline_tss_loggamma():
+    """Reference build_transformNPY, fixed-sensor branch, args.timesurface=1 together with LogTransform / GammaTransform (the
+    maps touch the polarity planes only, mem/transforms.py:205-208, :219-221)."""
+    import contextlib, io
+    import torch
+    from types import SimpleNamespace
+    ds = ref_shims.ref_module("datasets")
+    out = {}
+    cases = [  # name, is_train, n_events, kind, normalize, log, gamma on, gamma, seed
+        ("tl_a", True, 45000, "edge", 1, 1, 0, 0.5, 81), ("tl_b", True, 20000, "hot", 0, 1, 1, 0.5, 82),
+        ("tl_c", True, 38000, "uniform", 1, 0, 1, 0.7, 83), ("tl_eval", False, 45000, "edge", 1, 1, 1, 0.5, 84),
+    ]
+    for name, is_train, n, kind, norm, lg, gm, gamma, seed in cases:
+        args = SimpleNamespace(data_path="/data/N_imagenet", input_H=224, input_W=224, slice_max_evs=30000,
+                               max_random_shift_evs=15, timesurface=1, hotpixfilter=1, hotpix_num_stds=10, logtrafo=lg,
+                               gammatrafo=gm, gamma=gamma, normalize_events=norm, rand_aug=0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tf = ds.build_transformNPY(is_train, args)
+        ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
+        random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+        res = tf(ev.copy())
+        out[name + "_out"] = res.numpy()
+        out[name + "_meta"] = np.array([int(is_train), n, norm, lg, gm, seed], dtype=np.int64)
+        out[name + "_gamma"] = np.array(gamma, dtype=np.float64)
+        out[name + "_kind"] = np.array(kind)
+        print(f"event_pipeline_tss_loggamma {name}: nnz {int((res != 0).sum())} tss nnz {int((res[1] != 0).sum())} max {float(res.max()):.4f}")
+    np.savez_compressed(os.path.join(GOLD, "event_pipeline_tss_loggamma.npz"), **out)
+
+
 def golden_event_pipeline_var_loggamma():
     """Reference build_transformNPY on its variable-sensor branch with LogTransform / GammaTransform on: there they act on
     the float32 image after Resize (mem/datasets.py:639, :648-651), not on integer counts."""
@@ -885,7 +914,7 @@ SECTIONS = {"histogram": golden_histogram, "masks": golden_masks, "vit": golden_
             "vit_bf16": golden_vit_bf16, "finetune_remap": golden_finetune_remap, "dvae_train": golden_dvae_train, "event_pipeline_var": golden_event_pipeline_var, "randaug": golden_randaug,
             "event_pipeline_randaug": golden_event_pipeline_randaug, "event_pipeline_loggamma": golden_event_pipeline_loggamma,
             "event_pipeline_tss": golden_event_pipeline_tss, "event_pipeline_var_loggamma": golden_event_pipeline_var_loggamma,
-            "event_pipeline_var_tss": golden_event_pipeline_var_tss}
+            "event_pipeline_var_tss": golden_event_pipeline_var_tss, "event_pipeline_tss_loggamma": golden_event_pipeline_tss_loggamma}
 
 
 def main(argv):

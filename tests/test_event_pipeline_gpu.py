@@ -182,8 +182,6 @@ def test_bad_arguments_fail_loudly():
     from mem_b200.event_pipeline import AUG_DTYPE, EventBatchPipeline, PipelineConfig, post_raster, rasterise_augmented
     with pytest.raises(NotImplementedError):
         EventBatchPipeline(PipelineConfig(timesurface=True), channels=2)        # the time surface is the middle of 3 channels
-    with pytest.raises(NotImplementedError):
-        EventBatchPipeline(PipelineConfig(timesurface=True, logtrafo=True))
     ev = np.zeros((4, 4))
     with pytest.raises(ValueError):
         rasterise_augmented(ev, np.array([0, 4]), np.zeros(2, dtype=AUG_DTYPE), 100, 100)
@@ -397,13 +395,33 @@ def test_log_and_gamma_transforms_reference_golden(golden_dir):
         ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
         cfg = PipelineConfig(is_train=bool(is_train), normalize_events=bool(norm), logtrafo=bool(lg), gammatrafo=bool(gm),
                              gamma=float(z[name + "_gamma"]))
-        seed_all(seed)
-        got = EventBatchPipeline(cfg)([ev])
         want = z[name + "_out"]
-        assert tuple(got.shape) == (1,) + want.shape
-        assert np.array_equal(got[0].cpu().numpy(), want), (name, float(np.abs(got[0].cpu().numpy() - want).max()))
-    with pytest.raises(NotImplementedError):
-        EventBatchPipeline(PipelineConfig(is_train=True, logtrafo=True), fused=False)([ev])
+        for fused in (True, False):           # one kernel / rasterise + post-raster pass: the same table, the same bytes
+            seed_all(seed)
+            got = EventBatchPipeline(cfg, fused=fused)([ev])
+            assert tuple(got.shape) == (1,) + want.shape
+            assert np.array_equal(got[0].cpu().numpy(), want), (name, fused, float(np.abs(got[0].cpu().numpy() - want).max()))
+
+
+def test_time_surface_with_log_gamma_reference_golden(golden_dir):
+    """args.timesurface with args.logtrafo / args.gammatrafo (tests/golden/event_pipeline_tss_loggamma.npz, outputs of the
+    reference's build_transformNPY): the value table rides on the post-raster pass, the time-surface plane stays c / 255;
+    bit-exact."""
+    from mem_b200.event_pipeline import EventBatchPipeline, PipelineConfig
+    z = np.load(os.path.join(golden_dir, "event_pipeline_tss_loggamma.npz"))
+    names = sorted(k[:-4] for k in z.files if k.endswith("_out"))
+    assert len(names) == 4
+    for name in names:
+        is_train, n, norm, lg, gm, seed = (int(v) for v in z[name + "_meta"])
+        kind = str(z[name + "_kind"])
+        ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
+        cfg = PipelineConfig(is_train=bool(is_train), normalize_events=bool(norm), logtrafo=bool(lg), gammatrafo=bool(gm),
+                             gamma=float(z[name + "_gamma"]), timesurface=True)
+        seed_all(seed)
+        got = EventBatchPipeline(cfg)([ev])[0].cpu().numpy()
+        want = z[name + "_out"]
+        assert got.shape == want.shape and (got[1] != 0).any(), name
+        assert np.array_equal(got, want), (name, float(np.abs(got - want).max()))
 
 
 def test_time_surface_with_augmentations_reference_golden(golden_dir):

@@ -221,6 +221,28 @@ def test_log_and_gamma_transforms_match_the_reference(golden_dir):
     assert seen == 4 and value_table(False, False) is None
 
 
+def tss_loggamma_cases(golden_dir):
+    z = np.load(os.path.join(golden_dir, "event_pipeline_tss_loggamma.npz"))
+    for name in sorted(k[:-4] for k in z.files if k.endswith("_out")):
+        is_train, n, norm, lg, gm, seed = (int(v) for v in z[name + "_meta"])
+        kind = str(z[name + "_kind"])
+        ev = synth_events(np.random.default_rng(seed), n, 480, 640, kind, frac=(kind == "edge"))
+        cfg = PipelineCfg(is_train=bool(is_train), normalize_events=bool(norm), logtrafo=bool(lg), gammatrafo=bool(gm),
+                          gamma=float(z[name + "_gamma"]), timesurface=True)
+        yield name, ev, cfg, seed, z[name + "_out"]
+
+
+def test_time_surface_with_log_gamma_matches_the_reference(golden_dir):
+    """args.timesurface together with LogTransform / GammaTransform: the maps leave the time-surface plane alone."""
+    seen = 0
+    for name, ev, cfg, seed, want in tss_loggamma_cases(golden_dir):
+        seed_all(seed)
+        got = pipeline_ref(ev, cfg).numpy()
+        assert np.array_equal(got, want) and (got[1] != 0).any(), (name, float(np.abs(got - want).max()))
+        seen += 1
+    assert seen == 4
+
+
 def test_time_surface_chain_matches_the_reference(golden_dir):
     """args.timesurface=1: EventArrToImg(timeSurface=True) after the augmentations, middle channel kept
     (tests/golden/event_pipeline_tss.npz; two of the training cases draw RandomTimeFlip)."""
