@@ -78,6 +78,22 @@ __device__ __forceinline__ bool pixel_index_fast(double x, double y, int W, int 
   return ok;
 }
 
+// ... also returning the integer coordinates (for the 2-D granules of the HYBRID strategy)
+__device__ __forceinline__ bool pixel_xy_fast(double x, double y, int W, int H, long long npix, int& idx, int& xi, int& yi) {
+  if (x >= 0.0 && x < (double)W && y >= 0.0 && y < (double)H) {
+    xi = __double2int_rz(x);
+    yi = __double2int_rz(y);
+    idx = xi + W * yi;
+    return true;
+  }
+  long long i = 0;
+  const bool ok = pixel_index(x, y, W, npix, i);
+  idx = (int)i;
+  yi = ok ? idx / W : 0;
+  xi = ok ? idx - yi * W : 0;
+  return ok;
+}
+
 __device__ __forceinline__ unsigned long long order_key(double v) {
   unsigned long long b = (unsigned long long)__double_as_longlong(v);
   return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
@@ -1071,7 +1087,8 @@ __global__ void __launch_bounds__(32 * kFinRows) hist_private_finalize(const uns
 // concentrated streams (edges, hot regions): REDs to the same few L2 sectors serialise (10 M edge-like events: 270-430 us
 // against 85 us uniform).  HYBRID privatises only the HOT part of the sensor, chosen per call ON THE DEVICE:
 //   1. hist_hybrid_prepare zero-fills the L2 accumulators; its CTA 0 counts a sample of kHybSamples rows spread over the
-//      stream per 64-pixel granule, picks the most frequent granules (as many as fit a shared-memory tile), writes the
+//      stream per granule (an 8 x 8 pixel block: a line at any angle crosses few of them, a 64-pixel row segment would
+//      catch ~5 hot pixels of a steep edge), picks the most frequent granules (as many as fit a shared-memory tile), writes the
 //      granule -> slot map and decides the mode: privatise (1) when the sample is concentrated -- its effective number
 //      of granules 1 / sum p_g^2 is below half of the sensor's -- or the caller forced HYBRID, else plain L2 REDs
 //      (0: a uniform stream gains nothing from privatising a sixth of the sensor);
@@ -1081,7 +1098,7 @@ __global__ void __launch_bounds__(32 * kFinRows) hist_private_finalize(const uns
 //      its copy (mod 256, u16 per pixel) into its own slice of the workspace;
 //   3. hist_hybrid_finalize adds accumulators + slices.
 // The four launches are chained as programmatic dependent launches.
-constexpr int kHybGranule = 64;                 // pixels per granule (a power of two, multiple of 8)
+constexpr int kHybGranule = 64;                 // pixels per granule: a block of 8 rows x 8 columns
 constexpr int kHybSamples = 4096;               // rows the selector looks at (4 per thread, one batch of loads)
 constexpr int kHybMaxGranules = 16384;          // sensors up to 1 Mpixel (1280x720 = 14400 granules)
 constexpr int kHybHistBins = 1024;
@@ -1089,7 +1106,10 @@ constexpr int kHybSmemBytes = 222 * 1024;       // dynamic shared memory of hist
 
 struct HybState { int nsel; int mode; int pad[2]; };
 
-__host__ __device__ inline int hyb_granules(long long npix) { return (int)((npix + kHybGranule - 1) / kHybGranule); }
+__host__ __device__ inline int hyb_gw(int W) { return (W + 7) >> 3; }                       // granules per row of blocks
+__host__ __device__ inline long long hyb_granules(int W, int H) { return (long long)hyb_gw(W) * ((H + 7) >> 3); }
+__device__ __forceinline__ int hyb_granule_of(int xi, int yi, int gw) { return (yi >> 3) * gw + (xi >> 3); }
+__device__ __forceinline__ int hyb_offset_of(int xi, int yi) { return ((yi & 7) << 3) | (xi & 7); }
 // tile capacity in granules once the slot map has taken its share of the dynamic shared memory
 __host__ __device__ inline int hyb_tile_granules(int granules) {
   const int map_bytes = ((granules * 2 + 15) / 16) * 16;
@@ -1142,6 +1162,7 @@ __global__ void __launch_bounds__(kTileThreads) hist_hybrid_prepare(const double
   // ---- CTA 0: sample, select, decide
   constexpr int kPer = kHybSamples / kTileThreads, kBatch = 4;
   const long long step = max(1LL, n / kHybSamples);
+  const int gw = hyb_gw(W);
   for (int g = threadIdx.x; g < granules; g += kTileThreads) cnt[g] = 0u;
   for (int i = threadIdx.x; i < kHybHistBins; i += kTileThreads) hist[i] = 0;
   __syncthreads();
@@ -1156,9 +1177,9 @@ __global__ void __launch_bounds__(kTileThreads) hist_hybrid_prepare(const double
     }
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
-      int idx;
-      if (live[u] && (e[u].p == 1.0 || e[u].p == -1.0) && pixel_index_fast(e[u].x, e[u].y, W, H, npix, idx)) {
-        atomicAdd(&cnt[idx / kHybGranule], 1u);
+      int idx, xi, yi;
+      if (live[u] && (e[u].p == 1.0 || e[u].p == -1.0) && pixel_xy_fast(e[u].x, e[u].y, W, H, npix, idx, xi, yi)) {
+        atomicAdd(&cnt[hyb_granule_of(xi, yi, gw)], 1u);
       }
     }
   }
@@ -1252,6 +1273,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) hist_hybrid(
   constexpr int kStep = kTileThreads * kFuseUnroll;
   const long long stride = (long long)gridDim.x * kStep;
   const long long first = (long long)blockIdx.x * kStep;
+  const int gw = hyb_gw(W);
   pdl_launch_dependents();
   pdl_wait();                                   // map, mode and zeroed accumulators are visible from here on
   if (state->mode == 0) return;                 // the stream is not concentrated: hist_scatter_global did the work
@@ -1298,12 +1320,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) hist_hybrid(
     for (int u = 0; u < kFuseUnroll; ++u) {
       const bool pos = live[u] && cur[u].p == 1.0, neg = live[u] && cur[u].p == -1.0;
       if (pos || neg) {
-        int idx;
-        if (!pixel_index_fast(cur[u].x, cur[u].y, W, H, npix, idx)) {
+        int idx, xi, yi;
+        if (!pixel_xy_fast(cur[u].x, cur[u].y, W, H, npix, idx, xi, yi)) {
           bad = true;
         } else {
-          const unsigned int s = slot_map[idx / kHybGranule];
-          if (s != 0xffffu) atomicAdd(&tile[s * kHybGranule + (idx % kHybGranule)], pos ? 1u : 0x10000u);
+          const unsigned int s = slot_map[hyb_granule_of(xi, yi, gw)];
+          if (s != 0xffffu) atomicAdd(&tile[s * kHybGranule + hyb_offset_of(xi, yi)], pos ? 1u : 0x10000u);
           else atomicAdd(acc + (neg ? npix : 0) + idx, 1u);
         }
       }
@@ -1345,15 +1367,18 @@ __device__ __forceinline__ void hyb_store_px(uint8_t* __restrict__ out, long lon
 __global__ void __launch_bounds__(32 * kHybFinRows) hist_hybrid_finalize(
     const unsigned int* __restrict__ acc, const unsigned short* __restrict__ slot_map, const unsigned short* __restrict__ sel_list,
     const HybState* __restrict__ state, const unsigned short* __restrict__ slices, int n_slices, int tile_granules, int hot_blocks,
-    long long npix, int C, uint8_t* __restrict__ out) {
+    long long npix, int W, int H, int C, uint8_t* __restrict__ out) {
   __shared__ unsigned int part[kHybFinRows][32][8];      // pos | neg << 16 (sums < 65536: at most 160 slices x 255)
   pdl_wait();
   const int t = threadIdx.y * 32 + threadIdx.x;
   if ((int)blockIdx.x >= hot_blocks) {
     if (t < 256) {
       const long long px = (long long)((int)blockIdx.x - hot_blocks) * 256 + t;
-      if (px < npix && (state->mode == 0 || slot_map[px / kHybGranule] == 0xffffu))
-        hyb_store_px(out, px, C, acc[px] & 0xffu, acc[npix + px] & 0xffu);
+      if (px < npix) {
+        const int yi = (int)(px / W), xi = (int)(px - (long long)yi * W);
+        if (state->mode == 0 || slot_map[hyb_granule_of(xi, yi, hyb_gw(W))] == 0xffffu)
+          hyb_store_px(out, px, C, acc[px] & 0xffu, acc[npix + px] & 0xffu);
+      }
     }
     return;
   }
@@ -1379,11 +1404,13 @@ __global__ void __launch_bounds__(32 * kHybFinRows) hist_hybrid_finalize(
   for (int q = 0; q < 8; ++q) part[threadIdx.y][threadIdx.x][q] = sum[q];
   __syncthreads();
   if (t < 256) {                                            // 256 threads -> the 4 x 64 pixels of this block's granules
-    const int lane = t >> 3, q = t & 7;                     // (slot in block * 8 + octet, pixel in octet)
+    const int lane = t >> 3, q = t & 7;                     // (slot in block * 8 + octet = row of the 8 x 8 block, column)
     const int sl = (int)blockIdx.x * 4 + (lane >> 3);
     if (sl < nsel) {
-      const long long px = (long long)sel_list[sl] * kHybGranule + (lane & 7) * 8 + q;
-      if (px < npix) {
+      const int g = sel_list[sl], gw = hyb_gw(W), gy = g / gw, gx = g - gy * gw;
+      const int yi = gy * 8 + (lane & 7), xi = gx * 8 + q;
+      if (xi < W && yi < H) {
+        const long long px = (long long)yi * W + xi;
         unsigned int w = 0;
 #pragma unroll
         for (int g = 0; g < kHybFinRows; ++g) w += part[g][lane][q];
@@ -1826,13 +1853,13 @@ static Plan make_plan(int B, int64_t n, int H, int W, int timesurface, int strat
     // one long stream on a sensor that fits a shared-memory tile: a privatised copy per SM (immune to hot pixels)
     if (B == 1 && npix <= kTileMaxWords && n >= (1 << 18)) strategy = MEMB_HIST_PRIVATE;
     // one long stream on a larger sensor: privatise the hot granules, RED the rest
-    if (B == 1 && npix > kTileMaxWords && n >= kHybMinEvents && hyb_granules(npix) <= kHybMaxGranules) strategy = MEMB_HIST_HYBRID;
+    if (B == 1 && npix > kTileMaxWords && n >= kHybMinEvents && hyb_granules(W, H) <= kHybMaxGranules) strategy = MEMB_HIST_HYBRID;
     // (SORT -- events binned by pixel class first, no global atomics -- is correct but measured slower than HYBRID on every
     // distribution, profiles/r02_hist_sort_attempt.txt; MEMB_HIST_AUTO_LARGE=sort selects it here: tuning only)
     if (B == 1 && npix > kTileMaxWords && n >= kHybMinEvents && npix <= kSortMaxPixels && auto_large_is_sort()) strategy = MEMB_HIST_SORT;
   }
   if (strategy == MEMB_HIST_SORT && (B != 1 || timesurface || npix > kSortMaxPixels || n < 1)) strategy = MEMB_HIST_GLOBAL;
-  if (strategy == MEMB_HIST_HYBRID && (B != 1 || timesurface || hyb_granules(npix) > kHybMaxGranules || n < kHybSamples))
+  if (strategy == MEMB_HIST_HYBRID && (B != 1 || timesurface || hyb_granules(W, H) > kHybMaxGranules || n < kHybSamples))
     strategy = MEMB_HIST_GLOBAL;
   if (strategy == MEMB_HIST_PRIVATE && (B != 1 || npix > kTileMaxWords)) strategy = MEMB_HIST_GLOBAL;
   p.replicas = 1;
@@ -1851,7 +1878,7 @@ static Plan make_plan(int B, int64_t n, int H, int W, int timesurface, int strat
   p.off_last = round_up<size_t>(p.off_last, 16);
   p.ws_bytes = round_up<size_t>(p.off_last + (timesurface ? (size_t)B * npix * 8 : 0), 16);
   if (strategy == MEMB_HIST_HYBRID) {
-    p.granules = hyb_granules(npix);
+    p.granules = (int)hyb_granules(W, H);
     p.tile_granules = hyb_tile_granules(p.granules);
     if (const char* e = getenv("MEMB_HYB_TILE_GRANULES")) p.tile_granules = std::max(1, std::min(p.tile_granules, atoi(e)));   // tuning only
     p.off_map = round_up<size_t>(p.off_acc + (size_t)2 * npix * 4, 16);
@@ -1982,7 +2009,8 @@ static int run_hybrid(const double* ev, long long n, int W, int H, int C, const 
   const int cold_blocks = (int)ceil_div<long long>(npix, 256), hot_blocks = ceil_div(p.tile_granules, 4);
   MEMB_CUDA_OK(launch_pdl_smem(hist_hybrid_finalize, dim3(hot_blocks + cold_blocks), dim3(32, kHybFinRows), (size_t)0, stream,
                                (const unsigned int*)acc, (const unsigned short*)slot_map, (const unsigned short*)sel_list,
-                               (const HybState*)state, (const unsigned short*)slices, ctas, p.tile_granules, hot_blocks, npix, C, out));
+                               (const HybState*)state, (const unsigned short*)slices, ctas, p.tile_granules, hot_blocks, npix, W, H, C,
+                               out));
   MEMB_LAUNCH_OK("hist_hybrid_finalize");
   return MEMB_OK;
 }
