@@ -1163,9 +1163,6 @@ __global__ void __launch_bounds__(kTileThreads) hist_hybrid_prepare(const double
   constexpr int kPer = kHybSamples / kTileThreads, kBatch = 4;
   const long long step = max(1LL, n / kHybSamples);
   const int gw = hyb_gw(W);
-  for (int g = threadIdx.x; g < granules; g += kTileThreads) cnt[g] = 0u;
-  for (int i = threadIdx.x; i < kHybHistBins; i += kTileThreads) hist[i] = 0;
-  __syncthreads();
   for (int j = 0; j < kPer; j += kBatch) {
     Event e[kBatch];
     bool live[kBatch];
@@ -1174,6 +1171,11 @@ __global__ void __launch_bounds__(kTileThreads) hist_hybrid_prepare(const double
       const long long r = ((long long)(j + u) * kTileThreads + threadIdx.x) * step;
       live[u] = r < n;
       if (live[u]) e[u] = load_event<kAligned>(ev, r);
+    }
+    if (j == 0) {                                 // the counters are cleared while the (cold) sample rows are on their way
+      for (int g = threadIdx.x; g < granules; g += kTileThreads) cnt[g] = 0u;
+      for (int i = threadIdx.x; i < kHybHistBins; i += kTileThreads) hist[i] = 0;
+      __syncthreads();
     }
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
