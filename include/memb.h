@@ -295,6 +295,9 @@ typedef struct memb_gemm_desc {
   float alpha;             /* 0 is read as 1 */
   const float* alpha_dev;  /* optional device scalar multiplied into alpha (STORE / ATOMIC_ADD) */
   int32_t* err_flag;       /* device int, set before a trap if an internal wait times out (may be NULL) */
+  float* colsum;           /* MEMB_EPI_DGELU, bf16 output: optional [N] accumulator, += column sums of d over the M rows (the
+                              bias gradient of the layer whose GELU this is, mem/modeling_finetune.py:62-71 backward); fused
+                              into the CTA-pair kernel's epilogue (one red.add per column per 32 rows), else a separate pass */
 } memb_gemm_desc;
 
 int memb_gemm(const memb_gemm_desc* desc, memb_stream_t stream);

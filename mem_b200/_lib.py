@@ -66,7 +66,7 @@ class GemmDesc(_c.Structure):
         ("d", _vp), ("ldd", _i64), ("d2", _vp), ("ldd2", _i64),
         ("bias", _vp), ("aux", _vp), ("ldaux", _i64), ("colscale", _vp), ("rowscale", _vp),
         ("rows_per_group", _i32), ("out_group_rows", _i32), ("out_group_stride", _i32), ("out_row_offset", _i32),
-        ("rowmask", _vp), ("maskvec", _vp), ("alpha", _f32), ("alpha_dev", _vp), ("err_flag", _vp),
+        ("rowmask", _vp), ("maskvec", _vp), ("alpha", _f32), ("alpha_dev", _vp), ("err_flag", _vp), ("colsum", _vp),
     ]
 
 

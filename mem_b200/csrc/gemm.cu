@@ -570,6 +570,13 @@ extern "C" int memb_gemm(const memb_gemm_desc* gp, memb_stream_t stream) {
     if (int rc = gemm_pair::try_launch(g, stream, &handled)) return rc;
     if (handled) return MEMB_OK;
   }
+  if (g.colsum != nullptr) {
+    MEMB_REQUIRE(g.epilogue == MEMB_EPI_DGELU && g.out_dtype == MEMB_DT_BF16, "gemm: colsum rides on the DGELU epilogue with a bf16 output");
+    memb_gemm_desc plain = g;        // this kernel has no fused column sums: the same GEMM, then one pass over its output
+    plain.colsum = nullptr;
+    if (int rc = memb_gemm(&plain, stream)) return rc;
+    return memb_colsum_bf16(g.d, g.ldd, g.m, g.n, g.colsum, stream);
+  }
   const int eb = g.in_dtype == MEMB_DT_BF16 ? 2 : 4;
   const int block_k = kSwizzleBytes / eb;
   const int block_n = (g.block_n == 128 || g.block_n == 256) ? g.block_n : ((g.n % 256 == 0 || g.n > 1024) ? 256 : 128);

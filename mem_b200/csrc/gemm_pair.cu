@@ -53,6 +53,7 @@ struct Params {
   int rows_per_group;
   int has_d2;
   int* err_flag;
+  float* colsum;   // DGELU: += column sums of the output (may be NULL)
 };
 
 template <int BLOCK_N, int EPI>
@@ -337,6 +338,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&abar[slot], (aux_phases >> slot) & 1u, p.err_flag, 5);
           aux_phases ^= 1u << slot;
           uint32_t pk[16];
+          float cs[32];     // this lane's row of the chunk, kept for the column sums
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 q = ld_shared_v4(sw64(buf, lane, j));
@@ -346,10 +348,28 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               const float g0 = __uint_as_float(a[8 * j + 2 * t]) * gelu_grad(bf16_lo(w[t]));
               const float g1 = __uint_as_float(a[8 * j + 2 * t + 1]) * gelu_grad(bf16_hi(w[t]));
               pk[4 * j + t] = pack_bf16x2(g0, g1);
+              cs[8 * j + 2 * t] = g0;
+              cs[8 * j + 2 * t + 1] = g1;
             }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) st_shared_v4(sw64(buf, lane, j), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          if (p.colsum != nullptr) {
+            // column sums over the warp's 32 rows: a butterfly that halves the values a lane holds at every step (31 shuffles);
+            // lane l ends with column l, one 128-byte red.add per warp and chunk
+            const bool row_ok = live && row0 + lane < p.M;
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+              const bool up = (lane & s) != 0;
+#pragma unroll
+              for (int k = 0; k < s; ++k) {
+                float lo = cs[k], hi = cs[k + s];
+                if (s == 16 && !row_ok) { lo = 0.f; hi = 0.f; }
+                cs[k] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, up ? lo : hi, s);
+              }
+            }
+            if (col + lane < p.N) atomicAdd(p.colsum + col + lane, cs[0]);
+          }
           fence_proxy_async();
           __syncwarp();
           if (elect_one()) {
@@ -531,6 +551,7 @@ int try_launch(const memb_gemm_desc& g, cudaStream_t stream, bool* handled) {
   p.bias = g.bias; p.colscale = g.colscale; p.rowscale = g.rowscale; p.rows_per_group = std::max(1, g.rows_per_group);
   p.has_d2 = g.d2 != nullptr;
   p.err_flag = g.err_flag;
+  p.colsum = (epi == MEMB_EPI_DGELU) ? g.colsum : nullptr;
 
   CUtensorMap t[5];
   if (int rc = make_tmap(&t[0], g.a, 2, g.m, g.k, g.lda, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;

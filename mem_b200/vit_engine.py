@@ -493,8 +493,9 @@ class VitEngine:
             G = lambda n: flat.g(pre + n)  # noqa: E731
             # ---- MLP branch (dz = its branch backward, produced by the previous LayerNorm backward)
             ops.gemm(dz, s["act"], out=G("mlp.fc2.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD)
-            ops.gemm(dz, flat.w16(pre + "mlp.fc2.weight"), out=dh, b_layout=1, epilogue=EPI_DGELU, aux=s["fpre"])
-            _lib.check(lib.memb_colsum_bf16(dh.data_ptr(), hidden, M, hidden, G("mlp.fc1.bias").data_ptr(), sp))
+            # fc1's bias gradient (column sums of dh) leaves the same epilogue
+            ops.gemm(dz, flat.w16(pre + "mlp.fc2.weight"), out=dh, b_layout=1, epilogue=EPI_DGELU, aux=s["fpre"],
+                     colsum=G("mlp.fc1.bias"))
             ops.gemm(dh, s["ln2"], out=G("mlp.fc1.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD)
             ops.gemm(dh, flat.w16(pre + "mlp.fc1.weight"), out=dln, b_layout=1)
             # ---- attention branch (its branch backward rides on the LayerNorm backward of norm2)

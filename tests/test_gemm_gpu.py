@@ -94,6 +94,29 @@ def test_dgelu(lib, M, N, K, block_n):
     assert rel_err(out, x.grad) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(3152, 3072, 768), (1000, 384, 1600), (300, 768, 768)])
+def test_dgelu_fused_column_sums(lib, M, N, K):
+    """The DGELU epilogue's optional bias gradient: += column sums of its own output over the M rows (M tails, N not a
+    multiple of the tile, accumulation into a non-zero buffer; M = 300 takes the single-CTA kernel + separate pass)."""
+    from mem_b200 import ops
+    A, B, acc, g = operands(M, N, K, 1, 7)
+    pre = (torch.randn(M, N, device="cuda", generator=g) * 1.5).bfloat16()
+    start = torch.randn(N, device="cuda", generator=g)
+    cs = start.clone()
+    out = ops.gemm(A, B, b_layout=1, epilogue=EPI_DGELU, aux=pre, colsum=cs)
+    plain = ops.gemm(A, B, b_layout=1, epilogue=EPI_DGELU, aux=pre)
+    torch.cuda.synchronize()
+    assert torch.equal(out, plain)                           # the extra reduction does not touch the stored tile
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).backward(acc)
+    want = x.grad.double().sum(0)
+    got = (cs - start).double()
+    scale = x.grad.double().abs().sum(0)                     # error budget: bf16-level error per term (fitted GELU derivative)
+    assert float(((got - want).abs() / scale).max()) < 4e-3
+    # against the sum of what was stored (bf16-rounded terms): rounding noise only, it averages out over the rows
+    assert float(((got - out.double().sum(0)).abs() / scale).max()) < 5e-4
+
+
 def test_pair_and_single_cta_agree(lib):
     """M below the pair kernel's threshold runs on the single-CTA kernel: same math, same GELU."""
     from mem_b200 import ops

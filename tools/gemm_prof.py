@@ -34,6 +34,7 @@ cases = {
     "fc1_gelu": (lambda: ops.gemm(x, w1, out=out_h, epilogue=EPI_BIAS_GELU, bias=bias1, d2=pre_h), 2.0 * M * Hd * D),
     "fc2_residual": (lambda: ops.gemm(h, w2, out=out_res, epilogue=EPI_RESIDUAL, bias=biasD, aux=res, d2=br, colscale=gamma), 2.0 * M * Hd * D),
     "fc2_dgrad_dgelu": (lambda: ops.gemm(x, w2, out=out_h, b_layout=1, epilogue=EPI_DGELU, aux=pre_h), 2.0 * M * Hd * D),
+    "fc2_dgrad_dgelu_colsum": (lambda: ops.gemm(x, w2, out=out_h, b_layout=1, epilogue=EPI_DGELU, aux=pre_h, colsum=bias1), 2.0 * M * Hd * D),
     "fc1_dgrad": (lambda: ops.gemm(h, w1, out=br, b_layout=1), 2.0 * M * Hd * D),
     "proj_residual": (lambda: ops.gemm(x, wp, out=out_res, epilogue=EPI_RESIDUAL, bias=biasD, aux=res, d2=br, colscale=gamma), 2.0 * M * D * D),
     "proj_dgrad": (lambda: ops.gemm(x, wp, out=br, b_layout=1), 2.0 * M * D * D),
