@@ -264,6 +264,9 @@ int memb_hist_raw_u8(const uint8_t* raw, int64_t n_records, int format, int H, i
 #define MEMB_EPI_ATOMIC_ADD 3 /* d += alpha*acc (fp32, split-K, red.global.add)                           */
 #define MEMB_EPI_DGELU 4      /* d = acc * gelu'(aux) (aux = bf16 pre-activation)                          */
 #define MEMB_EPI_ARGMAX 5     /* d[row] = max over n of key(acc + bias, n) (uint64, atomicMax)             */
+#define MEMB_EPI_STORE_ROWDOT 6 /* d = bf16(acc); rowdot[r / g][n / 64][r % g] = sum over the 64 columns of one head of
+                                   d * aux (aux: bf16 [M,N]; g = rows_per_group; N % 64 == 0): the attention backward's
+                                   rowsum(dO * O) leaves the GEMM that produces dO (proj dgrad)                */
 
 typedef struct memb_gemm_desc {
   const void* a;  /* a_layout 0: [M,K] row-major (K-major); 1: [K,M] row-major (MN-major, bf16 only) */
@@ -298,6 +301,7 @@ typedef struct memb_gemm_desc {
   float* colsum;           /* MEMB_EPI_DGELU, bf16 output: optional [N] accumulator, += column sums of d over the M rows (the
                               bias gradient of the layer whose GELU this is, mem/modeling_finetune.py:62-71 backward); fused
                               into the CTA-pair kernel's epilogue (one red.add per column per 32 rows), else a separate pass */
+  float* rowdot;           /* MEMB_EPI_STORE_ROWDOT: fp32 [ceil(M / g)][N / 64][g], written (not accumulated) */
 } memb_gemm_desc;
 
 int memb_gemm(const memb_gemm_desc* desc, memb_stream_t stream);
@@ -442,6 +446,11 @@ int memb_attention_pack_bias(const float* dense /* [H, N, ld] */, int ld, int N,
                              memb_stream_t stream);
 int memb_attention_fwd(const void* qkv, const float* bias, int ld_ds, int B, int N, int H, int head_dim, float scale,
                        void* out, float* lse, memb_stream_t stream);
+/* delta[b][h][q] = sum over d of a[b, q, h, d] * b[b, q, h, d] (bf16 [B*N, H*64] both): rowsum(dO * O) of the attention
+ * backward as a separate pass. */
+int memb_rowdot_heads(const void* a, const void* b, int B, int N, int H, float* delta, memb_stream_t stream);
+/* out == NULL: the first B*H*N floats of the workspace already hold rowsum(dO * O) (memb_rowdot_heads layout), e.g. left
+ * there by the GEMM that produced dout (MEMB_EPI_STORE_ROWDOT); otherwise the call computes it from out and dout. */
 size_t memb_attention_bwd_workspace_bytes(int B, int N, int H);
 int memb_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias,
                        const float* biasT, int ld_ds, int B, int N, int H, int head_dim, float scale, void* dqkv,

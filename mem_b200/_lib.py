@@ -52,7 +52,7 @@ SIGNATURES = {
 
 DT_BF16, DT_F32 = 0, 1
 ATTN_BIAS_FLOATS_PER_HEAD = 52 * 256 * 4  # MEMB_ATTN_BIAS_FLOATS_PER_HEAD
-EPI_STORE, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_ATOMIC_ADD, EPI_DGELU, EPI_ARGMAX = 0, 1, 2, 3, 4, 5
+EPI_STORE, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_ATOMIC_ADD, EPI_DGELU, EPI_ARGMAX, EPI_STORE_ROWDOT = 0, 1, 2, 3, 4, 5, 6
 
 
 class GemmDesc(_c.Structure):
@@ -66,7 +66,7 @@ class GemmDesc(_c.Structure):
         ("d", _vp), ("ldd", _i64), ("d2", _vp), ("ldd2", _i64),
         ("bias", _vp), ("aux", _vp), ("ldaux", _i64), ("colscale", _vp), ("rowscale", _vp),
         ("rows_per_group", _i32), ("out_group_rows", _i32), ("out_group_stride", _i32), ("out_row_offset", _i32),
-        ("rowmask", _vp), ("maskvec", _vp), ("alpha", _f32), ("alpha_dev", _vp), ("err_flag", _vp), ("colsum", _vp),
+        ("rowmask", _vp), ("maskvec", _vp), ("alpha", _f32), ("alpha_dev", _vp), ("err_flag", _vp), ("colsum", _vp), ("rowdot", _vp),
     ]
 
 
@@ -94,6 +94,7 @@ SIGNATURES.update({
     "memb_attention_pack_bias": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "memb_attention_fwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
     "memb_attention_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "memb_rowdot_heads": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "memb_attention_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "memb_fill_f32": (_i32, [_vp, _i64, _f32, _vp]),
     "memb_cast_bf16": (_i32, [_vp, _vp, _i64, _vp]),

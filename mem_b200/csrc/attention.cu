@@ -371,7 +371,8 @@ constexpr int COL_DV = 256, COL_DK = 320, COL_DQ = 384;  // S^T at 128*buf, dP^T
 }  // namespace bwd
 
 struct BwdParams {
-  const float* nl_delta;  // [2][B*H*N]: -lse*log2e, rowsum(dO*O)   (attn_bwd_prep)
+  const float* lse;       // [B*H*N] natural-log row logsumexp of the forward
+  const float* delta;     // [B*H*N] rowsum(dO*O): attn_rowdot_heads, or the producer of dO (memb_gemm MEMB_EPI_STORE_ROWDOT)
   const float* biasT;
   int ldb, B, N, H;
   float scale, c1;
@@ -379,11 +380,10 @@ struct BwdParams {
   int write_ds;
 };
 
-// nl[b,h,q] = -lse*log2(e), delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]: eight lanes per (b, q, h) row of 64, one
-// 16-byte load of O and of dO each (a warp reads 512 contiguous bytes per instruction), 3 shuffles, lane 0 writes.
-__global__ void __launch_bounds__(256) attn_bwd_prep(const bf16* __restrict__ out, const bf16* __restrict__ dout,
-                                                     const float* __restrict__ lse, int B, int N, int H,
-                                                     float* __restrict__ nl_delta) {
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]: eight lanes per (b, q, h) row of 64, one 16-byte load of O and of dO
+// each (a warp reads 512 contiguous bytes per instruction), 3 shuffles, lane 0 writes.
+__global__ void __launch_bounds__(256) attn_rowdot_heads(const bf16* __restrict__ out, const bf16* __restrict__ dout,
+                                                         int B, int N, int H, float* __restrict__ delta) {
   static_assert(kHeadDim == 64, "eight 16-byte loads cover one head row");
   const long long total = (long long)B * N * H;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -409,8 +409,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep(const bf16* __restrict__ ou
     const unsigned int bq = iu / (unsigned int)H, h = iu - bq * H;
     const unsigned int b = bq / (unsigned int)N, q = bq - b * N;
     const long long o = ((long long)b * H + h) * N + q;
-    nl_delta[o] = -lse[o] * kLog2e;
-    nl_delta[total + o] = d;
+    delta[o] = d;
   }
 }
 
@@ -525,9 +524,9 @@ attention_bwd_tc(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
     float* nl = reinterpret_cast<float*>(smem + OFF_NL);
     float* dl = reinterpret_cast<float*>(smem + OFF_DELTA);
     const int q = threadIdx.x;
-    const long long o = (long long)blockIdx.x * p.N + q, total = (long long)p.B * p.H * p.N;
-    nl[q] = q < p.N ? __ldg(p.nl_delta + o) : -INFINITY;
-    dl[q] = q < p.N ? __ldg(p.nl_delta + total + o) : 0.f;
+    const long long o = (long long)blockIdx.x * p.N + q;
+    nl[q] = q < p.N ? -__ldg(p.lse + o) * kLog2e : -INFINITY;
+    dl[q] = q < p.N ? __ldg(p.delta + o) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -785,6 +784,16 @@ extern "C" int memb_attention_trace_dump(long long* host, int max_pairs) {
 }
 #endif
 
+extern "C" int memb_rowdot_heads(const void* a, const void* b, int B, int N, int H, float* delta, memb_stream_t s) {
+  MEMB_REQUIRE(a && b && delta && B > 0 && N > 0 && H > 0, "rowdot_heads: bad arguments");
+  MEMB_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0, "rowdot_heads: operands must be 16-byte aligned");
+  const long long rows = (long long)B * N * H;
+  MEMB_REQUIRE(rows < (1LL << 28), "rowdot_heads: B*N*H = %lld is beyond the kernel's 32-bit row indexing", rows);
+  attn_rowdot_heads<<<(unsigned)ceil_div<long long>(rows * 8, 256), 256, 0, s>>>((const bf16*)a, (const bf16*)b, B, N, H, delta);
+  MEMB_LAUNCH_OK("attn_rowdot_heads");
+  return MEMB_OK;
+}
+
 extern "C" size_t memb_attention_bwd_workspace_bytes(int B, int N, int H) {
   return (size_t)2 * (size_t)B * (size_t)N * (size_t)H * sizeof(float);
 }
@@ -794,7 +803,7 @@ extern "C" int memb_attention_bwd(const void* qkv, const void* out, const void* 
                                   void* dsT, void* workspace, size_t ws_bytes, memb_stream_t s) {
   (void)bias;  // the backward reads the transposed copy only
   if (int rc = check_shape(B, N, H, head_dim, ldb, dsT != nullptr)) return rc;
-  MEMB_REQUIRE(qkv && out && dout && lse && dqkv && workspace, "attention_bwd: null pointer");
+  MEMB_REQUIRE(qkv && dout && lse && dqkv && workspace, "attention_bwd: null pointer");
   MEMB_REQUIRE(ws_bytes >= memb_attention_bwd_workspace_bytes(B, N, H), "attention_bwd: workspace too small");
   MEMB_REQUIRE((bias == nullptr) == (biasT == nullptr), "attention_bwd: bias and its transpose go together");
   MEMB_REQUIRE(!biasT || (reinterpret_cast<uintptr_t>(biasT) & 15u) == 0, "attention_bwd: biasT must be 16-byte aligned");
@@ -828,10 +837,12 @@ extern "C" int memb_attention_bwd(const void* qkv, const void* out, const void* 
   }
   const long long rows = (long long)B * N * H;
   MEMB_REQUIRE(rows < (1LL << 28), "attention_bwd: B*N*H = %lld is beyond the 32-bit row indexing of the prep kernel", rows);
-  attn_bwd_prep<<<(unsigned)ceil_div<long long>(rows * 8, 256), 256, 0, s>>>((const bf16*)out, (const bf16*)dout, lse, B, N, H,
-                                                                         (float*)workspace);
-  MEMB_LAUNCH_OK("attn_bwd_prep");
-  BwdParams p{(const float*)workspace, biasT, ldb, B, N, H, scale, scale * kLog2e, (bf16*)dqkv, dsT ? 1 : 0};
+  if (out != nullptr) {       // out == NULL: the caller's producer of dO already left delta in the workspace
+    attn_rowdot_heads<<<(unsigned)ceil_div<long long>(rows * 8, 256), 256, 0, s>>>((const bf16*)out, (const bf16*)dout, B, N, H,
+                                                                               (float*)workspace);
+    MEMB_LAUNCH_OK("attn_rowdot_heads");
+  }
+  BwdParams p{lse, (const float*)workspace, biasT, ldb, B, N, H, scale, scale * kLog2e, (bf16*)dqkv, dsT ? 1 : 0};
   attention_bwd_tc<<<B * H, kBwdThreads, bwd::SMEM_BYTES, s>>>(tq, tdo, tds, tdq, p);
   MEMB_LAUNCH_OK("attention_bwd_tc");
   return MEMB_OK;

@@ -564,11 +564,22 @@ extern "C" int memb_gemm(const memb_gemm_desc* gp, memb_stream_t stream) {
   MEMB_REQUIRE(g.m > 0 && g.n > 0 && g.k > 0, "gemm: m, n, k must be positive (%d, %d, %d)", g.m, g.n, g.k);
   MEMB_REQUIRE(g.a && g.b && g.d, "gemm: null operand");
   MEMB_REQUIRE(g.in_dtype == MEMB_DT_BF16 || g.in_dtype == MEMB_DT_F32, "gemm: in_dtype must be bf16 or fp32(tf32)");
-  MEMB_REQUIRE(g.epilogue >= MEMB_EPI_STORE && g.epilogue <= MEMB_EPI_ARGMAX, "gemm: unknown epilogue %d", g.epilogue);
+  MEMB_REQUIRE(g.epilogue >= MEMB_EPI_STORE && g.epilogue <= MEMB_EPI_STORE_ROWDOT, "gemm: unknown epilogue %d", g.epilogue);
+  if (g.epilogue == MEMB_EPI_STORE_ROWDOT)
+    MEMB_REQUIRE(g.aux && g.rowdot && g.rows_per_group > 0 && g.n % 64 == 0 && g.m % g.rows_per_group == 0 &&
+                     g.out_dtype == MEMB_DT_BF16 && g.ldd == g.n && g.ldaux == g.n && !g.bias,
+                 "gemm: STORE_ROWDOT needs bf16 d and aux (dense [M,N], N %% 64 == 0), rowdot, rows_per_group dividing M, no bias");
   {  // large bf16 K-major-A problems with a fused epilogue run on the CTA-pair kernel
     bool handled = false;
     if (int rc = gemm_pair::try_launch(g, stream, &handled)) return rc;
     if (handled) return MEMB_OK;
+  }
+  if (g.epilogue == MEMB_EPI_STORE_ROWDOT) {   // this kernel has no fused row dots: the plain GEMM, then one pass over d and aux
+    memb_gemm_desc plain = g;
+    plain.epilogue = MEMB_EPI_STORE;
+    plain.aux = nullptr; plain.ldaux = 0; plain.rowdot = nullptr; plain.rows_per_group = 0;
+    if (int rc = memb_gemm(&plain, stream)) return rc;
+    return memb_rowdot_heads(g.d, g.aux, g.m / g.rows_per_group, g.rows_per_group, g.n / 64, g.rowdot, stream);
   }
   if (g.colsum != nullptr) {
     MEMB_REQUIRE(g.epilogue == MEMB_EPI_DGELU && g.out_dtype == MEMB_DT_BF16, "gemm: colsum rides on the DGELU epilogue with a bf16 output");

@@ -20,7 +20,8 @@
 //   STORE      d = bf16(acc + bias)
 //   BIAS_GELU  d = bf16(gelu(acc + bias)),  d2 = bf16(acc + bias)
 //   RESIDUAL   d = aux + rowscale[row / rows_per_group] * colscale[n] * (acc + bias)  (fp32), d2 = bf16(acc + bias)
-//   DGELU      d = bf16(acc * gelu'(aux))
+//   DGELU      d = bf16(acc * gelu'(aux))            (+ optional column sums of d: the bias gradient)
+//   ROWDOT     d = bf16(acc), rowdot = per-head row sums of d * aux   (the attention backward's rowsum(dO * O))
 #include <algorithm>
 #include <cstdlib>
 
@@ -54,7 +55,10 @@ struct Params {
   int has_d2;
   int* err_flag;
   float* colsum;   // DGELU: += column sums of the output (may be NULL)
+  float* rowdot;   // STORE_ROWDOT: [M / rows_per_group][N / 64][rows_per_group]
 };
+// epilogues that stream a bf16 aux tile of the output's shape through the per-warp staging ring
+template <int EPI> constexpr bool kAuxBf16 = (EPI == MEMB_EPI_DGELU || EPI == MEMB_EPI_STORE_ROWDOT);
 
 template <int BLOCK_N, int EPI>
 struct Cfg {
@@ -114,7 +118,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_d);
     if (EPI == MEMB_EPI_BIAS_GELU || EPI == MEMB_EPI_RESIDUAL) prefetch_tmap(&tmap_d2);
-    if (EPI == MEMB_EPI_RESIDUAL || EPI == MEMB_EPI_DGELU) prefetch_tmap(&tmap_aux);
+    if (EPI == MEMB_EPI_RESIDUAL || kAuxBf16<EPI>) prefetch_tmap(&tmap_aux);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -225,7 +229,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t vbs = smem_u32(vb) + (half * kCols) * 4;
 
       // aux prefetch for the first chunk(s) of this tile (overlaps the tail of the main loop)
-      if constexpr (EPI == MEMB_EPI_DGELU) {
+      if constexpr (kAuxBf16<EPI>) {
         if (elect_one()) {
           bulk_wait_read<0>();
 #pragma unroll
@@ -246,6 +250,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tma_load_2d_addr(stg + slot * 4096, &tmap_aux, smem_u32(&abar[slot]), colw, row0);
         }
         __syncwarp();
+      }
+      float dot = 0.f;               // ROWDOT: this lane's row, running over the 64 columns of one head
+      long long dot_base = 0;        // rowdot index of (image, head 0, row in image)
+      if constexpr (EPI == MEMB_EPI_STORE_ROWDOT) {
+        const int row = min(row0 + lane, p.M - 1), img = row / p.rows_per_group;
+        dot_base = (long long)img * (p.N >> 6) * p.rows_per_group + (row - img * p.rows_per_group);
       }
       float rs = 1.0f;
       if constexpr (EPI == MEMB_EPI_RESIDUAL) {
@@ -376,6 +386,46 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (store_ok) tma_store_2d(&tmap_d, buf, col, row0);
             bulk_commit();
           }
+        } else if constexpr (EPI == MEMB_EPI_STORE_ROWDOT) {
+          const uint32_t slot = ring & 3;
+          const uint32_t buf = stg + slot * 2048;
+          if (c + 2 < kChunks) {   // the aux tile two chunks ahead (its slot held the store of two chunks ago)
+            if (elect_one()) {
+              const uint32_t s2 = (ring + 2) & 3;
+              bulk_wait_read<1>();
+              fence_proxy_async();
+              mbar_arrive_expect_tx(&abar[s2], 32 * 64);
+              tma_load_2d_addr(stg + s2 * 2048, &tmap_aux, smem_u32(&abar[s2]), col + 64, row0);
+            }
+            __syncwarp();
+          }
+          mbar_wait(&abar[slot], (aux_phases >> slot) & 1u, p.err_flag, 5);
+          aux_phases ^= 1u << slot;
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 q = ld_shared_v4(sw64(buf, lane, j));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint32_t v = pack_bf16x2(__uint_as_float(a[8 * j + 2 * t]), __uint_as_float(a[8 * j + 2 * t + 1]));
+              pk[4 * j + t] = v;
+              dot = fmaf(bf16_lo(v), bf16_lo(w[t]), dot);      // the stored (rounded) value times aux, fp32 accumulation
+              dot = fmaf(bf16_hi(v), bf16_hi(w[t]), dot);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) st_shared_v4(sw64(buf, lane, j), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (elect_one()) {
+            if (store_ok) tma_store_2d(&tmap_d, buf, col, row0);
+            bulk_commit();
+          }
+          if (c & 1) {             // two 32-column chunks = one head
+            if (store_ok && row0 + lane < p.M) p.rowdot[dot_base + (long long)(col >> 6) * p.rows_per_group] = dot;
+            dot = 0.f;
+          }
         } else if constexpr (EPI == MEMB_EPI_RESIDUAL) {
           const uint32_t slot = ring & 1;
           const uint32_t buf = stg + slot * 4096, buf2 = stg + 8192;
@@ -499,6 +549,9 @@ static int dispatch_epi(int epi, const Params& p, const CUtensorMap* t, cudaStre
     case MEMB_EPI_BIAS_GELU: return launch<BLOCK_N, B_MN, MEMB_EPI_BIAS_GELU>(p, t, s);
     case MEMB_EPI_RESIDUAL: return launch<BLOCK_N, B_MN, MEMB_EPI_RESIDUAL>(p, t, s);
     case MEMB_EPI_DGELU: return launch<BLOCK_N, B_MN, MEMB_EPI_DGELU>(p, t, s);
+    case MEMB_EPI_STORE_ROWDOT:
+      if constexpr (BLOCK_N == 192) return fail(MEMB_EINVAL, "gemm_pair: row dots need tiles of whole heads");
+      else return launch<BLOCK_N, B_MN, MEMB_EPI_STORE_ROWDOT>(p, t, s);
     default: return fail(MEMB_EINVAL, "gemm_pair: unsupported epilogue %d", epi);
   }
 }
@@ -528,7 +581,8 @@ int try_launch(const memb_gemm_desc& g, cudaStream_t stream, bool* handled) {
   if (disabled) return MEMB_OK;
   if (g.in_dtype != MEMB_DT_BF16 || g.a_layout != 0 || g.split_precision) return MEMB_OK;
   const int epi = g.epilogue;
-  if (!(epi == MEMB_EPI_STORE || epi == MEMB_EPI_BIAS_GELU || epi == MEMB_EPI_RESIDUAL || epi == MEMB_EPI_DGELU)) return MEMB_OK;
+  if (!(epi == MEMB_EPI_STORE || epi == MEMB_EPI_BIAS_GELU || epi == MEMB_EPI_RESIDUAL || epi == MEMB_EPI_DGELU ||
+        epi == MEMB_EPI_STORE_ROWDOT)) return MEMB_OK;
   if (g.m < 512 || g.n < 128 || g.n % 32 != 0 || g.k % 8 != 0) return MEMB_OK;
   if (g.act || g.out_split || g.rowmask || g.out_group_rows > 0 || g.alpha_dev || (g.alpha != 0.0f && g.alpha != 1.0f)) return MEMB_OK;
   const bool d_f32 = epi == MEMB_EPI_RESIDUAL;
@@ -537,12 +591,15 @@ int try_launch(const memb_gemm_desc& g, cudaStream_t stream, bool* handled) {
   if (!aligned16(g.a, g.lda, 2) || !aligned16(g.b, g.ldb, 2) || !aligned16(g.d, g.ldd, d_f32 ? 4 : 2)) return MEMB_OK;
   if (g.d2 && !aligned16(g.d2, g.ldd2, 2)) return MEMB_OK;
   if (epi == MEMB_EPI_RESIDUAL && (!g.aux || !aligned16(g.aux, g.ldaux, 4))) return MEMB_OK;
-  if (epi == MEMB_EPI_DGELU && (!g.aux || !aligned16(g.aux, g.ldaux, 2))) return MEMB_OK;
+  if ((epi == MEMB_EPI_DGELU || epi == MEMB_EPI_STORE_ROWDOT) && (!g.aux || !aligned16(g.aux, g.ldaux, 2))) return MEMB_OK;
+  if (epi == MEMB_EPI_STORE_ROWDOT && (!g.rowdot || g.n % 64 != 0 || g.rows_per_group <= 0)) return MEMB_OK;
   if (epi == MEMB_EPI_RESIDUAL && g.rowscale && g.rows_per_group <= 0) return MEMB_OK;
 
   const bool b_mn = g.b_layout != 0;
   const int m_pairs = ceil_div(g.m, 2 * BLOCK_M);
-  const int bn = pick_block_n(m_pairs, g.n, b_mn, (g.block_n == 128 || g.block_n == 192 || g.block_n == 256) ? g.block_n : 0);
+  // (192-wide tiles split a warp's columns at 96: not whole heads for the row dots; MN-major B halves come as 64-column boxes)
+  const int bn = pick_block_n(m_pairs, g.n, b_mn || epi == MEMB_EPI_STORE_ROWDOT,
+                              (g.block_n == 128 || g.block_n == 192 || g.block_n == 256) ? g.block_n : 0);
   Params p{};
   p.M = g.m; p.N = g.n; p.K = g.k;
   p.num_n_tiles = ceil_div(g.n, bn);
@@ -552,6 +609,7 @@ int try_launch(const memb_gemm_desc& g, cudaStream_t stream, bool* handled) {
   p.has_d2 = g.d2 != nullptr;
   p.err_flag = g.err_flag;
   p.colsum = (epi == MEMB_EPI_DGELU) ? g.colsum : nullptr;
+  p.rowdot = (epi == MEMB_EPI_STORE_ROWDOT) ? g.rowdot : nullptr;
 
   CUtensorMap t[5];
   if (int rc = make_tmap(&t[0], g.a, 2, g.m, g.k, g.lda, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
@@ -572,7 +630,7 @@ int try_launch(const memb_gemm_desc& g, cudaStream_t stream, bool* handled) {
   }
   if (epi == MEMB_EPI_RESIDUAL) {
     if (int rc = make_tmap(&t[4], g.aux, 4, g.m, g.n, g.ldaux, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-  } else if (epi == MEMB_EPI_DGELU) {
+  } else if (epi == MEMB_EPI_DGELU || epi == MEMB_EPI_STORE_ROWDOT) {
     if (int rc = make_tmap(&t[4], g.aux, 2, g.m, g.n, g.ldaux, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
   }
 

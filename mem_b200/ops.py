@@ -30,7 +30,7 @@ def _ptr(t):
 def gemm(a, b, *, out=None, out_dtype=None, a_layout=0, b_layout=0, epilogue=EPI_STORE, bias=None,
          aux=None, d2=None, colscale=None, rowscale=None, rows_per_group=0, alpha=1.0, act=0, splits=0,
          block_n=0, split_precision=False, out_split=False, row_remap=None, rowmask=None, maskvec=None,
-         m=None, n=None, k=None, alpha_dev=None, colsum=None):
+         m=None, n=None, k=None, alpha_dev=None, colsum=None, rowdot=None):
     """``D[M,N] = epilogue(A @ B^T)`` on the tcgen05 GEMM.
 
     a: ``[M,K]`` (a_layout 0) or ``[K,M]`` (a_layout 1); b: ``[N,K]`` (b_layout 0) or ``[K,N]``
@@ -74,6 +74,7 @@ def gemm(a, b, *, out=None, out_dtype=None, a_layout=0, b_layout=0, epilogue=EPI
     g.alpha = alpha
     g.alpha_dev = _ptr(alpha_dev)
     g.colsum = _ptr(colsum)          # EPI_DGELU: [N] fp32, += column sums of the output (the fused bias gradient)
+    g.rowdot = _ptr(rowdot)          # EPI_STORE_ROWDOT: fp32 [M / rows_per_group, N / 64, rows_per_group] = per-head rowsum(out * aux)
     g.err_flag = _err_flag(torch, a.device).data_ptr()
     lib = _lib.load()
     _lib.check(lib.memb_gemm(ctypes.byref(g), _lib.stream_ptr(torch, a.device)))

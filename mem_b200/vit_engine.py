@@ -22,7 +22,7 @@ import math
 import torch
 
 from . import _lib, ops
-from ._lib import (DT_BF16, DT_F32, EPI_ATOMIC_ADD, EPI_BIAS_GELU, EPI_DGELU, EPI_RESIDUAL, EPI_STORE)
+from ._lib import (DT_BF16, DT_F32, EPI_ATOMIC_ADD, EPI_BIAS_GELU, EPI_DGELU, EPI_RESIDUAL, EPI_STORE, EPI_STORE_ROWDOT)
 
 CHUNK = 1024  # flat-buffer alignment (elements) == AdamW chunk size
 
@@ -501,9 +501,11 @@ class VitEngine:
             # ---- attention branch (its branch backward rides on the LayerNorm backward of norm2)
             ln_bwd_then_branch(dln, s["xmid"], blk.norm2, s["mu2"], s["rs2"], G("norm2.weight"), G("norm2.bias"), i, 1)
             ops.gemm(dz, s["ao"], out=G("attn.proj.weight"), a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD)
-            ops.gemm(dz, flat.w16(pre + "attn.proj.weight"), out=dao, b_layout=1)
+            # dO = dz W_proj; the same epilogue leaves rowsum(dO * O) per head in the attention backward's workspace
+            ops.gemm(dz, flat.w16(pre + "attn.proj.weight"), out=dao, b_layout=1, epilogue=EPI_STORE_ROWDOT, aux=s["ao"],
+                     rowdot=attn_ws, rows_per_group=N)
             bias_pair = s["bias"]
-            _lib.check(lib.memb_attention_bwd(s["qkv"].data_ptr(), s["ao"].data_ptr(), dao.data_ptr(), s["lse"].data_ptr(),
+            _lib.check(lib.memb_attention_bwd(s["qkv"].data_ptr(), None, dao.data_ptr(), s["lse"].data_ptr(),
                                               ops._ptr(bias_pair[0]) if bias_pair else None,
                                               ops._ptr(bias_pair[1]) if bias_pair else None, ldk, B, N, H, D // H, scale,
                                               dqkv.data_ptr(), ds.data_ptr() if bias_pair else None,

@@ -7,7 +7,7 @@ import torch
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
 
-from mem_b200._lib import EPI_BIAS_GELU, EPI_DGELU, EPI_RESIDUAL, EPI_STORE  # noqa: E402
+from mem_b200._lib import EPI_BIAS_GELU, EPI_DGELU, EPI_RESIDUAL, EPI_STORE, EPI_STORE_ROWDOT  # noqa: E402
 
 
 def rel_err(a, b):
@@ -115,6 +115,28 @@ def test_dgelu_fused_column_sums(lib, M, N, K):
     assert float(((got - want).abs() / scale).max()) < 4e-3
     # against the sum of what was stored (bf16-rounded terms): rounding noise only, it averages out over the rows
     assert float(((got - out.double().sum(0)).abs() / scale).max()) < 5e-4
+
+
+@pytest.mark.parametrize("Bimg,Ntok,N,K,block_n", [(16, 197, 768, 768, 0), (16, 197, 768, 768, 256), (5, 200, 1024, 512, 0),
+                                                    (2, 150, 128, 256, 0)])
+def test_store_rowdot(lib, Bimg, Ntok, N, K, block_n):
+    """The proj-dgrad epilogue that also leaves the attention backward's rowsum(dO * O): d = bf16(acc) as the plain store,
+    rowdot[img][head][token] = sum over the head's 64 columns of d * aux (M tails, both tile widths, rows of one tile in
+    different images; M = 300 takes the single-CTA kernel + separate pass)."""
+    from mem_b200 import ops
+    M = Bimg * Ntok
+    A, B, acc, g = operands(M, N, K, 1, 9)
+    aux = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    rd = torch.full((Bimg, N // 64, Ntok), float("nan"), device="cuda")
+    out = ops.gemm(A, B, b_layout=1, epilogue=EPI_STORE_ROWDOT, aux=aux, rowdot=rd, rows_per_group=Ntok, block_n=block_n)
+    plain = ops.gemm(A, B, b_layout=1, block_n=block_n)
+    torch.cuda.synchronize()
+    assert torch.equal(out, plain)
+    want = (out.float() * aux.float()).view(Bimg, Ntok, N // 64, 64).sum(-1).permute(0, 2, 1)
+    assert torch.isfinite(rd).all()
+    assert float((rd - want).abs().max()) < 2e-5 * float((out.float().abs() * aux.float().abs()).view(Bimg, Ntok, -1, 64).sum(-1).max())
+    with pytest.raises(ValueError):
+        ops.gemm(A, B, b_layout=1, epilogue=EPI_STORE_ROWDOT, aux=aux, rowdot=rd, rows_per_group=Ntok + 1)
 
 
 def test_pair_and_single_cta_agree(lib):

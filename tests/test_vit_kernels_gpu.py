@@ -124,6 +124,19 @@ def test_attention_fwd_bwd(L, B, N, H, with_bias):
     got = dqkv.float().view(B, N, 3, D)
     for i, name in enumerate("qkv"):
         assert rel_err(got[:, :, i], g[:, :, i]) < 2e-2, name
+    # the caller may hand in rowsum(dO * O) itself (out = NULL): here from the separate pass, bit-identical result
+    delta = torch.empty(B, H, N, device="cuda")
+    ck(L.memb_rowdot_heads(out.data_ptr(), dout.data_ptr(), B, N, H, delta.data_ptr(), sp()))
+    want_delta = (out.float() * dout.float()).view(B, N, H, 64).sum(-1).permute(0, 2, 1)
+    assert float((delta - want_delta).abs().max()) < 1e-4 * max(1.0, float(want_delta.abs().max()))
+    ws2 = torch.zeros_like(ws)
+    ws2.view(torch.float32)[:B * H * N] = delta.flatten()
+    dqkv2 = torch.zeros_like(dqkv)
+    ds2 = torch.zeros_like(ds) if with_bias else None
+    ck(L.memb_attention_bwd(qkv.data_ptr(), None, dout.data_ptr(), lse.data_ptr(),
+                            bias_p.data_ptr() if with_bias else None, biasT_p.data_ptr() if with_bias else None, ldk, B, N, H, 64,
+                            scale, dqkv2.data_ptr(), ds2.data_ptr() if with_bias else None, ws2.data_ptr(), ws2.numel(), sp()))
+    assert torch.equal(dqkv2, dqkv) and (not with_bias or torch.equal(ds2, ds))
     if with_bias:
         dbiasT = torch.zeros(H, N, ldk, device="cuda")   # the kernel emits dS^T[b, h, key, query]
         ck(L.memb_batch_reduce_bf16(ds.data_ptr(), B, H * N * ldk, dbiasT.data_ptr(), sp()))

@@ -7,7 +7,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mem_b200 import ops  # noqa: E402
-from mem_b200._lib import EPI_ATOMIC_ADD, EPI_BIAS_GELU, EPI_DGELU, EPI_RESIDUAL, EPI_STORE  # noqa: E402
+from mem_b200._lib import EPI_ATOMIC_ADD, EPI_BIAS_GELU, EPI_DGELU, EPI_RESIDUAL, EPI_STORE, EPI_STORE_ROWDOT  # noqa: E402
 
 torch.manual_seed(0)
 M, D, Hd = 128 * 197, 768, 3072
@@ -29,6 +29,7 @@ pre_h = torch.empty(M, Hd, device=dev, dtype=torch.bfloat16)
 out_res = torch.empty(M, D, device=dev)
 br = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
 gw = torch.zeros(Hd, D, device=dev)
+rd = torch.zeros(128, D // 64, 197, device=dev)
 cases = {
     "qkv_store": (lambda: ops.gemm(x, wqkv, out=out_qkv, bias=bias3), 2.0 * M * 3 * D * D),
     "fc1_gelu": (lambda: ops.gemm(x, w1, out=out_h, epilogue=EPI_BIAS_GELU, bias=bias1, d2=pre_h), 2.0 * M * Hd * D),
@@ -38,6 +39,7 @@ cases = {
     "fc1_dgrad": (lambda: ops.gemm(h, w1, out=br, b_layout=1), 2.0 * M * Hd * D),
     "proj_residual": (lambda: ops.gemm(x, wp, out=out_res, epilogue=EPI_RESIDUAL, bias=biasD, aux=res, d2=br, colscale=gamma), 2.0 * M * D * D),
     "proj_dgrad": (lambda: ops.gemm(x, wp, out=br, b_layout=1), 2.0 * M * D * D),
+    "proj_dgrad_rowdot": (lambda: ops.gemm(x, wp, out=br, b_layout=1, epilogue=EPI_STORE_ROWDOT, aux=x, rowdot=rd, rows_per_group=197), 2.0 * M * D * D),
     "qkv_dgrad": (lambda: ops.gemm(out_qkv, wqkv, out=br, b_layout=1), 2.0 * M * 3 * D * D),
     "fc1_wgrad": (lambda: ops.gemm(h, x, out=gw, a_layout=1, b_layout=1, epilogue=EPI_ATOMIC_ADD), 2.0 * M * Hd * D),
 }
